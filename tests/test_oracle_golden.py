@@ -1,0 +1,108 @@
+"""Pin the CPU oracle (oracle/esn_oracle.py) against outputs of the reference's
+own source files, committed under tests/golden/ by oracle/make_golden.py."""
+import itertools
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import esn_oracle as oc
+from tests.conftest import LAZY_CASES, decode_boundary, load_golden
+
+
+def test_forced_states_match_reference_update():
+    z = load_golden("eager_small.npz")
+    for n_in in (3, 7):
+        W = sp.csr_matrix(z[f"W_{n_in}"])
+        states = oc.forced_states(z[f"u_{n_in}"], 60, W, z[f"Win_{n_in}"], z[f"b_{n_in}"], 0.5)
+        np.testing.assert_allclose(states, z[f"states_{n_in}"], rtol=0, atol=1e-15)
+
+
+@pytest.mark.parametrize("n_in", (3, 7))
+@pytest.mark.parametrize("n_spinup,batch", list(itertools.product((0, 10), (None, 33, 10_000))))
+def test_ridge_train_matches_reference(n_in, n_spinup, batch):
+    z = load_golden("eager_small.npz")
+    W = sp.csr_matrix(z[f"W_{n_in}"])
+    u = z[f"u_{n_in}"]
+    Wout = oc.ridge_train(u, u, n_spinup, batch, W, z[f"Win_{n_in}"], z[f"b_{n_in}"], 0.5, 1e-6)
+    ref = z[f"Wout_{n_in}_{n_spinup}_{batch}"]
+    assert Wout.shape == (n_in, 120)
+    assert oc.max_normalised_err(Wout, ref) < 1e-9
+
+
+def test_separate_targets_and_all_spinup():
+    z = load_golden("eager_small.npz")
+    # the y != u cases were generated with a fresh 7->3 reservoir of the same seeds:
+    # W and b equal the 7-input ones, Win too (same seed, same shape)
+    W = sp.csr_matrix(z["W_7"])
+    args = (W, z["Win_7"], z["b_7"], 0.5, 1e-6)
+    Wout = oc.ridge_train(z["u_7"], z["y_sep"], 5, 100, *args)
+    assert oc.max_normalised_err(Wout, z["Wout_sep"]) < 1e-9
+    Wz = oc.ridge_train(z["u_7"], z["y_sep"], 500, None, *args)
+    assert np.array_equal(Wz, z["Wout_allspin"])
+    assert not Wz.any()
+
+
+@pytest.mark.parametrize("n_in", (3, 7))
+@pytest.mark.parametrize("n_spinup", (0, 10))
+def test_closed_loop_matches_reference(n_in, n_spinup):
+    z = load_golden("eager_small.npz")
+    W = sp.csr_matrix(z[f"W_{n_in}"])
+    pred = oc.closed_loop(z[f"u_{n_in}"], 25, n_spinup, W, z[f"Win_{n_in}"], z[f"b_{n_in}"], 0.5,
+                          z[f"Wout_{n_in}_10_33"])
+    ref = z[f"pred_{n_in}_{n_spinup}"]
+    assert pred.shape == (n_in, 26)
+    assert np.array_equal(pred[:, 0], z[f"u_{n_in}"][:, n_spinup])
+    np.testing.assert_allclose(pred, ref, rtol=0, atol=1e-12)
+
+
+def test_l96_case():
+    z = load_golden("eager_l96.npz")
+    W = sp.csr_matrix(z["W"])
+    T = int(z["n_train"])
+    data = z["data"]
+    Wout = oc.ridge_train(data[:, :T], data[:, :T], 0, int(z["batch"]), W, z["Win"], z["b"], 0.5, 1e-6)
+    assert oc.max_normalised_err(Wout, z["Wout"]) < 1e-7
+    pred = oc.closed_loop(data[:, int(z["test_offset"]):], int(z["n_steps"]), int(z["n_spinup"]),
+                          W, z["Win"], z["b"], 0.5, z["Wout"])
+    np.testing.assert_allclose(pred, z["pred"], rtol=0, atol=1e-10)
+
+
+@pytest.mark.parametrize("name", LAZY_CASES)
+def test_lazy_train_and_predict(name):
+    z = load_golden(f"lazy_{name}.npz")
+    field = z["field"]
+    nsp = field.ndim - 1
+    chunks = tuple(int(c) for c in z["chunks"])
+    depth = {a: int(z["overlap"][a]) for a in range(nsp)}
+    depth[nsp] = 0
+    boundary = decode_boundary(z)
+    W = sp.csr_matrix(z["W"])
+    common = (W, z["Win"], z["b"], float(z["leak"]))
+
+    blk = next(oc.halo_blocks(field, chunks, depth, boundary))[1]
+    assert np.array_equal(oc.inner_mask(blk.shape, depth), z["inner_mask"])
+
+    wout = oc.lazy_train(field, chunks, depth, boundary, int(z["n_spinup_train"]), int(z["batch"]),
+                         *common, float(z["beta"]))
+    ref = z["wout_groups"]
+    assert wout.shape == ref.shape
+    assert np.array_equal(np.isnan(wout), np.isnan(ref))
+    assert oc.max_normalised_err(wout, ref) < 1e-9
+
+    pred = oc.lazy_predict(field, chunks, depth, boundary, int(z["n_steps"]), int(z["n_spinup"]),
+                           *common, ref)
+    assert pred.shape == field.shape[:-1] + (int(z["n_steps"]) + 1,)
+    assert np.array_equal(np.isnan(pred), np.isnan(z["pred"]))
+    np.testing.assert_allclose(pred, z["pred"], rtol=0, atol=1e-11)
+
+
+def test_wout_block_layout_shapes():
+    # shapes pinned by xesn/test/lazy.py:46-88 (4 / 4x6 / 4x6x5 domains, chunks 2 / 2x3 / 2x3x5)
+    N = 7
+    assert oc.wout_block_layout(np.zeros((2, 2, N))).shape == (2, 2 * N)
+    assert oc.wout_block_layout(np.zeros((2, 2, 6, N))).shape == (2 * 6, 2 * N)
+    assert oc.wout_block_layout(np.zeros((2, 2, 1, 30, N))).shape == (2 * 6 * 5, 2 * N, 1)
+    g = np.arange(2 * 3 * 4 * 5, dtype=float).reshape(2, 3, 4, 5)
+    lay = oc.wout_block_layout(g)
+    assert np.array_equal(lay[4:8, 10:15], g[1, 2])
