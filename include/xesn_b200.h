@@ -1,0 +1,128 @@
+/* xesn_b200 -- C ABI of the B200-native ESN hot path.
+ *
+ * Drop-in boundary for the numerical layer of timothyas/xesn (v0.2.2).  The reference has no
+ * FFI of its own (it is pure Python over numpy/cupy); each entry point below replaces one of
+ * its hot-path functions, cited as <file>:<lines> relative to the upstream tree.  The Python
+ * classes `xesn_b200.ESN` / `xesn_b200.LazyESN` bind these through ctypes.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a CUDA error code (>0) or -1/-2 (bad argument /
+ *     unsupported size) on failure; `xesn_last_error()` describes the last failure;
+ *   - all `*_dev` pointers are DEVICE pointers owned by the caller (e.g. torch tensors);
+ *     `stream` is a `cudaStream_t` passed as `void*` (NULL = default stream); calls are
+ *     asynchronous with respect to the host unless stated otherwise;
+ *   - all floating-point data is IEEE binary64, row-major; "series" arrays are time-LAST like the
+ *     reference's `(n_vars, n_time)` DataArrays;
+ *   - G = number of independent reservoirs ("groups": LazyESN chunks, or 1 for the eager ESN);
+ *     all groups share one (W, Win, b) as in xesn/lazyesn.py:175-177;
+ *   - handles are not thread safe; one handle lives on one device.
+ */
+#ifndef XESN_B200_H
+#define XESN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct xesn_reservoir xesn_reservoir;
+
+/* Rows of time series, optionally gathered through an index map (the halo of a LazyESN group,
+ * xesn/lazyesn.py:165-167, or the identity for the eager ESN).
+ *   row r of group g, time t  =  data[src(g,r) * ld + t]
+ *   src(g,r) = map ? map[g*rows + r] : g*rows + r ;  map value m < 0 -> constant fill[-1-m]
+ *   zero_row[g*rows + r] != 0 -> the row reads as 0 for all t (cell masked because it is NaN at
+ *   the first time step: xesn/lazyesn.py:287-289, :362-364). */
+typedef struct {
+    const double* data_dev;
+    int64_t ld;
+    const int32_t* map_dev;          /* may be NULL */
+    const double* fill_dev;          /* may be NULL when map has no negative entries */
+    const uint8_t* zero_row_dev;     /* may be NULL */
+} xesn_series;
+
+const char* xesn_last_error(void);
+int xesn_abi_version(void);
+
+/* ---- reservoir handle: uploads W (CSR, HOST arrays, column indices sorted within rows),
+ *      Win (HOST, [N][I] row-major) and the bias vector (HOST, [N]).
+ *      Replaces the attributes set by ESN.build, xesn/esn.py:147-187. */
+int xesn_reservoir_create(xesn_reservoir** out, int device, int32_t n_reservoir, int32_t n_input,
+                          const int32_t* indptr, const int32_t* indices, const double* values,
+                          const double* win, const double* bias, double leak_rate);
+int xesn_reservoir_destroy(xesn_reservoir* h);
+
+/* ---- a1: one update, r' = (1-a) r + a tanh(W r + Win u + b)      xesn/esn.py:458-460 (_update),
+ *      xesn/lazyesn.py:319-322 (_update_nd).  r_in/r_out: [G][N]; u: [G][I]; NaN inputs count as 0. */
+int xesn_update(xesn_reservoir* h, const double* r_in_dev, const double* u_dev, double* r_out_dev,
+                int32_t n_groups, void* stream);
+
+/* ---- teacher-forced run of `n_steps` updates from `r_carry_dev` ([G][N], updated in place)
+ *      on inputs u(t0 .. t0+n_steps-1).  xesn/esn.py:498-499 (spin-up), :506-507 (training
+ *      states), xesn/lazyesn.py:301-316 (_spinup).  If states_dev != NULL it receives
+ *      [G][n_steps+1][N]: row k = state before consuming u(t0+k) (the reference's rT buffer).
+ *      scratch_dev: xesn_forced_scratch_bytes() bytes. */
+int64_t xesn_forced_scratch_bytes(xesn_reservoir* h, int32_t n_groups, int32_t n_steps, int32_t gathered);
+int xesn_forced_run(xesn_reservoir* h, const xesn_series* u, int64_t t0, int32_t n_steps, int32_t n_groups,
+                    double* r_carry_dev, double* states_dev, void* scratch_dev, int64_t scratch_bytes,
+                    void* stream);
+
+/* ---- a2/a5: ridge training for G groups                     xesn/esn.py:463-520 (_train_1d),
+ *      xesn/lazyesn.py:264-298 (_train_nd).  Streams the time axis in chunks of `chunk` steps:
+ *      drive GEMM -> persistent recurrence -> Gram (R^T R, lower triangle) and Y R accumulation on
+ *      the FP64 tensor pipe; the state history is never materialised beyond one chunk.
+ *      y rows are paired with the state that has seen u(0..t-1) exactly as the reference does.
+ *        gram_dev : [G][N][N] workspace (lower triangle = R R^T + beta I on return from
+ *                   xesn_train_accumulate; destroyed by xesn_ridge_solve)
+ *        wout_dev : [G][O][N]; holds Y R^T after accumulate, Wout after solve
+ *        info_dev : [G] ints, 0 = ok, k>0 = leading minor k not positive definite */
+int64_t xesn_train_scratch_bytes(xesn_reservoir* h, int32_t n_output, int32_t n_groups, int32_t chunk,
+                                 int32_t gathered_u, int32_t gathered_y);
+int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_series* y, int32_t n_output,
+                          int32_t n_groups, int64_t n_time, int64_t n_spinup, int32_t chunk,
+                          double* gram_dev, double* wout_dev, void* scratch_dev, int64_t scratch_bytes,
+                          void* stream);
+/* (R R^T + beta I) solve: xesn/esn.py:516-520.  beta_dev: [G] or NULL (then beta_scalar is used). */
+int xesn_ridge_solve(xesn_reservoir* h, int32_t n_output, int32_t n_groups, const double* beta_dev,
+                     double beta_scalar, double* gram_dev, double* wout_dev, int32_t* info_dev,
+                     void* scratch_dev, int64_t scratch_bytes, void* stream);
+
+/* ---- a3/a6: closed-loop forecast                            xesn/esn.py:264-268 (ESN.predict),
+ *      xesn/lazyesn.py:226-236 (+ _update_nd, _readout, overlap per step).
+ *      The domain is a flat vector of `n_cells` values.  in_map [G][I] gathers every group's
+ *      (halo'd) input from it (negative -> fill constant, NaN -> 0); out_map [G][O] scatters the
+ *      readout back.  Eager ESN: G=1, identity maps.
+ *        field_dev  : [n_cells] initial condition (truth at n_spinup); overwritten with the last step
+ *        r_dev      : [G][N] reservoir states after spin-up; updated in place
+ *        pred_dev   : [n_cells][n_steps+1] (time last); column 0 is written with the initial field
+ *      scratch: xesn_predict_scratch_bytes(). */
+int64_t xesn_predict_scratch_bytes(xesn_reservoir* h, int32_t n_output, int32_t n_groups, int64_t n_cells);
+int xesn_predict(xesn_reservoir* h, const double* wout_dev, int32_t n_output, int32_t n_groups,
+                 int64_t n_cells, const int32_t* in_map_dev, const double* fill_dev,
+                 const int32_t* out_map_dev, double* field_dev, double* r_dev, int32_t n_steps,
+                 double* pred_dev, void* scratch_dev, int64_t scratch_bytes, void* stream);
+/* one closed-loop step (used by the multi-GPU LazyESN driver, which exchanges halos between
+ * steps): r <- update(r, gather(field_in)); field_out[out_map] = Wout r; optionally also
+ * pred_col_dev[cell * pred_stride]. */
+int xesn_predict_step(xesn_reservoir* h, const double* wout_dev, int32_t n_output, int32_t n_groups,
+                      const int32_t* in_map_dev, const double* fill_dev, const int32_t* out_map_dev,
+                      const double* field_in_dev, double* field_out_dev, double* r_dev,
+                      double* pred_col_dev, int64_t pred_stride, void* scratch_dev, int64_t scratch_bytes,
+                      void* stream);
+
+/* ---- building blocks exposed for parity tests and benchmarks ---- */
+/* C = alpha * op(A) op(B) + beta * C on the FP64 tensor pipe; flags: 1 = A is [M][K] (else [K][M]),
+ * 2 = B is [N][K] (else [K][N]), 4 = only lower-triangular tiles (square C). */
+int xesn_gemm_f64(const double* a_dev, int64_t lda, const double* b_dev, int64_t ldb, double* c_dev, int64_t ldc,
+                  int32_t m, int32_t n, int32_t k, double alpha, double beta, int32_t flags, void* stream);
+/* readout v[g][o] = Wout[g][o][:] . r[g][:]   (xesn/esn.py:268, xesn/lazyesn.py:325-327) */
+int xesn_readout(const double* wout_dev, const double* r_dev, double* v_dev, int32_t n_reservoir,
+                 int32_t n_output, int32_t n_groups, void* stream);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
+int64_t xesn_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XESN_B200_H */

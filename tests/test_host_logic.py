@@ -1,0 +1,208 @@
+"""CPU tests of the host side: option handling mirrors the reference's API tests
+(xesn/test/esn.py, xesn/test/lazy.py), halo index maps against the oracle's np.pad halo,
+the C-ABI library loads and exports every declared symbol.  No GPU compute here."""
+import ctypes
+import os
+import re
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle import esn_oracle as oc
+from tests.conftest import ESN_KW, ROOT
+from xesn_b200 import ESN, LazyESN, XesnError, _lib
+from xesn_b200 import halo
+from xesn_b200.esn import auto_chunk
+
+
+def kw():
+    return {k: dict(v) for k, v in ESN_KW.items()}
+
+
+# --------------------------------------------------------------------------- C ABI
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(_lib.LIB_PATH), "run `python __graft_entry__.py` first"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    header = open(os.path.join(ROOT, "include", "xesn_b200.h")).read()
+    declared = set(re.findall(r"\b(xesn_[a-z0-9_]+)\s*\(", header))
+    declared -= {"xesn_series"}
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/xesn_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib.xesn_abi_version.restype = ctypes.c_int
+    assert lib.xesn_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    esn = ESN(3, 3, 20, 0.5, 1e-6, **kw())
+    esn.build()
+    with pytest.raises(XesnError):
+        esn.train(np.zeros((3, 10)))
+    with pytest.raises(XesnError):
+        ESN(3, 3, 20, 0.5, 1e-6, **kw()).train(np.zeros((3, 10)))  # not built
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "xesn_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("the oracle", ""), f"{f} mentions the oracle package"
+
+
+# --------------------------------------------------------------------------- ESN options (xesn/test/esn.py)
+def test_defaults_warn_and_filtering():
+    with pytest.warns(UserWarning, match="Did not find 'input_kwargs'"):
+        esn = ESN(3, 3, 20, 0.5, 1e-6, adjacency_kwargs=kw()["adjacency_kwargs"], bias_kwargs=kw()["bias_kwargs"])
+    assert esn.input_kwargs == {"factor": 1.0, "distribution": "uniform", "normalization": "multiply",
+                                "is_sparse": False, "random_seed": None}
+    with pytest.warns(UserWarning, match="'blah' not allowed"):
+        k = kw()
+        k["bias_kwargs"]["blah"] = 1
+        esn = ESN(3, 3, 20, 0.5, 1e-6, **k)
+    assert "blah" not in esn.bias_kwargs
+    # user dicts are filtered, NOT merged with the defaults (esn.py:375-387)
+    k = kw()
+    k["adjacency_kwargs"] = {"factor": 0.9, "distribution": "uniform", "is_sparse": True, "connectedness": 3}
+    esn = ESN(3, 3, 20, 0.5, 1e-6, **k)
+    assert "format" not in esn.adjacency_kwargs
+    esn.build()
+    assert esn.W.format == "coo"  # SparseRandomMatrix default (matrix.py:240)
+    assert esn.input_factor == 0.5 and esn.adjacency_factor == 0.9 and esn.bias_factor == 0.5
+
+
+def test_negative_bias_and_density_errors():
+    k = kw()
+    k["bias_kwargs"]["factor"] = -1.0
+    with pytest.raises(ValueError):
+        ESN(3, 3, 20, 0.5, 1e-6, **k)
+    k = kw()
+    k["adjacency_kwargs"].pop("connectedness")
+    k["adjacency_kwargs"]["density"] = 1.5
+    with pytest.raises(ValueError):
+        ESN(3, 3, 20, 0.5, 1e-6, **k).build()
+    k["adjacency_kwargs"]["density"] = 0.5
+    with pytest.warns(RuntimeWarning, match="density is >20%"):
+        ESN(3, 3, 20, 0.5, 1e-6, **k).build()
+
+
+def test_build_shapes_and_str():
+    esn = ESN(4, 2, 30, 0.5, 1e-6, **kw())
+    assert str(esn) == repr(esn) and str(esn).startswith("ESN\n")
+    esn.build()
+    assert esn.W.shape == (30, 30) and esn.W.nnz == 150
+    assert esn.Win.shape == (30, 4) and esn.bias_vector.shape == (30,)
+    with pytest.raises(Exception, match="Wout has not been computed"):
+        esn.to_xds()
+    attrs = esn._get_attrs()
+    assert list(attrs) == ["n_input", "n_output", "n_reservoir", "leak_rate", "tikhonov_parameter",
+                           "input_kwargs", "adjacency_kwargs", "bias_kwargs"]
+
+
+def test_auto_chunk_bounds():
+    assert auto_chunk(16000, 1, 20000, None) >= 512
+    assert auto_chunk(16000, 1, 20000, 100) == 100
+    assert auto_chunk(100, 1, 10, None) == 10
+    assert auto_chunk(6000, 256, 4096, None) >= 64
+    assert 16 * 6000 * 256 * auto_chunk(6000, 256, 4096, None) <= (4 << 30)
+
+
+# --------------------------------------------------------------------------- LazyESN shell (xesn/test/lazy.py)
+def lazy_kw(**over):
+    d = dict(esn_chunks={"x": 3, "time": 1000}, overlap={"x": 1, "time": 0}, boundary=0, n_reservoir=20,
+             leak_rate=0.5, tikhonov_parameter=1e-6, persist=True, **kw())
+    d.update(over)
+    return d
+
+
+def test_lazy_basic_properties():
+    esn = LazyESN(**lazy_kw())
+    assert str(esn) == repr(esn) and str(esn).startswith("LazyESN\n")
+    assert esn.esn_chunks == esn.output_chunks
+    assert esn.input_chunks == {"x": 5, "time": 1000}
+    assert esn.n_input == 5 and esn.n_output == 3
+    assert esn.ndim_state == 1
+    assert esn._r_chunks == (20,)
+    assert esn._Wout_chunks == (3, 20)
+    e3 = LazyESN(**lazy_kw(esn_chunks={"x": 2, "y": 3, "z": 5}, overlap={"x": 1, "y": 1, "z": 0}))
+    assert e3.ndim_state == 3 and e3._r_chunks == (1, 1, 20) and e3._Wout_chunks == (30, 20, 1)
+    assert e3.n_input == 4 * 5 * 5 and e3.n_output == 30
+
+
+@pytest.mark.parametrize("attr,expected", [("overlap", 0), ("esn_chunks", -1)])
+def test_lazy_default_time(attr, expected):
+    k = lazy_kw()
+    k[attr].pop("time")
+    esn = LazyESN(**k)
+    assert getattr(esn, attr)["time"] == expected
+
+
+def test_lazy_errors():
+    with pytest.raises(NotImplementedError):
+        LazyESN(**lazy_kw(overlap={"x": 1, "y": 1, "z": 1, "time": 0},
+                          esn_chunks={"x": 2, "y": 2, "z": 2, "time": 1000}))
+    with pytest.raises(ValueError):
+        LazyESN(**lazy_kw(esn_chunks={"x": 3, "y": -1, "time": 1000}, overlap={"x": 3, "y": 0, "time": 1000}))
+    attrs = LazyESN(**lazy_kw())._get_attrs()
+    assert list(attrs)[:7] == ["esn_chunks", "overlap", "boundary", "n_reservoir", "leak_rate",
+                               "tikhonov_parameter", "persist"]
+
+
+# --------------------------------------------------------------------------- halo maps == dask overlap restated
+CASES = [
+    ((12,), (3,), (1,), "periodic"),
+    ((4,), (2,), (1,), 0.0),
+    ((9,), (3,), (2,), float("nan")),
+    ((6, 8), (3, 4), (1, 1), "periodic"),
+    ((6, 8), (3, 2), (2, 1), {0: "reflect", 1: 0.5}),
+    ((6, 4), (2, 4), (1, 0), "periodic"),
+    ((4, 6, 2), (2, 3, 2), (1, 1, 0), {0: "periodic", 1: 0.0, 2: "reflect"}),
+    ((4, 6, 4), (2, 3, 2), (1, 1, 0), {0: 7.0, 1: 3.0}),
+]
+
+
+@pytest.mark.parametrize("shape,chunks,ovl,boundary", CASES)
+def test_halo_maps_match_oracle_blocks(shape, chunks, ovl, boundary):
+    nsp = len(shape)
+    names = ("x", "y", "z")[:nsp]
+    b = {names[k]: v for k, v in boundary.items()} if isinstance(boundary, dict) else boundary
+    rules = halo.normalise_boundary(b, names, ovl)
+    grid, in_map, out_map, fill = halo.build_maps(shape, chunks, ovl, rules)
+    field = np.random.RandomState(1).normal(size=shape + (3,))
+    depth = {a: ovl[a] for a in range(nsp)}
+    depth[nsp] = 0
+    flat = field.reshape(-1, 3)
+    blocks = list(oc.halo_blocks(field, chunks, depth, boundary))
+    assert len(blocks) == in_map.shape[0] == int(np.prod(grid))
+    for k, (g, blk) in enumerate(blocks):
+        want = blk.reshape(-1, 3)
+        got = np.where(in_map[k][:, None] >= 0, flat[np.maximum(in_map[k], 0)], fill[-1 - np.minimum(in_map[k], -1)][:, None])
+        np.testing.assert_array_equal(got, np.nan_to_num(want, nan=0.0))
+        inner = oc.inner_mask(blk.shape, depth).reshape(-1)
+        np.testing.assert_array_equal(flat[out_map[k]], want[inner])
+    # every cell is predicted by exactly one group
+    assert sorted(out_map.reshape(-1).tolist()) == list(range(int(np.prod(shape))))
+
+
+def test_halo_errors():
+    with pytest.raises(ValueError):
+        halo.build_maps((10,), (3,), (1,), ["periodic"])
+    with pytest.raises(ValueError):
+        halo.normalise_boundary({"y": 0.0}, ("x",), (1,))
+    with pytest.raises(NotImplementedError):
+        halo.normalise_boundary("nearest", ("x",), (1,))
+
+
+@pytest.mark.parametrize("grid", [(4,), (2, 3), (2, 3, 2)])
+def test_wout_block_layout_roundtrip(grid):
+    G, O, N = int(np.prod(grid)), 5, 7
+    w = np.random.RandomState(0).normal(size=(G, O, N))
+    blocks = halo.wout_to_blocks(w, grid)
+    np.testing.assert_array_equal(blocks, oc.wout_block_layout(w.reshape(grid + (O, N))))
+    np.testing.assert_array_equal(halo.blocks_to_wout(blocks, grid, O, N), w)

@@ -1,0 +1,89 @@
+"""ctypes binding of libxesn_b200.so (C ABI declared in include/xesn_b200.h).
+
+There is no CPU fallback: if the shared library is missing or a call fails the
+error is raised immediately.  Build with `python __graft_entry__.py` or
+`bash xesn_b200/csrc/build.sh`.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libxesn_b200.so")
+
+c_i32p = C.POINTER(C.c_int32)
+c_f64p = C.POINTER(C.c_double)
+
+
+class Series(C.Structure):
+    """`xesn_series` of include/xesn_b200.h: time-last rows, optionally index-gathered."""
+    _fields_ = [
+        ("data_dev", C.c_void_p),
+        ("ld", C.c_int64),
+        ("map_dev", C.c_void_p),
+        ("fill_dev", C.c_void_p),
+        ("zero_row_dev", C.c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/xesn_b200.h declares
+SIGNATURES = {
+    "xesn_last_error": (C.c_char_p, []),
+    "xesn_abi_version": (C.c_int, []),
+    "xesn_launch_count": (C.c_int64, []),
+    "xesn_reservoir_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]),
+    "xesn_reservoir_destroy": (C.c_int, [C.c_void_p]),
+    "xesn_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "xesn_forced_scratch_bytes": (C.c_int64, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
+    "xesn_forced_run": (C.c_int, [C.c_void_p, C.POINTER(Series), C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "xesn_train_scratch_bytes": (C.c_int64, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "xesn_train_accumulate": (C.c_int, [C.c_void_p, C.POINTER(Series), C.POINTER(Series), C.c_int32, C.c_int32,
+                                        C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_int64, C.c_void_p]),
+    "xesn_ridge_solve": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "xesn_predict_scratch_bytes": (C.c_int64, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64]),
+    "xesn_predict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
+                               C.c_void_p]),
+    "xesn_predict_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                    C.c_void_p]),
+    "xesn_gemm_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
+                                C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_void_p]),
+    "xesn_readout": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+}
+
+_lib = None
+
+
+class XesnError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library once; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise XesnError(
+                f"{LIB_PATH} not found: the sm_100a CUDA library has not been built "
+                f"(run `python __graft_entry__.py` or `bash xesn_b200/csrc/build.sh`). There is no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().xesn_last_error().decode("utf-8", "replace")
+        raise XesnError(f"libxesn_b200 call failed (code {rc}): {msg}")
+
+
+def launch_count():
+    return int(load().xesn_launch_count())

@@ -1,0 +1,435 @@
+// extern "C" entry points of libxesn_b200.so (declared in include/xesn_b200.h).
+#include <cstdarg>
+#include <cstring>
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/xesn_b200.h"
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace xesn {
+
+static thread_local std::string g_error;
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+namespace {
+__global__ void strided_copy_kernel(const double* __restrict__ src, double* __restrict__ dst, long long dst_stride,
+                                    long long n) {
+    long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) dst[k * dst_stride] = src[k];
+}
+inline long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
+}  // namespace
+
+}  // namespace xesn
+
+using namespace xesn;
+
+struct xesn_reservoir {
+    int device = 0;
+    int N = 0, I = 0;
+    long long nnz = 0;
+    double alpha = 0.0;
+    int* d_indptr = nullptr;
+    int* d_indices = nullptr;
+    double* d_values = nullptr;
+    double* d_win = nullptr;
+    double* d_bias = nullptr;
+    int cluster = 1;
+    int max_slice_nnz = 0;
+};
+
+extern "C" {
+
+const char* xesn_last_error(void) { return g_error.c_str(); }
+int xesn_abi_version(void) { return 1; }
+int64_t xesn_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int xesn_reservoir_create(xesn_reservoir** out, int device, int32_t N, int32_t I, const int32_t* indptr,
+                          const int32_t* indices, const double* values, const double* win, const double* bias,
+                          double leak_rate) {
+    XESN_REQUIRE(out && indptr && win && bias, "null pointer");
+    XESN_REQUIRE(N > 0 && I > 0, "n_reservoir and n_input must be positive");
+    XESN_CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    XESN_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("xesn_b200 is built for sm_100a (Blackwell B200) only; device %d is sm_%d%d", device, prop.major,
+                  prop.minor);
+        return -2;
+    }
+    const long long nnz = indptr[N];
+    XESN_REQUIRE(nnz >= 0 && indptr[0] == 0, "malformed CSR indptr");
+    XESN_REQUIRE(nnz == 0 || (indices && values), "null CSR arrays");
+    for (int i = 0; i < N; ++i) XESN_REQUIRE(indptr[i + 1] >= indptr[i], "CSR indptr must be non-decreasing");
+    for (long long k = 0; k < nnz; ++k) XESN_REQUIRE(indices[k] >= 0 && indices[k] < N, "CSR column index out of range");
+
+    auto* h = new xesn_reservoir();
+    h->device = device, h->N = N, h->I = I, h->nnz = nnz, h->alpha = leak_rate;
+    XESN_CUDA_OK(cudaMalloc(&h->d_indptr, sizeof(int) * (N + 1)));
+    XESN_CUDA_OK(cudaMalloc(&h->d_indices, sizeof(int) * (nnz > 0 ? nnz : 1)));
+    XESN_CUDA_OK(cudaMalloc(&h->d_values, sizeof(double) * (nnz > 0 ? nnz : 1)));
+    XESN_CUDA_OK(cudaMalloc(&h->d_win, sizeof(double) * (size_t)N * I));
+    XESN_CUDA_OK(cudaMalloc(&h->d_bias, sizeof(double) * N));
+    XESN_CUDA_OK(cudaMemcpy(h->d_indptr, indptr, sizeof(int) * (N + 1), cudaMemcpyHostToDevice));
+    if (nnz) {
+        XESN_CUDA_OK(cudaMemcpy(h->d_indices, indices, sizeof(int) * nnz, cudaMemcpyHostToDevice));
+        XESN_CUDA_OK(cudaMemcpy(h->d_values, values, sizeof(double) * nnz, cudaMemcpyHostToDevice));
+    }
+    XESN_CUDA_OK(cudaMemcpy(h->d_win, win, sizeof(double) * (size_t)N * I, cudaMemcpyHostToDevice));
+    XESN_CUDA_OK(cudaMemcpy(h->d_bias, bias, sizeof(double) * N, cudaMemcpyHostToDevice));
+
+    h->cluster = recur_cluster_size(N);
+    const int upc = (N + h->cluster - 1) / h->cluster;
+    int mx = 0;
+    for (int c = 0; c < h->cluster; ++c) {
+        int lo = c * upc < N ? c * upc : N, hi = (c + 1) * upc < N ? (c + 1) * upc : N;
+        int s = indptr[hi] - indptr[lo];
+        if (s > mx) mx = s;
+    }
+    h->max_slice_nnz = mx;
+    *out = h;
+    return 0;
+}
+
+int xesn_reservoir_destroy(xesn_reservoir* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaFree(h->d_indptr);
+    cudaFree(h->d_indices);
+    cudaFree(h->d_values);
+    cudaFree(h->d_win);
+    cudaFree(h->d_bias);
+    delete h;
+    return 0;
+}
+
+int xesn_update(xesn_reservoir* h, const double* r_in, const double* u, double* r_out, int32_t G, void* stream) {
+    XESN_REQUIRE(h && r_in && u && r_out && G > 0, "bad arguments");
+    XESN_REQUIRE(r_in != r_out, "r_in and r_out must not alias");
+    StepArgs a = {};
+    a.indptr = h->d_indptr, a.indices = h->d_indices, a.values = h->d_values;
+    a.Win = h->d_win, a.bias = h->d_bias, a.u = u, a.drive = nullptr;
+    a.r_in = r_in, a.r_out = r_out, a.N = h->N, a.I = h->I, a.alpha = h->alpha;
+    return launch_step_update(a, G, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// drive for a chunk: D[g][t][n] = sum_i U_g[i][t0+t] Win[n][i] + b[n]
+// ---------------------------------------------------------------------------------------------
+static int chunk_inputs(xesn_reservoir* h, const xesn_series* s, int rows, int G, long long t0, int m, double* stage,
+                        long long stage_ld, const double** base, long long* ld, long long* gstride,
+                        cudaStream_t st) {
+    if (s->map_dev || s->zero_row_dev) {
+        int rc = launch_gather_series(s->data_dev, s->ld, t0, s->map_dev, s->fill_dev, s->zero_row_dev, stage, stage_ld,
+                                      (long long)G * rows, m, st);
+        if (rc) return rc;
+        *base = stage, *ld = stage_ld, *gstride = (long long)rows * stage_ld;
+    } else {
+        *base = s->data_dev + t0, *ld = s->ld, *gstride = (long long)rows * s->ld;
+    }
+    return 0;
+}
+
+static int drive_gemm(xesn_reservoir* h, const double* ubase, long long ldu, long long ugstride, int G, int m, double* D,
+                      cudaStream_t st) {
+    GemmArgs g = {};
+    g.A = ubase, g.lda = ldu, g.strideA = ugstride;           // A(t,i) = U[i*ld + t]   (MN-contiguous)
+    g.B = h->d_win, g.ldb = h->I, g.strideB = 0;              // B(i,n) = Win[n*I + i]  (K-contiguous)
+    g.C = D, g.ldc = h->N, g.strideC = (long long)m * h->N;
+    g.bias = h->d_bias;
+    g.M = m, g.N = h->N, g.K = h->I, g.batch = G;
+    g.alpha = 1.0, g.beta = 0.0, g.flags = GEMM_B_KMAJOR;
+    return launch_gemm_f64(g, st);
+}
+
+static RecurArgs recur_args(xesn_reservoir* h) {
+    RecurArgs r = {};
+    r.indptr = h->d_indptr, r.indices = h->d_indices, r.values = h->d_values;
+    r.N = h->N, r.alpha = h->alpha, r.smem_nnz = h->max_slice_nnz;
+    return r;
+}
+
+constexpr int FORCED_CHUNK = 512;
+
+int64_t xesn_forced_scratch_bytes(xesn_reservoir* h, int32_t G, int32_t n_steps, int32_t gathered) {
+    if (!h) return -1;
+    long long c = n_steps < FORCED_CHUNK ? (n_steps > 0 ? n_steps : 1) : FORCED_CHUNK;
+    long long cld = round_up(c, 2);
+    long long d = (long long)G * c * h->N + 2LL * G * h->N;
+    if (gathered) d += (long long)G * h->I * cld;
+    return d * 8 + 256;
+}
+
+int xesn_forced_run(xesn_reservoir* h, const xesn_series* u, int64_t t0, int32_t n_steps, int32_t G, double* carry,
+                    double* states, void* scratch, int64_t scratch_bytes, void* stream) {
+    XESN_REQUIRE(h && u && carry && G > 0 && n_steps >= 0, "bad arguments");
+    const int gathered = (u->map_dev || u->zero_row_dev) ? 1 : 0;
+    XESN_REQUIRE(scratch && scratch_bytes >= xesn_forced_scratch_bytes(h, G, n_steps, gathered), "scratch too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = h->N;
+    const long long c = n_steps < FORCED_CHUNK ? (n_steps > 0 ? n_steps : 1) : FORCED_CHUNK;
+    const long long cld = round_up(c, 2);
+    double* D = (double*)scratch;
+    double* pp = D + (long long)G * c * N;
+    double* Uc = pp + 2LL * G * N;
+    if (states && n_steps == 0) {
+        XESN_CUDA_OK(cudaMemcpyAsync(states, carry, sizeof(double) * (size_t)G * N, cudaMemcpyDeviceToDevice, st));
+    }
+    for (long long s0 = 0; s0 < n_steps; s0 += c) {
+        const int m = (int)(n_steps - s0 < c ? n_steps - s0 : c);
+        const double* ub;
+        long long ldu, ugs;
+        int rc = chunk_inputs(h, u, h->I, G, t0 + s0, m, Uc, cld, &ub, &ldu, &ugs, st);
+        if (rc) return rc;
+        rc = drive_gemm(h, ub, ldu, ugs, G, m, D, st);
+        if (rc) return rc;
+        RecurArgs r = recur_args(h);
+        r.drive = D, r.drive_group_stride = (long long)m * N;
+        r.steps = m;
+        r.carry = carry;
+        if (states) {
+            r.states = states + s0 * N, r.state_group_stride = (long long)(n_steps + 1) * N, r.store_all = 1;
+        } else {
+            r.states = pp, r.state_group_stride = 2LL * N, r.store_all = 0;
+        }
+        rc = launch_recur_forced(r, G, h->max_slice_nnz, st);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// training
+// ---------------------------------------------------------------------------------------------
+struct TrainLayout {
+    long long cld;
+    long long carry, Uc, Yc, D, R, total;  // offsets in doubles
+};
+static TrainLayout train_layout(xesn_reservoir* h, int O, int G, int chunk, int gu, int gy) {
+    TrainLayout L;
+    L.cld = round_up(chunk, 2);
+    long long off = 0;
+    L.carry = off, off += round_up((long long)G * h->N, 2);
+    L.Uc = off, off += gu ? (long long)G * h->I * L.cld : 0;
+    L.Yc = off, off += gy ? (long long)G * O * L.cld : 0;
+    L.D = off, off += round_up((long long)G * chunk * h->N, 2);
+    L.R = off, off += round_up((long long)G * (chunk + 1) * h->N, 2);
+    L.total = off;
+    return L;
+}
+
+int64_t xesn_train_scratch_bytes(xesn_reservoir* h, int32_t O, int32_t G, int32_t chunk, int32_t gu, int32_t gy) {
+    if (!h || chunk <= 0) return -1;
+    long long train = train_layout(h, O, G, chunk, gu, gy).total;
+    long long solve = cholesky_workspace_doubles(h->N, G);
+    return (train > solve ? train : solve) * 8 + 256;
+}
+
+int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_series* y, int32_t O, int32_t G,
+                          int64_t T, int64_t n_spinup, int32_t chunk, double* gram, double* wout, void* scratch,
+                          int64_t scratch_bytes, void* stream) {
+    XESN_REQUIRE(h && u && y && gram && wout && scratch, "null pointer");
+    XESN_REQUIRE(O > 0 && G > 0 && chunk > 0 && T >= 0 && n_spinup >= 0 && n_spinup <= T, "bad sizes");
+    const int gu = (u->map_dev || u->zero_row_dev) ? 1 : 0, gy = (y->map_dev || y->zero_row_dev) ? 1 : 0;
+    XESN_REQUIRE(scratch_bytes >= xesn_train_scratch_bytes(h, O, G, chunk, gu, gy), "scratch too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = h->N;
+    const TrainLayout L = train_layout(h, O, G, chunk, gu, gy);
+    double* base = (double*)scratch;
+    double *carry = base + L.carry, *Uc = base + L.Uc, *Yc = base + L.Yc, *D = base + L.D, *R = base + L.R;
+
+    XESN_CUDA_OK(cudaMemsetAsync(carry, 0, sizeof(double) * (size_t)G * N, st));
+    XESN_CUDA_OK(cudaMemsetAsync(gram, 0, sizeof(double) * (size_t)G * N * N, st));
+    XESN_CUDA_OK(cudaMemsetAsync(wout, 0, sizeof(double) * (size_t)G * O * N, st));
+
+    // spin-up (states not stored): xesn/esn.py:498-499
+    for (long long t0 = 0; t0 < n_spinup; t0 += chunk) {
+        const int m = (int)(n_spinup - t0 < chunk ? n_spinup - t0 : chunk);
+        const double* ub;
+        long long ldu, ugs;
+        int rc = chunk_inputs(h, u, h->I, G, t0, m, Uc, L.cld, &ub, &ldu, &ugs, st);
+        if (rc) return rc;
+        if ((rc = drive_gemm(h, ub, ldu, ugs, G, m, D, st))) return rc;
+        RecurArgs r = recur_args(h);
+        r.drive = D, r.drive_group_stride = (long long)m * N, r.steps = m, r.carry = carry;
+        r.states = R, r.state_group_stride = 2LL * N, r.store_all = 0;
+        if ((rc = launch_recur_forced(r, G, h->max_slice_nnz, st))) return rc;
+    }
+    // accumulate: xesn/esn.py:502-513
+    for (long long t0 = n_spinup; t0 < T; t0 += chunk) {
+        const int m = (int)(T - t0 < chunk ? T - t0 : chunk);
+        const double *ub, *yb;
+        long long ldu, ugs, ldy, ygs;
+        int rc = chunk_inputs(h, u, h->I, G, t0, m, Uc, L.cld, &ub, &ldu, &ugs, st);
+        if (rc) return rc;
+        if ((rc = chunk_inputs(h, y, O, G, t0, m, Yc, L.cld, &yb, &ldy, &ygs, st))) return rc;
+        if ((rc = drive_gemm(h, ub, ldu, ugs, G, m, D, st))) return rc;
+        RecurArgs r = recur_args(h);
+        const long long rgs = (long long)(m + 1) * N;
+        r.drive = D, r.drive_group_stride = (long long)m * N, r.steps = m, r.carry = carry;
+        r.states = R, r.state_group_stride = rgs, r.store_all = 1;
+        if ((rc = launch_recur_forced(r, G, h->max_slice_nnz, st))) return rc;
+        // rbar += R^T R  (rows 0..m-1: the state that has seen u(..t-1) pairs with y(t))
+        GemmArgs g = {};
+        g.A = R, g.lda = N, g.strideA = rgs;
+        g.B = R, g.ldb = N, g.strideB = rgs;
+        g.C = gram, g.ldc = N, g.strideC = (long long)N * N;
+        g.M = N, g.N = N, g.K = m, g.batch = G, g.alpha = 1.0, g.beta = 1.0, g.flags = GEMM_LOWER;
+        if ((rc = launch_gemm_f64(g, st))) return rc;
+        // ybar += Y R
+        GemmArgs q = {};
+        q.A = yb, q.lda = ldy, q.strideA = ygs;
+        q.B = R, q.ldb = N, q.strideB = rgs;
+        q.C = wout, q.ldc = N, q.strideC = (long long)O * N;
+        q.M = O, q.N = N, q.K = m, q.batch = G, q.alpha = 1.0, q.beta = 1.0, q.flags = GEMM_A_KMAJOR;
+        if ((rc = launch_gemm_f64(q, st))) return rc;
+    }
+    return 0;
+}
+
+int xesn_ridge_solve(xesn_reservoir* h, int32_t O, int32_t G, const double* beta_dev, double beta_scalar, double* gram,
+                     double* wout, int32_t* info, void* scratch, int64_t scratch_bytes, void* stream) {
+    XESN_REQUIRE(h && gram && wout && info && scratch, "null pointer");
+    XESN_REQUIRE(scratch_bytes >= cholesky_workspace_doubles(h->N, G) * 8, "scratch too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = h->N;
+    int rc = launch_add_diag(gram, N, (long long)N * N, N, G, beta_dev, beta_scalar, st);
+    if (rc) return rc;
+    return launch_cholesky_solve_ws(gram, N, (long long)N * N, wout, N, (long long)O * N, N, O, G, info, (double*)scratch,
+                                    st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// closed loop
+// ---------------------------------------------------------------------------------------------
+constexpr int INLINE_PROJECTION_MAX_GROUPS = 4;
+
+int64_t xesn_predict_scratch_bytes(xesn_reservoir* h, int32_t O, int32_t G, int64_t n_cells) {
+    if (!h) return -1;
+    long long d = round_up((long long)G * h->I, 2) + 2 * round_up((long long)G * h->N, 2) + round_up(n_cells, 2);
+    return d * 8 + 256;
+}
+
+int xesn_predict_step(xesn_reservoir* h, const double* wout, int32_t O, int32_t G, const int32_t* in_map,
+                      const double* fill, const int32_t* out_map, const double* field_in, double* field_out, double* r,
+                      double* pred_col, int64_t pred_stride, void* scratch, int64_t scratch_bytes, void* stream) {
+    XESN_REQUIRE(h && wout && in_map && field_in && field_out && r && scratch, "null pointer");
+    XESN_REQUIRE(scratch_bytes >= xesn_predict_scratch_bytes(h, O, G, 0), "scratch too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = h->N, I = h->I;
+    double* Ug = (double*)scratch;
+    double* drive = Ug + round_up((long long)G * I, 2);
+    double* r_new = drive + round_up((long long)G * N, 2);
+    int rc;
+    StepArgs a = {};
+    a.indptr = h->d_indptr, a.indices = h->d_indices, a.values = h->d_values;
+    a.Win = h->d_win, a.bias = h->d_bias, a.N = N, a.I = I, a.alpha = h->alpha;
+    a.r_in = r, a.r_out = r_new;
+    if (G > INLINE_PROJECTION_MAX_GROUPS) {
+        if ((rc = launch_gather_vec(field_in, 1, in_map, fill, Ug, (long long)G * I, 1, st))) return rc;
+        GemmArgs g = {};
+        g.A = Ug, g.lda = I, g.strideA = 0;
+        g.B = h->d_win, g.ldb = I, g.strideB = 0;
+        g.C = drive, g.ldc = N, g.strideC = 0;
+        g.bias = h->d_bias;
+        g.M = G, g.N = N, g.K = I, g.batch = 1, g.alpha = 1.0, g.beta = 0.0, g.flags = GEMM_A_KMAJOR | GEMM_B_KMAJOR;
+        if ((rc = launch_gemm_f64(g, st))) return rc;
+        a.drive = drive;
+    } else {
+        a.field = field_in, a.in_map = in_map, a.fill = fill;
+    }
+    if ((rc = launch_step_update(a, G, st))) return rc;
+    XESN_CUDA_OK(cudaMemcpyAsync(r, r_new, sizeof(double) * (size_t)G * N, cudaMemcpyDeviceToDevice, st));
+    ReadoutArgs q = {};
+    q.Wout = wout, q.r = r, q.v = field_out, q.v_stride = 1, q.v_copy = pred_col, q.v_copy_stride = pred_stride;
+    q.out_map = out_map, q.N = N, q.O = O;
+    return launch_readout(q, G, st);
+}
+
+int xesn_predict(xesn_reservoir* h, const double* wout, int32_t O, int32_t G, int64_t n_cells, const int32_t* in_map,
+                 const double* fill, const int32_t* out_map, double* field, double* r, int32_t n_steps, double* pred,
+                 void* scratch, int64_t scratch_bytes, void* stream) {
+    XESN_REQUIRE(h && wout && in_map && field && r && pred && scratch, "null pointer");
+    XESN_REQUIRE(n_steps >= 0 && n_cells > 0, "bad sizes");
+    XESN_REQUIRE(scratch_bytes >= xesn_predict_scratch_bytes(h, O, G, n_cells), "scratch too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = h->N, I = h->I;
+    double* Ug = (double*)scratch;
+    double* drive = Ug + round_up((long long)G * I, 2);
+    double* r_alt = drive + round_up((long long)G * N, 2);
+    double* field_alt = r_alt + round_up((long long)G * N, 2);
+    const long long ldp = (long long)n_steps + 1;
+
+    strided_copy_kernel<<<(unsigned)((n_cells + 255) / 256), 256, 0, st>>>(field, pred, ldp, n_cells);
+    XESN_CUDA_OK(cudaGetLastError());
+    count_launch();
+    // cells not covered by out_map keep their previous value in both field buffers
+    XESN_CUDA_OK(cudaMemcpyAsync(field_alt, field, sizeof(double) * n_cells, cudaMemcpyDeviceToDevice, st));
+
+    double* rbuf[2] = {r, r_alt};
+    double* fbuf[2] = {field, field_alt};
+    int rc;
+    for (int n = 1; n <= n_steps; ++n) {
+        const int cur = (n - 1) & 1, nxt = n & 1;
+        StepArgs a = {};
+        a.indptr = h->d_indptr, a.indices = h->d_indices, a.values = h->d_values;
+        a.Win = h->d_win, a.bias = h->d_bias, a.N = N, a.I = I, a.alpha = h->alpha;
+        a.r_in = rbuf[cur], a.r_out = rbuf[nxt];
+        if (G > INLINE_PROJECTION_MAX_GROUPS) {
+            if ((rc = launch_gather_vec(fbuf[cur], 1, in_map, fill, Ug, (long long)G * I, 1, st))) return rc;
+            GemmArgs g = {};
+            g.A = Ug, g.lda = I, g.strideA = 0;
+            g.B = h->d_win, g.ldb = I, g.strideB = 0;
+            g.C = drive, g.ldc = N, g.strideC = 0;
+            g.bias = h->d_bias;
+            g.M = G, g.N = N, g.K = I, g.batch = 1, g.alpha = 1.0, g.beta = 0.0;
+            g.flags = GEMM_A_KMAJOR | GEMM_B_KMAJOR;
+            if ((rc = launch_gemm_f64(g, st))) return rc;
+            a.drive = drive;
+        } else {
+            a.field = fbuf[cur], a.in_map = in_map, a.fill = fill;
+        }
+        if ((rc = launch_step_update(a, G, st))) return rc;
+        ReadoutArgs q = {};
+        q.Wout = wout, q.r = rbuf[nxt], q.v = fbuf[nxt], q.v_stride = 1;
+        q.v_copy = pred + n, q.v_copy_stride = ldp, q.out_map = out_map, q.N = N, q.O = O;
+        if ((rc = launch_readout(q, G, st))) return rc;
+    }
+    if (n_steps & 1) {
+        XESN_CUDA_OK(cudaMemcpyAsync(r, r_alt, sizeof(double) * (size_t)G * N, cudaMemcpyDeviceToDevice, st));
+        XESN_CUDA_OK(cudaMemcpyAsync(field, field_alt, sizeof(double) * n_cells, cudaMemcpyDeviceToDevice, st));
+    }
+    return 0;
+}
+
+int xesn_gemm_f64(const double* a, int64_t lda, const double* b, int64_t ldb, double* c, int64_t ldc, int32_t m,
+                  int32_t n, int32_t k, double alpha, double beta, int32_t flags, void* stream) {
+    XESN_REQUIRE(a && b && c, "null pointer");
+    GemmArgs g = {};
+    g.A = a, g.lda = lda, g.B = b, g.ldb = ldb, g.C = c, g.ldc = ldc;
+    g.M = m, g.N = n, g.K = k, g.batch = 1, g.alpha = alpha, g.beta = beta, g.flags = flags;
+    return launch_gemm_f64(g, (cudaStream_t)stream);
+}
+
+int xesn_readout(const double* wout, const double* r, double* v, int32_t N, int32_t O, int32_t G, void* stream) {
+    XESN_REQUIRE(wout && r && v, "null pointer");
+    ReadoutArgs q = {};
+    q.Wout = wout, q.r = r, q.v = v, q.v_stride = 1, q.N = N, q.O = O;
+    return launch_readout(q, G, (cudaStream_t)stream);
+}
+
+}  // extern "C"

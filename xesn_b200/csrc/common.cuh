@@ -1,0 +1,55 @@
+// Shared helpers for the xesn_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+
+namespace xesn {
+
+// last error string, returned through the C ABI (xesn_last_error)
+void set_error(const char* fmt, ...);
+// kernel-launch counter exported as xesn_launch_count()
+void count_launch(int n = 1);
+
+#define XESN_CUDA_OK(expr)                                                              \
+    do {                                                                                \
+        cudaError_t _e = (expr);                                                        \
+        if (_e != cudaSuccess) {                                                        \
+            ::xesn::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,      \
+                              cudaGetErrorString(_e));                                  \
+            return (int)_e;                                                             \
+        }                                                                               \
+    } while (0)
+
+#define XESN_REQUIRE(cond, msg)                                                         \
+    do {                                                                                \
+        if (!(cond)) {                                                                  \
+            ::xesn::set_error("invalid argument: %s (%s:%d)", msg, __FILE__, __LINE__); \
+            return -1;                                                                  \
+        }                                                                               \
+    } while (0)
+
+// ---- internal launchers shared between translation units -------------------------------------
+enum GemmFlags : int {
+    GEMM_A_KMAJOR = 1,   // A[m*lda + k]   (else A[k*lda + m])
+    GEMM_B_KMAJOR = 2,   // B[n*ldb + k]   (else B[k*ldb + n])
+    GEMM_LOWER = 4,      // only tiles touching the lower triangle (tile_n <= tile_m) are computed
+};
+
+struct GemmArgs {
+    const double* A;
+    const double* B;
+    double* C;
+    const double* bias;  // optional, length N, added to every row of C
+    int M, N, K;
+    long long lda, ldb, ldc;
+    long long strideA, strideB, strideC;  // per batch entry (0 = shared)
+    int batch;
+    double alpha, beta;
+    int flags;
+};
+
+// C = alpha * op(A) op(B) + beta * C (+ bias), FP64 on the tensor pipe (DMMA m8n8k4)
+int launch_gemm_f64(const GemmArgs& a, cudaStream_t stream);
+
+}  // namespace xesn

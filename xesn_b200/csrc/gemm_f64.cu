@@ -1,0 +1,227 @@
+// FP64 GEMM / SYRK on the tensor pipe (DMMA m8n8k4) for sm_100a.
+//
+// This is the one dense contraction engine of the ESN hot path.  It replaces the numpy
+// `@` / cuBLAS dgemm calls of the reference at
+//   * xesn/esn.py:510  `rbar += rT.T @ rT`        (Gram, symmetric: lower tiles only)
+//   * xesn/esn.py:509  `ybar += y[:, i0:i1] @ rT`
+//   * xesn/esn.py:459  `Win @ u` for a whole chunk of time steps (the "drive")
+// and is re-used by the blocked Cholesky / triangular solves that replace
+// `scipy.linalg.solve(..., assume_a="sym")` (xesn/esn.py:516-520).
+//
+// tcgen05 has no FP64 kind, so FP64 tensor work on Blackwell is `mma.sync ... f64`
+// (SASS: DMMA.8x8x4).  Operand tiles are staged with cp.async (LDGSTS) through a 4-stage
+// shared-memory ring; each operand may be K-contiguous or MN-contiguous in global memory,
+// so the time-last (n_vars, n_time) arrays of the reference are consumed without a transpose.
+//
+// CTA tile 128x128x16, 256 threads = 8 warps (2 x 4), warp tile 64x32 -> 32 DMMA per k4 step
+// against 12 LDS.64 (shared memory padded so fragment loads are bank-conflict free).
+#include "common.cuh"
+
+namespace xesn {
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16;
+constexpr int NTHREADS = 256;
+constexpr int STAGES = 4;
+constexpr int LD_MN = BM + 4;  // tile stored [BK][LD_MN]  (operand MN-contiguous in global)
+constexpr int LD_K = BK + 4;   // tile stored [BM][LD_K]   (operand K-contiguous in global)
+constexpr int TILE_DOUBLES = BM * LD_K;  // 2560 >= BK*LD_MN = 2112
+constexpr int STAGE_DOUBLES = 2 * TILE_DOUBLES;
+constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * (int)sizeof(double);  // 160 KB
+
+__device__ __forceinline__ void cp_async16(double* dst, const double* src, int src_bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8(double* dst, const double* src, int src_bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// Copy one operand tile (128 along MN, 16 along K) into shared memory, zero-filling outside
+// [0,MN) x [0,K).  `g` is the batch-adjusted base pointer of the operand.
+template <bool KMAJOR>
+__device__ __forceinline__ void load_tile(double* s, const double* __restrict__ g, long long ld, int mn0, int k0,
+                                          int MN, int K, bool vec16, int tid) {
+    if (!KMAJOR) {
+#pragma unroll
+        for (int pass = 0; pass < 4; ++pass) {
+            int row = pass * 4 + (tid >> 6);
+            int v = tid & 63;
+            int k = k0 + row, mn = mn0 + 2 * v;
+            double* dst = s + row * LD_MN + 2 * v;
+            int valid = (k < K) ? min(max(MN - mn, 0), 2) : 0;
+            const double* src = valid ? g + (long long)k * ld + mn : g;
+            if (vec16) {
+                cp_async16(dst, src, valid * 8);
+            } else {
+                cp_async8(dst, src, valid >= 1 ? 8 : 0);
+                cp_async8(dst + 1, valid >= 2 ? src + 1 : g, valid >= 2 ? 8 : 0);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int pass = 0; pass < 4; ++pass) {
+            int row = pass * 32 + (tid >> 3);
+            int v = tid & 7;
+            int mn = mn0 + row, k = k0 + 2 * v;
+            double* dst = s + row * LD_K + 2 * v;
+            int valid = (mn < MN) ? min(max(K - k, 0), 2) : 0;
+            const double* src = valid ? g + (long long)mn * ld + k : g;
+            if (vec16) {
+                cp_async16(dst, src, valid * 8);
+            } else {
+                cp_async8(dst, src, valid >= 1 ? 8 : 0);
+                cp_async8(dst + 1, valid >= 2 ? src + 1 : g, valid >= 2 ? 8 : 0);
+            }
+        }
+    }
+}
+
+template <bool KMAJOR>
+__device__ __forceinline__ double frag(const double* s, int mn, int k) {
+    return KMAJOR ? s[mn * LD_K + k] : s[k * LD_MN + mn];
+}
+
+template <bool A_K, bool B_K>
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_kernel(GemmArgs p, int tiles_n, int vecA, int vecB) {
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 2, wn = warp & 3;
+
+    int ti, tj;
+    if (p.flags & GEMM_LOWER) {
+        // linear index -> (ti >= tj) of the lower triangle
+        long long x = blockIdx.x;
+        int i = (int)((sqrt(8.0 * (double)x + 1.0) - 1.0) * 0.5);
+        while ((long long)(i + 1) * (i + 2) / 2 <= x) ++i;
+        while ((long long)i * (i + 1) / 2 > x) --i;
+        ti = i;
+        tj = (int)(x - (long long)i * (i + 1) / 2);
+    } else {
+        ti = blockIdx.x / tiles_n;
+        tj = blockIdx.x % tiles_n;
+    }
+    const int m0 = ti * BM, n0 = tj * BN;
+    const int bz = blockIdx.y;
+    const double* A = p.A + (long long)bz * p.strideA;
+    const double* B = p.B + (long long)bz * p.strideB;
+    double* C = p.C + (long long)bz * p.strideC;
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    const int ktiles = (p.K + BK - 1) / BK;
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < ktiles) {
+            load_tile<A_K>(smem + s * STAGE_DOUBLES, A, p.lda, m0, s * BK, p.M, p.K, vecA, tid);
+            load_tile<B_K>(smem + s * STAGE_DOUBLES + TILE_DOUBLES, B, p.ldb, n0, s * BK, p.N, p.K, vecB, tid);
+        }
+        cp_async_commit();
+    }
+
+    const int fr = lane >> 2, fk = lane & 3;
+    for (int kt = 0; kt < ktiles; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+            int nk = kt + STAGES - 1;
+            if (nk < ktiles) {
+                int s = nk % STAGES;
+                load_tile<A_K>(smem + s * STAGE_DOUBLES, A, p.lda, m0, nk * BK, p.M, p.K, vecA, tid);
+                load_tile<B_K>(smem + s * STAGE_DOUBLES + TILE_DOUBLES, B, p.ldb, n0, nk * BK, p.N, p.K, vecB, tid);
+            }
+            cp_async_commit();
+        }
+        const double* As = smem + (kt % STAGES) * STAGE_DOUBLES;
+        const double* Bs = As + TILE_DOUBLES;
+#pragma unroll
+        for (int kk = 0; kk < BK / 4; ++kk) {
+            double a[8], b[4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = frag<A_K>(As, wm * 64 + i * 8 + fr, kk * 4 + fk);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = frag<B_K>(Bs, wn * 32 + j * 8 + fr, kk * 4 + fk);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // epilogue: C = alpha*acc + beta*C (+ bias[n])
+    const double alpha = p.alpha, beta = p.beta;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int m = m0 + wm * 64 + i * 8 + fr;
+        if (m >= p.M) continue;
+        double* crow = C + (long long)m * p.ldc;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int n = n0 + wn * 32 + j * 8 + fk * 2;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                if (n + e < p.N) {
+                    double v = alpha * acc[i][j][e];
+                    if (beta != 0.0) v += beta * crow[n + e];
+                    if (p.bias) v += p.bias[n + e];
+                    crow[n + e] = v;
+                }
+            }
+        }
+    }
+}
+
+inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+}  // namespace
+
+int launch_gemm_f64(const GemmArgs& a, cudaStream_t stream) {
+    if (a.M <= 0 || a.N <= 0 || a.batch <= 0) return 0;
+    const int tiles_m = (a.M + BM - 1) / BM, tiles_n = (a.N + BN - 1) / BN;
+    long long ntiles;
+    if (a.flags & GEMM_LOWER) {
+        if (a.M != a.N) {
+            set_error("gemm: GEMM_LOWER needs a square output");
+            return -1;
+        }
+        ntiles = (long long)tiles_m * (tiles_m + 1) / 2;
+    } else {
+        ntiles = (long long)tiles_m * tiles_n;
+    }
+    const int vecA = aligned16(a.A) && (a.lda % 2 == 0) && (a.strideA % 2 == 0);
+    const int vecB = aligned16(a.B) && (a.ldb % 2 == 0) && (a.strideB % 2 == 0);
+    dim3 grid((unsigned)ntiles, (unsigned)a.batch);
+    const bool ak = a.flags & GEMM_A_KMAJOR, bk = a.flags & GEMM_B_KMAJOR;
+    void (*kern)(GemmArgs, int, int, int) =
+        ak ? (bk ? gemm_f64_kernel<true, true> : gemm_f64_kernel<true, false>)
+           : (bk ? gemm_f64_kernel<false, true> : gemm_f64_kernel<false, false>);
+    static bool attr_done[4] = {false, false, false, false};
+    int which = (ak ? 2 : 0) + (bk ? 1 : 0);
+    if (!attr_done[which]) {
+        XESN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr_done[which] = true;
+    }
+    kern<<<grid, NTHREADS, SMEM_BYTES, stream>>>(a, tiles_n, vecA, vecB);
+    count_launch();
+    XESN_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace xesn

@@ -1,0 +1,74 @@
+// Argument blocks + launchers of the non-GEMM kernels (internal to the library).
+#pragma once
+#include "common.cuh"
+
+namespace xesn {
+
+struct RecurArgs {
+    const int* indptr;       // CSR of W, shared by every group
+    const int* indices;
+    const double* values;
+    const double* drive;     // [G][steps][N] : Win u_t + b for every step of the chunk
+    long long drive_group_stride;
+    double* states;          // [G][rows][N] : row 0 <- carry; store_all ? rows 1..steps written : ping-pong rows 0/1
+    long long state_group_stride;
+    double* carry;           // [G][N] state entering the chunk; overwritten with the state leaving it
+    int N;
+    int steps;
+    int store_all;
+    double alpha;
+    // filled by the launcher
+    int units_per_cta;
+    int smem_nnz;            // capacity (entries) of the shared-memory CSR slice
+    int w_in_smem;
+};
+
+struct StepArgs {
+    const int* indptr;
+    const int* indices;
+    const double* values;
+    const double* Win;    // [N][I] (inline projection) -- used when drive == nullptr
+    const double* bias;   // [N]
+    const double* u;      // [G][I] dense inputs, or (when in_map != nullptr) gathered from `field`:
+    const double* field;  //   u[g][k] = in_map[g*I+k] >= 0 ? field[in_map[..]] : fill[-1-in_map[..]]
+    const int* in_map;
+    const double* fill;
+    const double* drive;  // [G][N] precomputed Win u + b, or nullptr
+    const double* r_in;   // [G][N]
+    double* r_out;        // [G][N]
+    int N, I;
+    double alpha;
+};
+
+struct ReadoutArgs {
+    const double* Wout;   // [G][O][N]
+    const double* r;      // [G][N]
+    double* v;            // destination; element (g,o) lands at v[dst * v_stride]
+    long long v_stride;
+    double* v_copy;       // optional second destination (trajectory output)
+    long long v_copy_stride;
+    const int* out_map;   // optional [G][O] -> dst index; identity (g*O+o) when null
+    int N, O;
+};
+
+int launch_recur_forced(RecurArgs a, int n_groups, int max_slice_nnz, cudaStream_t stream);
+int recur_cluster_size(int N);
+int launch_step_update(const StepArgs& a, int n_groups, cudaStream_t stream);
+int launch_readout(const ReadoutArgs& a, int n_groups, cudaStream_t stream);
+int launch_gather_vec(const double* src, long long src_stride, const int* map, const double* fill, double* out,
+                      long long n, int mask_nan, cudaStream_t stream);
+int launch_gather_series(const double* src, long long ld_src, long long t0, const int* map, const double* fill,
+                         const unsigned char* zero_row, double* out, long long ld_out, long long rows, int nt,
+                         cudaStream_t stream);
+
+// ---- ridge solve (cholesky.cu) ---------------------------------------------------------------
+// In-place blocked Cholesky of the lower triangle of `batch` SPD matrices A[b] (n x n, row-major,
+// leading dimension lda), then X = A^{-1} B for B[b] (n x nrhs, row-major, ldb) in place.
+// info[b] = 0 on success, k>0 if the leading minor of order k is not positive definite.
+long long cholesky_workspace_doubles(int n, int batch);
+int launch_cholesky_solve_ws(double* A, long long lda, long long strideA, double* B, long long ldb, long long strideB,
+                             int n, int nrhs, int batch, int* info, double* work, cudaStream_t stream);
+int launch_add_diag(double* A, long long lda, long long strideA, int n, int batch, const double* beta_dev,
+                    double beta_scalar, cudaStream_t stream);
+
+}  // namespace xesn

@@ -1,0 +1,316 @@
+"""`xesn_b200.LazyESN` -- drop-in for `xesn.LazyESN` (reference xesn/lazyesn.py:18-261).
+
+The reference chunks the domain with dask, builds halos with
+`dask.array.overlap.overlap` and maps `_train_nd` / `_spinup` / `_update_nd` /
+`_readout` over the blocks (lazyesn.py:264-327).  Here every chunk ("group") is
+one independent reservoir of a single batched CUDA computation: all groups share
+(W, Win, b), the halos are index gathers (xesn_b200/halo.py) and the per-group
+ridge systems are factorised as one batch.  With `torch.distributed` initialised
+(one process per GPU) the groups are split in contiguous slabs over the ranks:
+training needs no communication; during `predict` the ranks exchange the
+freshly predicted cells once per step.
+"""
+import ctypes
+import warnings
+from functools import reduce
+
+import numpy as np
+
+from . import _lib
+from .esn import ESN, _is_dataarray, _ptr, _time_last, _torch, auto_chunk, xr
+from . import halo as _halo
+
+
+def _prod(seq):
+    return reduce(lambda a, b: a * b, seq)
+
+
+def _dist():
+    """(rank, world) of the torch.distributed job, (0, 1) when not initialised."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+class LazyESN(ESN):
+    __slots__ = ("esn_chunks", "overlap", "persist", "boundary",
+                 "_grid", "_dims", "_maps", "_wout_blocks_host")
+
+    @property
+    def output_chunks(self):
+        return self.esn_chunks
+
+    @property
+    def input_chunks(self):
+        return {k: self.output_chunks[k] + 2 * self.overlap[k] for k in self.output_chunks.keys()}
+
+    @property
+    def ndim_state(self):
+        """Number of non-time axes."""
+        return len(self.overlap) - 1
+
+    @property
+    def _r_chunks(self):
+        return tuple(1 for _ in range(self.ndim_state - 1)) + (self.n_reservoir,)
+
+    @property
+    def _Wout_chunks(self):
+        return (self.n_output, self.n_reservoir) + tuple(1 for _ in range(self.ndim_state - 2))
+
+    def __init__(self, esn_chunks, overlap, boundary, n_reservoir, leak_rate, tikhonov_parameter, persist=False,
+                 input_kwargs=None, adjacency_kwargs=None, bias_kwargs=None, *, device=None):
+        self.overlap, self.boundary, self.persist, self.esn_chunks = overlap, boundary, persist, esn_chunks
+        # like the reference (lazyesn.py:98-105) the caller's dicts get a trivial "time" entry
+        self.overlap.setdefault("time", 0)
+        self.esn_chunks.setdefault("time", -1)
+        if any(c < 0 for k, c in self.esn_chunks.items() if k != "time"):
+            raise ValueError("LazyESN.__init__: Cannot have negative numbers or Nones in non-temporal axis "
+                             "locations of esn_chunks. Provide the actual value please.")
+        n_output = _prod([c for k, c in self.output_chunks.items() if k != "time"])
+        n_input = _prod([c for k, c in self.input_chunks.items() if k != "time"])
+        super().__init__(n_input=n_input, n_output=n_output, n_reservoir=n_reservoir, leak_rate=leak_rate,
+                         tikhonov_parameter=tikhonov_parameter, input_kwargs=input_kwargs,
+                         adjacency_kwargs=adjacency_kwargs, bias_kwargs=bias_kwargs, device=device)
+        if sum(1 for d in self.overlap.values() if d > 0) > 2:
+            raise NotImplementedError("LazyESN.__init__: cannot overlap more than 2 axes")
+        self._grid = self._dims = self._maps = self._wout_blocks_host = None
+
+    def __str__(self):
+        bdy = "\n" + self._dictstr(self.boundary) if isinstance(self.boundary, dict) else str(self.boundary)
+        head = ("LazyESN\n"
+                f"    input_chunks:\n{self._dictstr(self.input_chunks)}---\n"
+                f"    output_chunks:\n{self._dictstr(self.output_chunks)}---\n"
+                f"    overlap:\n{self._dictstr(self.overlap)}---\n"
+                f'    {"boundary:":<24s}{bdy}\n---\n')
+        return head + super().__str__().replace("ESN\n", "", 1)
+
+    __repr__ = __str__
+
+    # ------------------------------------------------------------------ geometry
+    def _space_dims(self, y):
+        """Names of the space axes in array order (time last)."""
+        dims = getattr(y, "dims", None)
+        if dims is not None:
+            return tuple(d for d in dims[:-1])
+        names = tuple(k for k in self.esn_chunks.keys() if k != "time")
+        if len(names) != y.ndim - 1:
+            raise ValueError(f"LazyESN: data has {y.ndim - 1} space axes but esn_chunks names {names}")
+        return names
+
+    def _geometry(self, y):
+        dims = self._space_dims(y)
+        shape = tuple(int(n) for n in y.shape[:-1])
+        chunks = tuple(int(self.esn_chunks[d]) for d in dims)
+        depth = tuple(int(self.overlap[d]) for d in dims)
+        key = (dims, shape)
+        if self._maps is None or self._maps[0] != key:
+            rules = _halo.normalise_boundary(self.boundary, dims, depth)
+            grid, in_map, out_map, fill = _halo.build_maps(shape, chunks, depth, rules)
+            assert in_map.shape[1] == self.n_input and out_map.shape[1] == self.n_output
+            self._maps = (key, grid, in_map, out_map, fill)
+        self._dims, self._grid = dims, self._maps[1]
+        return self._maps[1:]
+
+    def _my_groups(self, n_groups):
+        rank, world = _dist()
+        if world == 1:
+            return 0, n_groups
+        if n_groups % world:
+            raise ValueError(f"LazyESN: {n_groups} groups do not divide over {world} ranks")
+        per = n_groups // world
+        return rank * per, (rank + 1) * per
+
+    # ------------------------------------------------------------------ Wout in the reference's block layout
+    @property
+    def Wout(self):
+        if self._wout_blocks_host is None and self._wout_dev is not None:
+            self._wout_blocks_host = _halo.wout_to_blocks(self._gather_wout_groups(), self._grid)
+        return self._wout_blocks_host
+
+    @Wout.setter
+    def Wout(self, value):
+        self._wout_blocks_host = None if value is None else np.asarray(value, dtype=np.float64)
+        self._wout_dev = None
+
+    @property
+    def Wout_groups(self):
+        """(G, O, N) readouts, group index in C order over the group grid."""
+        return self._gather_wout_groups()
+
+    def _gather_wout_groups(self):
+        torch = _torch()
+        w = self._wout_dev
+        rank, world = _dist()
+        if world > 1:
+            import torch.distributed as dist
+            parts = [torch.empty_like(w) for _ in range(world)]
+            dist.all_gather(parts, w.contiguous())
+            w = torch.cat(parts, dim=0)
+        return w.cpu().numpy()
+
+    def _wout_device_groups(self, g0, g1):
+        if self._wout_dev is None:
+            if self._wout_blocks_host is None:
+                raise _lib.XesnError("LazyESN: no readout matrix; call train() first")
+            if self._grid is None:
+                raise _lib.XesnError("LazyESN: geometry unknown; call predict() with data first")
+            w = _halo.blocks_to_wout(self._wout_blocks_host, self._grid, self.n_output, self.n_reservoir)
+            torch = _torch()
+            self._wout_dev = torch.from_numpy(np.ascontiguousarray(w[g0:g1])).to(self._device_reservoir().device)
+        return self._wout_dev
+
+    # ------------------------------------------------------------------ train
+    def train(self, y, n_spinup=0, batch_size=None):
+        """Per-group ridge regression (reference lazyesn.py:148-187 + `_train_nd` :264-298)."""
+        _time_last(y, "LazyESN.train", "y")
+        torch = _torch()
+        grid, in_map, out_map, fill = self._geometry(y)
+        n_time = int(y.shape[-1])
+        assert n_time >= n_spinup
+        G_all = in_map.shape[0]
+        g0, g1 = self._my_groups(G_all)
+        res = self._device_reservoir()
+        dev = res.device
+
+        field_dev, in_l, out_l, masked = self._upload_local(y, in_map[g0:g1], out_map[g0:g1], slice(None))
+        zero_u = masked[np.maximum(in_l, 0)] & (in_l >= 0)
+        zero_y = masked[out_l]
+        t_in = torch.from_numpy(in_l.reshape(-1)).to(dev)
+        t_out = torch.from_numpy(out_l.reshape(-1)).to(dev)
+        t_fill = torch.from_numpy(fill).to(dev)
+        t_zu = torch.from_numpy(zero_u.reshape(-1).astype(np.uint8)).to(dev) if zero_u.any() else None
+        t_zy = torch.from_numpy(zero_y.reshape(-1).astype(np.uint8)).to(dev) if zero_y.any() else None
+        ld = field_dev.stride(0)
+        u_series = _lib.Series(_ptr(field_dev), ld, _ptr(t_in), _ptr(t_fill), _ptr(t_zu))
+        y_series = _lib.Series(_ptr(field_dev), ld, _ptr(t_out), _ptr(t_fill), _ptr(t_zy))
+        wout = self._train_device(None, None, g1 - g0, n_time, n_spinup, batch_size, u_series, y_series,
+                                  keepalive=(field_dev, t_in, t_out, t_fill, t_zu, t_zy))
+        if zero_y.any():
+            # masked target cells: the reference leaves NaN rows (lazyesn.py:292-297)
+            wout[torch.from_numpy(zero_y).to(dev)] = float("nan")
+        self._wout_dev = wout
+        self._wout_blocks_host = None
+        self._check_info_groups()
+
+    def _check_info_groups(self):
+        info = self.last_info.cpu().numpy()
+        if info.any():
+            bad = np.nonzero(info)[0]
+            warnings.warn(f"LazyESN.train: the ridge system of {bad.size} group(s) is not positive definite; "
+                          f"their readout is NaN. Increase tikhonov_parameter.", RuntimeWarning)
+            self._wout_dev[_torch().as_tensor(bad, device=self._wout_dev.device)] = float("nan")
+
+    def _upload_local(self, y, in_map, out_map, tslice):
+        """Upload only the cells this rank's groups touch; returns the device rows, the maps
+        re-indexed to those rows and the per-row mask `isnan(first time sample)`."""
+        torch = _torch()
+        dev = self._device_reservoir().device
+        if isinstance(y, torch.Tensor):
+            flat = y.reshape(-1, y.shape[-1])[:, tslice]
+            used = np.unique(np.concatenate([in_map[in_map >= 0].ravel(), out_map.ravel()]))
+            rows = flat[torch.from_numpy(used).to(flat.device)].to(device=dev, dtype=torch.float64).contiguous()
+            masked_rows = torch.isnan(rows[:, 0]).cpu().numpy()
+        else:
+            data = getattr(y, "data", y) if getattr(y, "dims", None) is not None else y
+            if hasattr(data, "compute"):
+                data = data.compute()
+            flat = np.asarray(data, dtype=np.float64).reshape(-1, data.shape[-1])[:, tslice]
+            used = np.unique(np.concatenate([in_map[in_map >= 0].ravel(), out_map.ravel()]))
+            host = torch.from_numpy(np.ascontiguousarray(flat[used]))
+            try:
+                host = host.pin_memory()
+            except Exception:  # pragma: no cover
+                pass
+            rows = host.to(dev, non_blocking=True)
+            masked_rows = np.isnan(flat[used, 0])
+        lookup = np.full(int(used.max()) + 1 if used.size else 1, -1, dtype=np.int64)
+        lookup[used] = np.arange(used.size)
+        in_l = np.where(in_map >= 0, lookup[np.maximum(in_map, 0)], in_map).astype(np.int32)
+        out_l = lookup[out_map].astype(np.int32)
+        return rows, in_l, out_l, masked_rows
+
+    # ------------------------------------------------------------------ predict
+    def predict(self, y, n_steps, n_spinup):
+        """Closed-loop forecast of the whole domain (reference lazyesn.py:190-248)."""
+        _time_last(y, "LazyESN.predict", "y")
+        assert y.shape[-1] >= n_spinup + 1
+        torch = _torch()
+        grid, in_map, out_map, fill = self._geometry(y)
+        G_all = in_map.shape[0]
+        g0, g1 = self._my_groups(G_all)
+        G = g1 - g0
+        rank, world = _dist()
+        res = self._device_reservoir()
+        lib, dev = res._lib, res.device
+        N, O, I = self.n_reservoir, self.n_output, self.n_input
+        n_cells = int(np.prod(y.shape[:-1]))
+        wout = self._wout_device_groups(g0, g1)
+
+        # ---- spin-up on the halo'd truth (lazyesn.py:215-221, `_spinup` :301-316)
+        truth_dev, in_l, out_l, masked = self._upload_local(y, in_map[g0:g1], out_map[g0:g1], slice(0, n_spinup + 1))
+        zero_u = masked[np.maximum(in_l, 0)] & (in_l >= 0)
+        t_in_l = torch.from_numpy(in_l.reshape(-1)).to(dev)
+        t_fill = torch.from_numpy(fill).to(dev)
+        t_zu = torch.from_numpy(zero_u.reshape(-1).astype(np.uint8)).to(dev) if zero_u.any() else None
+        with torch.cuda.device(dev):
+            st = self._stream()
+            r = torch.zeros((G, N), dtype=torch.float64, device=dev)
+            series = _lib.Series(_ptr(truth_dev), truth_dev.stride(0), _ptr(t_in_l), _ptr(t_fill), _ptr(t_zu))
+            nb = max(lib.xesn_forced_scratch_bytes(res.handle, G, n_spinup, 1),
+                     lib.xesn_predict_scratch_bytes(res.handle, O, G, n_cells))
+            scratch = torch.empty(nb, dtype=torch.uint8, device=dev)
+            _lib.check(lib.xesn_forced_run(res.handle, ctypes.byref(series), 0, n_spinup, G, _ptr(r), None,
+                                           _ptr(scratch), nb, st))
+
+            # ---- closed loop on the global cell vector
+            field = self._initial_field(y, n_spinup, dev)
+            t_in = torch.from_numpy(in_map[g0:g1].reshape(-1)).to(dev)
+            t_out = torch.from_numpy(out_map[g0:g1].reshape(-1)).to(dev)
+            pred = torch.empty((n_cells, n_steps + 1), dtype=torch.float64, device=dev)
+            if world == 1:
+                _lib.check(lib.xesn_predict(res.handle, _ptr(wout), O, G, n_cells, _ptr(t_in), _ptr(t_fill),
+                                            _ptr(t_out), _ptr(field), _ptr(r), n_steps, _ptr(pred), _ptr(scratch),
+                                            nb, st))
+            else:
+                self._predict_multi(lib, res, wout, G, g0, n_cells, t_in, t_fill, t_out, out_map, field, r,
+                                    n_steps, pred, scratch, nb, st)
+        out = pred.cpu().numpy().reshape(tuple(y.shape[:-1]) + (n_steps + 1,))
+        if _is_dataarray(y):
+            fdims, fcoords = self._get_fcoords(y.dims, y.coords, n_steps, n_spinup)
+            return xr.DataArray(out, coords=fcoords, dims=fdims)
+        return out
+
+    def _initial_field(self, y, n_spinup, dev):
+        torch = _torch()
+        if isinstance(y, torch.Tensor):
+            return y[..., n_spinup].reshape(-1).to(device=dev, dtype=torch.float64).contiguous().clone()
+        data = getattr(y, "data", y) if getattr(y, "dims", None) is not None else y
+        col = data[..., n_spinup]
+        if hasattr(col, "compute"):
+            col = col.compute()
+        return torch.from_numpy(np.ascontiguousarray(np.asarray(col, dtype=np.float64).reshape(-1))).to(dev)
+
+    def _predict_multi(self, lib, res, wout, G, g0, n_cells, t_in, t_fill, t_out, out_map, field, r, n_steps,
+                       pred, scratch, nb, st):
+        """One process per GPU: every rank advances its slab of groups, then the ranks
+        all-gather the cells they own (NCCL over NVLink) -- the per-step neighbour exchange
+        that dask's `overlap` performs in the reference (lazyesn.py:235)."""
+        torch = _torch()
+        import torch.distributed as dist
+        rank, world = _dist()
+        O = self.n_output
+        dev = res.device
+        # cells owned per rank, in rank order; equal counts because the groups divide evenly
+        owned = torch.from_numpy(out_map.reshape(world, -1).astype(np.int64)).to(dev)
+        mine = owned[rank]
+        pred[:, 0] = field
+        nxt = field.clone()
+        gathered = torch.empty((world, mine.numel()), dtype=torch.float64, device=dev)
+        for n in range(1, n_steps + 1):
+            _lib.check(lib.xesn_predict_step(res.handle, _ptr(wout), O, G, _ptr(t_in), _ptr(t_fill), _ptr(t_out),
+                                             _ptr(field), _ptr(nxt), _ptr(r), None, 0, _ptr(scratch), nb, st))
+            dist.all_gather_into_tensor(gathered, nxt[mine].contiguous())
+            nxt[owned.reshape(-1)] = gathered.reshape(-1)
+            pred[:, n] = nxt
+            field, nxt = nxt, field
