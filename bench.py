@@ -1,0 +1,418 @@
+#!/usr/bin/env python
+"""Benchmark of the ESN hot path: reservoir unit-steps/s (train + predict).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload eager16k|lazy]
+
+A "step" is one full pass of the hot path over one synthetic series:
+`train` (recurrence + Gram accumulation + ridge solve) followed by `predict` (spin-up + closed
+loop).  Default workload = BASELINE.json configs[1]: eager ESN, n_reservoir=16000, Lorenz-96
+(40 variables), 20 000 training steps, predict with 500 spin-up + 1000 forecast steps.
+unit-steps = G * N * (T_train + n_spinup_pred + n_steps_pred); `build()` and
+the upload of the reservoir matrices are outside the timed region.
+
+  value : K steps timed with CUDA events, inputs already resident in HBM
+  e2e   : the same K steps through the public API (ESN.train / ESN.predict) with pinned HOST
+          inputs -> H2D inside the timed region, readout + forecast copied back to the host
+  N > 1 : eager ESN does not shard (all-to-all of the state every ~microsecond), so the ranks run
+          independent replicas ("replicas only", weak scaling).  `--workload lazy` shards LazyESN
+          groups over the ranks instead (weak scaling, halo exchange per forecast step).
+  --impl reference : the reference's numpy algorithm (oracle port of xesn/esn.py) on the host cores,
+          timed on a bounded sample of the same workload and extrapolated linearly in T.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "reservoir unit-steps/sec (train+predict)"
+UNIT = "unit-steps/s"
+
+ESN_KW = dict(
+    input_kwargs=dict(factor=0.5, distribution="uniform", normalization="svd", random_seed=0),
+    adjacency_kwargs=dict(factor=0.9, distribution="uniform", normalization="svd", is_sparse=True,
+                          connectedness=5, format="csr", random_seed=1),
+    bias_kwargs=dict(factor=0.5, distribution="uniform", random_seed=2),
+)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]
+    "eager16k": dict(kind="eager", n_vars=40, n_reservoir=16000, n_train=20000, n_spinup_train=0,
+                     pred_spinup=500, pred_steps=1000, leak=0.5, beta=1e-6),
+    # BASELINE.json configs[0] (the reference's own CPU-sized case), handy for quick checks
+    "eager1k": dict(kind="eager", n_vars=40, n_reservoir=1000, n_train=20000, n_spinup_train=0,
+                    pred_spinup=500, pred_steps=1000, leak=0.5, beta=1e-6),
+    # BASELINE.json configs[2] per GPU: 16 groups of 16 variables, overlap 1, N=2000 (weak scaling)
+    "lazy": dict(kind="lazy", groups_per_gpu=16, chunk=16, overlap=1, n_reservoir=2000, n_train=20000,
+                 n_spinup_train=0, pred_spinup=500, pred_steps=1000, leak=0.5, beta=1e-6),
+}
+
+
+def unit_steps(w, n_groups):
+    return n_groups * w["n_reservoir"] * (w["n_train"] + w["pred_spinup"] + w["pred_steps"])
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- CPU baseline (oracle port)
+def cpu_baseline(w, data, W, Win, b, sample_train=300, sample_pred=100, time_solve=True):
+    """Oracle port (numpy restatement of xesn/esn.py `_train_1d` + predict loop) on the host cores,
+    on a bounded sample, extrapolated linearly in the number of time steps.  Eager workload only."""
+    from oracle import esn_oracle as oc
+    N = w["n_reservoir"]
+    u = data[:, :sample_train]
+    t0 = time.perf_counter()
+    rr, yr = oc.ridge_accumulate(u, u, 0, sample_train, W, Win, b, w["leak"])
+    t_acc = time.perf_counter() - t0
+    t_solve = None
+    if time_solve:
+        t0 = time.perf_counter()
+        Wout = oc.ridge_solve(rr, yr, w["beta"])
+        t_solve = time.perf_counter() - t0
+    else:
+        Wout = np.zeros((u.shape[0], N))
+    del rr
+    t0 = time.perf_counter()
+    oc.closed_loop(data[:, :sample_pred + 1], sample_pred, sample_pred // 2, W, Win, b, w["leak"], Wout)
+    t_pred = (time.perf_counter() - t0) / (sample_pred + sample_pred // 2)
+    return {"per_train_step_s": t_acc / sample_train, "solve_s": t_solve, "per_predict_step_s": t_pred}
+
+
+def cpu_extrapolate(w, parts, solve_s):
+    total = (w["n_train"] * parts["per_train_step_s"] + solve_s
+             + (w["pred_spinup"] + w["pred_steps"]) * parts["per_predict_step_s"])
+    return unit_steps(w, 1) / total, total
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([p.get("num_threads", 1) for p in threadpool_info()] or [os.cpu_count()])
+    except Exception:
+        return os.cpu_count()
+
+
+def build_eager_matrices(w):
+    """Host build of (W, Win, b) with the reference's conventions (outside every timed region)."""
+    from xesn_b200 import ESN
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        esn = ESN(w["n_vars"], w["n_vars"], w["n_reservoir"], w["leak"], w["beta"], **{k: dict(v) for k, v in ESN_KW.items()})
+        esn.build()
+    return esn
+
+
+def run_reference(args, w, rank):
+    if rank != 0:
+        return
+    if w["kind"] != "eager":
+        print(json.dumps({"impl": "reference", "unavailable": "reference arm implemented for the eager workload only"}))
+        return
+    from xesn_b200.synthetic import lorenz96
+    import scipy.sparse as sp
+    esn = build_eager_matrices(w)
+    W = sp.csr_matrix(esn.W)
+    n_t = 400
+    data = lorenz96(w["n_vars"], n_t + 200)
+    sample_train, sample_pred = (200, 60) if w["n_reservoir"] > 4000 else (2000, 500)
+    # the N^3/3 solve does not depend on T: time it once (first warm-up step) and reuse it
+    first = cpu_baseline(w, data, W, esn.Win, esn.bias_vector, sample_train, sample_pred, time_solve=True)
+    solve_s = first["solve_s"]
+    for _ in range(max(args.warmup - 1, 0)):
+        cpu_baseline(w, data, W, esn.Win, esn.bias_vector, sample_train, sample_pred, time_solve=False)
+    vals, totals = [], []
+    for _ in range(args.steps):
+        parts = cpu_baseline(w, data, W, esn.Win, esn.bias_vector, sample_train, sample_pred, time_solve=False)
+        v, total = cpu_extrapolate(w, parts, solve_s)
+        vals.append(v)
+        totals.append(total)
+    value = float(np.mean(vals))
+    cores = blas_threads()
+    sample = (f"oracle port of xesn/esn.py on {cores} host threads: {sample_train} train steps + Gram, "
+              f"{sample_pred + sample_pred // 2} predict steps per bench step, ridge solve (N^3/3) timed once "
+              f"({solve_s:.1f} s); extrapolated linearly to {w['n_train']} train + {w['pred_spinup'] + w['pred_steps']} predict steps")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": float(np.mean(totals)) * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.workload, w, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(name, w, world):
+    cfg = {"workload": name, "inputs": "larger than L2 (Gram accumulator 2 GB >> 126 MB L2)"}
+    cfg.update({k: v for k, v in w.items() if k != "kind"})
+    cfg["parallelism"] = "single GPU" if world == 1 else (
+        f"{world} independent replicas (eager ESN does not shard)" if w["kind"] == "eager"
+        else f"LazyESN groups sharded over {world} ranks, halo all-gather per forecast step")
+    return cfg
+
+
+# --------------------------------------------------------------------------- FP64 tensor peak probe
+def dgemm_peak(torch, n=8192, reps=6):
+    """cuBLAS DGEMM n^3 (the FP64 counterpart of MEASURED_PEAKS.json's bf16 probe): burst best-of-reps."""
+    a = torch.randn((n, n), dtype=torch.float64, device="cuda")
+    b = torch.randn((n, n), dtype=torch.float64, device="cuda")
+    c = torch.empty_like(a)
+    torch.matmul(a, b, out=c)
+    best = 1e30
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b, out=c)
+        e1.record()
+        e1.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b, c
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+# --------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="eager16k", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    w = dict(WORKLOADS[args.workload])
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, w, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from xesn_b200 import _lib, launch_count
+    from xesn_b200.synthetic import lorenz96
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    dev = torch.device(f"cuda:{local_rank}")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------------------------ build the workload
+    t_total = w["n_train"] + w["pred_spinup"] + w["pred_steps"] + 1
+    if w["kind"] == "eager":
+        esn = build_eager_matrices(w)
+        data = lorenz96(w["n_vars"], t_total)
+        n_groups_total = world  # replicas
+        train_host = torch.from_numpy(np.ascontiguousarray(data[:, :w["n_train"]])).pin_memory()
+        test_host = torch.from_numpy(np.ascontiguousarray(data[:, w["n_train"]:])).pin_memory()
+        train_dev, test_dev = train_host.to(dev), test_host.to(dev)
+        esn._device_reservoir()
+
+        def step_device():
+            esn._wout_dev = esn._train_device(train_dev, train_dev, 1, w["n_train"], w["n_spinup_train"], None)
+            esn._wout_host = None
+            return esn._predict_device(test_dev, w["pred_steps"], w["pred_spinup"])
+
+        def step_e2e():
+            esn.train(train_host, n_spinup=w["n_spinup_train"])
+            wout = esn.Wout                       # D2H of the readout
+            pred = esn.predict(test_host, n_steps=w["pred_steps"], n_spinup=w["pred_spinup"])  # D2H of the forecast
+            return wout, pred
+
+        h2d = train_host.numel() * 8 + test_host.numel() * 8
+        d2h = w["n_vars"] * w["n_reservoir"] * 8 + w["n_vars"] * (w["pred_steps"] + 1) * 8
+    else:
+        from xesn_b200 import LazyESN
+        n_vars = w["groups_per_gpu"] * w["chunk"] * world
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            esn = LazyESN({"x": w["chunk"]}, {"x": w["overlap"]}, "periodic", w["n_reservoir"], w["leak"], w["beta"],
+                          **{k: dict(v) for k, v in ESN_KW.items()})
+            esn.build()
+        data = lorenz96(n_vars, t_total)
+        n_groups_total = w["groups_per_gpu"] * world
+        train_host = torch.from_numpy(np.ascontiguousarray(data[:, :w["n_train"]])).pin_memory()
+        test_host = torch.from_numpy(np.ascontiguousarray(data[:, w["n_train"]:])).pin_memory()
+        train_dev, test_dev = train_host.to(dev), test_host.to(dev)
+        esn._device_reservoir()
+
+        def step_device():
+            esn.train(train_dev, n_spinup=w["n_spinup_train"])
+            return esn.predict(test_dev, n_steps=w["pred_steps"], n_spinup=w["pred_spinup"])
+
+        def step_e2e():
+            esn.train(train_host, n_spinup=w["n_spinup_train"])
+            pred = esn.predict(test_host, n_steps=w["pred_steps"], n_spinup=w["pred_spinup"])
+            return pred
+
+        h2d = (train_host.numel() + test_host.numel()) * 8 // world
+        d2h = n_vars * (w["pred_steps"] + 1) * 8
+
+    units = unit_steps(w, n_groups_total)
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ------------------------------------------------------------------ device-resident timing
+    for _ in range(args.warmup):
+        step_device()
+    torch.cuda.synchronize()
+    launches0 = launch_count()
+    _lib.profile_enable(True)
+    with ClockSampler(local_rank) as clocks:
+        ms_total = timed(step_device, args.steps)
+    prof = _lib.profile_read()
+    _lib.profile_enable(False)
+    launches = launch_count() - launches0
+    ms_per_step = ms_total / args.steps
+    value = units / (ms_per_step * 1e-3)
+
+    # ------------------------------------------------------------------ end-to-end timing (host buffers)
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps) / args.steps
+    e2e_value = units / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ------------------------------------------------------------------ roofline of the dominant kernel
+    N = w["n_reservoir"]
+    G_local = 1 if w["kind"] == "eager" else w["groups_per_gpu"]
+    n_gram, ms_gram = prof["gram_syrk"]
+    peak_tf = dgemm_peak(torch)
+    # algorithmic FP64 flops of the Gram accumulation: N(N+1) per reservoir per time step (one triangle)
+    gram_flops = float(G_local) * N * (N + 1) * w["n_train"] * args.steps
+    achieved = gram_flops / (ms_gram * 1e-3) / 1e12 if ms_gram > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(args.workload, {}).get("gram_syrk_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {
+        "bound": "tensor", "kernel": "gemm_f64_kernel<MN,MN> lower (Gram SYRK, DMMA.8x8x4)",
+        "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
+        "traffic": traffic,
+        "peak_source": "cuBLAS DGEMM 8192^3 burst measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+        "launches": n_gram, "avg_launch_ms": ms_gram / n_gram if n_gram else None,
+        "flops_per_launch": gram_flops / n_gram if n_gram else None,
+    }
+    phases = {k: {"regions": v[0], "ms_per_step": v[1] / args.steps} for k, v in prof.items() if v[0]}
+
+    cpu = None
+    if not args.no_cpu_baseline and w["kind"] == "eager":
+        import scipy.sparse as sp
+        big = N > 4000
+        st, sp_ = (200, 60) if big else (2000, 500)
+        parts = cpu_baseline(w, data, sp.csr_matrix(esn.W), esn.Win, esn.bias_vector, st, sp_, time_solve=True)
+        v, total = cpu_extrapolate(w, parts, parts["solve_s"])
+        cores = blas_threads()
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": (f"oracle port of xesn/esn.py:_train_1d + predict loop, numpy/scipy on {cores} threads: "
+                          f"{st} train steps + Gram ({parts['per_train_step_s'] * 1e3:.2f} ms/step), full N^3/3 solve "
+                          f"({parts['solve_s']:.1f} s), {sp_ + sp_ // 2} predict steps "
+                          f"({parts['per_predict_step_s'] * 1e3:.2f} ms/step); extrapolated linearly to the full "
+                          f"workload ({total:.1f} s)")}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.workload, w, world),
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": int(launches),
+        "clocks": clocks.summary(),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "phases_ms_per_step": phases,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -121,6 +121,12 @@ int xesn_readout(const double* wout_dev, const double* r_dev, double* v_dev, int
                  int32_t n_output, int32_t n_groups, void* stream);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 int64_t xesn_launch_count(void);
+/* per-phase device timers (CUDA events on the launching stream).  enable(1) clears and starts
+ * recording, enable(0) stops.  read() synchronises on the recorded events and returns the number
+ * of timed regions and their summed duration for class
+ * 0 drive GEMM, 1 recurrence, 2 Gram SYRK, 3 Y.R GEMM, 4 ridge solve, 5 closed loop, 6 halo gather. */
+int xesn_profile_enable(int32_t on);
+int xesn_profile_read(int32_t cls, int64_t* n_regions, double* total_ms);
 
 #ifdef __cplusplus
 }

@@ -41,13 +41,13 @@ def forced_states(u, n_steps, W, Win, b, alpha, r0=None):
     return out
 
 
-def ridge_train(u, y, n_spinup, batch_size, W, Win, b, alpha, beta, return_gram=False):
-    """Ridge-regression readout.  Restates xesn/esn.py:463-520 (`_train_1d`).
+def ridge_accumulate(u, y, n_spinup, batch_size, W, Win, b, alpha):
+    """Spin-up + batched Gram accumulation.  Restates xesn/esn.py:476-513 (the part of
+    `_train_1d` before the solve).  Returns (rbar (N,N), ybar (O,N)) without the Tikhonov term.
 
-    u:(I,T), y:(O,T) time-last.  The state that has seen u[:, :t] is regressed
-    onto y[:, t]; Gram terms are accumulated batch by batch exactly in the
-    reference's order (batch boundaries change the floating-point sum order).
-    """
+    u:(I,T), y:(O,T) time-last.  The state that has seen u[:, :t] is regressed onto y[:, t];
+    Gram terms are accumulated batch by batch in the reference's order (batch boundaries
+    change the floating-point sum order)."""
     N = Win.shape[0]
     O, T = y.shape
     B = T if batch_size is None else batch_size
@@ -69,9 +69,20 @@ def ridge_train(u, y, n_spinup, batch_size, W, Win, b, alpha, beta, return_gram=
         yr += y[:, lo:hi] @ states[:m]
         rr += states[:m].T @ states[:m]
         states[0] = states[m].copy()
+    return rr, yr
 
-    rr += beta * np.eye(N)
-    Wout = _sym_solve(rr.T, yr.T, assume_a="sym").T
+
+def ridge_solve(rr, yr, beta):
+    """Tikhonov term + symmetric solve.  Restates xesn/esn.py:516-520 (modifies rr in place
+    like the reference does)."""
+    rr += beta * np.eye(rr.shape[0])
+    return _sym_solve(rr.T, yr.T, assume_a="sym").T
+
+
+def ridge_train(u, y, n_spinup, batch_size, W, Win, b, alpha, beta, return_gram=False):
+    """Ridge-regression readout.  Restates xesn/esn.py:463-520 (`_train_1d`)."""
+    rr, yr = ridge_accumulate(u, y, n_spinup, batch_size, W, Win, b, alpha)
+    Wout = ridge_solve(rr, yr, beta)
     if return_gram:
         return Wout, rr, yr
     return Wout

@@ -52,6 +52,8 @@ SIGNATURES = {
                                     C.c_void_p]),
     "xesn_gemm_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
                                 C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_void_p]),
+    "xesn_profile_enable": (C.c_int, [C.c_int32]),
+    "xesn_profile_read": (C.c_int, [C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "xesn_readout": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
 }
 
@@ -87,3 +89,21 @@ def check(rc):
 
 def launch_count():
     return int(load().xesn_launch_count())
+
+
+PROFILE_CLASSES = ("drive_gemm", "recurrence", "gram_syrk", "yr_gemm", "ridge_solve", "closed_loop", "halo_gather")
+
+
+def profile_enable(on=True):
+    check(load().xesn_profile_enable(1 if on else 0))
+
+
+def profile_read():
+    """{class name: (regions, total_ms)} of the phases timed since profile_enable(True)."""
+    lib = load()
+    out = {}
+    for k, name in enumerate(PROFILE_CLASSES):
+        n, ms = C.c_int64(0), C.c_double(0.0)
+        check(lib.xesn_profile_read(k, C.byref(n), C.byref(ms)))
+        out[name] = (int(n.value), float(ms.value))
+    return out

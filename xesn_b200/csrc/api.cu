@@ -25,6 +25,39 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// ---- per-phase device timers: CUDA events recorded on the launching stream ----
+struct ProfRec {
+    int cls;
+    cudaEvent_t a, b;
+};
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_prof_pool;
+static cudaEvent_t prof_event() {
+    cudaEvent_t e;
+    if (!g_prof_pool.empty()) {
+        e = g_prof_pool.back();
+        g_prof_pool.pop_back();
+    } else {
+        cudaEventCreate(&e);
+    }
+    return e;
+}
+void prof_begin(int cls, cudaStream_t st) {
+    if (!g_prof_on) return;
+    ProfRec r{cls, prof_event(), prof_event()};
+    cudaEventRecord(r.a, st);
+    g_prof.push_back(r);
+}
+void prof_end(int cls, cudaStream_t st) {
+    if (!g_prof_on) return;
+    for (size_t i = g_prof.size(); i-- > 0;)
+        if (g_prof[i].cls == cls) {
+            cudaEventRecord(g_prof[i].b, st);
+            return;
+        }
+}
+
 namespace {
 __global__ void strided_copy_kernel(const double* __restrict__ src, double* __restrict__ dst, long long dst_stride,
                                     long long n) {
@@ -57,6 +90,31 @@ extern "C" {
 const char* xesn_last_error(void) { return g_error.c_str(); }
 int xesn_abi_version(void) { return 1; }
 int64_t xesn_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int xesn_profile_enable(int on) {
+    for (auto& r : g_prof) {
+        g_prof_pool.push_back(r.a);
+        g_prof_pool.push_back(r.b);
+    }
+    g_prof.clear();
+    g_prof_on = on != 0;
+    return 0;
+}
+
+int xesn_profile_read(int cls, int64_t* n_regions, double* total_ms) {
+    XESN_REQUIRE(n_regions && total_ms && cls >= 0 && cls < PROF_N, "bad arguments");
+    long long n = 0;
+    double ms = 0.0;
+    for (auto& r : g_prof) {
+        if (r.cls != cls) continue;
+        XESN_CUDA_OK(cudaEventSynchronize(r.b));
+        float t = 0.f;
+        XESN_CUDA_OK(cudaEventElapsedTime(&t, r.a, r.b));
+        ms += t, ++n;
+    }
+    *n_regions = n, *total_ms = ms;
+    return 0;
+}
 
 int xesn_reservoir_create(xesn_reservoir** out, int device, int32_t N, int32_t I, const int32_t* indptr,
                           const int32_t* indices, const double* values, const double* win, const double* bias,
@@ -134,6 +192,7 @@ static int chunk_inputs(xesn_reservoir* h, const xesn_series* s, int rows, int G
                         long long stage_ld, const double** base, long long* ld, long long* gstride,
                         cudaStream_t st) {
     if (s->map_dev || s->zero_row_dev) {
+        ProfScope prof(PROF_GATHER, st);
         int rc = launch_gather_series(s->data_dev, s->ld, t0, s->map_dev, s->fill_dev, s->zero_row_dev, stage, stage_ld,
                                       (long long)G * rows, m, st);
         if (rc) return rc;
@@ -146,6 +205,7 @@ static int chunk_inputs(xesn_reservoir* h, const xesn_series* s, int rows, int G
 
 static int drive_gemm(xesn_reservoir* h, const double* ubase, long long ldu, long long ugstride, int G, int m, double* D,
                       cudaStream_t st) {
+    ProfScope prof(PROF_DRIVE, st);
     GemmArgs g = {};
     g.A = ubase, g.lda = ldu, g.strideA = ugstride;           // A(t,i) = U[i*ld + t]   (MN-contiguous)
     g.B = h->d_win, g.ldb = h->I, g.strideB = 0;              // B(i,n) = Win[n*I + i]  (K-contiguous)
@@ -282,21 +342,30 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
         const long long rgs = (long long)(m + 1) * N;
         r.drive = D, r.drive_group_stride = (long long)m * N, r.steps = m, r.carry = carry;
         r.states = R, r.state_group_stride = rgs, r.store_all = 1;
-        if ((rc = launch_recur_forced(r, G, h->max_slice_nnz, st))) return rc;
+        {
+            ProfScope prof(PROF_RECUR, st);
+            if ((rc = launch_recur_forced(r, G, h->max_slice_nnz, st))) return rc;
+        }
         // rbar += R^T R  (rows 0..m-1: the state that has seen u(..t-1) pairs with y(t))
         GemmArgs g = {};
         g.A = R, g.lda = N, g.strideA = rgs;
         g.B = R, g.ldb = N, g.strideB = rgs;
         g.C = gram, g.ldc = N, g.strideC = (long long)N * N;
         g.M = N, g.N = N, g.K = m, g.batch = G, g.alpha = 1.0, g.beta = 1.0, g.flags = GEMM_LOWER;
-        if ((rc = launch_gemm_f64(g, st))) return rc;
+        {
+            ProfScope prof(PROF_GRAM, st);
+            if ((rc = launch_gemm_f64(g, st))) return rc;
+        }
         // ybar += Y R
         GemmArgs q = {};
         q.A = yb, q.lda = ldy, q.strideA = ygs;
         q.B = R, q.ldb = N, q.strideB = rgs;
         q.C = wout, q.ldc = N, q.strideC = (long long)O * N;
         q.M = O, q.N = N, q.K = m, q.batch = G, q.alpha = 1.0, q.beta = 1.0, q.flags = GEMM_A_KMAJOR;
-        if ((rc = launch_gemm_f64(q, st))) return rc;
+        {
+            ProfScope prof(PROF_YR, st);
+            if ((rc = launch_gemm_f64(q, st))) return rc;
+        }
     }
     return 0;
 }
@@ -307,6 +376,7 @@ int xesn_ridge_solve(xesn_reservoir* h, int32_t O, int32_t G, const double* beta
     XESN_REQUIRE(scratch_bytes >= cholesky_workspace_doubles(h->N, G) * 8, "scratch too small");
     cudaStream_t st = (cudaStream_t)stream;
     const int N = h->N;
+    ProfScope prof(PROF_SOLVE, st);
     int rc = launch_add_diag(gram, N, (long long)N * N, N, G, beta_dev, beta_scalar, st);
     if (rc) return rc;
     return launch_cholesky_solve_ws(gram, N, (long long)N * N, wout, N, (long long)O * N, N, O, G, info, (double*)scratch,
@@ -373,6 +443,7 @@ int xesn_predict(xesn_reservoir* h, const double* wout, int32_t O, int32_t G, in
     double* r_alt = drive + round_up((long long)G * N, 2);
     double* field_alt = r_alt + round_up((long long)G * N, 2);
     const long long ldp = (long long)n_steps + 1;
+    ProfScope prof(PROF_PREDICT, st);
 
     strided_copy_kernel<<<(unsigned)((n_cells + 255) / 256), 256, 0, st>>>(field, pred, ldp, n_cells);
     XESN_CUDA_OK(cudaGetLastError());

@@ -29,6 +29,17 @@ void count_launch(int n = 1);
         }                                                                               \
     } while (0)
 
+// optional per-phase device timers (xesn_profile_enable / xesn_profile_read)
+enum ProfClass : int { PROF_DRIVE = 0, PROF_RECUR, PROF_GRAM, PROF_YR, PROF_SOLVE, PROF_PREDICT, PROF_GATHER, PROF_N };
+void prof_begin(int cls, cudaStream_t st);
+void prof_end(int cls, cudaStream_t st);
+struct ProfScope {
+    int cls;
+    cudaStream_t st;
+    ProfScope(int c, cudaStream_t s) : cls(c), st(s) { prof_begin(cls, st); }
+    ~ProfScope() { prof_end(cls, st); }
+};
+
 // ---- internal launchers shared between translation units -------------------------------------
 enum GemmFlags : int {
     GEMM_A_KMAJOR = 1,   // A[m*lda + k]   (else A[k*lda + m])
