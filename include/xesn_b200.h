@@ -52,6 +52,9 @@ int xesn_reservoir_create(xesn_reservoir** out, int device, int32_t n_reservoir,
                           const int32_t* indptr, const int32_t* indices, const double* values,
                           const double* win, const double* bias, double leak_rate);
 int xesn_reservoir_destroy(xesn_reservoir* h);
+/* Synchronous health check: *status_host = 0 if every persistent-kernel poll completed, 1 if one
+ * timed out (the CTAs of a cluster lost co-residency; results of that run are invalid). */
+int xesn_reservoir_status(xesn_reservoir* h, int32_t* status_host);
 
 /* ---- a1: one update, r' = (1-a) r + a tanh(W r + Win u + b)      xesn/esn.py:458-460 (_update),
  *      xesn/lazyesn.py:319-322 (_update_nd).  r_in/r_out: [G][N]; u: [G][I]; NaN inputs count as 0. */

@@ -33,6 +33,7 @@ SIGNATURES = {
     "xesn_reservoir_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]),
     "xesn_reservoir_destroy": (C.c_int, [C.c_void_p]),
+    "xesn_reservoir_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "xesn_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "xesn_forced_scratch_bytes": (C.c_int64, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
     "xesn_forced_run": (C.c_int, [C.c_void_p, C.POINTER(Series), C.c_int64, C.c_int32, C.c_int32, C.c_void_p,

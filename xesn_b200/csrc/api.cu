@@ -81,6 +81,10 @@ struct xesn_reservoir {
     double* d_values = nullptr;
     double* d_win = nullptr;
     double* d_bias = nullptr;
+    int* d_status = nullptr;
+    double* d_ro_partial = nullptr;
+    int* d_ro_counters = nullptr;
+    long long ro_partial_cap = 0, ro_counter_cap = 0;
     int cluster = 1;
     int max_slice_nnz = 0;
 };
@@ -142,6 +146,8 @@ int xesn_reservoir_create(xesn_reservoir** out, int device, int32_t N, int32_t I
     XESN_CUDA_OK(cudaMalloc(&h->d_values, sizeof(double) * (nnz > 0 ? nnz : 1)));
     XESN_CUDA_OK(cudaMalloc(&h->d_win, sizeof(double) * (size_t)N * I));
     XESN_CUDA_OK(cudaMalloc(&h->d_bias, sizeof(double) * N));
+    XESN_CUDA_OK(cudaMalloc(&h->d_status, sizeof(int)));
+    XESN_CUDA_OK(cudaMemset(h->d_status, 0, sizeof(int)));
     XESN_CUDA_OK(cudaMemcpy(h->d_indptr, indptr, sizeof(int) * (N + 1), cudaMemcpyHostToDevice));
     if (nnz) {
         XESN_CUDA_OK(cudaMemcpy(h->d_indices, indices, sizeof(int) * nnz, cudaMemcpyHostToDevice));
@@ -171,7 +177,16 @@ int xesn_reservoir_destroy(xesn_reservoir* h) {
     cudaFree(h->d_values);
     cudaFree(h->d_win);
     cudaFree(h->d_bias);
+    cudaFree(h->d_status);
+    cudaFree(h->d_ro_partial);
+    cudaFree(h->d_ro_counters);
     delete h;
+    return 0;
+}
+
+int xesn_reservoir_status(xesn_reservoir* h, int32_t* status_host) {
+    XESN_REQUIRE(h && status_host, "null pointer");
+    XESN_CUDA_OK(cudaMemcpy(status_host, h->d_status, sizeof(int), cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -219,7 +234,7 @@ static int drive_gemm(xesn_reservoir* h, const double* ubase, long long ldu, lon
 static RecurArgs recur_args(xesn_reservoir* h) {
     RecurArgs r = {};
     r.indptr = h->d_indptr, r.indices = h->d_indices, r.values = h->d_values;
-    r.N = h->N, r.alpha = h->alpha, r.smem_nnz = h->max_slice_nnz;
+    r.N = h->N, r.alpha = h->alpha, r.smem_nnz = h->max_slice_nnz, r.status = h->d_status;
     return r;
 }
 
@@ -229,7 +244,7 @@ int64_t xesn_forced_scratch_bytes(xesn_reservoir* h, int32_t G, int32_t n_steps,
     if (!h) return -1;
     long long c = n_steps < FORCED_CHUNK ? (n_steps > 0 ? n_steps : 1) : FORCED_CHUNK;
     long long cld = round_up(c, 2);
-    long long d = (long long)G * c * h->N + 2LL * G * h->N;
+    long long d = (long long)G * c * h->N + (long long)G * (c + 1) * h->N;
     if (gathered) d += (long long)G * h->I * cld;
     return d * 8 + 256;
 }
@@ -245,7 +260,7 @@ int xesn_forced_run(xesn_reservoir* h, const xesn_series* u, int64_t t0, int32_t
     const long long cld = round_up(c, 2);
     double* D = (double*)scratch;
     double* pp = D + (long long)G * c * N;
-    double* Uc = pp + 2LL * G * N;
+    double* Uc = pp + (long long)G * (c + 1) * N;
     if (states && n_steps == 0) {
         XESN_CUDA_OK(cudaMemcpyAsync(states, carry, sizeof(double) * (size_t)G * N, cudaMemcpyDeviceToDevice, st));
     }
@@ -262,9 +277,9 @@ int xesn_forced_run(xesn_reservoir* h, const xesn_series* u, int64_t t0, int32_t
         r.steps = m;
         r.carry = carry;
         if (states) {
-            r.states = states + s0 * N, r.state_group_stride = (long long)(n_steps + 1) * N, r.store_all = 1;
+            r.states = states + s0 * N, r.state_group_stride = (long long)(n_steps + 1) * N;
         } else {
-            r.states = pp, r.state_group_stride = 2LL * N, r.store_all = 0;
+            r.states = pp, r.state_group_stride = (long long)(m + 1) * N;
         }
         rc = launch_recur_forced(r, G, h->max_slice_nnz, st);
         if (rc) return rc;
@@ -326,7 +341,7 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
         if ((rc = drive_gemm(h, ub, ldu, ugs, G, m, D, st))) return rc;
         RecurArgs r = recur_args(h);
         r.drive = D, r.drive_group_stride = (long long)m * N, r.steps = m, r.carry = carry;
-        r.states = R, r.state_group_stride = 2LL * N, r.store_all = 0;
+        r.states = R, r.state_group_stride = (long long)(m + 1) * N;
         if ((rc = launch_recur_forced(r, G, h->max_slice_nnz, st))) return rc;
     }
     // accumulate: xesn/esn.py:502-513
@@ -341,7 +356,7 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
         RecurArgs r = recur_args(h);
         const long long rgs = (long long)(m + 1) * N;
         r.drive = D, r.drive_group_stride = (long long)m * N, r.steps = m, r.carry = carry;
-        r.states = R, r.state_group_stride = rgs, r.store_all = 1;
+        r.states = R, r.state_group_stride = rgs;
         {
             ProfScope prof(PROF_RECUR, st);
             if ((rc = launch_recur_forced(r, G, h->max_slice_nnz, st))) return rc;
@@ -388,6 +403,59 @@ int xesn_ridge_solve(xesn_reservoir* h, int32_t O, int32_t G, const double* beta
 // ---------------------------------------------------------------------------------------------
 constexpr int INLINE_PROJECTION_MAX_GROUPS = 4;
 
+// readout scratch owned by the handle: partial sums of the split reservoir axis + arrival counters
+static int ensure_readout_scratch(xesn_reservoir* h, int O, int G, int* n_slices) {
+    const int S = readout_slices(h->N, O, G);
+    *n_slices = S;
+    if (S == 1) return 0;
+    const long long need_p = (long long)G * S * O, need_c = (long long)G * ((O + 7) / 8);
+    if (need_p > h->ro_partial_cap) {
+        if (h->d_ro_partial) XESN_CUDA_OK(cudaFree(h->d_ro_partial));
+        XESN_CUDA_OK(cudaMalloc(&h->d_ro_partial, sizeof(double) * need_p));
+        h->ro_partial_cap = need_p;
+    }
+    if (need_c > h->ro_counter_cap) {
+        if (h->d_ro_counters) XESN_CUDA_OK(cudaFree(h->d_ro_counters));
+        XESN_CUDA_OK(cudaMalloc(&h->d_ro_counters, sizeof(int) * need_c));
+        XESN_CUDA_OK(cudaMemset(h->d_ro_counters, 0, sizeof(int) * need_c));
+        h->ro_counter_cap = need_c;
+    }
+    return 0;
+}
+
+// r_out = update(r_in, gather(field_in));  field_out[out_map] = Wout r_out  (+ optional copy)
+static int closed_loop_step(xesn_reservoir* h, const double* wout, int O, int G, const int32_t* in_map,
+                            const double* fill, const int32_t* out_map, const double* field_in, double* field_out,
+                            const double* r_in, double* r_out, double* pred_col, long long pred_stride, double* Ug,
+                            double* drive, int n_slices, cudaStream_t st) {
+    const int N = h->N, I = h->I;
+    int rc;
+    StepArgs a = {};
+    a.indptr = h->d_indptr, a.indices = h->d_indices, a.values = h->d_values;
+    a.Win = h->d_win, a.bias = h->d_bias, a.N = N, a.I = I, a.alpha = h->alpha;
+    a.r_in = r_in, a.r_out = r_out;
+    if (G > INLINE_PROJECTION_MAX_GROUPS) {
+        if ((rc = launch_gather_vec(field_in, 1, in_map, fill, Ug, (long long)G * I, 1, st))) return rc;
+        GemmArgs g = {};
+        g.A = Ug, g.lda = I, g.strideA = 0;
+        g.B = h->d_win, g.ldb = I, g.strideB = 0;
+        g.C = drive, g.ldc = N, g.strideC = 0;
+        g.bias = h->d_bias;
+        g.M = G, g.N = N, g.K = I, g.batch = 1, g.alpha = 1.0, g.beta = 0.0;
+        g.flags = GEMM_A_KMAJOR | GEMM_B_KMAJOR;
+        if ((rc = launch_gemm_f64(g, st))) return rc;
+        a.drive = drive;
+    } else {
+        a.field = field_in, a.in_map = in_map, a.fill = fill;
+    }
+    if ((rc = launch_step_update(a, G, st))) return rc;
+    ReadoutArgs q = {};
+    q.Wout = wout, q.r = r_out, q.v = field_out, q.v_stride = 1;
+    q.v_copy = pred_col, q.v_copy_stride = pred_stride, q.out_map = out_map, q.N = N, q.O = O;
+    q.n_slices = n_slices, q.partial = h->d_ro_partial, q.counters = h->d_ro_counters;
+    return launch_readout(q, G, st);
+}
+
 int64_t xesn_predict_scratch_bytes(xesn_reservoir* h, int32_t O, int32_t G, int64_t n_cells) {
     if (!h) return -1;
     long long d = round_up((long long)G * h->I, 2) + 2 * round_up((long long)G * h->N, 2) + round_up(n_cells, 2);
@@ -404,30 +472,13 @@ int xesn_predict_step(xesn_reservoir* h, const double* wout, int32_t O, int32_t 
     double* Ug = (double*)scratch;
     double* drive = Ug + round_up((long long)G * I, 2);
     double* r_new = drive + round_up((long long)G * N, 2);
-    int rc;
-    StepArgs a = {};
-    a.indptr = h->d_indptr, a.indices = h->d_indices, a.values = h->d_values;
-    a.Win = h->d_win, a.bias = h->d_bias, a.N = N, a.I = I, a.alpha = h->alpha;
-    a.r_in = r, a.r_out = r_new;
-    if (G > INLINE_PROJECTION_MAX_GROUPS) {
-        if ((rc = launch_gather_vec(field_in, 1, in_map, fill, Ug, (long long)G * I, 1, st))) return rc;
-        GemmArgs g = {};
-        g.A = Ug, g.lda = I, g.strideA = 0;
-        g.B = h->d_win, g.ldb = I, g.strideB = 0;
-        g.C = drive, g.ldc = N, g.strideC = 0;
-        g.bias = h->d_bias;
-        g.M = G, g.N = N, g.K = I, g.batch = 1, g.alpha = 1.0, g.beta = 0.0, g.flags = GEMM_A_KMAJOR | GEMM_B_KMAJOR;
-        if ((rc = launch_gemm_f64(g, st))) return rc;
-        a.drive = drive;
-    } else {
-        a.field = field_in, a.in_map = in_map, a.fill = fill;
-    }
-    if ((rc = launch_step_update(a, G, st))) return rc;
+    int S, rc;
+    if ((rc = ensure_readout_scratch(h, O, G, &S))) return rc;
+    if ((rc = closed_loop_step(h, wout, O, G, in_map, fill, out_map, field_in, field_out, r, r_new, pred_col,
+                               pred_stride, Ug, drive, S, st)))
+        return rc;
     XESN_CUDA_OK(cudaMemcpyAsync(r, r_new, sizeof(double) * (size_t)G * N, cudaMemcpyDeviceToDevice, st));
-    ReadoutArgs q = {};
-    q.Wout = wout, q.r = r, q.v = field_out, q.v_stride = 1, q.v_copy = pred_col, q.v_copy_stride = pred_stride;
-    q.out_map = out_map, q.N = N, q.O = O;
-    return launch_readout(q, G, st);
+    return 0;
 }
 
 int xesn_predict(xesn_reservoir* h, const double* wout, int32_t O, int32_t G, int64_t n_cells, const int32_t* in_map,
@@ -443,6 +494,8 @@ int xesn_predict(xesn_reservoir* h, const double* wout, int32_t O, int32_t G, in
     double* r_alt = drive + round_up((long long)G * N, 2);
     double* field_alt = r_alt + round_up((long long)G * N, 2);
     const long long ldp = (long long)n_steps + 1;
+    int S, rc;
+    if ((rc = ensure_readout_scratch(h, O, G, &S))) return rc;
     ProfScope prof(PROF_PREDICT, st);
 
     strided_copy_kernel<<<(unsigned)((n_cells + 255) / 256), 256, 0, st>>>(field, pred, ldp, n_cells);
@@ -453,32 +506,11 @@ int xesn_predict(xesn_reservoir* h, const double* wout, int32_t O, int32_t G, in
 
     double* rbuf[2] = {r, r_alt};
     double* fbuf[2] = {field, field_alt};
-    int rc;
     for (int n = 1; n <= n_steps; ++n) {
         const int cur = (n - 1) & 1, nxt = n & 1;
-        StepArgs a = {};
-        a.indptr = h->d_indptr, a.indices = h->d_indices, a.values = h->d_values;
-        a.Win = h->d_win, a.bias = h->d_bias, a.N = N, a.I = I, a.alpha = h->alpha;
-        a.r_in = rbuf[cur], a.r_out = rbuf[nxt];
-        if (G > INLINE_PROJECTION_MAX_GROUPS) {
-            if ((rc = launch_gather_vec(fbuf[cur], 1, in_map, fill, Ug, (long long)G * I, 1, st))) return rc;
-            GemmArgs g = {};
-            g.A = Ug, g.lda = I, g.strideA = 0;
-            g.B = h->d_win, g.ldb = I, g.strideB = 0;
-            g.C = drive, g.ldc = N, g.strideC = 0;
-            g.bias = h->d_bias;
-            g.M = G, g.N = N, g.K = I, g.batch = 1, g.alpha = 1.0, g.beta = 0.0;
-            g.flags = GEMM_A_KMAJOR | GEMM_B_KMAJOR;
-            if ((rc = launch_gemm_f64(g, st))) return rc;
-            a.drive = drive;
-        } else {
-            a.field = fbuf[cur], a.in_map = in_map, a.fill = fill;
-        }
-        if ((rc = launch_step_update(a, G, st))) return rc;
-        ReadoutArgs q = {};
-        q.Wout = wout, q.r = rbuf[nxt], q.v = fbuf[nxt], q.v_stride = 1;
-        q.v_copy = pred + n, q.v_copy_stride = ldp, q.out_map = out_map, q.N = N, q.O = O;
-        if ((rc = launch_readout(q, G, st))) return rc;
+        if ((rc = closed_loop_step(h, wout, O, G, in_map, fill, out_map, fbuf[cur], fbuf[nxt], rbuf[cur], rbuf[nxt],
+                                   pred + n, ldp, Ug, drive, S, st)))
+            return rc;
     }
     if (n_steps & 1) {
         XESN_CUDA_OK(cudaMemcpyAsync(r, r_alt, sizeof(double) * (size_t)G * N, cudaMemcpyDeviceToDevice, st));
@@ -499,7 +531,7 @@ int xesn_gemm_f64(const double* a, int64_t lda, const double* b, int64_t ldb, do
 int xesn_readout(const double* wout, const double* r, double* v, int32_t N, int32_t O, int32_t G, void* stream) {
     XESN_REQUIRE(wout && r && v, "null pointer");
     ReadoutArgs q = {};
-    q.Wout = wout, q.r = r, q.v = v, q.v_stride = 1, q.N = N, q.O = O;
+    q.Wout = wout, q.r = r, q.v = v, q.v_stride = 1, q.N = N, q.O = O, q.n_slices = 1;
     return launch_readout(q, G, (cudaStream_t)stream);
 }
 

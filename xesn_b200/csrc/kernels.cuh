@@ -10,12 +10,12 @@ struct RecurArgs {
     const double* values;
     const double* drive;     // [G][steps][N] : Win u_t + b for every step of the chunk
     long long drive_group_stride;
-    double* states;          // [G][rows][N] : row 0 <- carry; store_all ? rows 1..steps written : ping-pong rows 0/1
+    double* states;          // [G][steps+1][N] ring: row 0 <- carry, rows 1..steps written (pre-filled "unset")
     long long state_group_stride;
+    int* status;             // device int, set to 1 if a poll timed out (co-residency lost: never expected)
     double* carry;           // [G][N] state entering the chunk; overwritten with the state leaving it
     int N;
     int steps;
-    int store_all;
     double alpha;
     // filled by the launcher
     int units_per_cta;
@@ -49,12 +49,18 @@ struct ReadoutArgs {
     long long v_copy_stride;
     const int* out_map;   // optional [G][O] -> dst index; identity (g*O+o) when null
     int N, O;
+    // split of the reservoir axis (filled by the caller from readout_slices(); 1 = no split)
+    int n_slices;
+    double* partial;      // [G][n_slices][O] scratch
+    int* counters;        // [G][ceil(O/8)] zero-initialised once; the kernel re-arms them
+    int slice;            // filled by the launcher
 };
 
 int launch_recur_forced(RecurArgs a, int n_groups, int max_slice_nnz, cudaStream_t stream);
 int recur_cluster_size(int N);
 int launch_step_update(const StepArgs& a, int n_groups, cudaStream_t stream);
-int launch_readout(const ReadoutArgs& a, int n_groups, cudaStream_t stream);
+int readout_slices(int N, int O, int n_groups);
+int launch_readout(ReadoutArgs a, int n_groups, cudaStream_t stream);
 int launch_gather_vec(const double* src, long long src_stride, const int* map, const double* fill, double* out,
                       long long n, int mask_nan, cudaStream_t stream);
 int launch_gather_series(const double* src, long long ld_src, long long t0, const int* map, const double* fill,

@@ -31,12 +31,6 @@ __device__ __forceinline__ double ld_cg(const double* p) {
     asm volatile("ld.global.cg.f64 %0, [%1];\n" : "=d"(v) : "l"(p));
     return v;
 }
-__device__ __forceinline__ void cluster_arrive() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
-}
-__device__ __forceinline__ void cluster_wait() {
-    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
-}
 __device__ __forceinline__ unsigned cluster_ctarank() {
     unsigned r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
@@ -67,6 +61,27 @@ __device__ __forceinline__ double leaky(double pre, double r_old, double alpha, 
     // alpha * tanh(p) + (1 - alpha) * r, each product rounded (no FMA contraction) as numpy does
     return __dadd_rn(__dmul_rn(alpha, tanh(pre)), __dmul_rn(one_minus_alpha, r_old));
 }
+
+// ---- data-as-flag exchange of the state vector -------------------------------------------------
+// The state ring buffer is pre-filled with an all-ones bit pattern (a NaN no arithmetic produces
+// here).  A consumer polls the few entries of r_t it needs straight from L2 until they are no
+// longer that pattern; an 8-byte aligned store is single-copy atomic, so a non-sentinel value IS
+// the finished value.  No barrier and no fence sit on the per-step critical path (a release at
+// cluster scope compiles to MEMBAR.ALL.GPU, which cost ~2.5 us per step in the first version).
+constexpr long long UNSET_BITS = -1LL;
+constexpr int KW = 8;              // gathers in flight per unit and pass
+constexpr int SPIN_LIMIT = 1 << 22;  // ~1-2 s of polling, then the run is flagged as failed
+
+__device__ __forceinline__ double ld_flag(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];\n" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_flag(double* p, double v) {
+    if (__double_as_longlong(v) == UNSET_BITS) v = __longlong_as_double(0x7FF8000000000000LL);
+    asm volatile("st.relaxed.gpu.global.f64 [%0], %1;\n" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ bool unset(double v) { return __double_as_longlong(v) == UNSET_BITS; }
 
 template <int UPT>
 __global__ void __launch_bounds__(RC_THREADS, 1) recur_forced_kernel(RecurArgs p) {
@@ -99,45 +114,77 @@ __global__ void __launch_bounds__(RC_THREADS, 1) recur_forced_kernel(RecurArgs p
     double* states = p.states + (long long)g * p.state_group_stride;
     const double* drive = p.drive + (long long)g * p.drive_group_stride;
 
-    int unit[UPT], row_lo[UPT], row_len[UPT];
+    int unit[UPT], row_len[UPT], max_len = 0;
+    const int* idx[UPT];
+    const double* val[UPT];
     double r_cur[UPT], d_next[UPT];
 #pragma unroll
     for (int j = 0; j < UPT; ++j) {
         unit[j] = u0 + tid + j * RC_THREADS;
-        bool ok = unit[j] < u1;
-        row_lo[j] = ok ? p.indptr[unit[j]] : 0;
-        row_len[j] = ok ? p.indptr[unit[j] + 1] - row_lo[j] : 0;
+        const bool ok = unit[j] < u1;
+        const int lo = ok ? p.indptr[unit[j]] : 0;
+        row_len[j] = ok ? p.indptr[unit[j] + 1] - lo : 0;
+        max_len = max(max_len, row_len[j]);
+        idx[j] = idx_base + lo;
+        val[j] = val_base + lo;
         r_cur[j] = ok ? p.carry[(long long)g * p.N + unit[j]] : 0.0;
         d_next[j] = (ok && p.steps > 0) ? drive[unit[j]] : 0.0;
-        if (ok) states[unit[j]] = r_cur[j];  // row 0 = state entering the chunk
+        if (ok) st_flag(states + unit[j], r_cur[j]);  // row 0 = state entering the chunk
         else unit[j] = -1;
     }
     const double alpha = p.alpha, oma = 1.0 - p.alpha;
-    cluster_arrive();
-    cluster_wait();
+    bool aborted = false;
 
     for (int t = 0; t < p.steps; ++t) {
-        const long long in_row = p.store_all ? t : (t & 1);
-        const long long out_row = p.store_all ? t + 1 : ((t + 1) & 1);
-        const double* r_prev = states + in_row * p.N;
-        double* r_next = states + out_row * p.N;
+        const double* r_prev = states + (long long)t * p.N;
+        double* r_next = states + (long long)(t + 1) * p.N;
+        double acc[UPT];
+#pragma unroll
+        for (int j = 0; j < UPT; ++j) acc[j] = 0.0;
+
+        for (int k0 = 0; k0 < max_len; k0 += KW) {
+            double gv[UPT][KW];
+#pragma unroll
+            for (int j = 0; j < UPT; ++j)
+#pragma unroll
+                for (int k = 0; k < KW; ++k) gv[j][k] = (k0 + k < row_len[j]) ? __longlong_as_double(UNSET_BITS) : 0.0;
+            int spins = 0;
+            bool miss;
+            do {
+#pragma unroll
+                for (int j = 0; j < UPT; ++j)
+#pragma unroll
+                    for (int k = 0; k < KW; ++k)
+                        if (unset(gv[j][k])) gv[j][k] = ld_flag(r_prev + idx[j][k0 + k]);
+                miss = false;
+#pragma unroll
+                for (int j = 0; j < UPT; ++j)
+#pragma unroll
+                    for (int k = 0; k < KW; ++k) miss |= unset(gv[j][k]);
+                if (miss && !aborted && ((++spins & 1023) == 0)) {
+                    if (spins >= SPIN_LIMIT) atomicExch(p.status, 1);
+                    aborted = *reinterpret_cast<volatile int*>(p.status) != 0;
+                }
+            } while (miss && !aborted);
+#pragma unroll
+            for (int j = 0; j < UPT; ++j)
+#pragma unroll
+                for (int k = 0; k < KW; ++k)
+                    if (k0 + k < row_len[j]) acc[j] = __dadd_rn(acc[j], __dmul_rn(val[j][k0 + k], gv[j][k]));
+        }
 #pragma unroll
         for (int j = 0; j < UPT; ++j) {
             if (unit[j] >= 0) {
-                double wr = sparse_row_dot(idx_base + row_lo[j], val_base + row_lo[j], row_len[j], r_prev);
-                double pre = __dadd_rn(wr, d_next[j]);
+                const double pre = __dadd_rn(acc[j], d_next[j]);
                 r_cur[j] = leaky(pre, r_cur[j], alpha, oma);
-                r_next[unit[j]] = r_cur[j];
+                st_flag(r_next + unit[j], r_cur[j]);
             }
         }
-        cluster_arrive();
-        // prefetch the next step's drive while the barrier completes
         if (t + 1 < p.steps) {
 #pragma unroll
             for (int j = 0; j < UPT; ++j)
                 if (unit[j] >= 0) d_next[j] = __ldg(drive + (long long)(t + 1) * p.N + unit[j]);
         }
-        cluster_wait();
     }
 #pragma unroll
     for (int j = 0; j < UPT; ++j)
@@ -185,41 +232,75 @@ __global__ void __launch_bounds__(SU_THREADS) step_update_kernel(StepArgs p) {
 }
 
 // ------------------------------------------------------------------------------------------
-// batched readout GEMV: v[g][o] = Wout[g][o][:] . r[g][:], one warp per output row
+// batched readout GEMV: v[g][o] = Wout[g][o][:] . r[g][:]
+// One warp per (output row, n-slice).  When the batch is too small to fill the GPU the reservoir
+// axis is split into S slices; the last CTA to finish a row block sums the S partials in slice
+// order (deterministic) -- "last block reduces", no second launch.
 // ------------------------------------------------------------------------------------------
 constexpr int RO_THREADS = 256;
 constexpr int RO_WARPS = RO_THREADS / 32;
 
 __global__ void __launch_bounds__(RO_THREADS) readout_kernel(ReadoutArgs p) {
-    const int g = blockIdx.y;
+    __shared__ int s_last;
+    const int g = blockIdx.z;
+    const int rb = blockIdx.y;
+    const int sl = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int o = blockIdx.x * RO_WARPS + warp;
-    if (o >= p.O) return;
-    const double* w = p.Wout + ((long long)g * p.O + o) * p.N;
-    const double* r = p.r + (long long)g * p.N;
-    double acc0 = 0.0, acc1 = 0.0;
-    const bool vec = ((((uintptr_t)w) & 15) == 0) && ((((uintptr_t)r) & 15) == 0);
-    int n = 0;
-    if (vec) {
-        const double2* w2 = reinterpret_cast<const double2*>(w);
-        const double2* r2 = reinterpret_cast<const double2*>(r);
-        const int n2 = p.N >> 1;
-        for (int k = lane; k < n2; k += 32) {
-            double2 a = __ldcs(w2 + k);  // streamed once: evict-first
-            double2 b = __ldg(r2 + k);
-            acc0 = fma(a.x, b.x, acc0);
-            acc1 = fma(a.y, b.y, acc1);
+    const int o = rb * RO_WARPS + warp;
+    const int n_lo = sl * p.slice, n_hi = min(p.N, n_lo + p.slice);
+    double acc = 0.0;
+    if (o < p.O) {
+        const double* w = p.Wout + ((long long)g * p.O + o) * p.N;
+        const double* r = p.r + (long long)g * p.N;
+        double acc0 = 0.0, acc1 = 0.0;
+        int n = n_lo;
+        const bool vec = ((((uintptr_t)(w + n_lo)) & 15) == 0) && ((((uintptr_t)(r + n_lo)) & 15) == 0);
+        if (vec) {
+            const double2* w2 = reinterpret_cast<const double2*>(w + n_lo);
+            const double2* r2 = reinterpret_cast<const double2*>(r + n_lo);
+            const int n2 = (n_hi - n_lo) >> 1;
+            for (int k = lane; k < n2; k += 32) {
+                double2 a = __ldcs(w2 + k);  // streamed once: evict-first
+                double2 b = __ldcg(r2 + k);
+                acc0 = fma(a.x, b.x, acc0);
+                acc1 = fma(a.y, b.y, acc1);
+            }
+            n = n_lo + (n2 << 1);
         }
-        n = n2 << 1;
-    }
-    for (int k = n + lane; k < p.N; k += 32) acc0 = fma(w[k], r[k], acc0);
-    double acc = acc0 + acc1;
+        for (int k = n + lane; k < n_hi; k += 32) acc0 = fma(w[k], __ldcg(r + k), acc0);
+        acc = acc0 + acc1;
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (lane == 0) {
-        long long dst = p.out_map ? (long long)p.out_map[(long long)g * p.O + o] : (long long)g * p.O + o;
-        p.v[dst * p.v_stride] = acc;
-        if (p.v_copy) p.v_copy[dst * p.v_copy_stride] = acc;
+        for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    }
+    if (p.n_slices == 1) {
+        if (o < p.O && lane == 0) {
+            long long dst = p.out_map ? (long long)p.out_map[(long long)g * p.O + o] : (long long)g * p.O + o;
+            p.v[dst * p.v_stride] = acc;
+            if (p.v_copy) p.v_copy[dst * p.v_copy_stride] = acc;
+        }
+        return;
+    }
+    if (o < p.O && lane == 0) p.partial[((long long)g * p.n_slices + sl) * p.O + o] = acc;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int* cnt = p.counters + (long long)g * gridDim.y + rb;
+        int prev = atomicAdd(cnt, 1);
+        s_last = (prev == p.n_slices - 1);
+        if (s_last) *cnt = 0;  // re-arm for the next launch
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x < RO_WARPS) {
+        const int oo = rb * RO_WARPS + threadIdx.x;
+        if (oo < p.O) {
+            double sum = 0.0;
+            for (int k = 0; k < p.n_slices; ++k) sum += __ldcg(p.partial + ((long long)g * p.n_slices + k) * p.O + oo);
+            long long dst = p.out_map ? (long long)p.out_map[(long long)g * p.O + oo] : (long long)g * p.O + oo;
+            p.v[dst * p.v_stride] = sum;
+            if (p.v_copy) p.v_copy[dst * p.v_copy_stride] = sum;
+        }
     }
 }
 
@@ -289,6 +370,10 @@ int launch_recur_forced(RecurArgs a, int n_groups, int max_slice_nnz, cudaStream
     a.w_in_smem = smem_needed <= 200 * 1024;
     size_t smem = a.w_in_smem ? (size_t)smem_needed : 0;
 
+    // every row of the ring the kernel will write/poll starts as the "unset" pattern
+    XESN_CUDA_OK(cudaMemset2DAsync(a.states, sizeof(double) * a.state_group_stride, 0xFF,
+                                   sizeof(double) * (size_t)(a.steps + 1) * a.N, n_groups, stream));
+
     void (*kern)(RecurArgs) = upt == 1 ? recur_forced_kernel<1> : (upt == 2 ? recur_forced_kernel<2> : recur_forced_kernel<4>);
     XESN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 16));
     if (C > 8) XESN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -338,8 +423,19 @@ int launch_step_update(const StepArgs& a, int n_groups, cudaStream_t stream) {
     return 0;
 }
 
-int launch_readout(const ReadoutArgs& a, int n_groups, cudaStream_t stream) {
-    dim3 grid((a.O + RO_WARPS - 1) / RO_WARPS, n_groups);
+int readout_slices(int N, int O, int n_groups) {
+    const long long row_blocks = (long long)((O + RO_WARPS - 1) / RO_WARPS) * n_groups;
+    long long s = (2 * 148 + row_blocks - 1) / row_blocks;
+    const long long max_s = (N + 255) / 256;
+    if (s > max_s) s = max_s;
+    return (int)(s < 1 ? 1 : s);
+}
+
+int launch_readout(ReadoutArgs a, int n_groups, cudaStream_t stream) {
+    if (a.n_slices < 1 || !a.partial || !a.counters) a.n_slices = 1;
+    a.slice = (a.N + a.n_slices - 1) / a.n_slices;
+    a.slice += a.slice & 1;  // even, keeps double2 alignment of the slices
+    dim3 grid(a.n_slices, (a.O + RO_WARPS - 1) / RO_WARPS, n_groups);
     readout_kernel<<<grid, RO_THREADS, 0, stream>>>(a);
     XESN_CUDA_OK(cudaGetLastError());
     count_launch();

@@ -321,7 +321,17 @@ class ESN:
         del keepalive
         return wout
 
+    def _check_status(self):
+        """Raise if a persistent-kernel poll timed out (see xesn_reservoir_status)."""
+        import ctypes
+        res = self._device_reservoir()
+        st = ctypes.c_int32(0)
+        _lib.check(res._lib.xesn_reservoir_status(res.handle, ctypes.byref(st)))
+        if st.value:
+            raise _lib.XesnError("xesn_b200: the recurrence kernel timed out waiting for a peer CTA; results invalid")
+
     def _check_info(self):
+        self._check_status()
         info = self.last_info.cpu().numpy()
         if info.any():
             bad = np.nonzero(info)[0]
@@ -344,6 +354,7 @@ class ESN:
         y_dev = self._to_device(y, "y")
         pred = self._predict_device(y_dev, n_steps, n_spinup)
         out = pred.cpu().numpy()
+        self._check_status()
         if _is_dataarray(y):
             fdims, fcoords = self._get_fcoords(y.dims, y.coords, n_steps, n_spinup)
             return xr.DataArray(out, coords=fcoords, dims=fdims)

@@ -194,6 +194,7 @@ class LazyESN(ESN):
         self._check_info_groups()
 
     def _check_info_groups(self):
+        self._check_status()
         info = self.last_info.cpu().numpy()
         if info.any():
             bad = np.nonzero(info)[0]
@@ -276,6 +277,7 @@ class LazyESN(ESN):
                 self._predict_multi(lib, res, wout, G, g0, n_cells, t_in, t_fill, t_out, out_map, field, r,
                                     n_steps, pred, scratch, nb, st)
         out = pred.cpu().numpy().reshape(tuple(y.shape[:-1]) + (n_steps + 1,))
+        self._check_status()
         if _is_dataarray(y):
             fdims, fcoords = self._get_fcoords(y.dims, y.coords, n_steps, n_spinup)
             return xr.DataArray(out, coords=fcoords, dims=fdims)
