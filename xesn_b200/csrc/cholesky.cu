@@ -21,81 +21,134 @@ namespace {
 
 constexpr int NB = 128;
 constexpr int LDS = NB + 1;
-constexpr int PD_THREADS = 256;
-constexpr int PD_SMEM = (NB * LDS + NB * (NB + 1) / 2) * (int)sizeof(double) + 16;
-
-__device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }
+constexpr int PD_THREADS = 256;  // 16 x 16 threads, thread (ty,tx) owns entries (ty+16a, tx+16b), a,b < 8
+constexpr int PD_SMEM = (NB * LDS + 4 * NB) * (int)sizeof(double) + 16;
 
 // A: base of matrix 0; block (j0, j0) of size nbj is factored in place; inv(L_jj) is written to
 // Linv (NB x NB row-major per matrix, zero above the diagonal, identity in the padding).
+// The block lives in REGISTERS (8x8 per thread, cyclic distribution so every thread stays busy as
+// the factorisation front advances); shared memory only carries the current column/row.
 __global__ void __launch_bounds__(PD_THREADS, 1)
 potrf_diag_kernel(double* A, long long lda, long long strideA, int j0, int nbj, double* Linv, long long strideLinv,
                   int* info) {
     extern __shared__ __align__(16) double sm[];
-    double* S = sm;             // [NB][LDS]
-    double* X = sm + NB * LDS;  // packed lower triangle
-    __shared__ int s_fail;
+    double* S = sm;                      // [NB][LDS] the factor, for the inversion phase
+    double* colbuf = sm + NB * LDS;      // [NB]
+    double* rowbuf = colbuf + NB;        // [2][NB]
+    __shared__ double s_piv;
     const int tid = threadIdx.x;
+    const int ty = tid >> 4, tx = tid & 15;
     const int b = blockIdx.x;
     double* Ab = A + (long long)b * strideA + (long long)j0 * lda + j0;
     double* Lb = Linv + (long long)b * strideLinv;
-    if (tid == 0) s_fail = 0;
 
-    for (int e = tid; e < NB * NB; e += PD_THREADS) {
-        int i = e / NB, j = e % NB;
-        double v = 0.0;
-        if (i < nbj && j <= i) v = Ab[(long long)i * lda + j];
-        else if (i >= nbj && i == j) v = 1.0;
-        S[i * LDS + j] = v;
+    double a[8][8];
+#pragma unroll
+    for (int x = 0; x < 8; ++x)
+#pragma unroll
+        for (int y = 0; y < 8; ++y) {
+            const int i = ty + 16 * x, j = tx + 16 * y;
+            double v = 0.0;
+            if (i < nbj && j <= i) v = Ab[(long long)i * lda + j];
+            else if (i >= nbj && i == j) v = 1.0;
+            a[x][y] = v;
+        }
+
+    // ---- factorisation (right-looking, one column per step) ----
+#pragma unroll
+    for (int ka = 0; ka < 8; ++ka) {
+        for (int kx = 0; kx < 16; ++kx) {
+            const int k = ka * 16 + kx;
+            if (ty == kx && tx == kx) {
+                const double piv = a[ka][ka];
+                if (!(piv > 0.0) || !(piv < 1.7e308)) atomicCAS(&info[b], 0, j0 + k + 1);  // not positive definite
+                s_piv = sqrt(piv);
+            }
+            __syncthreads();
+            const double d = s_piv, rinv = 1.0 / d;
+            if (tx == kx) {
+#pragma unroll
+                for (int x = 0; x < 8; ++x) {
+                    const int i = ty + 16 * x;
+                    if (i > k) {
+                        a[x][ka] *= rinv;
+                        colbuf[i] = a[x][ka];
+                    } else if (i == k) {
+                        a[x][ka] = d;
+                    }
+                }
+            }
+            __syncthreads();
+            double li[8], lj[8];
+#pragma unroll
+            for (int x = 0; x < 8; ++x) li[x] = colbuf[ty + 16 * x];
+#pragma unroll
+            for (int y = 0; y < 8; ++y) lj[y] = colbuf[tx + 16 * y];
+#pragma unroll
+            for (int x = 0; x < 8; ++x)
+#pragma unroll
+                for (int y = 0; y < 8; ++y) {
+                    const int i = ty + 16 * x, j = tx + 16 * y;
+                    if (j > k && j <= i) a[x][y] = fma(-li[x], lj[y], a[x][y]);
+                }
+        }
     }
+#pragma unroll
+    for (int x = 0; x < 8; ++x)
+#pragma unroll
+        for (int y = 0; y < 8; ++y) {
+            const int i = ty + 16 * x, j = tx + 16 * y;
+            const double v = (j <= i) ? a[x][y] : 0.0;
+            S[i * LDS + j] = v;
+            if (i < nbj && j <= i) Ab[(long long)i * lda + j] = v;
+        }
     __syncthreads();
 
-    for (int k = 0; k < NB; ++k) {
-        double piv = S[k * LDS + k];
-        if (!(piv > 0.0) || !(piv < 1.7e308)) {  // <= 0, NaN or inf: not positive definite
-            if (tid == 0 && !s_fail) {
-                s_fail = 1;
-                atomicCAS(&info[b], 0, j0 + k + 1);
+    // ---- inverse: L X = I by forward substitution, one row per step ----
+#pragma unroll
+    for (int x = 0; x < 8; ++x)
+#pragma unroll
+        for (int y = 0; y < 8; ++y) a[x][y] = (ty + 16 * x == tx + 16 * y) ? 1.0 : 0.0;
+#pragma unroll
+    for (int ka = 0; ka < 8; ++ka) {
+        for (int kx = 0; kx < 16; ++kx) {
+            const int k = ka * 16 + kx;
+            double* rb = rowbuf + (k & 1) * NB;
+            if (ty == kx) {
+                const double dinv = 1.0 / S[k * LDS + k];
+#pragma unroll
+                for (int y = 0; y < 8; ++y) {
+                    const int j = tx + 16 * y;
+                    if (j <= k) {
+                        a[ka][y] *= dinv;
+                        rb[j] = a[ka][y];
+                    } else {
+                        rb[j] = 0.0;
+                    }
+                }
             }
-        }
-        double d = sqrt(piv);
-        double rinv = 1.0 / d;
-        __syncthreads();
-        if (tid == 0) S[k * LDS + k] = d;
-        for (int i = k + 1 + tid; i < NB; i += PD_THREADS) S[i * LDS + k] *= rinv;
-        __syncthreads();
-        const int w = NB - 1 - k;
-        for (int e = tid; e < w * w; e += PD_THREADS) {
-            int i = k + 1 + e / w, j = k + 1 + e % w;
-            if (j <= i) S[i * LDS + j] -= S[i * LDS + k] * S[j * LDS + k];
-        }
-        __syncthreads();
-    }
-
-    // inverse: thread j solves L x = e_j by forward substitution (column j of inv(L))
-    if (tid < NB) {
-        const int j = tid;
-        X[tri(j, j)] = 1.0 / S[j * LDS + j];
-        for (int i = j + 1; i < NB; ++i) {
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            int m = j;
-            for (; m + 4 <= i; m += 4) {
-                a0 = fma(S[i * LDS + m], X[tri(m, j)], a0);
-                a1 = fma(S[i * LDS + m + 1], X[tri(m + 1, j)], a1);
-                a2 = fma(S[i * LDS + m + 2], X[tri(m + 2, j)], a2);
-                a3 = fma(S[i * LDS + m + 3], X[tri(m + 3, j)], a3);
-            }
-            for (; m < i; ++m) a0 = fma(S[i * LDS + m], X[tri(m, j)], a0);
-            X[tri(i, j)] = -((a0 + a1) + (a2 + a3)) / S[i * LDS + i];
+            __syncthreads();
+            double lik[8], xk[8];
+#pragma unroll
+            for (int x = 0; x < 8; ++x) lik[x] = S[(ty + 16 * x) * LDS + k];
+#pragma unroll
+            for (int y = 0; y < 8; ++y) xk[y] = rb[tx + 16 * y];
+#pragma unroll
+            for (int x = 0; x < 8; ++x)
+#pragma unroll
+                for (int y = 0; y < 8; ++y) {
+                    const int i = ty + 16 * x;
+                    if (i > k) a[x][y] = fma(-lik[x], xk[y], a[x][y]);
+                }
         }
     }
-    __syncthreads();
-
-    for (int e = tid; e < NB * NB; e += PD_THREADS) {
-        int i = e / NB, j = e % NB;
-        if (i < nbj && j <= i) Ab[(long long)i * lda + j] = S[i * LDS + j];
-        Lb[e] = (j <= i) ? X[tri(i, j)] : 0.0;
-    }
+#pragma unroll
+    for (int x = 0; x < 8; ++x)
+#pragma unroll
+        for (int y = 0; y < 8; ++y) {
+            const int i = ty + 16 * x, j = tx + 16 * y;
+            Lb[i * NB + j] = (j <= i) ? a[x][y] : 0.0;
+        }
 }
 
 __global__ void add_diag_kernel(double* A, long long lda, long long strideA, int n, const double* beta, double beta_scalar) {
@@ -133,40 +186,62 @@ int launch_cholesky_solve_ws(double* A, long long lda, long long strideA, double
     const long long strideLinv = (long long)nblk * NB * NB;
     XESN_CUDA_OK(cudaMemsetAsync(info, 0, sizeof(int) * batch, stream));
 
-    // ---- factorisation ----
-    for (int jb = 0; jb < nblk; ++jb) {
-        const int j0 = jb * NB;
-        const int nbj = min(NB, n - j0);
-        double* Linv_j = work + (long long)jb * NB * NB;
-        potrf_diag_kernel<<<batch, PD_THREADS, PD_SMEM, stream>>>(A, lda, strideA, j0, nbj, Linv_j, strideLinv, info);
-        XESN_CUDA_OK(cudaGetLastError());
-        count_launch();
-        const int rest = n - j0 - nbj;
-        if (rest <= 0) break;
-        GemmArgs g = {};
-        // panel: L_ij = A_ij * inv(L_jj)^T   (in place: a tile reads only the rows it writes)
-        g.A = A + (long long)(j0 + nbj) * lda + j0;
-        g.lda = lda, g.strideA = strideA;
-        g.B = Linv_j, g.ldb = NB, g.strideB = strideLinv;
-        g.C = A + (long long)(j0 + nbj) * lda + j0;
-        g.ldc = lda, g.strideC = strideA;
-        g.M = rest, g.N = nbj, g.K = nbj;
-        g.batch = batch, g.alpha = 1.0, g.beta = 0.0;
-        g.flags = GEMM_A_KMAJOR | GEMM_B_KMAJOR;
-        int rc = launch_gemm_f64(g, stream);
-        if (rc) return rc;
-        // trailing: A_22 -= L_21 L_21^T (lower tiles only)
-        GemmArgs t = {};
-        t.A = A + (long long)(j0 + nbj) * lda + j0;
-        t.lda = lda, t.strideA = strideA;
-        t.B = t.A, t.ldb = lda, t.strideB = strideA;
-        t.C = A + (long long)(j0 + nbj) * lda + (j0 + nbj);
-        t.ldc = lda, t.strideC = strideA;
-        t.M = rest, t.N = rest, t.K = nbj;
-        t.batch = batch, t.alpha = -1.0, t.beta = 1.0;
-        t.flags = GEMM_A_KMAJOR | GEMM_B_KMAJOR | GEMM_LOWER;
-        rc = launch_gemm_f64(t, stream);
-        if (rc) return rc;
+    // ---- factorisation: outer panels of OUTER columns, 128-wide sub-blocks inside a panel ----
+    // Inside a panel the updates have K = 128; the trailing matrix is updated once per panel with
+    // K = OUTER, which keeps the DMMA GEMM in its efficient regime and halves/quarters the
+    // read-modify-write traffic of the trailing matrix.
+    const int OUTER = n >= 4096 ? 512 : (n >= 1024 ? 256 : NB);
+    for (int J = 0; J < n; J += OUTER) {
+        const int Jend = min(J + OUTER, n);
+        for (int j0 = J; j0 < Jend; j0 += NB) {
+            const int jb = j0 / NB;
+            const int nbj = min(NB, n - j0);
+            double* Linv_j = work + (long long)jb * NB * NB;
+            potrf_diag_kernel<<<batch, PD_THREADS, PD_SMEM, stream>>>(A, lda, strideA, j0, nbj, Linv_j, strideLinv, info);
+            XESN_CUDA_OK(cudaGetLastError());
+            count_launch();
+            const int rest = n - j0 - nbj;
+            if (rest <= 0) break;
+            GemmArgs g = {};
+            // panel: L_ij = A_ij * inv(L_jj)^T   (in place: a tile reads only the rows it writes)
+            g.A = A + (long long)(j0 + nbj) * lda + j0;
+            g.lda = lda, g.strideA = strideA;
+            g.B = Linv_j, g.ldb = NB, g.strideB = strideLinv;
+            g.C = A + (long long)(j0 + nbj) * lda + j0;
+            g.ldc = lda, g.strideC = strideA;
+            g.M = rest, g.N = nbj, g.K = nbj;
+            g.batch = batch, g.alpha = 1.0, g.beta = 0.0;
+            g.flags = GEMM_A_KMAJOR | GEMM_B_KMAJOR;
+            int rc = launch_gemm_f64(g, stream);
+            if (rc) return rc;
+            // remaining columns of this panel: A[j1:, j1:Jend] -= L[j1:, j0:j1] L[j1:Jend, j0:j1]^T
+            const int j1 = j0 + nbj;
+            const int pw = Jend - j1;
+            if (pw > 0) {
+                GemmArgs u = {};
+                u.A = A + (long long)j1 * lda + j0, u.lda = lda, u.strideA = strideA;
+                u.B = A + (long long)j1 * lda + j0, u.ldb = lda, u.strideB = strideA;
+                u.C = A + (long long)j1 * lda + j1, u.ldc = lda, u.strideC = strideA;
+                u.M = n - j1, u.N = pw, u.K = nbj;
+                u.batch = batch, u.alpha = -1.0, u.beta = 1.0;
+                u.flags = GEMM_A_KMAJOR | GEMM_B_KMAJOR;
+                rc = launch_gemm_f64(u, stream);
+                if (rc) return rc;
+            }
+        }
+        // trailing: A_22 -= L_21 L_21^T (lower tiles only), K = width of the panel
+        const int rest = n - Jend;
+        if (rest > 0) {
+            GemmArgs t = {};
+            t.A = A + (long long)Jend * lda + J, t.lda = lda, t.strideA = strideA;
+            t.B = t.A, t.ldb = lda, t.strideB = strideA;
+            t.C = A + (long long)Jend * lda + Jend, t.ldc = lda, t.strideC = strideA;
+            t.M = rest, t.N = rest, t.K = Jend - J;
+            t.batch = batch, t.alpha = -1.0, t.beta = 1.0;
+            t.flags = GEMM_A_KMAJOR | GEMM_B_KMAJOR | GEMM_LOWER;
+            int rc = launch_gemm_f64(t, stream);
+            if (rc) return rc;
+        }
     }
 
     // ---- forward sweep:  Z L^T = B   (B is nrhs x n, row-major: every row is one right-hand side) ----

@@ -21,6 +21,7 @@ struct RecurArgs {
     int units_per_cta;
     int smem_nnz;            // capacity (entries) of the shared-memory CSR slice
     int w_in_smem;
+    int n_pad;               // N rounded up to even: size of the shared-memory state copy
 };
 
 struct StepArgs {

@@ -23,7 +23,7 @@
 namespace xesn {
 namespace {
 
-constexpr int RC_THREADS = 512;
+constexpr int RC_THREADS = 1024;
 constexpr int KMAX = 16;  // gathers issued back-to-back before the first FMA
 
 __device__ __forceinline__ double ld_cg(const double* p) {
@@ -63,15 +63,24 @@ __device__ __forceinline__ double leaky(double pre, double r_old, double alpha, 
 }
 
 // ---- data-as-flag exchange of the state vector -------------------------------------------------
-// The state ring buffer is pre-filled with an all-ones bit pattern (a NaN no arithmetic produces
-// here).  A consumer polls the few entries of r_t it needs straight from L2 until they are no
-// longer that pattern; an 8-byte aligned store is single-copy atomic, so a non-sentinel value IS
-// the finished value.  No barrier and no fence sit on the per-step critical path (a release at
-// cluster scope compiles to MEMBAR.ALL.GPU, which cost ~2.5 us per step in the first version).
+// Every CTA of the cluster keeps a full copy of r_t in shared memory (random gathers from shared
+// memory cost ~6 cycles per warp; the same gathers from L2 cost one L1 wavefront per lane and
+// bounded the first version at ~2.5 us per step).  After computing its slice of r_{t+1} a CTA
+// stores it to the state ring in global memory -- which the Gram kernel needs anyway -- and
+// refreshes its shared copy with COALESCED polling loads of the other slices: the ring is
+// pre-filled with an all-ones bit pattern (a NaN no arithmetic produces here) and an aligned
+// 8-byte store is single-copy atomic, so a value that is no longer that pattern IS the finished
+// value.  No fence and no cluster barrier sit on the per-step critical path (a release at cluster
+// scope compiles to MEMBAR.ALL.GPU per warp: 6.4 us per step in the first version).
 constexpr long long UNSET_BITS = -1LL;
-constexpr int KW = 8;              // gathers in flight per unit and pass
 constexpr int SPIN_LIMIT = 1 << 22;  // ~1-2 s of polling, then the run is flagged as failed
+constexpr int POLL_BATCH = 4;        // 16-byte pieces in flight per thread while refreshing the copy
 
+__device__ __forceinline__ double2 ld_flag2(const double* p) {
+    double2 v;
+    asm volatile("ld.relaxed.gpu.global.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ double ld_flag(const double* p) {
     double v;
     asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];\n" : "=d"(v) : "l"(p) : "memory");
@@ -83,6 +92,13 @@ __device__ __forceinline__ void st_flag(double* p, double v) {
 }
 __device__ __forceinline__ bool unset(double v) { return __double_as_longlong(v) == UNSET_BITS; }
 
+// bounded spin bookkeeping: returns true once the run has been flagged as failed
+__device__ __forceinline__ bool poll_expired(int& spins, int* status) {
+    if ((++spins & 255) != 0) return false;
+    if (spins >= SPIN_LIMIT) atomicExch(status, 1);
+    return *reinterpret_cast<volatile int*>(status) != 0;
+}
+
 template <int UPT>
 __global__ void __launch_bounds__(RC_THREADS, 1) recur_forced_kernel(RecurArgs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -90,17 +106,19 @@ __global__ void __launch_bounds__(RC_THREADS, 1) recur_forced_kernel(RecurArgs p
     const unsigned c = cluster_ctarank();
     const int g = blockIdx.x / C;
     const int tid = threadIdx.x;
+    const int N = p.N;
     const int upc = p.units_per_cta;
     const int u0 = c * upc;
-    const int u1 = min(p.N, u0 + upc);
+    const int u1 = min(N, u0 + upc);
+    if (u0 >= N) return;  // nothing to produce, nobody waits for this CTA
 
+    double* s_r = reinterpret_cast<double*>(smem_raw);  // [n_pad] copy of r_t
     // ---- stage this CTA's CSR slice of W in shared memory (or fall back to global) ----
-    const int slice_lo = (u0 < p.N) ? p.indptr[u0] : 0;
-    const int slice_hi = (u0 < p.N) ? p.indptr[u1] : 0;
+    const int slice_lo = p.indptr[u0], slice_hi = p.indptr[u1];
     const int* idx_base = p.indices;
     const double* val_base = p.values;
     if (p.w_in_smem) {
-        double* s_val = reinterpret_cast<double*>(smem_raw);
+        double* s_val = s_r + p.n_pad;
         int* s_idx = reinterpret_cast<int*>(s_val + p.smem_nnz);
         for (int k = slice_lo + tid; k < slice_hi; k += RC_THREADS) {
             s_val[k - slice_lo] = p.values[k];
@@ -109,86 +127,101 @@ __global__ void __launch_bounds__(RC_THREADS, 1) recur_forced_kernel(RecurArgs p
         idx_base = s_idx - slice_lo;
         val_base = s_val - slice_lo;
     }
-    __syncthreads();
-
     double* states = p.states + (long long)g * p.state_group_stride;
     const double* drive = p.drive + (long long)g * p.drive_group_stride;
+    const double* carry = p.carry + (long long)g * N;
+    for (int i = tid; i < N; i += RC_THREADS) s_r[i] = carry[i];
 
-    int unit[UPT], row_len[UPT], max_len = 0;
-    const int* idx[UPT];
-    const double* val[UPT];
+    int unit[UPT], row_lo[UPT], row_len[UPT];
     double r_cur[UPT], d_next[UPT];
 #pragma unroll
     for (int j = 0; j < UPT; ++j) {
         unit[j] = u0 + tid + j * RC_THREADS;
         const bool ok = unit[j] < u1;
-        const int lo = ok ? p.indptr[unit[j]] : 0;
-        row_len[j] = ok ? p.indptr[unit[j] + 1] - lo : 0;
-        max_len = max(max_len, row_len[j]);
-        idx[j] = idx_base + lo;
-        val[j] = val_base + lo;
-        r_cur[j] = ok ? p.carry[(long long)g * p.N + unit[j]] : 0.0;
+        row_lo[j] = ok ? p.indptr[unit[j]] : 0;
+        row_len[j] = ok ? p.indptr[unit[j] + 1] - row_lo[j] : 0;
+        r_cur[j] = ok ? carry[unit[j]] : 0.0;
         d_next[j] = (ok && p.steps > 0) ? drive[unit[j]] : 0.0;
-        if (ok) st_flag(states + unit[j], r_cur[j]);  // row 0 = state entering the chunk
+        if (ok) st_flag(states + unit[j], r_cur[j]);  // row 0 = state entering the chunk (read by the Gram kernel)
         else unit[j] = -1;
     }
     const double alpha = p.alpha, oma = 1.0 - p.alpha;
+    const bool vec2 = (N % 2 == 0) && ((reinterpret_cast<uintptr_t>(states) & 15) == 0);
     bool aborted = false;
+    __syncthreads();
 
     for (int t = 0; t < p.steps; ++t) {
-        const double* r_prev = states + (long long)t * p.N;
-        double* r_next = states + (long long)(t + 1) * p.N;
-        double acc[UPT];
-#pragma unroll
-        for (int j = 0; j < UPT; ++j) acc[j] = 0.0;
-
-        for (int k0 = 0; k0 < max_len; k0 += KW) {
-            double gv[UPT][KW];
-#pragma unroll
-            for (int j = 0; j < UPT; ++j)
-#pragma unroll
-                for (int k = 0; k < KW; ++k) gv[j][k] = (k0 + k < row_len[j]) ? __longlong_as_double(UNSET_BITS) : 0.0;
-            int spins = 0;
-            bool miss;
-            do {
-#pragma unroll
-                for (int j = 0; j < UPT; ++j)
-#pragma unroll
-                    for (int k = 0; k < KW; ++k)
-                        if (unset(gv[j][k])) gv[j][k] = ld_flag(r_prev + idx[j][k0 + k]);
-                miss = false;
-#pragma unroll
-                for (int j = 0; j < UPT; ++j)
-#pragma unroll
-                    for (int k = 0; k < KW; ++k) miss |= unset(gv[j][k]);
-                if (miss && !aborted && ((++spins & 1023) == 0)) {
-                    if (spins >= SPIN_LIMIT) atomicExch(p.status, 1);
-                    aborted = *reinterpret_cast<volatile int*>(p.status) != 0;
-                }
-            } while (miss && !aborted);
-#pragma unroll
-            for (int j = 0; j < UPT; ++j)
-#pragma unroll
-                for (int k = 0; k < KW; ++k)
-                    if (k0 + k < row_len[j]) acc[j] = __dadd_rn(acc[j], __dmul_rn(val[j][k0 + k], gv[j][k]));
-        }
+        double* r_next = states + (long long)(t + 1) * N;
+        // ---- my units: W r_t from the shared copy, tanh, leak; publish to the ring ----
 #pragma unroll
         for (int j = 0; j < UPT; ++j) {
             if (unit[j] >= 0) {
-                const double pre = __dadd_rn(acc[j], d_next[j]);
+                const int* ix = idx_base + row_lo[j];
+                const double* vl = val_base + row_lo[j];
+                double acc = 0.0;
+#pragma unroll 4
+                for (int k = 0; k < row_len[j]; ++k) acc = __dadd_rn(acc, __dmul_rn(vl[k], s_r[ix[k]]));
+                const double pre = __dadd_rn(acc, d_next[j]);
                 r_cur[j] = leaky(pre, r_cur[j], alpha, oma);
                 st_flag(r_next + unit[j], r_cur[j]);
             }
         }
-        if (t + 1 < p.steps) {
+        if (t + 1 == p.steps) break;
 #pragma unroll
-            for (int j = 0; j < UPT; ++j)
-                if (unit[j] >= 0) d_next[j] = __ldg(drive + (long long)(t + 1) * p.N + unit[j]);
+        for (int j = 0; j < UPT; ++j)
+            if (unit[j] >= 0) d_next[j] = __ldg(drive + (long long)(t + 1) * N + unit[j]);
+        __syncthreads();  // every gather of r_t is done: the shared copy may be overwritten
+#pragma unroll
+        for (int j = 0; j < UPT; ++j)
+            if (unit[j] >= 0) s_r[unit[j]] = r_cur[j];
+        // ---- refresh the other CTAs' slices of r_{t+1} with coalesced polling loads ----
+        if (C > 1) {
+            if (vec2) {
+                const int n2 = N >> 1;
+                for (int q0 = tid; q0 < n2; q0 += RC_THREADS * POLL_BATCH) {
+                    double2 v[POLL_BATCH];
+                    bool need[POLL_BATCH];
+#pragma unroll
+                    for (int b = 0; b < POLL_BATCH; ++b) {
+                        const int q = q0 + b * RC_THREADS;
+                        // pieces lying entirely inside my own slice are already in the copy
+                        need[b] = (q < n2) && !(2 * q >= u0 && 2 * q + 1 < u1);
+                        v[b].x = v[b].y = __longlong_as_double(UNSET_BITS);
+                    }
+                    int spins = 0;
+                    bool miss;
+                    do {
+#pragma unroll
+                        for (int b = 0; b < POLL_BATCH; ++b)
+                            if (need[b] && (unset(v[b].x) || unset(v[b].y)))
+                                v[b] = ld_flag2(r_next + 2 * (q0 + b * RC_THREADS));
+                        miss = false;
+#pragma unroll
+                        for (int b = 0; b < POLL_BATCH; ++b) miss |= need[b] && (unset(v[b].x) || unset(v[b].y));
+                        if (miss && !aborted) aborted = poll_expired(spins, p.status);
+                    } while (miss && !aborted);
+#pragma unroll
+                    for (int b = 0; b < POLL_BATCH; ++b)
+                        if (need[b]) *reinterpret_cast<double2*>(s_r + 2 * (q0 + b * RC_THREADS)) = v[b];
+                }
+            } else {
+                for (int q = tid; q < N; q += RC_THREADS) {
+                    if (q >= u0 && q < u1) continue;
+                    double v = ld_flag(r_next + q);
+                    int spins = 0;
+                    while (unset(v) && !aborted) {
+                        aborted = poll_expired(spins, p.status);
+                        v = ld_flag(r_next + q);
+                    }
+                    s_r[q] = v;
+                }
+            }
         }
+        __syncthreads();
     }
 #pragma unroll
     for (int j = 0; j < UPT; ++j)
-        if (unit[j] >= 0) p.carry[(long long)g * p.N + unit[j]] = r_cur[j];
+        if (unit[j] >= 0) p.carry[(long long)g * N + unit[j]] = r_cur[j];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -342,40 +375,49 @@ __global__ void gather_series_kernel(const double* __restrict__ src, long long l
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
+static int recur_geometry(int N, int* C_out, int* upt_out) {
+    int need = (N + RC_THREADS - 1) / RC_THREADS;
+    int C = 1;
+    while (C < need && C < 16) C <<= 1;
+    int per = (N + C - 1) / C;
+    int upt = (per + RC_THREADS - 1) / RC_THREADS;
+    *C_out = C, *upt_out = upt;
+    return upt <= 2 ? 0 : -2;
+}
+
+int recur_cluster_size(int N) {
+    int C, upt;
+    recur_geometry(N, &C, &upt);
+    return C;
+}
+
 int launch_recur_forced(RecurArgs a, int n_groups, int max_slice_nnz, cudaStream_t stream) {
     if (a.steps <= 0 || n_groups <= 0) return 0;
-    // choose cluster size / units per thread
-    int C = 1, upt = 1;
-    const int per_cta1 = RC_THREADS;
-    if (a.N <= per_cta1) {
-        C = 1, upt = 1;
-    } else {
-        // prefer more CTAs (shorter serial path per step) up to the non-portable limit of 16
-        int need = (a.N + per_cta1 - 1) / per_cta1;
-        C = 1;
-        while (C < need && C < 16) C <<= 1;
-        int per = (a.N + C - 1) / C;
-        upt = (per + RC_THREADS - 1) / RC_THREADS;
-        if (upt > 4) {
-            set_error("recur_forced: n_reservoir=%d exceeds the persistent kernel capacity (%d)", a.N,
-                      16 * RC_THREADS * 4);
-            return -2;
-        }
-        if (upt == 3) upt = 4;
+    int C, upt;
+    if (recur_geometry(a.N, &C, &upt)) {
+        set_error("recur_forced: n_reservoir=%d exceeds the persistent kernel capacity (%d)", a.N, 16 * RC_THREADS * 2);
+        return -2;
     }
     a.units_per_cta = (a.N + C - 1) / C;
-    (void)max_slice_nnz;
-    // shared-memory residency of the CSR slice: conservative bound = nnz of the densest slice
-    long long smem_needed = (long long)a.smem_nnz * 12 + 16;
-    a.w_in_smem = smem_needed <= 200 * 1024;
-    size_t smem = a.w_in_smem ? (size_t)smem_needed : 0;
+    a.smem_nnz = max_slice_nnz + (max_slice_nnz & 1);
+    a.n_pad = (a.N + 1) & ~1;
+    // shared memory: full state copy (always) + this CTA's CSR slice of W (if it fits)
+    const long long smem_r = (long long)a.n_pad * 8;
+    const long long smem_w = (long long)a.smem_nnz * 12 + 16;
+    const long long limit = 227 * 1024;
+    if (smem_r > limit) {
+        set_error("recur_forced: n_reservoir=%d does not fit the shared-memory state copy", a.N);
+        return -2;
+    }
+    a.w_in_smem = (smem_r + smem_w <= limit);
+    const size_t smem = (size_t)(smem_r + (a.w_in_smem ? smem_w : 0));
 
     // every row of the ring the kernel will write/poll starts as the "unset" pattern
     XESN_CUDA_OK(cudaMemset2DAsync(a.states, sizeof(double) * a.state_group_stride, 0xFF,
                                    sizeof(double) * (size_t)(a.steps + 1) * a.N, n_groups, stream));
 
-    void (*kern)(RecurArgs) = upt == 1 ? recur_forced_kernel<1> : (upt == 2 ? recur_forced_kernel<2> : recur_forced_kernel<4>);
-    XESN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 16));
+    void (*kern)(RecurArgs) = upt == 1 ? recur_forced_kernel<1> : recur_forced_kernel<2>;
+    XESN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
     if (C > 8) XESN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
 
     cudaLaunchConfig_t cfg = {};
@@ -393,14 +435,6 @@ int launch_recur_forced(RecurArgs a, int n_groups, int max_slice_nnz, cudaStream
     XESN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, a));
     count_launch();
     return 0;
-}
-
-int recur_cluster_size(int N) {
-    if (N <= RC_THREADS) return 1;
-    int need = (N + RC_THREADS - 1) / RC_THREADS;
-    int C = 1;
-    while (C < need && C < 16) C <<= 1;
-    return C;
 }
 
 int launch_step_update(const StepArgs& a, int n_groups, cudaStream_t stream) {
