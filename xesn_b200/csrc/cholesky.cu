@@ -79,15 +79,16 @@ potrf_diag_kernel(double* A, long long lda, long long strideA, int j0, int nbj, 
                 }
             }
             __syncthreads();
+            // only register blocks that can still change: x >= ka (rows > k), ka <= y <= x
             double li[8], lj[8];
 #pragma unroll
-            for (int x = 0; x < 8; ++x) li[x] = colbuf[ty + 16 * x];
+            for (int x = ka; x < 8; ++x) li[x] = colbuf[ty + 16 * x];
 #pragma unroll
-            for (int y = 0; y < 8; ++y) lj[y] = colbuf[tx + 16 * y];
+            for (int y = ka; y < 8; ++y) lj[y] = colbuf[tx + 16 * y];
 #pragma unroll
-            for (int x = 0; x < 8; ++x)
+            for (int x = ka; x < 8; ++x)
 #pragma unroll
-                for (int y = 0; y < 8; ++y) {
+                for (int y = ka; y <= x; ++y) {
                     const int i = ty + 16 * x, j = tx + 16 * y;
                     if (j > k && j <= i) a[x][y] = fma(-li[x], lj[y], a[x][y]);
                 }
@@ -128,15 +129,16 @@ potrf_diag_kernel(double* A, long long lda, long long strideA, int j0, int nbj, 
                 }
             }
             __syncthreads();
+            // rows i > k (x >= ka) and columns j <= k (y <= ka) are the only ones touched
             double lik[8], xk[8];
 #pragma unroll
-            for (int x = 0; x < 8; ++x) lik[x] = S[(ty + 16 * x) * LDS + k];
+            for (int x = ka; x < 8; ++x) lik[x] = S[(ty + 16 * x) * LDS + k];
 #pragma unroll
-            for (int y = 0; y < 8; ++y) xk[y] = rb[tx + 16 * y];
+            for (int y = 0; y <= ka; ++y) xk[y] = rb[tx + 16 * y];
 #pragma unroll
-            for (int x = 0; x < 8; ++x)
+            for (int x = ka; x < 8; ++x)
 #pragma unroll
-                for (int y = 0; y < 8; ++y) {
+                for (int y = 0; y <= ka; ++y) {
                     const int i = ty + 16 * x;
                     if (i > k) a[x][y] = fma(-lik[x], xk[y], a[x][y]);
                 }

@@ -33,6 +33,32 @@ def _dist():
     return 0, 1
 
 
+def partition_groups(n_groups, rank, world):
+    """Contiguous slab [g0, g1) of the C-ordered group list owned by `rank`."""
+    if world == 1:
+        return 0, n_groups
+    if n_groups % world:
+        raise ValueError(f"LazyESN: {n_groups} groups do not divide over {world} ranks")
+    per = n_groups // world
+    return rank * per, (rank + 1) * per
+
+
+def exchange_owned(field, owned, rank, gathered):
+    """All ranks publish the cells they own: field[owned[r]] of rank r is copied into `field`
+    of every rank.  `owned`: (world, cells_per_rank) int64 tensor, `gathered`: scratch of the
+    same shape in field's dtype.  One collective per forecast step -- the neighbour exchange
+    dask's `overlap` performs in the reference (lazyesn.py:235)."""
+    import torch.distributed as dist
+    mine = field[owned[rank]].contiguous()
+    try:
+        dist.all_gather_into_tensor(gathered, mine)
+    except (RuntimeError, NotImplementedError):  # backends without the fused variant
+        parts = [gathered[r] for r in range(gathered.shape[0])]
+        dist.all_gather(parts, mine)
+    field[owned.reshape(-1)] = gathered.reshape(-1)
+    return field
+
+
 class LazyESN(ESN):
     __slots__ = ("esn_chunks", "overlap", "persist", "boundary",
                  "_grid", "_dims", "_maps", "_wout_blocks_host")
@@ -114,12 +140,7 @@ class LazyESN(ESN):
 
     def _my_groups(self, n_groups):
         rank, world = _dist()
-        if world == 1:
-            return 0, n_groups
-        if n_groups % world:
-            raise ValueError(f"LazyESN: {n_groups} groups do not divide over {world} ranks")
-        per = n_groups // world
-        return rank * per, (rank + 1) * per
+        return partition_groups(n_groups, rank, world)
 
     # ------------------------------------------------------------------ Wout in the reference's block layout
     @property
@@ -305,14 +326,12 @@ class LazyESN(ESN):
         dev = res.device
         # cells owned per rank, in rank order; equal counts because the groups divide evenly
         owned = torch.from_numpy(out_map.reshape(world, -1).astype(np.int64)).to(dev)
-        mine = owned[rank]
         pred[:, 0] = field
         nxt = field.clone()
-        gathered = torch.empty((world, mine.numel()), dtype=torch.float64, device=dev)
+        gathered = torch.empty(tuple(owned.shape), dtype=torch.float64, device=dev)
         for n in range(1, n_steps + 1):
             _lib.check(lib.xesn_predict_step(res.handle, _ptr(wout), O, G, _ptr(t_in), _ptr(t_fill), _ptr(t_out),
                                              _ptr(field), _ptr(nxt), _ptr(r), None, 0, _ptr(scratch), nb, st))
-            dist.all_gather_into_tensor(gathered, nxt[mine].contiguous())
-            nxt[owned.reshape(-1)] = gathered.reshape(-1)
+            exchange_owned(nxt, owned, rank, gathered)
             pred[:, n] = nxt
             field, nxt = nxt, field
