@@ -307,7 +307,7 @@ def main():
 
         def step_device():
             esn.train(train_dev, n_spinup=w["n_spinup_train"])
-            return esn.predict(test_dev, n_steps=w["pred_steps"], n_spinup=w["pred_spinup"])
+            return esn._predict_core(test_dev, w["pred_steps"], w["pred_spinup"])
 
         def step_e2e():
             esn.train(train_host, n_spinup=w["n_spinup_train"])

@@ -29,14 +29,6 @@ constexpr int TILE_DOUBLES = BM * LD_K;  // 2560 >= BK*LD_MN = 2112
 constexpr int STAGE_DOUBLES = 2 * TILE_DOUBLES;
 constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * (int)sizeof(double);  // 160 KB
 
-__device__ __forceinline__ void cp_async16(double* dst, const double* src, int src_bytes) {
-    unsigned s = (unsigned)__cvta_generic_to_shared(dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async8(double* dst, const double* src, int src_bytes) {
-    unsigned s = (unsigned)__cvta_generic_to_shared(dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(src), "r"(src_bytes) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -49,53 +41,77 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
-// Copy one operand tile (128 along MN, 16 along K) into shared memory, zero-filling outside
-// [0,MN) x [0,K).  `g` is the batch-adjusted base pointer of the operand.
-template <bool KMAJOR>
-__device__ __forceinline__ void load_tile(double* s, const double* __restrict__ g, long long ld, int mn0, int k0,
-                                          int MN, int K, bool vec16, int tid) {
-    if (!KMAJOR) {
+// Per-thread state for copying one operand tile (128 along MN, 16 along K) per k-tile into shared
+// memory, zero-filling outside [0,MN) x [0,K).  Everything that does not depend on the k-tile
+// (source pointers, shared-memory offsets, MN-edge byte counts) is computed once; inside the main
+// loop a copy is one add + one LDGSTS.  (The first version recomputed ~900 integer instructions per
+// k-tile per warp, which left the DMMA pipe idle 22 % of the time -- profiles/gram_syrk_r01_v1.txt.)
+template <bool KMAJOR, bool VEC>
+struct TileLoader {
+    const char* src[4];
+    const char* base;
+    unsigned dst[4];
+    int mn_bytes[4];
+    int kpos[4];
+    long long step;
+
+    __device__ __forceinline__ void init(const double* g, long long ld, int mn0, int MN, int tid) {
+        base = reinterpret_cast<const char*>(g);
 #pragma unroll
-        for (int pass = 0; pass < 4; ++pass) {
-            int row = pass * 4 + (tid >> 6);
-            int v = tid & 63;
-            int k = k0 + row, mn = mn0 + 2 * v;
-            double* dst = s + row * LD_MN + 2 * v;
-            int valid = (k < K) ? min(max(MN - mn, 0), 2) : 0;
-            const double* src = valid ? g + (long long)k * ld + mn : g;
-            if (vec16) {
-                cp_async16(dst, src, valid * 8);
+        for (int p = 0; p < 4; ++p) {
+            if (!KMAJOR) {
+                const int row = p * 4 + (tid >> 6), v = tid & 63;
+                const int mn = mn0 + 2 * v;
+                mn_bytes[p] = min(max(MN - mn, 0), 2) * 8;
+                src[p] = mn_bytes[p] ? reinterpret_cast<const char*>(g + (long long)row * ld + mn) : base;
+                dst[p] = (unsigned)((row * LD_MN + 2 * v) * sizeof(double));
+                kpos[p] = row;
             } else {
-                cp_async8(dst, src, valid >= 1 ? 8 : 0);
-                cp_async8(dst + 1, valid >= 2 ? src + 1 : g, valid >= 2 ? 8 : 0);
+                const int row = p * 32 + (tid >> 3), v = tid & 7;
+                const int mn = mn0 + row;
+                mn_bytes[p] = (mn < MN) ? 16 : 0;
+                src[p] = mn_bytes[p] ? reinterpret_cast<const char*>(g + (long long)mn * ld + 2 * v) : base;
+                dst[p] = (unsigned)((row * LD_K + 2 * v) * sizeof(double));
+                kpos[p] = 2 * v;
             }
         }
-    } else {
+        step = KMAJOR ? (long long)BK * sizeof(double) : (long long)BK * ld * sizeof(double);
+    }
+
+    // `smem_tile`: shared-space byte address of this operand's tile in the target stage
+    template <bool FULL>
+    __device__ __forceinline__ void load(unsigned smem_tile, int kt, int K) const {
+        const long long off = (long long)kt * step;
 #pragma unroll
-        for (int pass = 0; pass < 4; ++pass) {
-            int row = pass * 32 + (tid >> 3);
-            int v = tid & 7;
-            int mn = mn0 + row, k = k0 + 2 * v;
-            double* dst = s + row * LD_K + 2 * v;
-            int valid = (mn < MN) ? min(max(K - k, 0), 2) : 0;
-            const double* src = valid ? g + (long long)mn * ld + k : g;
-            if (vec16) {
-                cp_async16(dst, src, valid * 8);
+        for (int p = 0; p < 4; ++p) {
+            int bytes = mn_bytes[p];
+            if (!FULL) {
+                const int k = kt * BK + kpos[p];
+                if (!KMAJOR) bytes = (k < K) ? bytes : 0;
+                else bytes = min(bytes, max(K - k, 0) * 8);
+            }
+            const char* sp = bytes ? src[p] + off : base;
+            const unsigned d = smem_tile + dst[p];
+            if (VEC) {
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(sp), "r"(bytes) : "memory");
             } else {
-                cp_async8(dst, src, valid >= 1 ? 8 : 0);
-                cp_async8(dst + 1, valid >= 2 ? src + 1 : g, valid >= 2 ? 8 : 0);
+                const int b0 = min(bytes, 8), b1 = max(bytes - 8, 0);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(sp), "r"(b0) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d + 8), "l"(b1 ? sp + 8 : base),
+                             "r"(b1)
+                             : "memory");
             }
         }
     }
-}
+};
 
 template <bool KMAJOR>
 __device__ __forceinline__ double frag(const double* s, int mn, int k) {
     return KMAJOR ? s[mn * LD_K + k] : s[k * LD_MN + mn];
 }
 
-template <bool A_K, bool B_K>
-__global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_kernel(GemmArgs p, int tiles_n, int vecA, int vecB) {
+template <bool A_K, bool B_K, bool VEC>
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_kernel(GemmArgs p, int tiles_n) {
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 2, wn = warp & 3;
@@ -115,9 +131,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_kernel(GemmArgs p, int t
     }
     const int m0 = ti * BM, n0 = tj * BN;
     const int bz = blockIdx.y;
-    const double* A = p.A + (long long)bz * p.strideA;
-    const double* B = p.B + (long long)bz * p.strideB;
     double* C = p.C + (long long)bz * p.strideC;
+
+    TileLoader<A_K, VEC> la;
+    TileLoader<B_K, VEC> lb;
+    la.init(p.A + (long long)bz * p.strideA, p.lda, m0, p.M, tid);
+    lb.init(p.B + (long long)bz * p.strideB, p.ldb, n0, p.N, tid);
+    const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem);
+    constexpr unsigned STAGE_BYTES = STAGE_DOUBLES * sizeof(double);
+    constexpr unsigned TILE_BYTES = TILE_DOUBLES * sizeof(double);
 
     double acc[8][4][2];
 #pragma unroll
@@ -126,11 +148,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_kernel(GemmArgs p, int t
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     const int ktiles = (p.K + BK - 1) / BK;
+    const int kfull = p.K / BK;  // k-tiles that need no K-edge handling
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
         if (s < ktiles) {
-            load_tile<A_K>(smem + s * STAGE_DOUBLES, A, p.lda, m0, s * BK, p.M, p.K, vecA, tid);
-            load_tile<B_K>(smem + s * STAGE_DOUBLES + TILE_DOUBLES, B, p.ldb, n0, s * BK, p.N, p.K, vecB, tid);
+            if (s < kfull) {
+                la.template load<true>(smem_base + s * STAGE_BYTES, s, p.K);
+                lb.template load<true>(smem_base + s * STAGE_BYTES + TILE_BYTES, s, p.K);
+            } else {
+                la.template load<false>(smem_base + s * STAGE_BYTES, s, p.K);
+                lb.template load<false>(smem_base + s * STAGE_BYTES + TILE_BYTES, s, p.K);
+            }
         }
         cp_async_commit();
     }
@@ -140,11 +168,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_kernel(GemmArgs p, int t
         cp_async_wait<STAGES - 2>();
         __syncthreads();
         {
-            int nk = kt + STAGES - 1;
+            const int nk = kt + STAGES - 1;
             if (nk < ktiles) {
-                int s = nk % STAGES;
-                load_tile<A_K>(smem + s * STAGE_DOUBLES, A, p.lda, m0, nk * BK, p.M, p.K, vecA, tid);
-                load_tile<B_K>(smem + s * STAGE_DOUBLES + TILE_DOUBLES, B, p.ldb, n0, nk * BK, p.N, p.K, vecB, tid);
+                const unsigned sb = smem_base + (nk % STAGES) * STAGE_BYTES;
+                if (nk < kfull) {
+                    la.template load<true>(sb, nk, p.K);
+                    lb.template load<true>(sb + TILE_BYTES, nk, p.K);
+                } else {
+                    la.template load<false>(sb, nk, p.K);
+                    lb.template load<false>(sb + TILE_BYTES, nk, p.K);
+                }
             }
             cp_async_commit();
         }
@@ -205,20 +238,24 @@ int launch_gemm_f64(const GemmArgs& a, cudaStream_t stream) {
     } else {
         ntiles = (long long)tiles_m * tiles_n;
     }
-    const int vecA = aligned16(a.A) && (a.lda % 2 == 0) && (a.strideA % 2 == 0);
-    const int vecB = aligned16(a.B) && (a.ldb % 2 == 0) && (a.strideB % 2 == 0);
+    const bool vec = aligned16(a.A) && (a.lda % 2 == 0) && (a.strideA % 2 == 0) && aligned16(a.B) &&
+                     (a.ldb % 2 == 0) && (a.strideB % 2 == 0);
     dim3 grid((unsigned)ntiles, (unsigned)a.batch);
     const bool ak = a.flags & GEMM_A_KMAJOR, bk = a.flags & GEMM_B_KMAJOR;
-    void (*kern)(GemmArgs, int, int, int) =
-        ak ? (bk ? gemm_f64_kernel<true, true> : gemm_f64_kernel<true, false>)
-           : (bk ? gemm_f64_kernel<false, true> : gemm_f64_kernel<false, false>);
-    static bool attr_done[4] = {false, false, false, false};
-    int which = (ak ? 2 : 0) + (bk ? 1 : 0);
+    void (*table[8])(GemmArgs, int) = {
+        gemm_f64_kernel<false, false, false>, gemm_f64_kernel<false, false, true>,
+        gemm_f64_kernel<false, true, false>,  gemm_f64_kernel<false, true, true>,
+        gemm_f64_kernel<true, false, false>,  gemm_f64_kernel<true, false, true>,
+        gemm_f64_kernel<true, true, false>,   gemm_f64_kernel<true, true, true>,
+    };
+    const int which = (ak ? 4 : 0) + (bk ? 2 : 0) + (vec ? 1 : 0);
+    void (*kern)(GemmArgs, int) = table[which];
+    static bool attr_done[8] = {false, false, false, false, false, false, false, false};
     if (!attr_done[which]) {
         XESN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_done[which] = true;
     }
-    kern<<<grid, NTHREADS, SMEM_BYTES, stream>>>(a, tiles_n, vecA, vecB);
+    kern<<<grid, NTHREADS, SMEM_BYTES, stream>>>(a, tiles_n);
     count_launch();
     XESN_CUDA_OK(cudaGetLastError());
     return 0;

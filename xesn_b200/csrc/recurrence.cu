@@ -23,7 +23,7 @@
 namespace xesn {
 namespace {
 
-constexpr int RC_THREADS = 1024;
+constexpr int RC_THREADS = 512;
 constexpr int KMAX = 16;  // gathers issued back-to-back before the first FMA
 
 __device__ __forceinline__ double ld_cg(const double* p) {
@@ -74,7 +74,7 @@ __device__ __forceinline__ double leaky(double pre, double r_old, double alpha, 
 // scope compiles to MEMBAR.ALL.GPU per warp: 6.4 us per step in the first version).
 constexpr long long UNSET_BITS = -1LL;
 constexpr int SPIN_LIMIT = 1 << 22;  // ~1-2 s of polling, then the run is flagged as failed
-constexpr int POLL_BATCH = 4;        // 16-byte pieces in flight per thread while refreshing the copy
+constexpr int POLL_BATCH = 16;       // 16-byte pieces in flight per thread while refreshing the copy
 
 __device__ __forceinline__ double2 ld_flag2(const double* p) {
     double2 v;
@@ -180,29 +180,27 @@ __global__ void __launch_bounds__(RC_THREADS, 1) recur_forced_kernel(RecurArgs p
                 const int n2 = N >> 1;
                 for (int q0 = tid; q0 < n2; q0 += RC_THREADS * POLL_BATCH) {
                     double2 v[POLL_BATCH];
-                    bool need[POLL_BATCH];
+                    unsigned pending = 0;  // bit b: piece b still has an unset half
 #pragma unroll
                     for (int b = 0; b < POLL_BATCH; ++b) {
                         const int q = q0 + b * RC_THREADS;
                         // pieces lying entirely inside my own slice are already in the copy
-                        need[b] = (q < n2) && !(2 * q >= u0 && 2 * q + 1 < u1);
-                        v[b].x = v[b].y = __longlong_as_double(UNSET_BITS);
+                        if ((q < n2) && !(2 * q >= u0 && 2 * q + 1 < u1)) pending |= 1u << b;
                     }
+                    const unsigned mine = pending;
                     int spins = 0;
-                    bool miss;
-                    do {
+                    while (pending && !aborted) {
 #pragma unroll
                         for (int b = 0; b < POLL_BATCH; ++b)
-                            if (need[b] && (unset(v[b].x) || unset(v[b].y)))
-                                v[b] = ld_flag2(r_next + 2 * (q0 + b * RC_THREADS));
-                        miss = false;
+                            if (pending & (1u << b)) v[b] = ld_flag2(r_next + 2 * (q0 + b * RC_THREADS));
 #pragma unroll
-                        for (int b = 0; b < POLL_BATCH; ++b) miss |= need[b] && (unset(v[b].x) || unset(v[b].y));
-                        if (miss && !aborted) aborted = poll_expired(spins, p.status);
-                    } while (miss && !aborted);
+                        for (int b = 0; b < POLL_BATCH; ++b)
+                            if ((pending & (1u << b)) && !unset(v[b].x) && !unset(v[b].y)) pending &= ~(1u << b);
+                        if (pending) aborted = poll_expired(spins, p.status);
+                    }
 #pragma unroll
                     for (int b = 0; b < POLL_BATCH; ++b)
-                        if (need[b]) *reinterpret_cast<double2*>(s_r + 2 * (q0 + b * RC_THREADS)) = v[b];
+                        if (mine & (1u << b)) *reinterpret_cast<double2*>(s_r + 2 * (q0 + b * RC_THREADS)) = v[b];
                 }
             } else {
                 for (int q = tid; q < N; q += RC_THREADS) {
@@ -257,7 +255,22 @@ __global__ void __launch_bounds__(SU_THREADS) step_update_kernel(StepArgs p) {
     } else {
         const double* wrow = p.Win + (long long)i * p.I;
         double acc = 0.0;
-        for (int k = 0; k < p.I; ++k) acc = fma(wrow[k], s_u[k], acc);
+        if ((p.I & 1) == 0 && ((reinterpret_cast<uintptr_t>(p.Win) & 15) == 0)) {
+            const double2* w2 = reinterpret_cast<const double2*>(wrow);
+            const double2* u2 = reinterpret_cast<const double2*>(s_u);
+            double acc1 = 0.0;
+#pragma unroll 10
+            for (int k = 0; k < (p.I >> 1); ++k) {
+                const double2 a = __ldg(w2 + k);
+                const double2 b = u2[k];
+                acc = fma(a.x, b.x, acc);
+                acc1 = fma(a.y, b.y, acc1);
+            }
+            acc += acc1;
+        } else {
+#pragma unroll 4
+            for (int k = 0; k < p.I; ++k) acc = fma(__ldg(wrow + k), s_u[k], acc);
+        }
         pre = __dadd_rn(__dadd_rn(wr, acc), p.bias[i]);
     }
     double r_old = ld_cg(r_in + i);
@@ -382,7 +395,9 @@ static int recur_geometry(int N, int* C_out, int* upt_out) {
     int per = (N + C - 1) / C;
     int upt = (per + RC_THREADS - 1) / RC_THREADS;
     *C_out = C, *upt_out = upt;
-    return upt <= 2 ? 0 : -2;
+    if (upt == 3) upt = 4;
+    *upt_out = upt;
+    return upt <= 4 ? 0 : -2;
 }
 
 int recur_cluster_size(int N) {
@@ -395,7 +410,7 @@ int launch_recur_forced(RecurArgs a, int n_groups, int max_slice_nnz, cudaStream
     if (a.steps <= 0 || n_groups <= 0) return 0;
     int C, upt;
     if (recur_geometry(a.N, &C, &upt)) {
-        set_error("recur_forced: n_reservoir=%d exceeds the persistent kernel capacity (%d)", a.N, 16 * RC_THREADS * 2);
+        set_error("recur_forced: n_reservoir=%d exceeds the persistent kernel capacity (%d)", a.N, 16 * RC_THREADS * 4);
         return -2;
     }
     a.units_per_cta = (a.N + C - 1) / C;
@@ -416,7 +431,8 @@ int launch_recur_forced(RecurArgs a, int n_groups, int max_slice_nnz, cudaStream
     XESN_CUDA_OK(cudaMemset2DAsync(a.states, sizeof(double) * a.state_group_stride, 0xFF,
                                    sizeof(double) * (size_t)(a.steps + 1) * a.N, n_groups, stream));
 
-    void (*kern)(RecurArgs) = upt == 1 ? recur_forced_kernel<1> : recur_forced_kernel<2>;
+    void (*kern)(RecurArgs) =
+        upt == 1 ? recur_forced_kernel<1> : (upt == 2 ? recur_forced_kernel<2> : recur_forced_kernel<4>);
     XESN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
     if (C > 8) XESN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
 

@@ -257,6 +257,16 @@ class LazyESN(ESN):
         """Closed-loop forecast of the whole domain (reference lazyesn.py:190-248)."""
         _time_last(y, "LazyESN.predict", "y")
         assert y.shape[-1] >= n_spinup + 1
+        pred = self._predict_core(y, n_steps, n_spinup)
+        out = pred.cpu().numpy().reshape(tuple(y.shape[:-1]) + (n_steps + 1,))
+        self._check_status()
+        if _is_dataarray(y):
+            fdims, fcoords = self._get_fcoords(y.dims, y.coords, n_steps, n_spinup)
+            return xr.DataArray(out, coords=fcoords, dims=fdims)
+        return out
+
+    def _predict_core(self, y, n_steps, n_spinup):
+        """Forecast on the device: returns the (n_cells, n_steps+1) trajectory tensor."""
         torch = _torch()
         grid, in_map, out_map, fill = self._geometry(y)
         G_all = in_map.shape[0]
@@ -297,12 +307,7 @@ class LazyESN(ESN):
             else:
                 self._predict_multi(lib, res, wout, G, g0, n_cells, t_in, t_fill, t_out, out_map, field, r,
                                     n_steps, pred, scratch, nb, st)
-        out = pred.cpu().numpy().reshape(tuple(y.shape[:-1]) + (n_steps + 1,))
-        self._check_status()
-        if _is_dataarray(y):
-            fdims, fcoords = self._get_fcoords(y.dims, y.coords, n_steps, n_spinup)
-            return xr.DataArray(out, coords=fcoords, dims=fdims)
-        return out
+        return pred
 
     def _initial_field(self, y, n_spinup, dev):
         torch = _torch()
@@ -318,16 +323,35 @@ class LazyESN(ESN):
                        pred, scratch, nb, st):
         """One process per GPU: every rank advances its slab of groups, then the ranks
         all-gather the cells they own (NCCL over NVLink) -- the per-step neighbour exchange
-        that dask's `overlap` performs in the reference (lazyesn.py:235)."""
+        that dask's `overlap` performs in the reference (lazyesn.py:235).
+
+        When every rank's cells form one contiguous range of the flat domain (slabs along the
+        first axis, the normal case) the all-gather runs in place on the field vector and the
+        readout kernel writes the trajectory of the owned cells directly; the full trajectory is
+        assembled with one all-gather at the end.  Otherwise an index-based exchange is used."""
         torch = _torch()
         import torch.distributed as dist
         rank, world = _dist()
         O = self.n_output
         dev = res.device
-        # cells owned per rank, in rank order; equal counts because the groups divide evenly
-        owned = torch.from_numpy(out_map.reshape(world, -1).astype(np.int64)).to(dev)
-        pred[:, 0] = field
+        per = out_map.shape[0] // world * out_map.shape[1]
+        owned_np = out_map.reshape(world, -1)
+        contiguous = all(np.array_equal(np.sort(owned_np[k]), np.arange(k * per, (k + 1) * per)) for k in range(world))
         nxt = field.clone()
+        ld = pred.stride(0)
+        if contiguous:
+            lo, hi = rank * per, (rank + 1) * per
+            pred[lo:hi, 0] = field[lo:hi]
+            for n in range(1, n_steps + 1):
+                _lib.check(lib.xesn_predict_step(res.handle, _ptr(wout), O, G, _ptr(t_in), _ptr(t_fill), _ptr(t_out),
+                                                 _ptr(field), _ptr(nxt), _ptr(r), pred.data_ptr() + 8 * n, ld,
+                                                 _ptr(scratch), nb, st))
+                dist.all_gather_into_tensor(nxt, nxt[lo:hi])
+                field, nxt = nxt, field
+            dist.all_gather_into_tensor(pred, pred[lo:hi])
+            return
+        owned = torch.from_numpy(owned_np.astype(np.int64)).to(dev)
+        pred[:, 0] = field
         gathered = torch.empty(tuple(owned.shape), dtype=torch.float64, device=dev)
         for n in range(1, n_steps + 1):
             _lib.check(lib.xesn_predict_step(res.handle, _ptr(wout), O, G, _ptr(t_in), _ptr(t_fill), _ptr(t_out),
