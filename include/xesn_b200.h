@@ -127,7 +127,11 @@ int64_t xesn_launch_count(void);
 /* per-phase device timers (CUDA events on the launching stream).  enable(1) clears and starts
  * recording, enable(0) stops.  read() synchronises on the recorded events and returns the number
  * of timed regions and their summed duration for class
- * 0 drive GEMM, 1 recurrence, 2 Gram SYRK, 3 Y.R GEMM, 4 ridge solve, 5 closed loop, 6 halo gather. */
+ * 0 drive GEMM, 1 recurrence, 2 Gram SYRK, 3 Y.R GEMM, 4 ridge solve, 5 closed loop, 6 halo gather,
+ * 7 fused chunk kernel (recurrence of chunk c beside the Gram of chunk c-1). */
+/* The training pipeline normally runs recurrence(c) and Gram(c-1) side by side in one cooperative
+ * SM-specialised kernel; xesn_set_fused(h, 0) falls back to separate launches (A/B measurements). */
+int xesn_set_fused(xesn_reservoir* h, int32_t on);
 int xesn_profile_enable(int32_t on);
 int xesn_profile_read(int32_t cls, int64_t* n_regions, double* total_ms);
 

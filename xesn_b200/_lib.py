@@ -53,6 +53,7 @@ SIGNATURES = {
                                     C.c_void_p]),
     "xesn_gemm_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
                                 C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_void_p]),
+    "xesn_set_fused": (C.c_int, [C.c_void_p, C.c_int32]),
     "xesn_profile_enable": (C.c_int, [C.c_int32]),
     "xesn_profile_read": (C.c_int, [C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "xesn_readout": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
@@ -92,7 +93,8 @@ def launch_count():
     return int(load().xesn_launch_count())
 
 
-PROFILE_CLASSES = ("drive_gemm", "recurrence", "gram_syrk", "yr_gemm", "ridge_solve", "closed_loop", "halo_gather")
+PROFILE_CLASSES = ("drive_gemm", "recurrence", "gram_syrk", "yr_gemm", "ridge_solve", "closed_loop", "halo_gather",
+                   "fused_chunk")
 
 
 def profile_enable(on=True):

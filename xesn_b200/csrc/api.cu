@@ -4,6 +4,7 @@
 #include <atomic>
 #include <mutex>
 #include <string>
+#include <algorithm>
 #include <vector>
 
 #include "../../include/xesn_b200.h"
@@ -87,6 +88,11 @@ struct xesn_reservoir {
     long long ro_partial_cap = 0, ro_counter_cap = 0;
     int cluster = 1;
     int max_slice_nnz = 0;
+    int num_sms = 0;
+    std::vector<int> h_indptr;
+    int2* d_tiles = nullptr;  // Gram tile order of the fused chunk kernel
+    int n_tiles = 0;
+    int fused_enabled = 1;
 };
 
 extern "C" {
@@ -165,6 +171,20 @@ int xesn_reservoir_create(xesn_reservoir** out, int device, int32_t N, int32_t I
         if (s > mx) mx = s;
     }
     h->max_slice_nnz = mx;
+    h->num_sms = prop.multiProcessorCount;
+    h->h_indptr.assign(indptr, indptr + N + 1);
+    {
+        // lower-triangle tile list in super-rows of 12 tile rows, column by column (L2 locality)
+        const int T = (N + 127) / 128, H = 12;
+        std::vector<int2> tiles;
+        tiles.reserve((size_t)T * (T + 1) / 2);
+        for (int sb = 0; sb < T; sb += H)
+            for (int tj = 0; tj < (sb + H < T ? sb + H : T); ++tj)
+                for (int ti = (sb > tj ? sb : tj); ti < (sb + H < T ? sb + H : T); ++ti) tiles.push_back(make_int2(ti, tj));
+        h->n_tiles = (int)tiles.size();
+        XESN_CUDA_OK(cudaMalloc(&h->d_tiles, sizeof(int2) * tiles.size()));
+        XESN_CUDA_OK(cudaMemcpy(h->d_tiles, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice));
+    }
     *out = h;
     return 0;
 }
@@ -178,6 +198,7 @@ int xesn_reservoir_destroy(xesn_reservoir* h) {
     cudaFree(h->d_win);
     cudaFree(h->d_bias);
     cudaFree(h->d_status);
+    cudaFree(h->d_tiles);
     cudaFree(h->d_ro_partial);
     cudaFree(h->d_ro_counters);
     delete h;
@@ -292,7 +313,7 @@ int xesn_forced_run(xesn_reservoir* h, const xesn_series* u, int64_t t0, int32_t
 // ---------------------------------------------------------------------------------------------
 struct TrainLayout {
     long long cld;
-    long long carry, Uc, Yc, D, R, total;  // offsets in doubles
+    long long carry, Uc, Yc, D, R, D2, R2, total;  // offsets in doubles
 };
 static TrainLayout train_layout(xesn_reservoir* h, int O, int G, int chunk, int gu, int gy) {
     TrainLayout L;
@@ -303,6 +324,9 @@ static TrainLayout train_layout(xesn_reservoir* h, int O, int G, int chunk, int 
     L.Yc = off, off += gy ? (long long)G * O * L.cld : 0;
     L.D = off, off += round_up((long long)G * chunk * h->N, 2);
     L.R = off, off += round_up((long long)G * (chunk + 1) * h->N, 2);
+    // second drive / state-ring buffers: the fused chunk kernel runs recurrence(c) beside Gram(c-1)
+    L.D2 = off, off += round_up((long long)G * chunk * h->N, 2);
+    L.R2 = off, off += round_up((long long)G * (chunk + 1) * h->N, 2);
     L.total = off;
     return L;
 }
@@ -345,6 +369,71 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
         if ((rc = launch_recur_forced(r, G, h->max_slice_nnz, st))) return rc;
     }
     // accumulate: xesn/esn.py:502-513
+    int team = 0, upt = 0;
+    const bool fuse = h->fused_enabled && (N % 2 == 0) && fused_recur_geometry(N, G, &team, &upt) == 0 &&
+                      (long long)team * G < h->num_sms && T > n_spinup;
+    if (fuse) {
+        // software pipeline over chunks: launch c runs recurrence(c) || Gram(c-1) in one cooperative kernel
+        const int upc = (N + team - 1) / team;
+        int slice_nnz = 0;
+        for (int c = 0; c < team; ++c) {
+            const int lo = c * upc < N ? c * upc : N, hi = (c + 1) * upc < N ? (c + 1) * upc : N;
+            slice_nnz = std::max(slice_nnz, h->h_indptr[hi] - h->h_indptr[lo]);
+        }
+        double* Dbuf[2] = {D, base + L.D2};
+        double* Rbuf[2] = {R, base + L.R2};
+        const long long nch = (T - n_spinup + chunk - 1) / chunk;
+        auto chunk_t0 = [&](long long c) { return n_spinup + c * chunk; };
+        auto chunk_m = [&](long long c) { return (int)std::min<long long>(chunk, T - chunk_t0(c)); };
+        auto drive_for = [&](long long c) -> int {
+            const double* ub;
+            long long ldu, ugs;
+            int rc = chunk_inputs(h, u, h->I, G, chunk_t0(c), chunk_m(c), Uc, L.cld, &ub, &ldu, &ugs, st);
+            if (rc) return rc;
+            return drive_gemm(h, ub, ldu, ugs, G, chunk_m(c), Dbuf[c & 1], st);
+        };
+        int rc = drive_for(0);
+        if (rc) return rc;
+        for (long long c = 0; c <= nch; ++c) {
+            if (c + 1 < nch && (rc = drive_for(c + 1))) return rc;
+            RecurArgs r = recur_args(h);
+            if (c < nch) {
+                const int m = chunk_m(c);
+                r.drive = Dbuf[c & 1], r.drive_group_stride = (long long)m * N, r.steps = m, r.carry = carry;
+                r.states = Rbuf[c & 1], r.state_group_stride = (long long)(m + 1) * N;
+            }
+            GemmArgs g = {};
+            int ntiles = 0;
+            if (c >= 1) {
+                const int mp = chunk_m(c - 1);
+                const long long rgs = (long long)(mp + 1) * N;
+                double* Rp = Rbuf[(c - 1) & 1];
+                g.A = Rp, g.lda = N, g.strideA = rgs;
+                g.B = Rp, g.ldb = N, g.strideB = rgs;
+                g.C = gram, g.ldc = N, g.strideC = (long long)N * N;
+                g.M = N, g.N = N, g.K = mp, g.batch = G, g.alpha = 1.0, g.beta = 1.0, g.flags = GEMM_LOWER;
+                ntiles = h->n_tiles;
+            }
+            {
+                ProfScope prof(PROF_FUSED, st);
+                if ((rc = launch_fused_chunk(r, G, team, upt, slice_nnz, g, h->d_tiles, ntiles, h->num_sms, st))) return rc;
+            }
+            if (c >= 1) {
+                const int mp = chunk_m(c - 1);
+                const double* yb;
+                long long ldy, ygs;
+                if ((rc = chunk_inputs(h, y, O, G, chunk_t0(c - 1), mp, Yc, L.cld, &yb, &ldy, &ygs, st))) return rc;
+                GemmArgs q = {};
+                q.A = yb, q.lda = ldy, q.strideA = ygs;
+                q.B = Rbuf[(c - 1) & 1], q.ldb = N, q.strideB = (long long)(mp + 1) * N;
+                q.C = wout, q.ldc = N, q.strideC = (long long)O * N;
+                q.M = O, q.N = N, q.K = mp, q.batch = G, q.alpha = 1.0, q.beta = 1.0, q.flags = GEMM_A_KMAJOR;
+                ProfScope prof(PROF_YR, st);
+                if ((rc = launch_gemm_f64(q, st))) return rc;
+            }
+        }
+        return 0;
+    }
     for (long long t0 = n_spinup; t0 < T; t0 += chunk) {
         const int m = (int)(T - t0 < chunk ? T - t0 : chunk);
         const double *ub, *yb;
@@ -382,6 +471,13 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
             if ((rc = launch_gemm_f64(q, st))) return rc;
         }
     }
+    return 0;
+}
+
+// switch the fused recurrence+Gram chunk kernel on/off (A/B measurements, debugging)
+int xesn_set_fused(xesn_reservoir* h, int32_t on) {
+    XESN_REQUIRE(h, "null pointer");
+    h->fused_enabled = on != 0;
     return 0;
 }
 

@@ -30,7 +30,7 @@ void count_launch(int n = 1);
     } while (0)
 
 // optional per-phase device timers (xesn_profile_enable / xesn_profile_read)
-enum ProfClass : int { PROF_DRIVE = 0, PROF_RECUR, PROF_GRAM, PROF_YR, PROF_SOLVE, PROF_PREDICT, PROF_GATHER, PROF_N };
+enum ProfClass : int { PROF_DRIVE = 0, PROF_RECUR, PROF_GRAM, PROF_YR, PROF_SOLVE, PROF_PREDICT, PROF_GATHER, PROF_FUSED, PROF_N };
 void prof_begin(int cls, cudaStream_t st);
 void prof_end(int cls, cudaStream_t st);
 struct ProfScope {

@@ -1,0 +1,112 @@
+// Fused training-chunk kernel (sm_100a): SM-specialised persistent kernel.
+//
+//   CTAs [0, rec_ctas)      : the teacher-forced recurrence of time chunk c     (recur_body.cuh)
+//   CTAs [rec_ctas, grid)   : the Gram SYRK tiles  rbar += R^T R  of chunk c-1  (gemm_tile.cuh)
+//
+// The recurrence is a latency-bound serial chain that can use at most a handful of SMs
+// (~4.5 us per step at N=16000 on 16 SMs), the Gram accumulation is a throughput-bound FP64
+// tensor-pipe job for everything else.  Run back to back they cost t_rec + t_gram per chunk; run
+// side by side in ONE cooperative launch (one CTA per SM, so the recurrence CTAs are guaranteed
+// co-resident and the scheduler cannot scatter them) the chunk costs max(t_rec, t_gram * 148/132).
+// The two roles only share the state ring: the recurrence writes ring c while the Gram reads
+// ring c-1 (double-buffered by the caller).
+//
+// Tile order of the Gram role: a host-built list that walks the lower triangle in super-rows of
+// 12 tile rows, column by column, so the ~132 tiles in flight at any time touch about 12 + 11
+// operand panels (L2-resident) instead of ~130 distinct ones.
+#include "common.cuh"
+#include "gemm_tile.cuh"
+#include "kernels.cuh"
+#include "recur_body.cuh"
+
+namespace xesn {
+namespace {
+
+constexpr int FUSED_THREADS = 256;
+
+template <int UPT>
+__global__ void __launch_bounds__(FUSED_THREADS, 1)
+fused_chunk_kernel(RecurArgs rp, int rec_ctas, int team, GemmArgs gp, const int2* __restrict__ tiles, int ntiles) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    if ((int)blockIdx.x < rec_ctas) {
+        recur::recur_body<UPT, FUSED_THREADS>(rp, blockIdx.x % team, team, blockIdx.x / team, smem_raw);
+        return;
+    }
+    const int worker = blockIdx.x - rec_ctas, nworkers = gridDim.x - rec_ctas;
+    const long long total = (long long)ntiles * gp.batch;
+    for (long long t = worker; t < total; t += nworkers) {
+        const int2 ij = tiles[t % ntiles];
+        gemm::gemm_tile<false, false, true>(gp, ij.x, ij.y, (int)(t / ntiles), reinterpret_cast<double*>(smem_raw));
+    }
+}
+
+}  // namespace
+
+// team size / units per thread of the recurrence role for FUSED_THREADS-wide CTAs
+int fused_recur_geometry(int N, int n_groups, int* team_out, int* upt_out) {
+    // few, fat CTAs: the role must leave most SMs to the Gram; cap the recurrence at 32 CTAs
+    int best_team = -1, best_upt = 0;
+    for (int upt = 1; upt <= 8; upt <<= 1) {
+        int team = (N + FUSED_THREADS * upt - 1) / (FUSED_THREADS * upt);
+        if (team > 16) continue;
+        if ((long long)team * n_groups > 32) continue;
+        best_team = team, best_upt = upt;
+        break;
+    }
+    if (best_team < 0) return -2;
+    *team_out = best_team, *upt_out = best_upt;
+    return 0;
+}
+
+int fused_smem_bytes(const RecurArgs& a, int team, bool* w_in_smem) {
+    const int upc = (a.N + team - 1) / team;
+    (void)upc;
+    const long long n_pad = (a.N + 1) & ~1;
+    const long long smem_r = n_pad * 8;
+    const long long smem_w = (long long)(a.smem_nnz + (a.smem_nnz & 1)) * 12 + 16;
+    const long long limit = 227 * 1024;
+    if (smem_r > limit) return -1;
+    *w_in_smem = (smem_r + smem_w <= limit);
+    long long need = smem_r + (*w_in_smem ? smem_w : 0);
+    if (need < gemm::SMEM_BYTES) need = gemm::SMEM_BYTES;
+    return (int)need;
+}
+
+// rp.steps == 0 -> no recurrence role; ntiles == 0 -> no Gram role.
+int launch_fused_chunk(RecurArgs rp, int n_groups, int team, int upt, int max_slice_nnz, const GemmArgs& gp,
+                       const int2* tiles, int ntiles, int num_sms, cudaStream_t stream) {
+    const bool has_rec = rp.steps > 0;
+    rp.units_per_cta = (rp.N + team - 1) / team;
+    rp.smem_nnz = max_slice_nnz + (max_slice_nnz & 1);
+    rp.n_pad = (rp.N + 1) & ~1;
+    bool w_in_smem = false;
+    const int smem = fused_smem_bytes(rp, team, &w_in_smem);
+    if (smem < 0) {
+        set_error("fused chunk: n_reservoir=%d does not fit the shared-memory state copy", rp.N);
+        return -2;
+    }
+    rp.w_in_smem = w_in_smem;
+    int rec_ctas = has_rec ? team * n_groups : 0;
+    if (has_rec) {
+        XESN_CUDA_OK(cudaMemset2DAsync(rp.states, sizeof(double) * rp.state_group_stride, 0xFF,
+                                       sizeof(double) * (size_t)(rp.steps + 1) * rp.N, n_groups, stream));
+    }
+    int grid = num_sms;
+    if (ntiles == 0) grid = rec_ctas;
+    if (grid <= 0) return 0;
+    if (rec_ctas >= grid && ntiles > 0) {
+        set_error("fused chunk: recurrence role needs %d CTAs, device has %d SMs", rec_ctas, num_sms);
+        return -2;
+    }
+    void (*kern)(RecurArgs, int, int, GemmArgs, const int2*, int) =
+        upt == 1 ? fused_chunk_kernel<1>
+                 : (upt == 2 ? fused_chunk_kernel<2> : (upt == 4 ? fused_chunk_kernel<4> : fused_chunk_kernel<8>));
+    XESN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    GemmArgs g = gp;
+    void* args[] = {&rp, &rec_ctas, &team, &g, (void*)&tiles, &ntiles};
+    XESN_CUDA_OK(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(FUSED_THREADS), args, (size_t)smem, stream));
+    count_launch();
+    return 0;
+}
+
+}  // namespace xesn

@@ -59,6 +59,10 @@ struct ReadoutArgs {
 
 int launch_recur_forced(RecurArgs a, int n_groups, int max_slice_nnz, cudaStream_t stream);
 int recur_cluster_size(int N);
+// fused recurrence(c) || Gram(c-1) chunk kernel (fused_train.cu)
+int fused_recur_geometry(int N, int n_groups, int* team_out, int* upt_out);
+int launch_fused_chunk(RecurArgs rp, int n_groups, int team, int upt, int max_slice_nnz, const GemmArgs& gp,
+                       const int2* tiles, int ntiles, int num_sms, cudaStream_t stream);
 int launch_step_update(const StepArgs& a, int n_groups, cudaStream_t stream);
 int readout_slices(int N, int O, int n_groups);
 int launch_readout(ReadoutArgs a, int n_groups, cudaStream_t stream);

@@ -24,202 +24,18 @@ namespace xesn {
 namespace {
 
 constexpr int RC_THREADS = 512;
-constexpr int KMAX = 16;  // gathers issued back-to-back before the first FMA
-
-__device__ __forceinline__ double ld_cg(const double* p) {
-    double v;
-    asm volatile("ld.global.cg.f64 %0, [%1];\n" : "=d"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ unsigned cluster_ctarank() {
-    unsigned r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ unsigned cluster_nctarank() {
-    unsigned r;
-    asm volatile("mov.u32 %0, %%cluster_nctarank;\n" : "=r"(r));
-    return r;
-}
-
-// sum_k val[k] * r[idx[k]] in CSR order, multiply and add rounded separately like scipy's
-// csr_matvec, with all gathers of the row in flight before the first use.
-__device__ __forceinline__ double sparse_row_dot(const int* __restrict__ idx, const double* __restrict__ val,
-                                                 int len, const double* r_prev) {
-    double g[KMAX];
-#pragma unroll
-    for (int k = 0; k < KMAX; ++k) g[k] = (k < len) ? ld_cg(r_prev + idx[k]) : 0.0;
-    double acc = 0.0;
-#pragma unroll
-    for (int k = 0; k < KMAX; ++k)
-        if (k < len) acc = __dadd_rn(acc, __dmul_rn(val[k], g[k]));
-    for (int k = KMAX; k < len; ++k) acc = __dadd_rn(acc, __dmul_rn(val[k], ld_cg(r_prev + idx[k])));
-    return acc;
-}
-
-__device__ __forceinline__ double leaky(double pre, double r_old, double alpha, double one_minus_alpha) {
-    // alpha * tanh(p) + (1 - alpha) * r, each product rounded (no FMA contraction) as numpy does
-    return __dadd_rn(__dmul_rn(alpha, tanh(pre)), __dmul_rn(one_minus_alpha, r_old));
-}
-
-// ---- data-as-flag exchange of the state vector -------------------------------------------------
-// Every CTA of the cluster keeps a full copy of r_t in shared memory (random gathers from shared
-// memory cost ~6 cycles per warp; the same gathers from L2 cost one L1 wavefront per lane and
-// bounded the first version at ~2.5 us per step).  After computing its slice of r_{t+1} a CTA
-// stores it to the state ring in global memory -- which the Gram kernel needs anyway -- and
-// refreshes its shared copy with COALESCED polling loads of the other slices: the ring is
-// pre-filled with an all-ones bit pattern (a NaN no arithmetic produces here) and an aligned
-// 8-byte store is single-copy atomic, so a value that is no longer that pattern IS the finished
-// value.  No fence and no cluster barrier sit on the per-step critical path (a release at cluster
-// scope compiles to MEMBAR.ALL.GPU per warp: 6.4 us per step in the first version).
-constexpr long long UNSET_BITS = -1LL;
-constexpr int SPIN_LIMIT = 1 << 22;  // ~1-2 s of polling, then the run is flagged as failed
-constexpr int POLL_BATCH = 16;       // 16-byte pieces in flight per thread while refreshing the copy
-
-__device__ __forceinline__ double2 ld_flag2(const double* p) {
-    double2 v;
-    asm volatile("ld.relaxed.gpu.global.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ double ld_flag(const double* p) {
-    double v;
-    asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];\n" : "=d"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_flag(double* p, double v) {
-    if (__double_as_longlong(v) == UNSET_BITS) v = __longlong_as_double(0x7FF8000000000000LL);
-    asm volatile("st.relaxed.gpu.global.f64 [%0], %1;\n" ::"l"(p), "d"(v) : "memory");
-}
-__device__ __forceinline__ bool unset(double v) { return __double_as_longlong(v) == UNSET_BITS; }
-
-// bounded spin bookkeeping: returns true once the run has been flagged as failed
-__device__ __forceinline__ bool poll_expired(int& spins, int* status) {
-    if ((++spins & 255) != 0) return false;
-    if (spins >= SPIN_LIMIT) atomicExch(status, 1);
-    return *reinterpret_cast<volatile int*>(status) != 0;
-}
+}  // namespace
+}  // namespace xesn
+#include "recur_body.cuh"
+namespace xesn {
+namespace {
+using namespace recur;
 
 template <int UPT>
 __global__ void __launch_bounds__(RC_THREADS, 1) recur_forced_kernel(RecurArgs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned C = cluster_nctarank();
-    const unsigned c = cluster_ctarank();
-    const int g = blockIdx.x / C;
-    const int tid = threadIdx.x;
-    const int N = p.N;
-    const int upc = p.units_per_cta;
-    const int u0 = c * upc;
-    const int u1 = min(N, u0 + upc);
-    if (u0 >= N) return;  // nothing to produce, nobody waits for this CTA
-
-    double* s_r = reinterpret_cast<double*>(smem_raw);  // [n_pad] copy of r_t
-    // ---- stage this CTA's CSR slice of W in shared memory (or fall back to global) ----
-    const int slice_lo = p.indptr[u0], slice_hi = p.indptr[u1];
-    const int* idx_base = p.indices;
-    const double* val_base = p.values;
-    if (p.w_in_smem) {
-        double* s_val = s_r + p.n_pad;
-        int* s_idx = reinterpret_cast<int*>(s_val + p.smem_nnz);
-        for (int k = slice_lo + tid; k < slice_hi; k += RC_THREADS) {
-            s_val[k - slice_lo] = p.values[k];
-            s_idx[k - slice_lo] = p.indices[k];
-        }
-        idx_base = s_idx - slice_lo;
-        val_base = s_val - slice_lo;
-    }
-    double* states = p.states + (long long)g * p.state_group_stride;
-    const double* drive = p.drive + (long long)g * p.drive_group_stride;
-    const double* carry = p.carry + (long long)g * N;
-    for (int i = tid; i < N; i += RC_THREADS) s_r[i] = carry[i];
-
-    int unit[UPT], row_lo[UPT], row_len[UPT];
-    double r_cur[UPT], d_next[UPT];
-#pragma unroll
-    for (int j = 0; j < UPT; ++j) {
-        unit[j] = u0 + tid + j * RC_THREADS;
-        const bool ok = unit[j] < u1;
-        row_lo[j] = ok ? p.indptr[unit[j]] : 0;
-        row_len[j] = ok ? p.indptr[unit[j] + 1] - row_lo[j] : 0;
-        r_cur[j] = ok ? carry[unit[j]] : 0.0;
-        d_next[j] = (ok && p.steps > 0) ? drive[unit[j]] : 0.0;
-        if (ok) st_flag(states + unit[j], r_cur[j]);  // row 0 = state entering the chunk (read by the Gram kernel)
-        else unit[j] = -1;
-    }
-    const double alpha = p.alpha, oma = 1.0 - p.alpha;
-    const bool vec2 = (N % 2 == 0) && ((reinterpret_cast<uintptr_t>(states) & 15) == 0);
-    bool aborted = false;
-    __syncthreads();
-
-    for (int t = 0; t < p.steps; ++t) {
-        double* r_next = states + (long long)(t + 1) * N;
-        // ---- my units: W r_t from the shared copy, tanh, leak; publish to the ring ----
-#pragma unroll
-        for (int j = 0; j < UPT; ++j) {
-            if (unit[j] >= 0) {
-                const int* ix = idx_base + row_lo[j];
-                const double* vl = val_base + row_lo[j];
-                double acc = 0.0;
-#pragma unroll 4
-                for (int k = 0; k < row_len[j]; ++k) acc = __dadd_rn(acc, __dmul_rn(vl[k], s_r[ix[k]]));
-                const double pre = __dadd_rn(acc, d_next[j]);
-                r_cur[j] = leaky(pre, r_cur[j], alpha, oma);
-                st_flag(r_next + unit[j], r_cur[j]);
-            }
-        }
-        if (t + 1 == p.steps) break;
-#pragma unroll
-        for (int j = 0; j < UPT; ++j)
-            if (unit[j] >= 0) d_next[j] = __ldg(drive + (long long)(t + 1) * N + unit[j]);
-        __syncthreads();  // every gather of r_t is done: the shared copy may be overwritten
-#pragma unroll
-        for (int j = 0; j < UPT; ++j)
-            if (unit[j] >= 0) s_r[unit[j]] = r_cur[j];
-        // ---- refresh the other CTAs' slices of r_{t+1} with coalesced polling loads ----
-        if (C > 1) {
-            if (vec2) {
-                const int n2 = N >> 1;
-                for (int q0 = tid; q0 < n2; q0 += RC_THREADS * POLL_BATCH) {
-                    double2 v[POLL_BATCH];
-                    unsigned pending = 0;  // bit b: piece b still has an unset half
-#pragma unroll
-                    for (int b = 0; b < POLL_BATCH; ++b) {
-                        const int q = q0 + b * RC_THREADS;
-                        // pieces lying entirely inside my own slice are already in the copy
-                        if ((q < n2) && !(2 * q >= u0 && 2 * q + 1 < u1)) pending |= 1u << b;
-                    }
-                    const unsigned mine = pending;
-                    int spins = 0;
-                    while (pending && !aborted) {
-#pragma unroll
-                        for (int b = 0; b < POLL_BATCH; ++b)
-                            if (pending & (1u << b)) v[b] = ld_flag2(r_next + 2 * (q0 + b * RC_THREADS));
-#pragma unroll
-                        for (int b = 0; b < POLL_BATCH; ++b)
-                            if ((pending & (1u << b)) && !unset(v[b].x) && !unset(v[b].y)) pending &= ~(1u << b);
-                        if (pending) aborted = poll_expired(spins, p.status);
-                    }
-#pragma unroll
-                    for (int b = 0; b < POLL_BATCH; ++b)
-                        if (mine & (1u << b)) *reinterpret_cast<double2*>(s_r + 2 * (q0 + b * RC_THREADS)) = v[b];
-                }
-            } else {
-                for (int q = tid; q < N; q += RC_THREADS) {
-                    if (q >= u0 && q < u1) continue;
-                    double v = ld_flag(r_next + q);
-                    int spins = 0;
-                    while (unset(v) && !aborted) {
-                        aborted = poll_expired(spins, p.status);
-                        v = ld_flag(r_next + q);
-                    }
-                    s_r[q] = v;
-                }
-            }
-        }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int j = 0; j < UPT; ++j)
-        if (unit[j] >= 0) p.carry[(long long)g * N + unit[j]] = r_cur[j];
+    recur_body<UPT, RC_THREADS>(p, cluster_ctarank(), C, blockIdx.x / C, smem_raw);
 }
 
 // ------------------------------------------------------------------------------------------
