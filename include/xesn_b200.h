@@ -119,6 +119,12 @@ int xesn_predict_step(xesn_reservoir* h, const double* wout_dev, int32_t n_outpu
  * 2 = B is [N][K] (else [K][N]), 4 = only lower-triangular tiles (square C). */
 int xesn_gemm_f64(const double* a_dev, int64_t lda, const double* b_dev, int64_t ldb, double* c_dev, int64_t ldc,
                   int32_t m, int32_t n, int32_t k, double alpha, double beta, int32_t flags, void* stream);
+/* gram_dev (N x N, lower triangle) += S^T S for S = states_dev [n_rows][N], |S| <= 1, computed
+ * error-free on the int8 tensor cores (tcgen05 kind::i8) from the fixed-point digits of S.  Allocates
+ * its own scratch and synchronises: a test / measurement entry (the training pipeline runs the same
+ * device code inside the fused chunk kernel).  Replaces xesn/esn.py:510. */
+int xesn_gram_i8(const double* states_dev, int64_t lds, int32_t n_rows, int32_t n_reservoir, double* gram_dev,
+                 int64_t ldg, void* stream);
 /* readout v[g][o] = Wout[g][o][:] . r[g][:]   (xesn/esn.py:268, xesn/lazyesn.py:325-327) */
 int xesn_readout(const double* wout_dev, const double* r_dev, double* v_dev, int32_t n_reservoir,
                  int32_t n_output, int32_t n_groups, void* stream);

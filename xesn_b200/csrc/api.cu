@@ -10,8 +10,14 @@
 #include "../../include/xesn_b200.h"
 #include "common.cuh"
 #include "kernels.cuh"
+#include "gram_i8.cuh"
 
 namespace xesn {
+
+void gram_i8_tile_list(int N, std::vector<int2>& tiles);
+int launch_digitize(const double* states, long long lds, int n_rows, int N, int8_t* planes, long long ldp,
+                    long long plane_stride, int rows_pad, cudaStream_t stream);
+int launch_gram_i8(const gi8::GramI8Args& a, const int2* tiles, int ntiles, int num_sms, cudaStream_t stream);
 
 static thread_local std::string g_error;
 static std::atomic<long long> g_launches{0};
@@ -612,6 +618,38 @@ int xesn_predict(xesn_reservoir* h, const double* wout, int32_t O, int32_t G, in
         XESN_CUDA_OK(cudaMemcpyAsync(r, r_alt, sizeof(double) * (size_t)G * N, cudaMemcpyDeviceToDevice, st));
         XESN_CUDA_OK(cudaMemcpyAsync(field, field_alt, sizeof(double) * n_cells, cudaMemcpyDeviceToDevice, st));
     }
+    return 0;
+}
+
+// test / A-B entry: G (N x N, lower triangle) += S^T S for S = states [n_rows][N] through the int8
+// tensor-core path (digitise -> tcgen05 kind::i8 Gram).  Allocates its own scratch and synchronises.
+int xesn_gram_i8(const double* states, int64_t lds, int32_t n_rows, int32_t N, double* gram, int64_t ldg, void* stream) {
+    XESN_REQUIRE(states && gram && n_rows > 0 && N > 0, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0;
+    XESN_CUDA_OK(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    XESN_CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+    const long long ldp = round_up(N, 128);
+    const int rows_pad = (int)round_up(n_rows, gi8::KB);
+    const long long plane_stride = ldp * rows_pad;
+    int8_t* planes = nullptr;
+    int2* d_tiles = nullptr;
+    XESN_CUDA_OK(cudaMalloc(&planes, (size_t)plane_stride * gi8::NDIG));
+    std::vector<int2> tiles;
+    gram_i8_tile_list(N, tiles);
+    XESN_CUDA_OK(cudaMalloc(&d_tiles, sizeof(int2) * tiles.size()));
+    XESN_CUDA_OK(cudaMemcpyAsync(d_tiles, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, st));
+    int rc = launch_digitize(states, lds, n_rows, N, planes, ldp, plane_stride, rows_pad, st);
+    gi8::GramI8Args a = {};
+    a.planes = planes, a.ldp = ldp, a.plane_stride = plane_stride, a.group_stride = 0;
+    a.K = rows_pad, a.N = N, a.G = gram, a.ldg = ldg, a.strideG = 0, a.batch = 1;
+    if (!rc) rc = launch_gram_i8(a, d_tiles, (int)tiles.size(), prop.multiProcessorCount, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(planes);
+    cudaFree(d_tiles);
+    if (rc) return rc;
+    XESN_CUDA_OK(e);
     return 0;
 }
 
