@@ -138,6 +138,9 @@ int64_t xesn_launch_count(void);
 /* The training pipeline normally runs recurrence(c) and Gram(c-1) side by side in one cooperative
  * SM-specialised kernel; xesn_set_fused(h, 0) falls back to separate launches (A/B measurements). */
 int xesn_set_fused(xesn_reservoir* h, int32_t on);
+/* Gram accumulation engine of the fused pipeline: 1 (default) = error-free int8 digit planes on the
+ * tcgen05 tensor cores, 0 = FP64 DMMA. */
+int xesn_set_gram_mode(xesn_reservoir* h, int32_t mode);
 int xesn_profile_enable(int32_t on);
 int xesn_profile_read(int32_t cls, int64_t* n_regions, double* total_ms);
 

@@ -24,7 +24,7 @@ for (K, N) in [(32, 128), (64, 192), (96, 300), (512, 1000), (2048, 4000)]:
     G.zero_()
     _lib.check(lib.xesn_gram_i8(Sq.data_ptr(), N, K, N, G.data_ptr(), N, None))
     qi = torch.round(Sq * 2**20).to(torch.int64)
-    exact = (qi.T @ qi).to(torch.float64) / 2.0**40 if K * N < 3e6 else (Sq.T @ Sq)
+    exact = ((qi.cpu().T @ qi.cpu()).to(torch.float64) / 2.0**40).cuda() if K * N < 3e6 else (Sq.T @ Sq)
     print(f"   grid inputs: max abs diff vs exact {float((G - exact)[low].abs().max()):.3e}", flush=True)
 N, K = 16000, 2048
 S = (torch.rand((K, N), dtype=torch.float64, device="cuda") * 2 - 1)

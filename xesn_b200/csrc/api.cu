@@ -98,6 +98,9 @@ struct xesn_reservoir {
     std::vector<int> h_indptr;
     int2* d_tiles = nullptr;  // Gram tile order of the fused chunk kernel
     int n_tiles = 0;
+    int2* d_tiles_i8 = nullptr;  // 128 x 64 tiles of the int8 tensor-core Gram role
+    int n_tiles_i8 = 0;
+    int gram_mode = 1;  // 0 = FP64 DMMA, 1 = error-free int8 on tcgen05
     int fused_enabled = 1;
 };
 
@@ -190,6 +193,11 @@ int xesn_reservoir_create(xesn_reservoir** out, int device, int32_t N, int32_t I
         h->n_tiles = (int)tiles.size();
         XESN_CUDA_OK(cudaMalloc(&h->d_tiles, sizeof(int2) * tiles.size()));
         XESN_CUDA_OK(cudaMemcpy(h->d_tiles, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice));
+        std::vector<int2> t8;
+        gram_i8_tile_list(N, t8);
+        h->n_tiles_i8 = (int)t8.size();
+        XESN_CUDA_OK(cudaMalloc(&h->d_tiles_i8, sizeof(int2) * t8.size()));
+        XESN_CUDA_OK(cudaMemcpy(h->d_tiles_i8, t8.data(), sizeof(int2) * t8.size(), cudaMemcpyHostToDevice));
     }
     *out = h;
     return 0;
@@ -205,6 +213,7 @@ int xesn_reservoir_destroy(xesn_reservoir* h) {
     cudaFree(h->d_bias);
     cudaFree(h->d_status);
     cudaFree(h->d_tiles);
+    cudaFree(h->d_tiles_i8);
     cudaFree(h->d_ro_partial);
     cudaFree(h->d_ro_counters);
     delete h;
@@ -319,7 +328,8 @@ int xesn_forced_run(xesn_reservoir* h, const xesn_series* u, int64_t t0, int32_t
 // ---------------------------------------------------------------------------------------------
 struct TrainLayout {
     long long cld;
-    long long carry, Uc, Yc, D, R, D2, R2, total;  // offsets in doubles
+    long long carry, Uc, Yc, D, R, D2, R2, P1, P2, total;  // offsets in doubles
+    long long ldp, plane_stride;                          // digit planes (bytes)
 };
 static TrainLayout train_layout(xesn_reservoir* h, int O, int G, int chunk, int gu, int gy) {
     TrainLayout L;
@@ -333,6 +343,12 @@ static TrainLayout train_layout(xesn_reservoir* h, int O, int G, int chunk, int 
     // second drive / state-ring buffers: the fused chunk kernel runs recurrence(c) beside Gram(c-1)
     L.D2 = off, off += round_up((long long)G * chunk * h->N, 2);
     L.R2 = off, off += round_up((long long)G * (chunk + 1) * h->N, 2);
+    // int8 digit planes of the states, [G][8][round_up(chunk,32)][round_up(N,128)] bytes, double-buffered
+    L.ldp = round_up(h->N, 128);
+    L.plane_stride = L.ldp * round_up(chunk, gi8::KB);
+    const long long plane_doubles = round_up((long long)G * gi8::NDIG * L.plane_stride, 16) / 8;
+    L.P1 = off, off += plane_doubles;
+    L.P2 = off, off += plane_doubles;
     L.total = off;
     return L;
 }
@@ -388,6 +404,13 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
         }
         double* Dbuf[2] = {D, base + L.D2};
         double* Rbuf[2] = {R, base + L.R2};
+        const bool i8 = h->gram_mode == 1;
+        signed char* Pbuf[2] = {reinterpret_cast<signed char*>(base + L.P1), reinterpret_cast<signed char*>(base + L.P2)};
+        const long long plane_group = (long long)gi8::NDIG * L.plane_stride;
+        if (i8 && L.ldp > N) {  // padding columns must read as zero digits
+            XESN_CUDA_OK(cudaMemsetAsync(Pbuf[0], 0, (size_t)G * plane_group, st));
+            XESN_CUDA_OK(cudaMemsetAsync(Pbuf[1], 0, (size_t)G * plane_group, st));
+        }
         const long long nch = (T - n_spinup + chunk - 1) / chunk;
         auto chunk_t0 = [&](long long c) { return n_spinup + c * chunk; };
         auto chunk_m = [&](long long c) { return (int)std::min<long long>(chunk, T - chunk_t0(c)); };
@@ -408,7 +431,16 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
                 r.drive = Dbuf[c & 1], r.drive_group_stride = (long long)m * N, r.steps = m, r.carry = carry;
                 r.states = Rbuf[c & 1], r.state_group_stride = (long long)(m + 1) * N;
             }
+            if (i8 && c < nch) {
+                const int m = chunk_m(c);
+                const int mpad = (int)round_up(m, gi8::KB);
+                r.planes = Pbuf[c & 1], r.ldp = L.ldp, r.plane_stride = L.plane_stride, r.plane_group_stride = plane_group;
+                if (mpad > m)  // rows of the last K-block beyond the chunk read as zero
+                    XESN_CUDA_OK(cudaMemset2DAsync(Pbuf[c & 1] + (long long)m * L.ldp, (size_t)L.plane_stride, 0,
+                                                   (size_t)(mpad - m) * L.ldp, (size_t)gi8::NDIG * G, st));
+            }
             GemmArgs g = {};
+            gi8::GramI8Args g8 = {};
             int ntiles = 0;
             if (c >= 1) {
                 const int mp = chunk_m(c - 1);
@@ -418,11 +450,17 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
                 g.B = Rp, g.ldb = N, g.strideB = rgs;
                 g.C = gram, g.ldc = N, g.strideC = (long long)N * N;
                 g.M = N, g.N = N, g.K = mp, g.batch = G, g.alpha = 1.0, g.beta = 1.0, g.flags = GEMM_LOWER;
-                ntiles = h->n_tiles;
+                g8.planes = reinterpret_cast<const int8_t*>(Pbuf[(c - 1) & 1]);
+                g8.ldp = L.ldp, g8.plane_stride = L.plane_stride, g8.group_stride = plane_group;
+                g8.K = (int)round_up(mp, gi8::KB), g8.N = N, g8.G = gram, g8.ldg = N, g8.strideG = (long long)N * N;
+                g8.batch = G;
+                ntiles = i8 ? h->n_tiles_i8 : h->n_tiles;
             }
             {
                 ProfScope prof(PROF_FUSED, st);
-                if ((rc = launch_fused_chunk(r, G, team, upt, slice_nnz, g, h->d_tiles, ntiles, h->num_sms, st))) return rc;
+                rc = i8 ? launch_fused_chunk_i8(r, G, team, upt, slice_nnz, g8, h->d_tiles_i8, ntiles, h->num_sms, st)
+                        : launch_fused_chunk(r, G, team, upt, slice_nnz, g, h->d_tiles, ntiles, h->num_sms, st);
+                if (rc) return rc;
             }
             if (c >= 1) {
                 const int mp = chunk_m(c - 1);
@@ -477,6 +515,13 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
             if ((rc = launch_gemm_f64(q, st))) return rc;
         }
     }
+    return 0;
+}
+
+// 0 = FP64 DMMA Gram, 1 = error-free int8 tensor-core Gram (default; fused pipeline only)
+int xesn_set_gram_mode(xesn_reservoir* h, int32_t mode) {
+    XESN_REQUIRE(h && (mode == 0 || mode == 1), "bad arguments");
+    h->gram_mode = mode;
     return 0;
 }
 

@@ -16,6 +16,7 @@
 // operand panels (L2-resident) instead of ~130 distinct ones.
 #include "common.cuh"
 #include "gemm_tile.cuh"
+#include "gram_i8.cuh"
 #include "kernels.cuh"
 #include "recur_body.cuh"
 
@@ -38,6 +39,29 @@ fused_chunk_kernel(RecurArgs rp, int rec_ctas, int team, GemmArgs gp, const int2
         const int2 ij = tiles[t % ntiles];
         gemm::gemm_tile<false, false, true>(gp, ij.x, ij.y, (int)(t / ntiles), reinterpret_cast<double*>(smem_raw));
     }
+}
+
+// Gram role on the int8 tensor cores: tcgen05.mma kind::i8 on the digit planes written by the
+// recurrence role of the PREVIOUS launch (gram_i8.cuh).
+template <int UPT>
+__global__ void __launch_bounds__(FUSED_THREADS, 1)
+fused_chunk_i8_kernel(RecurArgs rp, int rec_ctas, int team, gi8::GramI8Args gp, const int2* __restrict__ tiles,
+                      int ntiles) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    if ((int)blockIdx.x < rec_ctas) {
+        recur::recur_body<UPT, FUSED_THREADS>(rp, blockIdx.x % team, team, blockIdx.x / team, smem_raw);
+        return;
+    }
+    const int worker = blockIdx.x - rec_ctas, nworkers = gridDim.x - rec_ctas;
+    const long long total = (long long)ntiles * gp.batch;
+    if (worker >= total) return;
+    gi8::GramI8Ctx ctx;
+    gi8::gram_i8_setup(ctx, smem_raw);
+    for (long long t = worker; t < total; t += nworkers) {
+        const int2 ij = tiles[t % ntiles];
+        gi8::gram_i8_tile(ctx, gp, ij.x, ij.y, (int)(t / ntiles));
+    }
+    gi8::gram_i8_teardown(ctx);
 }
 
 }  // namespace
@@ -69,6 +93,7 @@ int fused_smem_bytes(const RecurArgs& a, int team, bool* w_in_smem) {
     *w_in_smem = (smem_r + smem_w <= limit);
     long long need = smem_r + (*w_in_smem ? smem_w : 0);
     if (need < gemm::SMEM_BYTES) need = gemm::SMEM_BYTES;
+    if (need < gi8::SMEM_BYTES) need = gi8::SMEM_BYTES;
     return (int)need;
 }
 
@@ -103,6 +128,46 @@ int launch_fused_chunk(RecurArgs rp, int n_groups, int team, int upt, int max_sl
                  : (upt == 2 ? fused_chunk_kernel<2> : (upt == 4 ? fused_chunk_kernel<4> : fused_chunk_kernel<8>));
     XESN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     GemmArgs g = gp;
+    void* args[] = {&rp, &rec_ctas, &team, &g, (void*)&tiles, &ntiles};
+    XESN_CUDA_OK(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(FUSED_THREADS), args, (size_t)smem, stream));
+    count_launch();
+    return 0;
+}
+
+}  // namespace xesn
+
+namespace xesn {
+
+int launch_fused_chunk_i8(RecurArgs rp, int n_groups, int team, int upt, int max_slice_nnz,
+                          const gi8::GramI8Args& gp, const int2* tiles, int ntiles, int num_sms, cudaStream_t stream) {
+    const bool has_rec = rp.steps > 0;
+    rp.units_per_cta = (rp.N + team - 1) / team;
+    rp.smem_nnz = max_slice_nnz + (max_slice_nnz & 1);
+    rp.n_pad = (rp.N + 1) & ~1;
+    bool w_in_smem = false;
+    const int smem = fused_smem_bytes(rp, team, &w_in_smem);
+    if (smem < 0) {
+        set_error("fused chunk: n_reservoir=%d does not fit the shared-memory state copy", rp.N);
+        return -2;
+    }
+    rp.w_in_smem = w_in_smem;
+    int rec_ctas = has_rec ? team * n_groups : 0;
+    if (has_rec) {
+        XESN_CUDA_OK(cudaMemset2DAsync(rp.states, sizeof(double) * rp.state_group_stride, 0xFF,
+                                       sizeof(double) * (size_t)(rp.steps + 1) * rp.N, n_groups, stream));
+    }
+    int grid = num_sms;
+    if (ntiles == 0) grid = rec_ctas;
+    if (grid <= 0) return 0;
+    if (rec_ctas >= grid && ntiles > 0) {
+        set_error("fused chunk: recurrence role needs %d CTAs, device has %d SMs", rec_ctas, num_sms);
+        return -2;
+    }
+    void (*kern)(RecurArgs, int, int, gi8::GramI8Args, const int2*, int) =
+        upt == 1 ? fused_chunk_i8_kernel<1>
+                 : (upt == 2 ? fused_chunk_i8_kernel<2> : (upt == 4 ? fused_chunk_i8_kernel<4> : fused_chunk_i8_kernel<8>));
+    XESN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    gi8::GramI8Args g = gp;
     void* args[] = {&rp, &rec_ctas, &team, &g, (void*)&tiles, &ntiles};
     XESN_CUDA_OK(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(FUSED_THREADS), args, (size_t)smem, stream));
     count_launch();

@@ -3,6 +3,7 @@
 #pragma once
 #include "common.cuh"
 #include "kernels.cuh"
+#include "gram_i8.cuh"
 
 namespace xesn {
 namespace recur {
@@ -82,6 +83,14 @@ __device__ __forceinline__ bool poll_expired(int& spins, int* status) {
     return *reinterpret_cast<volatile int*>(status) != 0;
 }
 
+__device__ __forceinline__ void put_digits(signed char* planes, const RecurArgs& p, int row, int unit, double r) {
+    signed char d[gi8::NDIG];
+    gi8::state_digits(r, d);
+    signed char* dst = planes + (long long)row * p.ldp + unit;
+#pragma unroll
+    for (int a = 0; a < gi8::NDIG; ++a) dst[a * p.plane_stride] = d[a];
+}
+
 // The CTA `c` of the `C` CTAs that own reservoir `g` runs the whole chunk.  RC_THREADS = threads
 // taking part (the calling CTA's size); all C CTAs must be co-resident (cluster or cooperative launch).
 template <int UPT, int RC_THREADS>
@@ -112,6 +121,7 @@ __device__ __forceinline__ void recur_body(const RecurArgs& p, const unsigned c,
     double* states = p.states + (long long)g * p.state_group_stride;
     const double* drive = p.drive + (long long)g * p.drive_group_stride;
     const double* carry = p.carry + (long long)g * N;
+    signed char* digits = p.planes ? p.planes + (long long)g * p.plane_group_stride : nullptr;
     for (int i = tid; i < N; i += RC_THREADS) s_r[i] = carry[i];
 
     int unit[UPT], row_lo[UPT], row_len[UPT];
@@ -124,7 +134,10 @@ __device__ __forceinline__ void recur_body(const RecurArgs& p, const unsigned c,
         row_len[j] = ok ? p.indptr[unit[j] + 1] - row_lo[j] : 0;
         r_cur[j] = ok ? carry[unit[j]] : 0.0;
         d_next[j] = (ok && p.steps > 0) ? drive[unit[j]] : 0.0;
-        if (ok) st_flag(states + unit[j], r_cur[j]);  // row 0 = state entering the chunk (read by the Gram kernel)
+        if (ok) {
+            st_flag(states + unit[j], r_cur[j]);  // row 0 = state entering the chunk (read by the Gram kernel)
+            if (digits && p.steps > 0) put_digits(digits, p, 0, unit[j], r_cur[j]);
+        }
         else unit[j] = -1;
     }
     const double alpha = p.alpha, oma = 1.0 - p.alpha;
@@ -146,6 +159,9 @@ __device__ __forceinline__ void recur_body(const RecurArgs& p, const unsigned c,
                 const double pre = __dadd_rn(acc, d_next[j]);
                 r_cur[j] = leaky(pre, r_cur[j], alpha, oma);
                 st_flag(r_next + unit[j], r_cur[j]);
+                // fixed-point digit planes for the int8 tensor-core Gram: row t+1 pairs with y(t0+t+1);
+                // the state leaving the chunk (row `steps`) belongs to the next chunk's row 0
+                if (digits && t + 1 < p.steps) put_digits(digits, p, t + 1, unit[j], r_cur[j]);
             }
         }
         if (t + 1 == p.steps) break;

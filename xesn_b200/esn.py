@@ -98,6 +98,12 @@ class DeviceReservoir:
             indptr.ctypes.data, indices.ctypes.data, values.ctypes.data, win.ctypes.data, b.ctypes.data,
             float(leak_rate)))
         self._lib = lib
+        # A/B switches (environment): XESN_B200_GRAM=f64|i8, XESN_B200_FUSED=0|1
+        import os
+        if os.environ.get("XESN_B200_GRAM", "i8").lower() in ("f64", "fp64", "dmma", "0"):
+            _lib.check(lib.xesn_set_gram_mode(self._h, 0))
+        if os.environ.get("XESN_B200_FUSED", "1") == "0":
+            _lib.check(lib.xesn_set_fused(self._h, 0))
 
     @property
     def handle(self):
@@ -119,7 +125,7 @@ def auto_chunk(n_reservoir, n_groups, n_time, batch_size, budget_bytes=3 << 30):
     """Internal time-chunk length: bounds the (chunk+1, N) state ring + drive buffers
     (the reference's `batch_size` has the same purpose, esn.py:479-489).  Only the
     floating-point summation order of the Gram terms depends on it."""
-    per_step = 32 * n_reservoir * n_groups  # drive + state ring, double-buffered
+    per_step = 48 * n_reservoir * n_groups  # drive + state ring + int8 digit planes, double-buffered
     c = max(64, min(2048, budget_bytes // max(per_step, 1)))
     c = (c // 64) * 64
     if batch_size is not None:
