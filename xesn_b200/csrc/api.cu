@@ -172,7 +172,7 @@ int xesn_reservoir_create(xesn_reservoir** out, int device, int32_t N, int32_t I
     XESN_CUDA_OK(cudaMemcpy(h->d_bias, bias, sizeof(double) * N, cudaMemcpyHostToDevice));
 
     h->cluster = recur_cluster_size(N);
-    const int upc = (N + h->cluster - 1) / h->cluster;
+    const int upc = recur_units_per_cta(N, h->cluster);
     int mx = 0;
     for (int c = 0; c < h->cluster; ++c) {
         int lo = c * upc < N ? c * upc : N, hi = (c + 1) * upc < N ? (c + 1) * upc : N;
@@ -396,7 +396,7 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
                       (long long)team * G < h->num_sms && T > n_spinup;
     if (fuse) {
         // software pipeline over chunks: launch c runs recurrence(c) || Gram(c-1) in one cooperative kernel
-        const int upc = (N + team - 1) / team;
+        const int upc = recur_units_per_cta(N, team);
         int slice_nnz = 0;
         for (int c = 0; c < team; ++c) {
             const int lo = c * upc < N ? c * upc : N, hi = (c + 1) * upc < N ? (c + 1) * upc : N;

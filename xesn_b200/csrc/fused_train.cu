@@ -101,7 +101,7 @@ int fused_smem_bytes(const RecurArgs& a, int team, bool* w_in_smem) {
 int launch_fused_chunk(RecurArgs rp, int n_groups, int team, int upt, int max_slice_nnz, const GemmArgs& gp,
                        const int2* tiles, int ntiles, int num_sms, cudaStream_t stream) {
     const bool has_rec = rp.steps > 0;
-    rp.units_per_cta = (rp.N + team - 1) / team;
+    rp.units_per_cta = recur_units_per_cta(rp.N, team);
     rp.smem_nnz = max_slice_nnz + (max_slice_nnz & 1);
     rp.n_pad = (rp.N + 1) & ~1;
     bool w_in_smem = false;
@@ -141,7 +141,7 @@ namespace xesn {
 int launch_fused_chunk_i8(RecurArgs rp, int n_groups, int team, int upt, int max_slice_nnz,
                           const gi8::GramI8Args& gp, const int2* tiles, int ntiles, int num_sms, cudaStream_t stream) {
     const bool has_rec = rp.steps > 0;
-    rp.units_per_cta = (rp.N + team - 1) / team;
+    rp.units_per_cta = recur_units_per_cta(rp.N, team);
     rp.smem_nnz = max_slice_nnz + (max_slice_nnz & 1);
     rp.n_pad = (rp.N + 1) & ~1;
     bool w_in_smem = false;

@@ -61,6 +61,8 @@ struct ReadoutArgs {
 
 int launch_recur_forced(RecurArgs a, int n_groups, int max_slice_nnz, cudaStream_t stream);
 int recur_cluster_size(int N);
+// units owned by one CTA of a team: ceil(N / team) rounded up to a multiple of 8 (vector stores)
+inline int recur_units_per_cta(int N, int team) { return ((N + team - 1) / team + 7) & ~7; }
 // fused recurrence(c) || Gram(c-1) chunk kernel (fused_train.cu)
 int fused_recur_geometry(int N, int n_groups, int* team_out, int* upt_out);
 int launch_fused_chunk(RecurArgs rp, int n_groups, int team, int upt, int max_slice_nnz, const GemmArgs& gp,

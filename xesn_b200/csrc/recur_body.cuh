@@ -83,12 +83,57 @@ __device__ __forceinline__ bool poll_expired(int& spins, int* status) {
     return *reinterpret_cast<volatile int*>(status) != 0;
 }
 
-__device__ __forceinline__ void put_digits(signed char* planes, const RecurArgs& p, int row, int unit, double r) {
-    signed char d[gi8::NDIG];
-    gi8::state_digits(r, d);
-    signed char* dst = planes + (long long)row * p.ldp + unit;
+// publish UPT adjacent states (data-as-flag stores; every 8-byte element is single-copy atomic)
+template <int UPT>
+__device__ __forceinline__ void put_states(double* dst, const double (&r)[UPT], int nvalid) {
+    if (UPT >= 2 && nvalid == UPT && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
-    for (int a = 0; a < gi8::NDIG; ++a) dst[a * p.plane_stride] = d[a];
+        for (int j = 0; j < UPT; j += 2) {
+            double a = r[j], b = r[j + 1];
+            if (__double_as_longlong(a) == UNSET_BITS) a = __longlong_as_double(0x7FF8000000000000LL);
+            if (__double_as_longlong(b) == UNSET_BITS) b = __longlong_as_double(0x7FF8000000000000LL);
+            asm volatile("st.relaxed.gpu.global.v2.f64 [%0], {%1, %2};\n" ::"l"(dst + j), "d"(a), "d"(b) : "memory");
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < UPT; ++j)
+            if (j < nvalid) st_flag(dst + j, r[j]);
+    }
+}
+
+// fixed-point digits of UPT adjacent states -> one packed store per digit plane
+template <int UPT>
+__device__ __forceinline__ void put_digits(signed char* planes, const RecurArgs& p, int row, int ubase,
+                                           const double (&r)[UPT], int nvalid) {
+    signed char d[UPT][gi8::NDIG];
+#pragma unroll
+    for (int j = 0; j < UPT; ++j) gi8::state_digits(r[j], d[j]);
+    signed char* dst = planes + (long long)row * p.ldp + ubase;
+    if (nvalid == UPT && UPT >= 2) {
+#pragma unroll
+        for (int a = 0; a < gi8::NDIG; ++a) {
+            if (UPT == 2) {
+                unsigned short w = (unsigned short)((unsigned char)d[0][a] | ((unsigned)(unsigned char)d[1][a] << 8));
+                *reinterpret_cast<unsigned short*>(dst + a * p.plane_stride) = w;
+            } else if (UPT == 4) {
+                unsigned w = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) w |= (unsigned)(unsigned char)d[j][a] << (8 * j);
+                *reinterpret_cast<unsigned*>(dst + a * p.plane_stride) = w;
+            } else {
+                unsigned long long w = 0;
+#pragma unroll
+                for (int j = 0; j < UPT; ++j) w |= (unsigned long long)(unsigned char)d[j][a] << (8 * j);
+                *reinterpret_cast<unsigned long long*>(dst + a * p.plane_stride) = w;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < UPT; ++j)
+            if (j < nvalid)
+#pragma unroll
+                for (int a = 0; a < gi8::NDIG; ++a) dst[a * p.plane_stride + j] = d[j][a];
+    }
 }
 
 // The CTA `c` of the `C` CTAs that own reservoir `g` runs the whole chunk.  RC_THREADS = threads
@@ -124,22 +169,24 @@ __device__ __forceinline__ void recur_body(const RecurArgs& p, const unsigned c,
     signed char* digits = p.planes ? p.planes + (long long)g * p.plane_group_stride : nullptr;
     for (int i = tid; i < N; i += RC_THREADS) s_r[i] = carry[i];
 
-    int unit[UPT], row_lo[UPT], row_len[UPT];
+    // each thread owns UPT ADJACENT units (u0 and units_per_cta are multiples of 8), so its FP64
+    // states and its int8 digits go out as vector stores
+    const int ubase = u0 + tid * UPT;
+    int row_lo[UPT], row_len[UPT];
     double r_cur[UPT], d_next[UPT];
+    int nvalid = 0;
 #pragma unroll
     for (int j = 0; j < UPT; ++j) {
-        unit[j] = u0 + tid + j * RC_THREADS;
-        const bool ok = unit[j] < u1;
-        row_lo[j] = ok ? p.indptr[unit[j]] : 0;
-        row_len[j] = ok ? p.indptr[unit[j] + 1] - row_lo[j] : 0;
-        r_cur[j] = ok ? carry[unit[j]] : 0.0;
-        d_next[j] = (ok && p.steps > 0) ? drive[unit[j]] : 0.0;
-        if (ok) {
-            st_flag(states + unit[j], r_cur[j]);  // row 0 = state entering the chunk (read by the Gram kernel)
-            if (digits && p.steps > 0) put_digits(digits, p, 0, unit[j], r_cur[j]);
-        }
-        else unit[j] = -1;
+        const int unit = ubase + j;
+        const bool ok = unit < u1;
+        nvalid += ok ? 1 : 0;
+        row_lo[j] = ok ? p.indptr[unit] : 0;
+        row_len[j] = ok ? p.indptr[unit + 1] - row_lo[j] : 0;
+        r_cur[j] = ok ? carry[unit] : 0.0;
+        d_next[j] = (ok && p.steps > 0) ? drive[unit] : 0.0;
     }
+    put_states<UPT>(states + ubase, r_cur, nvalid);  // row 0 = state entering the chunk (read by the Gram kernel)
+    if (digits && p.steps > 0) put_digits<UPT>(digits, p, 0, ubase, r_cur, nvalid);
     const double alpha = p.alpha, oma = 1.0 - p.alpha;
     const bool vec2 = (N % 2 == 0) && ((reinterpret_cast<uintptr_t>(states) & 15) == 0);
     bool aborted = false;
@@ -148,30 +195,31 @@ __device__ __forceinline__ void recur_body(const RecurArgs& p, const unsigned c,
     for (int t = 0; t < p.steps; ++t) {
         double* r_next = states + (long long)(t + 1) * N;
         // ---- my units: W r_t from the shared copy, tanh, leak; publish to the ring ----
+        // (branch-free over the UPT units so their dependent chains interleave)
+        double pre[UPT];
 #pragma unroll
         for (int j = 0; j < UPT; ++j) {
-            if (unit[j] >= 0) {
-                const int* ix = idx_base + row_lo[j];
-                const double* vl = val_base + row_lo[j];
-                double acc = 0.0;
+            const int* ix = idx_base + row_lo[j];
+            const double* vl = val_base + row_lo[j];
+            double acc = 0.0;
 #pragma unroll 4
-                for (int k = 0; k < row_len[j]; ++k) acc = __dadd_rn(acc, __dmul_rn(vl[k], s_r[ix[k]]));
-                const double pre = __dadd_rn(acc, d_next[j]);
-                r_cur[j] = leaky(pre, r_cur[j], alpha, oma);
-                st_flag(r_next + unit[j], r_cur[j]);
-                // fixed-point digit planes for the int8 tensor-core Gram: row t+1 pairs with y(t0+t+1);
-                // the state leaving the chunk (row `steps`) belongs to the next chunk's row 0
-                if (digits && t + 1 < p.steps) put_digits(digits, p, t + 1, unit[j], r_cur[j]);
-            }
+            for (int k = 0; k < row_len[j]; ++k) acc = __dadd_rn(acc, __dmul_rn(vl[k], s_r[ix[k]]));
+            pre[j] = __dadd_rn(acc, d_next[j]);
         }
+#pragma unroll
+        for (int j = 0; j < UPT; ++j) r_cur[j] = leaky(pre[j], r_cur[j], alpha, oma);
+        put_states<UPT>(r_next + ubase, r_cur, nvalid);
+        // fixed-point digit planes for the int8 tensor-core Gram: row t+1 pairs with y(t0+t+1);
+        // the state leaving the chunk (row `steps`) belongs to the next chunk's row 0
+        if (digits && t + 1 < p.steps) put_digits<UPT>(digits, p, t + 1, ubase, r_cur, nvalid);
         if (t + 1 == p.steps) break;
 #pragma unroll
         for (int j = 0; j < UPT; ++j)
-            if (unit[j] >= 0) d_next[j] = __ldg(drive + (long long)(t + 1) * N + unit[j]);
+            if (j < nvalid) d_next[j] = __ldg(drive + (long long)(t + 1) * N + ubase + j);
         __syncthreads();  // every gather of r_t is done: the shared copy may be overwritten
 #pragma unroll
         for (int j = 0; j < UPT; ++j)
-            if (unit[j] >= 0) s_r[unit[j]] = r_cur[j];
+            if (j < nvalid) s_r[ubase + j] = r_cur[j];
         // ---- refresh the other CTAs' slices of r_{t+1} with coalesced polling loads ----
         if (C > 1) {
             if (vec2) {
@@ -217,7 +265,7 @@ __device__ __forceinline__ void recur_body(const RecurArgs& p, const unsigned c,
     }
 #pragma unroll
     for (int j = 0; j < UPT; ++j)
-        if (unit[j] >= 0) p.carry[(long long)g * N + unit[j]] = r_cur[j];
+        if (j < nvalid) p.carry[(long long)g * N + ubase + j] = r_cur[j];
 }
 
 }  // namespace recur

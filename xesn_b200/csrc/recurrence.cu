@@ -229,7 +229,7 @@ int launch_recur_forced(RecurArgs a, int n_groups, int max_slice_nnz, cudaStream
         set_error("recur_forced: n_reservoir=%d exceeds the persistent kernel capacity (%d)", a.N, 16 * RC_THREADS * 4);
         return -2;
     }
-    a.units_per_cta = (a.N + C - 1) / C;
+    a.units_per_cta = recur_units_per_cta(a.N, C);
     a.smem_nnz = max_slice_nnz + (max_slice_nnz & 1);
     a.n_pad = (a.N + 1) & ~1;
     // shared memory: full state copy (always) + this CTA's CSR slice of W (if it fits)
