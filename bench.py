@@ -376,19 +376,49 @@ def main():
             traffic = json.load(open(tpath)).get(args.workload, {}).get("dominant_kernel_dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {
-        "bound": "tensor",
-        "kernel": ("fused_chunk_kernel (Gram SYRK role, DMMA.8x8x4, beside the recurrence role)" if fused
-                   else "gemm_f64_kernel<MN,MN> lower (Gram SYRK, DMMA.8x8x4)"),
-        "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
-        "traffic": traffic,
-        "peak_source": "cuBLAS DGEMM 8192^3 burst measured in this run (MEASURED_PEAKS.json has no FP64 entry); "
-                       "hardware DMMA peak 128 flop/clk/SM = 37.2 TFLOP/s at 1965 MHz",
-        "launches": n_gram_launches, "avg_launch_ms": ms_gram / n_gram_launches,
-        "flops_per_launch": gram_flops / n_gram_launches,
-        "note": "achieved = algorithmic Gram flops N(N+1) per step / summed event time of the kernel launches that "
-                "carry them (the fused kernel also hosts the recurrence on its other SMs)",
-    }
+    i8 = fused and os.environ.get("XESN_B200_GRAM", "i8").lower() not in ("f64", "fp64", "dmma", "0")
+    if i8:
+        # the Gram role runs on the int8 tensor cores: 36 digit-pair MMAs replace each FP64 FMA
+        int_ops = 36.0 * gram_flops            # 36 pairs x (2 ops per MAC) x N(N+1)/2 MACs per step
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        bf16 = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops") or 1590.0
+        int8_peak = 2.0 * bf16
+        ach = int_ops / (ms_gram * 1e-3) / 1e12
+        roofline = {
+            "bound": "tensor",
+            "kernel": "fused_chunk_i8_kernel (Gram role: tcgen05.mma kind::i8 on fixed-point digit planes, beside "
+                      "the recurrence role)",
+            "achieved": ach, "peak": int8_peak, "unit": "TOP/s", "frac": ach / int8_peak,
+            "traffic": traffic,
+            "peak_source": ("2 x the measured sustained bf16 tensor peak of MEASURED_PEAKS.json (int8 runs at twice "
+                            "the bf16 rate on B200; no int8 entry is measured)" if peaks else
+                            "2 x the fallback bf16 peak of B200_PROFILING.md (MEASURED_PEAKS.json absent)"),
+            "launches": n_gram_launches, "avg_launch_ms": ms_gram / n_gram_launches,
+            "ops_per_launch": int_ops / n_gram_launches,
+            "fp64_equivalent_tflops": achieved, "fp64_dgemm_peak_tflops": peak_tf,
+            "fp64_equivalent_frac_of_dgemm_peak": achieved / peak_tf if peak_tf else None,
+            "note": "achieved = 36 x N(N+1) x T int8 ops (the digit-pair MMAs of one triangle) / summed event time of "
+                    "the fused launches; the same kernel hosts the recurrence on its other SMs and is currently "
+                    "bounded by whichever role finishes last",
+        }
+    else:
+        roofline = {
+            "bound": "tensor",
+            "kernel": ("fused_chunk_kernel (Gram SYRK role, DMMA.8x8x4, beside the recurrence role)" if fused
+                       else "gemm_f64_kernel<MN,MN> lower (Gram SYRK, DMMA.8x8x4)"),
+            "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
+            "traffic": traffic,
+            "peak_source": "cuBLAS DGEMM 8192^3 burst measured in this run (MEASURED_PEAKS.json has no FP64 entry); "
+                           "hardware DMMA peak 128 flop/clk/SM = 37.2 TFLOP/s at 1965 MHz",
+            "launches": n_gram_launches, "avg_launch_ms": ms_gram / n_gram_launches,
+            "flops_per_launch": gram_flops / n_gram_launches,
+            "note": "achieved = algorithmic Gram flops N(N+1) per step / summed event time of the kernel launches "
+                    "that carry them (the fused kernel also hosts the recurrence on its other SMs)",
+        }
     phases = {k: {"regions": v[0], "ms_per_step": v[1] / args.steps} for k, v in prof.items() if v[0]}
 
     cpu = None
@@ -410,6 +440,8 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
+        "gram_engine": ("int8 fixed-point digit planes on tcgen05 (error-free), FP64 everywhere else" if i8
+                        else "FP64 DMMA"),
         "config": workload_config(args.workload, w, world),
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h)},

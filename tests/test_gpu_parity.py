@@ -332,3 +332,42 @@ def test_ridge_normal_equations_full_size(torch):
     Wout = torch.from_numpy(esn.Wout).cuda()
     resid = (Wout @ A - rhs).abs().max() / rhs.abs().max()
     assert float(resid) < 1e-9, float(resid)
+
+
+# --------------------------------------------------------------------------- int8 tensor-core Gram, pipeline modes
+@pytest.mark.parametrize("K,N", [(32, 128), (70, 200), (512, 1000), (1030, 2501)])
+def test_gram_i8_is_error_free(torch, lib, K, N):
+    """The tcgen05 kind::i8 Gram of the fixed-point digit planes: bit-exact on inputs that live on a
+    2^-20 grid (every product and sum is an exact integer), FP64-rounding-level on random states,
+    upper triangle untouched."""
+    from xesn_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(K * 31 + N)
+    S = torch.rand((K, N), dtype=torch.float64, device="cuda", generator=g) * 2 - 1
+    S[0, 0], S[1, 1], S[2, 2] = 1.0, -1.0, 0.0   # range end points
+    low = torch.tril(torch.ones((N, N), device="cuda")).bool()
+    G = torch.zeros((N, N), dtype=torch.float64, device="cuda")
+    _lib.check(lib.xesn_gram_i8(S.data_ptr(), N, K, N, G.data_ptr(), N, None))
+    ref = S.T @ S
+    assert float((G - ref)[low].abs().max()) < 1e-14 * K
+    assert float(G[~low].abs().max()) == 0.0
+    Sq = torch.round(S * 2**20) / 2**20
+    qi = torch.round(Sq * 2**20).to(torch.int64).cpu()
+    exact = (qi.T @ qi).to(torch.float64) / 2.0**40
+    G.zero_()
+    _lib.check(lib.xesn_gram_i8(Sq.data_ptr(), N, K, N, G.data_ptr(), N, None))
+    _lib.check(lib.xesn_gram_i8(Sq.data_ptr(), N, K, N, G.data_ptr(), N, None))  # accumulates
+    assert torch.equal(G.cpu()[low.cpu()], (2.0 * exact)[low.cpu()])
+
+
+@pytest.mark.parametrize("mode", ["i8-fused", "f64-fused", "f64-unfused"])
+def test_pipeline_modes_agree(torch, monkeypatch, mode):
+    """The three training pipelines (int8 tensor-core Gram in the fused kernel, FP64 DMMA Gram in the
+    fused kernel, separate launches) give the same readout as the oracle."""
+    from xesn_b200.synthetic import lorenz96
+    monkeypatch.setenv("XESN_B200_GRAM", "i8" if mode.startswith("i8") else "f64")
+    monkeypatch.setenv("XESN_B200_FUSED", "0" if mode.endswith("unfused") else "1")
+    data = lorenz96(10, 1500)
+    esn = make_esn(10, 10, 700, beta=1e-5)
+    esn.train(data, n_spinup=40, batch_size=333)     # 5 chunks, odd sizes -> K padding of the digit planes
+    ref = oc.ridge_train(data, data, 40, 333, sp.csr_matrix(esn.W), esn.Win, esn.bias_vector, 0.5, 1e-5)
+    assert oc.max_normalised_err(esn.Wout, ref) < WOUT_TOL

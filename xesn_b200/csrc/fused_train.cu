@@ -14,6 +14,8 @@
 // Tile order of the Gram role: a host-built list that walks the lower triangle in super-rows of
 // 12 tile rows, column by column, so the ~132 tiles in flight at any time touch about 12 + 11
 // operand panels (L2-resident) instead of ~130 distinct ones.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "gemm_tile.cuh"
 #include "gram_i8.cuh"
@@ -68,12 +70,19 @@ fused_chunk_i8_kernel(RecurArgs rp, int rec_ctas, int team, gi8::GramI8Args gp, 
 
 // team size / units per thread of the recurrence role for FUSED_THREADS-wide CTAs
 int fused_recur_geometry(int N, int n_groups, int* team_out, int* upt_out) {
-    // few, fat CTAs: the role must leave most SMs to the Gram; cap the recurrence at 32 CTAs
+    // The recurrence role wants many thin CTAs (its per-step cost grows with the units per CTA),
+    // the Gram role wants the SMs.  Default: at most 512 units per thread block... per CTA 256 threads x
+    // UPT units, the smallest UPT whose total CTA count stays within the cap (32 CTAs for one big
+    // reservoir, 64 when many small reservoirs run side by side).  XESN_B200_REC_UPT / _REC_CAP override.
+    int cap = n_groups > 1 ? 64 : 32;
+    int force_upt = 0;
+    if (const char* e = getenv("XESN_B200_REC_CAP")) cap = atoi(e);
+    if (const char* e = getenv("XESN_B200_REC_UPT")) force_upt = atoi(e);
     int best_team = -1, best_upt = 0;
     for (int upt = 1; upt <= 8; upt <<= 1) {
+        if (force_upt && upt != force_upt) continue;
         int team = (N + FUSED_THREADS * upt - 1) / (FUSED_THREADS * upt);
-        if (team > 16) continue;
-        if ((long long)team * n_groups > 32) continue;
+        if ((long long)team * n_groups > cap) continue;
         best_team = team, best_upt = upt;
         break;
     }
