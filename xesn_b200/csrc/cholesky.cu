@@ -35,7 +35,7 @@ potrf_diag_kernel(double* A, long long lda, long long strideA, int j0, int nbj, 
     double* S = sm;                      // [NB][LDS] the factor, for the inversion phase
     double* colbuf = sm + NB * LDS;      // [NB]
     double* rowbuf = colbuf + NB;        // [2][NB]
-    __shared__ double s_piv;
+    __shared__ double s_piv[2];  // sqrt(pivot) and its reciprocal, computed once by the owner thread
     const int tid = threadIdx.x;
     const int ty = tid >> 4, tx = tid & 15;
     const int b = blockIdx.x;
@@ -62,10 +62,12 @@ potrf_diag_kernel(double* A, long long lda, long long strideA, int j0, int nbj, 
             if (ty == kx && tx == kx) {
                 const double piv = a[ka][ka];
                 if (!(piv > 0.0) || !(piv < 1.7e308)) atomicCAS(&info[b], 0, j0 + k + 1);  // not positive definite
-                s_piv = sqrt(piv);
+                const double dd = sqrt(piv);
+                s_piv[0] = dd;
+                s_piv[1] = 1.0 / dd;
             }
             __syncthreads();
-            const double d = s_piv, rinv = 1.0 / d;
+            const double d = s_piv[0], rinv = s_piv[1];
             if (tx == kx) {
 #pragma unroll
                 for (int x = 0; x < 8; ++x) {
@@ -190,16 +192,33 @@ int launch_cholesky_solve_ws(double* A, long long lda, long long strideA, double
 
     // ---- factorisation: outer panels of OUTER columns, 128-wide sub-blocks inside a panel ----
     // Inside a panel the updates have K = 128; the trailing matrix is updated once per panel with
-    // K = OUTER, which keeps the DMMA GEMM in its efficient regime and halves/quarters the
-    // read-modify-write traffic of the trailing matrix.
+    // K = OUTER, which keeps the DMMA GEMM in its efficient regime and quarters the read-modify-write
+    // traffic of the trailing matrix.  LOOK-AHEAD: the update of panel J is split into the narrow
+    // part that touches the next panel's columns (N) and the rest (T); the latency-bound chain of small
+    // kernels that factors panel J+1 runs on a second, high-priority stream while T(J) still occupies
+    // the GPU on the caller's stream.
     const int OUTER = n >= 4096 ? 512 : (n >= 1024 ? 256 : NB);
-    for (int J = 0; J < n; J += OUTER) {
-        const int Jend = min(J + OUTER, n);
+    static cudaStream_t side = nullptr;
+    static cudaEvent_t ev_panel[2] = {nullptr, nullptr}, ev_trail[2] = {nullptr, nullptr}, ev_fork = nullptr;
+    if (!side) {
+        int lo = 0, hi = 0;
+        XESN_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        XESN_CUDA_OK(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, hi));
+        for (int k = 0; k < 2; ++k) {
+            XESN_CUDA_OK(cudaEventCreateWithFlags(&ev_panel[k], cudaEventDisableTiming));
+            XESN_CUDA_OK(cudaEventCreateWithFlags(&ev_trail[k], cudaEventDisableTiming));
+        }
+        XESN_CUDA_OK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    }
+    XESN_CUDA_OK(cudaEventRecord(ev_fork, stream));
+    XESN_CUDA_OK(cudaStreamWaitEvent(side, ev_fork, 0));
+
+    auto factor_panel = [&](int J, int Jend, cudaStream_t s) -> int {
         for (int j0 = J; j0 < Jend; j0 += NB) {
             const int jb = j0 / NB;
             const int nbj = min(NB, n - j0);
             double* Linv_j = work + (long long)jb * NB * NB;
-            potrf_diag_kernel<<<batch, PD_THREADS, PD_SMEM, stream>>>(A, lda, strideA, j0, nbj, Linv_j, strideLinv, info);
+            potrf_diag_kernel<<<batch, PD_THREADS, PD_SMEM, s>>>(A, lda, strideA, j0, nbj, Linv_j, strideLinv, info);
             XESN_CUDA_OK(cudaGetLastError());
             count_launch();
             const int rest = n - j0 - nbj;
@@ -214,7 +233,7 @@ int launch_cholesky_solve_ws(double* A, long long lda, long long strideA, double
             g.M = rest, g.N = nbj, g.K = nbj;
             g.batch = batch, g.alpha = 1.0, g.beta = 0.0;
             g.flags = GEMM_A_KMAJOR | GEMM_B_KMAJOR;
-            int rc = launch_gemm_f64(g, stream);
+            int rc = launch_gemm_f64(g, s);
             if (rc) return rc;
             // remaining columns of this panel: A[j1:, j1:Jend] -= L[j1:, j0:j1] L[j1:Jend, j0:j1]^T
             const int j1 = j0 + nbj;
@@ -227,24 +246,53 @@ int launch_cholesky_solve_ws(double* A, long long lda, long long strideA, double
                 u.M = n - j1, u.N = pw, u.K = nbj;
                 u.batch = batch, u.alpha = -1.0, u.beta = 1.0;
                 u.flags = GEMM_A_KMAJOR | GEMM_B_KMAJOR;
-                rc = launch_gemm_f64(u, stream);
+                rc = launch_gemm_f64(u, s);
                 if (rc) return rc;
             }
         }
-        // trailing: A_22 -= L_21 L_21^T (lower tiles only), K = width of the panel
-        const int rest = n - Jend;
-        if (rest > 0) {
+        return 0;
+    };
+
+    int rc = factor_panel(0, min(OUTER, n), side);
+    if (rc) return rc;
+    int it = 0;
+    for (int J = 0; J < n; J += OUTER, ++it) {
+        const int Jend = min(J + OUTER, n);
+        const int Jend2 = min(Jend + OUTER, n);
+        XESN_CUDA_OK(cudaEventRecord(ev_panel[it & 1], side));            // panel J is final
+        if (Jend >= n) break;
+        // N(J) touches the same elements as T(J-1) (both update the columns of panel J+1): order them
+        if (it >= 1) XESN_CUDA_OK(cudaStreamWaitEvent(side, ev_trail[(it - 1) & 1], 0));
+        // N(J) on the side stream: columns of the next panel, A[Jend:, Jend:Jend2] -= L[Jend:, J:Jend] L[Jend:Jend2, J:Jend]^T
+        {
+            GemmArgs u = {};
+            u.A = A + (long long)Jend * lda + J, u.lda = lda, u.strideA = strideA;
+            u.B = A + (long long)Jend * lda + J, u.ldb = lda, u.strideB = strideA;
+            u.C = A + (long long)Jend * lda + Jend, u.ldc = lda, u.strideC = strideA;
+            u.M = n - Jend, u.N = Jend2 - Jend, u.K = Jend - J;
+            u.batch = batch, u.alpha = -1.0, u.beta = 1.0;
+            u.flags = GEMM_A_KMAJOR | GEMM_B_KMAJOR;
+            if ((rc = launch_gemm_f64(u, side))) return rc;
+        }
+        // T(J) on the caller's stream: everything right of the next panel (lower tiles)
+        XESN_CUDA_OK(cudaStreamWaitEvent(stream, ev_panel[it & 1], 0));
+        if (n - Jend2 > 0) {
             GemmArgs t = {};
-            t.A = A + (long long)Jend * lda + J, t.lda = lda, t.strideA = strideA;
+            t.A = A + (long long)Jend2 * lda + J, t.lda = lda, t.strideA = strideA;
             t.B = t.A, t.ldb = lda, t.strideB = strideA;
-            t.C = A + (long long)Jend * lda + Jend, t.ldc = lda, t.strideC = strideA;
-            t.M = rest, t.N = rest, t.K = Jend - J;
+            t.C = A + (long long)Jend2 * lda + Jend2, t.ldc = lda, t.strideC = strideA;
+            t.M = n - Jend2, t.N = n - Jend2, t.K = Jend - J;
             t.batch = batch, t.alpha = -1.0, t.beta = 1.0;
             t.flags = GEMM_A_KMAJOR | GEMM_B_KMAJOR | GEMM_LOWER;
-            int rc = launch_gemm_f64(t, stream);
-            if (rc) return rc;
+            if ((rc = launch_gemm_f64(t, stream))) return rc;
         }
+        XESN_CUDA_OK(cudaEventRecord(ev_trail[it & 1], stream));
+        // panel J+1 needs N(J) and T(J-1), both ordered before this point on the side stream;
+        // it runs while T(J) occupies the caller's stream
+        if ((rc = factor_panel(Jend, Jend2, side))) return rc;
     }
+    // join: the sweeps below run on the caller's stream
+    XESN_CUDA_OK(cudaStreamWaitEvent(stream, ev_panel[it & 1], 0));
 
     // ---- forward sweep:  Z L^T = B   (B is nrhs x n, row-major: every row is one right-hand side) ----
     for (int jb = 0; jb < nblk; ++jb) {
