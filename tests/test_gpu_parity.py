@@ -371,3 +371,19 @@ def test_pipeline_modes_agree(torch, monkeypatch, mode):
     esn.train(data, n_spinup=40, batch_size=333)     # 5 chunks, odd sizes -> K padding of the digit planes
     ref = oc.ridge_train(data, data, 40, 333, sp.csr_matrix(esn.W), esn.Win, esn.bias_vector, 0.5, 1e-5)
     assert oc.max_normalised_err(esn.Wout, ref) < WOUT_TOL
+
+
+def test_dense_adjacency_falls_back_to_global_w(torch, lib):
+    """A dense W (is_sparse=False) does not fit the shared-memory CSR slice: the recurrence reads it
+    from global memory instead (template WS=false), both stand-alone and inside the fused kernel."""
+    from xesn_b200.synthetic import lorenz96
+    over = dict(adjacency_kwargs=dict(factor=0.8, distribution="normal", normalization="eig", is_sparse=False,
+                                      random_seed=4))
+    esn = make_esn(6, 6, 600, beta=1e-4, **over)
+    data = lorenz96(6, 420)
+    states, _ = forced_states_gpu(torch, lib, esn, data, 100)
+    ref = oc.forced_states(data, 100, esn.W, esn.Win, esn.bias_vector, 0.5)
+    np.testing.assert_allclose(states, ref, rtol=0, atol=1e-10)
+    esn.train(data, n_spinup=7, batch_size=200)
+    refw = oc.ridge_train(data, data, 7, 200, esn.W, esn.Win, esn.bias_vector, 0.5, 1e-4)
+    assert oc.max_normalised_err(esn.Wout, refw) < WOUT_TOL

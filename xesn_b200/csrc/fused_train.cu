@@ -27,12 +27,12 @@ namespace {
 
 constexpr int FUSED_THREADS = 256;
 
-template <int UPT>
+template <int UPT, bool WS>
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
 fused_chunk_kernel(RecurArgs rp, int rec_ctas, int team, GemmArgs gp, const int2* __restrict__ tiles, int ntiles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     if ((int)blockIdx.x < rec_ctas) {
-        recur::recur_body<UPT, FUSED_THREADS>(rp, blockIdx.x % team, team, blockIdx.x / team, smem_raw);
+        recur::recur_body<UPT, FUSED_THREADS, WS>(rp, blockIdx.x % team, team, blockIdx.x / team, smem_raw);
         return;
     }
     const int worker = blockIdx.x - rec_ctas, nworkers = gridDim.x - rec_ctas;
@@ -45,13 +45,13 @@ fused_chunk_kernel(RecurArgs rp, int rec_ctas, int team, GemmArgs gp, const int2
 
 // Gram role on the int8 tensor cores: tcgen05.mma kind::i8 on the digit planes written by the
 // recurrence role of the PREVIOUS launch (gram_i8.cuh).
-template <int UPT>
+template <int UPT, bool WS>
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
 fused_chunk_i8_kernel(RecurArgs rp, int rec_ctas, int team, gi8::GramI8Args gp, const int2* __restrict__ tiles,
                       int ntiles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     if ((int)blockIdx.x < rec_ctas) {
-        recur::recur_body<UPT, FUSED_THREADS>(rp, blockIdx.x % team, team, blockIdx.x / team, smem_raw);
+        recur::recur_body<UPT, FUSED_THREADS, WS>(rp, blockIdx.x % team, team, blockIdx.x / team, smem_raw);
         return;
     }
     const int worker = blockIdx.x - rec_ctas, nworkers = gridDim.x - rec_ctas;
@@ -132,9 +132,15 @@ int launch_fused_chunk(RecurArgs rp, int n_groups, int team, int upt, int max_sl
         set_error("fused chunk: recurrence role needs %d CTAs, device has %d SMs", rec_ctas, num_sms);
         return -2;
     }
-    void (*kern)(RecurArgs, int, int, GemmArgs, const int2*, int) =
-        upt == 1 ? fused_chunk_kernel<1>
-                 : (upt == 2 ? fused_chunk_kernel<2> : (upt == 4 ? fused_chunk_kernel<4> : fused_chunk_kernel<8>));
+    void (*kern)(RecurArgs, int, int, GemmArgs, const int2*, int);
+    if (w_in_smem)
+        kern = upt == 1 ? fused_chunk_kernel<1, true>
+                        : (upt == 2 ? fused_chunk_kernel<2, true>
+                                    : (upt == 4 ? fused_chunk_kernel<4, true> : fused_chunk_kernel<8, true>));
+    else
+        kern = upt == 1 ? fused_chunk_kernel<1, false>
+                        : (upt == 2 ? fused_chunk_kernel<2, false>
+                                    : (upt == 4 ? fused_chunk_kernel<4, false> : fused_chunk_kernel<8, false>));
     XESN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     GemmArgs g = gp;
     void* args[] = {&rp, &rec_ctas, &team, &g, (void*)&tiles, &ntiles};
@@ -172,9 +178,15 @@ int launch_fused_chunk_i8(RecurArgs rp, int n_groups, int team, int upt, int max
         set_error("fused chunk: recurrence role needs %d CTAs, device has %d SMs", rec_ctas, num_sms);
         return -2;
     }
-    void (*kern)(RecurArgs, int, int, gi8::GramI8Args, const int2*, int) =
-        upt == 1 ? fused_chunk_i8_kernel<1>
-                 : (upt == 2 ? fused_chunk_i8_kernel<2> : (upt == 4 ? fused_chunk_i8_kernel<4> : fused_chunk_i8_kernel<8>));
+    void (*kern)(RecurArgs, int, int, gi8::GramI8Args, const int2*, int);
+    if (w_in_smem)
+        kern = upt == 1 ? fused_chunk_i8_kernel<1, true>
+                        : (upt == 2 ? fused_chunk_i8_kernel<2, true>
+                                    : (upt == 4 ? fused_chunk_i8_kernel<4, true> : fused_chunk_i8_kernel<8, true>));
+    else
+        kern = upt == 1 ? fused_chunk_i8_kernel<1, false>
+                        : (upt == 2 ? fused_chunk_i8_kernel<2, false>
+                                    : (upt == 4 ? fused_chunk_i8_kernel<4, false> : fused_chunk_i8_kernel<8, false>));
     XESN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     gi8::GramI8Args g = gp;
     void* args[] = {&rp, &rec_ctas, &team, &g, (void*)&tiles, &ntiles};

@@ -291,16 +291,30 @@ __device__ __forceinline__ void gram_i8_tile(GramI8Ctx& ctx, const GramI8Args& p
 }
 
 // ---- fixed-point image of a state: 8 balanced base-128 digits ----
-__device__ __forceinline__ void state_digits(double r, signed char (&d)[NDIG]) {
+// q = rint(r * 2^55);  q + BIAS has seven non-negative base-128 digits (d_a + 64) and a signed top
+// digit, so every digit is a shift and a mask.  Returned packed: w03 = bytes (d0,d1,d2,d3) with d0
+// (most significant digit) in the lowest byte, w47 = (d4,d5,d6,d7).
+__device__ __forceinline__ void state_digit_words(double r, unsigned& w03, unsigned& w47) {
     // |r| <= 1; non-finite states (diverged runs) are mapped to 0 here, the FP64 ring keeps them
-    long long q = (r == r && fabs(r) <= 1.0) ? __double2ll_rn(r * 36028797018963968.0 /* 2^55 */) : 0;
+    long long q = (fabs(r) <= 1.0) ? __double2ll_rn(r * 36028797018963968.0 /* 2^55 */) : 0;
+    constexpr long long BIAS = 64LL * (1LL + (1LL << 7) + (1LL << 14) + (1LL << 21) + (1LL << 28) + (1LL << 35) + (1LL << 42));
+    q += BIAS;
+    const unsigned lo = (unsigned)q, hi = (unsigned)((unsigned long long)q >> 32);
+    const unsigned e7 = lo & 127u, e6 = (lo >> 7) & 127u, e5 = (lo >> 14) & 127u, e4 = (lo >> 21) & 127u;
+    const unsigned e3 = __funnelshift_r(lo, hi, 28) & 127u, e2 = (hi >> 3) & 127u, e1 = (hi >> 10) & 127u;
+    const unsigned e0 = (unsigned)(((int)hi) >> 17) + 64u;  // signed top digit, biased like the others
+    w03 = __vsub4(e0 | (e1 << 8) | (e2 << 16) | (e3 << 24), 0x40404040u);
+    w47 = __vsub4(e4 | (e5 << 8) | (e6 << 16) | (e7 << 24), 0x40404040u);
+}
+
+__device__ __forceinline__ void state_digits(double r, signed char (&d)[NDIG]) {
+    unsigned w03, w47;
+    state_digit_words(r, w03, w47);
 #pragma unroll
-    for (int a = NDIG - 1; a > 0; --a) {
-        long long lo = ((q + 64) & 127) - 64;  // balanced remainder in [-64, 63]
-        d[a] = (signed char)lo;
-        q = (q - lo) >> 7;
+    for (int a = 0; a < 4; ++a) {
+        d[a] = (signed char)((w03 >> (8 * a)) & 255u);
+        d[a + 4] = (signed char)((w47 >> (8 * a)) & 255u);
     }
-    d[0] = (signed char)q;  // |q| <= 64
 }
 
 }  // namespace gi8

@@ -70,11 +70,17 @@ __device__ __forceinline__ double ld_flag(const double* p) {
     asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];\n" : "=d"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ double publishable(double v) {
+    return (v != v) ? __longlong_as_double(0x7FF8000000000000LL) : v;
+}
 __device__ __forceinline__ void st_flag(double* p, double v) {
-    if (__double_as_longlong(v) == UNSET_BITS) v = __longlong_as_double(0x7FF8000000000000LL);
+    v = publishable(v);
     asm volatile("st.relaxed.gpu.global.f64 [%0], %1;\n" ::"l"(p), "d"(v) : "memory");
 }
-__device__ __forceinline__ bool unset(double v) { return __double_as_longlong(v) == UNSET_BITS; }
+// Every published state is finite or the canonical quiet NaN (0x7FF8...), so the high word
+// 0xFFFFFFFF can only be the pre-filled "unset" pattern: one 32-bit compare per element.
+__device__ __forceinline__ bool unset(double v) { return __double2hiint(v) == -1; }
+
 
 // bounded spin bookkeeping: returns true once the run has been flagged as failed
 __device__ __forceinline__ bool poll_expired(int& spins, int* status) {
@@ -89,9 +95,7 @@ __device__ __forceinline__ void put_states(double* dst, const double (&r)[UPT], 
     if (UPT >= 2 && nvalid == UPT && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
         for (int j = 0; j < UPT; j += 2) {
-            double a = r[j], b = r[j + 1];
-            if (__double_as_longlong(a) == UNSET_BITS) a = __longlong_as_double(0x7FF8000000000000LL);
-            if (__double_as_longlong(b) == UNSET_BITS) b = __longlong_as_double(0x7FF8000000000000LL);
+            const double a = publishable(r[j]), b = publishable(r[j + 1]);
             asm volatile("st.relaxed.gpu.global.v2.f64 [%0], {%1, %2};\n" ::"l"(dst + j), "d"(a), "d"(b) : "memory");
         }
     } else {
@@ -105,26 +109,24 @@ __device__ __forceinline__ void put_states(double* dst, const double (&r)[UPT], 
 template <int UPT>
 __device__ __forceinline__ void put_digits(signed char* planes, const RecurArgs& p, int row, int ubase,
                                            const double (&r)[UPT], int nvalid) {
-    signed char d[UPT][gi8::NDIG];
+    unsigned w[UPT][2];  // w[j][0] = digits 0..3 of unit j (one byte each), w[j][1] = digits 4..7
 #pragma unroll
-    for (int j = 0; j < UPT; ++j) gi8::state_digits(r[j], d[j]);
+    for (int j = 0; j < UPT; ++j) gi8::state_digit_words(r[j], w[j][0], w[j][1]);
     signed char* dst = planes + (long long)row * p.ldp + ubase;
     if (nvalid == UPT && UPT >= 2) {
 #pragma unroll
         for (int a = 0; a < gi8::NDIG; ++a) {
+            const int h = a >> 2, sel = a & 3;  // byte `sel` of word `h`
             if (UPT == 2) {
-                unsigned short w = (unsigned short)((unsigned char)d[0][a] | ((unsigned)(unsigned char)d[1][a] << 8));
-                *reinterpret_cast<unsigned short*>(dst + a * p.plane_stride) = w;
-            } else if (UPT == 4) {
-                unsigned w = 0;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) w |= (unsigned)(unsigned char)d[j][a] << (8 * j);
-                *reinterpret_cast<unsigned*>(dst + a * p.plane_stride) = w;
+                const unsigned x = __byte_perm(w[0][h], w[1][h], sel | ((4 + sel) << 4));
+                *reinterpret_cast<unsigned short*>(dst + a * p.plane_stride) = (unsigned short)x;
             } else {
-                unsigned long long w = 0;
 #pragma unroll
-                for (int j = 0; j < UPT; ++j) w |= (unsigned long long)(unsigned char)d[j][a] << (8 * j);
-                *reinterpret_cast<unsigned long long*>(dst + a * p.plane_stride) = w;
+                for (int j0 = 0; j0 < UPT; j0 += 4) {
+                    const unsigned x01 = __byte_perm(w[j0][h], w[j0 + 1][h], sel | ((4 + sel) << 4));
+                    const unsigned x23 = __byte_perm(w[j0 + 2][h], w[j0 + 3][h], sel | ((4 + sel) << 4));
+                    *reinterpret_cast<unsigned*>(dst + a * p.plane_stride + j0) = __byte_perm(x01, x23, 0x5410);
+                }
             }
         }
     } else {
@@ -132,13 +134,14 @@ __device__ __forceinline__ void put_digits(signed char* planes, const RecurArgs&
         for (int j = 0; j < UPT; ++j)
             if (j < nvalid)
 #pragma unroll
-                for (int a = 0; a < gi8::NDIG; ++a) dst[a * p.plane_stride + j] = d[j][a];
+                for (int a = 0; a < gi8::NDIG; ++a)
+                    dst[a * p.plane_stride + j] = (signed char)((w[j][a >> 2] >> (8 * (a & 3))) & 255u);
     }
 }
 
 // The CTA `c` of the `C` CTAs that own reservoir `g` runs the whole chunk.  RC_THREADS = threads
 // taking part (the calling CTA's size); all C CTAs must be co-resident (cluster or cooperative launch).
-template <int UPT, int RC_THREADS>
+template <int UPT, int RC_THREADS, bool WS>
 __device__ __forceinline__ void recur_body(const RecurArgs& p, const unsigned c, const unsigned C, const int g,
                                            unsigned char* smem_raw) {
     const int tid = threadIdx.x;
@@ -151,17 +154,15 @@ __device__ __forceinline__ void recur_body(const RecurArgs& p, const unsigned c,
     double* s_r = reinterpret_cast<double*>(smem_raw);  // [n_pad] copy of r_t
     // ---- stage this CTA's CSR slice of W in shared memory (or fall back to global) ----
     const int slice_lo = p.indptr[u0], slice_hi = p.indptr[u1];
-    const int* idx_base = p.indices;
-    const double* val_base = p.values;
-    if (p.w_in_smem) {
-        double* s_val = s_r + p.n_pad;
-        int* s_idx = reinterpret_cast<int*>(s_val + p.smem_nnz);
+    // WS: the slice lives in shared memory with the column indices pre-multiplied to byte offsets
+    // into the state copy; else it is read from global memory (huge or dense W)
+    double* s_val = s_r + p.n_pad;
+    int* s_off = reinterpret_cast<int*>(s_val + p.smem_nnz);
+    if (WS) {
         for (int k = slice_lo + tid; k < slice_hi; k += RC_THREADS) {
             s_val[k - slice_lo] = p.values[k];
-            s_idx[k - slice_lo] = p.indices[k];
+            s_off[k - slice_lo] = p.indices[k] * (int)sizeof(double);
         }
-        idx_base = s_idx - slice_lo;
-        val_base = s_val - slice_lo;
     }
     double* states = p.states + (long long)g * p.state_group_stride;
     const double* drive = p.drive + (long long)g * p.drive_group_stride;
@@ -199,11 +200,20 @@ __device__ __forceinline__ void recur_body(const RecurArgs& p, const unsigned c,
         double pre[UPT];
 #pragma unroll
         for (int j = 0; j < UPT; ++j) {
-            const int* ix = idx_base + row_lo[j];
-            const double* vl = val_base + row_lo[j];
             double acc = 0.0;
+            if (WS) {
+                const int* of = s_off + (row_lo[j] - slice_lo);
+                const double* vl = s_val + (row_lo[j] - slice_lo);
 #pragma unroll 4
-            for (int k = 0; k < row_len[j]; ++k) acc = __dadd_rn(acc, __dmul_rn(vl[k], s_r[ix[k]]));
+                for (int k = 0; k < row_len[j]; ++k)
+                    acc = __dadd_rn(acc, __dmul_rn(vl[k], *reinterpret_cast<const double*>(
+                                                              reinterpret_cast<const char*>(s_r) + of[k])));
+            } else {
+                const int* ix = p.indices + row_lo[j];
+                const double* vl = p.values + row_lo[j];
+#pragma unroll 4
+                for (int k = 0; k < row_len[j]; ++k) acc = __dadd_rn(acc, __dmul_rn(__ldg(vl + k), s_r[__ldg(ix + k)]));
+            }
             pre[j] = __dadd_rn(acc, d_next[j]);
         }
 #pragma unroll

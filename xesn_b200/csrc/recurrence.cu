@@ -31,11 +31,11 @@ namespace xesn {
 namespace {
 using namespace recur;
 
-template <int UPT>
+template <int UPT, bool WS>
 __global__ void __launch_bounds__(RC_THREADS, 1) recur_forced_kernel(RecurArgs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned C = cluster_nctarank();
-    recur_body<UPT, RC_THREADS>(p, cluster_ctarank(), C, blockIdx.x / C, smem_raw);
+    recur_body<UPT, RC_THREADS, WS>(p, cluster_ctarank(), C, blockIdx.x / C, smem_raw);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -247,8 +247,11 @@ int launch_recur_forced(RecurArgs a, int n_groups, int max_slice_nnz, cudaStream
     XESN_CUDA_OK(cudaMemset2DAsync(a.states, sizeof(double) * a.state_group_stride, 0xFF,
                                    sizeof(double) * (size_t)(a.steps + 1) * a.N, n_groups, stream));
 
-    void (*kern)(RecurArgs) =
-        upt == 1 ? recur_forced_kernel<1> : (upt == 2 ? recur_forced_kernel<2> : recur_forced_kernel<4>);
+    void (*kern)(RecurArgs);
+    if (a.w_in_smem)
+        kern = upt == 1 ? recur_forced_kernel<1, true> : (upt == 2 ? recur_forced_kernel<2, true> : recur_forced_kernel<4, true>);
+    else
+        kern = upt == 1 ? recur_forced_kernel<1, false> : (upt == 2 ? recur_forced_kernel<2, false> : recur_forced_kernel<4, false>);
     XESN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
     if (C > 8) XESN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
 
