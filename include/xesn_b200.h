@@ -114,6 +114,26 @@ int xesn_predict_step(xesn_reservoir* h, const double* wout_dev, int32_t n_outpu
                       double* pred_col_dev, int64_t pred_stride, void* scratch_dev, int64_t scratch_bytes,
                       void* stream);
 
+/* ---- multi-GPU closed loop with the exchange inside the kernel (one process per GPU) ----
+ * xesn_p2p_alloc / _open / _close / _free: device buffers that peers map through CUDA IPC
+ * (handle64 = the 64-byte cudaIpcMemHandle_t, exchanged by the caller, e.g. torch.distributed).
+ * xesn_predict_p2p: like xesn_predict, but every rank runs ONE persistent kernel; the readout stores
+ * each predicted cell into the field buffer of every rank (NVLink P2P stores) and the ranks
+ * synchronise once per step on peer-mapped flags.  field_ptrs[parity*world + k]: rank k's field
+ * buffer of that parity as mapped in this process (n_cells doubles; parity 0 holds the initial
+ * condition on every rank), flag_ptrs[k]: rank k's flag array (world uint32, zero at allocation).
+ * step_base: number of forecast steps already run on these flags.  The last field is in
+ * parity n_steps&1.  Replaces the per-step dask overlap of xesn/lazyesn.py:235. */
+int xesn_p2p_alloc(int64_t bytes, void** ptr_out, uint8_t* handle64);
+int xesn_p2p_open(const uint8_t* handle64, void** ptr_out);
+int xesn_p2p_close(void* ptr);
+int xesn_p2p_free(void* ptr);
+int xesn_predict_p2p(xesn_reservoir* h, const double* wout_dev, int32_t n_output, int32_t n_groups, int64_t n_cells,
+                     const int32_t* in_map_dev, const double* fill_dev, const int32_t* out_map_dev, double* r_dev,
+                     int32_t n_steps, double* pred_dev, int32_t world, int32_t rank, uint32_t step_base,
+                     const uint64_t* field_ptrs, const uint64_t* flag_ptrs, void* scratch_dev, int64_t scratch_bytes,
+                     void* stream);
+
 /* ---- building blocks exposed for parity tests and benchmarks ---- */
 /* C = alpha * op(A) op(B) + beta * C on the FP64 tensor pipe; flags: 1 = A is [M][K] (else [K][M]),
  * 2 = B is [N][K] (else [K][N]), 4 = only lower-triangular tiles (square C). */

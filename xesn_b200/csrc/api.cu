@@ -1,5 +1,6 @@
 // extern "C" entry points of libxesn_b200.so (declared in include/xesn_b200.h).
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <atomic>
 #include <mutex>
@@ -89,6 +90,8 @@ struct xesn_reservoir {
     double* d_win = nullptr;
     double* d_bias = nullptr;
     int* d_status = nullptr;
+    unsigned* d_bar = nullptr;  // grid barrier words of the persistent forecast kernel
+    int persistent_predict = 1;
     double* d_ro_partial = nullptr;
     int* d_ro_counters = nullptr;
     long long ro_partial_cap = 0, ro_counter_cap = 0;
@@ -163,6 +166,9 @@ int xesn_reservoir_create(xesn_reservoir** out, int device, int32_t N, int32_t I
     XESN_CUDA_OK(cudaMalloc(&h->d_bias, sizeof(double) * N));
     XESN_CUDA_OK(cudaMalloc(&h->d_status, sizeof(int)));
     XESN_CUDA_OK(cudaMemset(h->d_status, 0, sizeof(int)));
+    XESN_CUDA_OK(cudaMalloc(&h->d_bar, 2 * sizeof(unsigned)));
+    XESN_CUDA_OK(cudaMemset(h->d_bar, 0, 2 * sizeof(unsigned)));
+    if (const char* e = getenv("XESN_B200_PREDICT")) h->persistent_predict = strcmp(e, "steps") != 0;
     XESN_CUDA_OK(cudaMemcpy(h->d_indptr, indptr, sizeof(int) * (N + 1), cudaMemcpyHostToDevice));
     if (nnz) {
         XESN_CUDA_OK(cudaMemcpy(h->d_indices, indices, sizeof(int) * nnz, cudaMemcpyHostToDevice));
@@ -212,6 +218,7 @@ int xesn_reservoir_destroy(xesn_reservoir* h) {
     cudaFree(h->d_win);
     cudaFree(h->d_bias);
     cudaFree(h->d_status);
+    cudaFree(h->d_bar);
     cudaFree(h->d_tiles);
     cudaFree(h->d_tiles_i8);
     cudaFree(h->d_ro_partial);
@@ -603,6 +610,32 @@ static int closed_loop_step(xesn_reservoir* h, const double* wout, int O, int G,
     return launch_readout(q, G, st);
 }
 
+// the persistent forecast kernel projects the input inline: use it while the per-step Win traffic
+// (every group reads its rows of Win) stays cache-sized; bandwidth-bound LazyESN shapes keep the
+// GEMM-based per-step path
+static bool predict_loop_eligible(xesn_reservoir* h, int G) {
+    return h->persistent_predict && (long long)G * h->N * h->I * 8 <= (64LL << 20) && (long long)h->I * 8 <= 200 * 1024;
+}
+
+static PredictLoopArgs predict_loop_args(xesn_reservoir* h, const double* wout, int O, int G, const int32_t* in_map,
+                                         const double* fill, const int32_t* out_map, double* const* fbuf,
+                                         double* const* rbuf, double* pred, long long ldp, int n_steps, int n_slices) {
+    PredictLoopArgs a = {};
+    a.indptr = h->d_indptr, a.indices = h->d_indices, a.values = h->d_values;
+    a.Win = h->d_win, a.bias = h->d_bias, a.Wout = wout;
+    a.in_map = in_map, a.fill = fill, a.out_map = out_map;
+    a.field[0] = fbuf[0], a.field[1] = fbuf[1], a.r[0] = rbuf[0], a.r[1] = rbuf[1];
+    a.pred = pred, a.ldp = ldp;
+    a.N = h->N, a.I = h->I, a.O = O, a.G = G, a.n_steps = n_steps, a.alpha = h->alpha;
+    a.n_slices = n_slices;
+    a.slice = (h->N + n_slices - 1) / n_slices;
+    a.slice += a.slice & 1;
+    a.partial = h->d_ro_partial, a.counters = h->d_ro_counters;
+    a.bar = h->d_bar, a.status = h->d_status;
+    a.world = 1, a.rank = 0, a.step_base = 0;
+    return a;
+}
+
 int64_t xesn_predict_scratch_bytes(xesn_reservoir* h, int32_t O, int32_t G, int64_t n_cells) {
     if (!h) return -1;
     long long d = round_up((long long)G * h->I, 2) + 2 * round_up((long long)G * h->N, 2) + round_up(n_cells, 2);
@@ -653,6 +686,15 @@ int xesn_predict(xesn_reservoir* h, const double* wout, int32_t O, int32_t G, in
 
     double* rbuf[2] = {r, r_alt};
     double* fbuf[2] = {field, field_alt};
+    if (predict_loop_eligible(h, G)) {
+        PredictLoopArgs a = predict_loop_args(h, wout, O, G, in_map, fill, out_map, fbuf, rbuf, pred, ldp, n_steps, S);
+        if ((rc = launch_predict_loop(a, h->num_sms, st))) return rc;
+        if (n_steps & 1) {
+            XESN_CUDA_OK(cudaMemcpyAsync(r, r_alt, sizeof(double) * (size_t)G * N, cudaMemcpyDeviceToDevice, st));
+            XESN_CUDA_OK(cudaMemcpyAsync(field, field_alt, sizeof(double) * n_cells, cudaMemcpyDeviceToDevice, st));
+        }
+        return 0;
+    }
     for (int n = 1; n <= n_steps; ++n) {
         const int cur = (n - 1) & 1, nxt = n & 1;
         if ((rc = closed_loop_step(h, wout, O, G, in_map, fill, out_map, fbuf[cur], fbuf[nxt], rbuf[cur], rbuf[nxt],
@@ -663,6 +705,70 @@ int xesn_predict(xesn_reservoir* h, const double* wout, int32_t O, int32_t G, in
         XESN_CUDA_OK(cudaMemcpyAsync(r, r_alt, sizeof(double) * (size_t)G * N, cudaMemcpyDeviceToDevice, st));
         XESN_CUDA_OK(cudaMemcpyAsync(field, field_alt, sizeof(double) * n_cells, cudaMemcpyDeviceToDevice, st));
     }
+    return 0;
+}
+
+// ---- peer-mapped buffers for the in-kernel multi-GPU exchange (CUDA IPC, one process per GPU) ----
+int xesn_p2p_alloc(int64_t bytes, void** ptr_out, uint8_t* handle64) {
+    XESN_REQUIRE(bytes > 0 && ptr_out && handle64, "bad arguments");
+    void* p = nullptr;
+    XESN_CUDA_OK(cudaMalloc(&p, (size_t)bytes));
+    XESN_CUDA_OK(cudaMemset(p, 0, (size_t)bytes));
+    cudaIpcMemHandle_t hd;
+    XESN_CUDA_OK(cudaIpcGetMemHandle(&hd, p));
+    static_assert(sizeof(hd) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64, &hd, 64);
+    *ptr_out = p;
+    return 0;
+}
+int xesn_p2p_open(const uint8_t* handle64, void** ptr_out) {
+    XESN_REQUIRE(handle64 && ptr_out, "bad arguments");
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handle64, 64);
+    XESN_CUDA_OK(cudaIpcOpenMemHandle(ptr_out, hd, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+int xesn_p2p_close(void* ptr) {
+    if (ptr) XESN_CUDA_OK(cudaIpcCloseMemHandle(ptr));
+    return 0;
+}
+int xesn_p2p_free(void* ptr) {
+    if (ptr) XESN_CUDA_OK(cudaFree(ptr));
+    return 0;
+}
+
+// Multi-GPU closed loop inside ONE persistent kernel per rank: field_ptrs[parity*world + k] is rank k's
+// field buffer of that parity as mapped in THIS process (k == rank: the local buffer), flag_ptrs[k] rank
+// k's flag array (world uint32).  Every rank must call this with the same n_steps / step_base.
+int xesn_predict_p2p(xesn_reservoir* h, const double* wout, int32_t O, int32_t G, int64_t n_cells,
+                     const int32_t* in_map, const double* fill, const int32_t* out_map, double* r, int32_t n_steps,
+                     double* pred, int32_t world, int32_t rank, uint32_t step_base, const uint64_t* field_ptrs,
+                     const uint64_t* flag_ptrs, void* scratch, int64_t scratch_bytes, void* stream) {
+    XESN_REQUIRE(h && wout && in_map && r && pred && field_ptrs && flag_ptrs && scratch, "null pointer");
+    XESN_REQUIRE(world >= 1 && world <= XESN_MAX_WORLD && rank >= 0 && rank < world, "bad world/rank");
+    XESN_REQUIRE(scratch_bytes >= xesn_predict_scratch_bytes(h, O, G, n_cells), "scratch too small");
+    XESN_REQUIRE((long long)h->I * 8 <= 200 * 1024, "n_input too large for the persistent forecast kernel");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = h->N, I = h->I;
+    double* Ug = (double*)scratch;
+    double* drive = Ug + round_up((long long)G * I, 2);
+    double* r_alt = drive + round_up((long long)G * N, 2);
+    int S, rc;
+    if ((rc = ensure_readout_scratch(h, O, G, &S))) return rc;
+    double* fbuf[2] = {reinterpret_cast<double*>(field_ptrs[0 * world + rank]),
+                       reinterpret_cast<double*>(field_ptrs[1 * world + rank])};
+    double* rbuf[2] = {r, r_alt};
+    const long long ldp = (long long)n_steps + 1;
+    ProfScope prof(PROF_PREDICT, st);
+    PredictLoopArgs a = predict_loop_args(h, wout, O, G, in_map, fill, out_map, fbuf, rbuf, pred, ldp, n_steps, S);
+    a.world = world, a.rank = rank, a.step_base = step_base;
+    for (int k = 0; k < world; ++k) {
+        a.peer_field[k] = reinterpret_cast<double*>(field_ptrs[k]);
+        a.peer_field[world + k] = reinterpret_cast<double*>(field_ptrs[world + k]);
+        a.peer_flags[k] = reinterpret_cast<unsigned*>(flag_ptrs[k]);
+    }
+    if ((rc = launch_predict_loop(a, h->num_sms, st))) return rc;
+    if (n_steps & 1) XESN_CUDA_OK(cudaMemcpyAsync(r, r_alt, sizeof(double) * (size_t)G * N, cudaMemcpyDeviceToDevice, st));
     return 0;
 }
 

@@ -80,6 +80,37 @@ int launch_gather_series(const double* src, long long ld_src, long long t0, cons
                          const unsigned char* zero_row, double* out, long long ld_out, long long rows, int nt,
                          cudaStream_t stream);
 
+// ---- persistent closed-loop forecast (predict_loop.cu) ----------------------------------------
+constexpr int XESN_MAX_WORLD = 8;
+struct PredictLoopArgs {
+    const int* indptr;
+    const int* indices;
+    const double* values;
+    const double* Win;
+    const double* bias;
+    const double* Wout;     // [G][O][N]
+    const int* in_map;      // [G][I] cell index or -1-k -> fill[k]
+    const double* fill;
+    const int* out_map;     // [G][O] cell index (nullptr: g*O+o)
+    double* field[2];       // [n_cells] ping-pong; field[0] holds the initial condition
+    double* r[2];           // [G][N] ping-pong; r[0] holds the state after spin-up
+    double* pred;           // [n_cells][ldp] trajectory, column n written at step n
+    long long ldp;
+    int N, I, O, G, n_steps;
+    double alpha;
+    int n_slices, slice;    // split of the reservoir axis in the readout
+    double* partial;        // [G][n_slices][O]
+    int* counters;          // [G][ceil(O/8)] zero-initialised, re-armed by the kernel
+    unsigned* bar;          // [2] grid barrier: arrival counter, generation
+    int* status;
+    // multi-GPU exchange through peer-mapped memory (world == 1: unused)
+    int world, rank;
+    unsigned step_base;                      // flags count steps monotonically across launches
+    double* peer_field[2 * XESN_MAX_WORLD];  // [parity][rank] -> that rank's field[parity]
+    unsigned* peer_flags[XESN_MAX_WORLD];    // [rank] -> that rank's flag array (one entry per source rank)
+};
+int launch_predict_loop(const PredictLoopArgs& a, int num_sms, cudaStream_t stream);
+
 // ---- ridge solve (cholesky.cu) ---------------------------------------------------------------
 // In-place blocked Cholesky of the lower triangle of `batch` SPD matrices A[b] (n x n, row-major,
 // leading dimension lda), then X = A^{-1} B for B[b] (n x nrhs, row-major, ldb) in place.
