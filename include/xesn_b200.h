@@ -127,6 +127,7 @@ int xesn_predict_step(xesn_reservoir* h, const double* wout_dev, int32_t n_outpu
 int xesn_p2p_alloc(int64_t bytes, void** ptr_out, uint8_t* handle64);
 int xesn_p2p_open(const uint8_t* handle64, void** ptr_out);
 int xesn_p2p_close(void* ptr);
+int xesn_memcpy_async(void* dst_dev, const void* src_dev, int64_t bytes, void* stream); /* device-to-device */
 int xesn_p2p_free(void* ptr);
 int xesn_predict_p2p(xesn_reservoir* h, const double* wout_dev, int32_t n_output, int32_t n_groups, int64_t n_cells,
                      const int32_t* in_map_dev, const double* fill_dev, const int32_t* out_map_dev, double* r_dev,

@@ -54,6 +54,7 @@ SIGNATURES = {
     "xesn_p2p_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),
     "xesn_p2p_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "xesn_p2p_close": (C.c_int, [C.c_void_p]),
+    "xesn_memcpy_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "xesn_p2p_free": (C.c_int, [C.c_void_p]),
     "xesn_predict_p2p": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_uint32,

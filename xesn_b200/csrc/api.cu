@@ -627,6 +627,12 @@ static PredictLoopArgs predict_loop_args(xesn_reservoir* h, const double* wout, 
     a.field[0] = fbuf[0], a.field[1] = fbuf[1], a.r[0] = rbuf[0], a.r[1] = rbuf[1];
     a.pred = pred, a.ldp = ldp;
     a.N = h->N, a.I = h->I, a.O = O, a.G = G, a.n_steps = n_steps, a.alpha = h->alpha;
+    // one readout item per CTA if possible: the phase then costs one pass, not several
+    {
+        const long long rows = (long long)G * ((O + 7) / 8);
+        const long long fit = rows > 0 ? h->num_sms / rows : 1;
+        if (n_slices > fit) n_slices = (int)(fit < 1 ? 1 : fit);
+    }
     a.n_slices = n_slices;
     a.slice = (h->N + n_slices - 1) / n_slices;
     a.slice += a.slice & 1;
@@ -726,6 +732,10 @@ int xesn_p2p_open(const uint8_t* handle64, void** ptr_out) {
     cudaIpcMemHandle_t hd;
     memcpy(&hd, handle64, 64);
     XESN_CUDA_OK(cudaIpcOpenMemHandle(ptr_out, hd, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+int xesn_memcpy_async(void* dst, const void* src, int64_t bytes, void* stream) {
+    XESN_CUDA_OK(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return 0;
 }
 int xesn_p2p_close(void* ptr) {

@@ -172,9 +172,8 @@ __global__ void __launch_bounds__(PL_THREADS, 1) predict_loop_kernel(PredictLoop
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
             }
-            bool finish = (p.n_slices == 1);
+            bool finish = (p.n_slices == 1) && lane == 0;
             double v = acc;
-            int oo = o;
             if (p.n_slices > 1) {
                 if (o < p.O && lane == 0) p.partial[((long long)g * p.n_slices + sl) * p.O + o] = acc;
                 __threadfence();
@@ -187,22 +186,21 @@ __global__ void __launch_bounds__(PL_THREADS, 1) predict_loop_kernel(PredictLoop
                 }
                 __syncthreads();
                 if (s_last) {
+                    // the last CTA to arrive combines the slices: warp w finishes row rb*8+w, the lanes
+                    // fetch different slices in parallel (fixed order -> deterministic)
                     __threadfence();
-                    // the first PL_WARPS threads each finish one row (deterministic slice order)
-                    oo = rb * PL_WARPS + tid;
-                    if (tid < PL_WARPS && oo < p.O) {
-                        double sum = 0.0;
-                        for (int k = 0; k < p.n_slices; ++k) sum += __ldcg(p.partial + ((long long)g * p.n_slices + k) * p.O + oo);
-                        v = sum;
-                        finish = true;
-                    }
+                    double sum = 0.0;
+                    if (o < p.O)
+                        for (int k = lane; k < p.n_slices; k += 32)
+                            sum += __ldcg(p.partial + ((long long)g * p.n_slices + k) * p.O + o);
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+                    v = sum;
+                    finish = (lane == 0);
                 }
-                if (!(s_last && tid < PL_WARPS)) finish = false;
-            } else {
-                finish = finish && (lane == 0);
             }
-            if (finish && oo < p.O) {
-                const long long cell = p.out_map ? (long long)p.out_map[(long long)g * p.O + oo] : (long long)g * p.O + oo;
+            if (finish && o < p.O) {
+                const long long cell = p.out_map ? (long long)p.out_map[(long long)g * p.O + o] : (long long)g * p.O + o;
                 field_nxt[cell] = v;
                 p.pred[cell * p.ldp + n] = v;
                 for (int k = 0; k < p.world; ++k)

@@ -154,12 +154,15 @@ __global__ void __launch_bounds__(RO_THREADS) readout_kernel(ReadoutArgs p) {
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    if (threadIdx.x < RO_WARPS) {
-        const int oo = rb * RO_WARPS + threadIdx.x;
-        if (oo < p.O) {
-            double sum = 0.0;
-            for (int k = 0; k < p.n_slices; ++k) sum += __ldcg(p.partial + ((long long)g * p.n_slices + k) * p.O + oo);
-            long long dst = p.out_map ? (long long)p.out_map[(long long)g * p.O + oo] : (long long)g * p.O + oo;
+    {
+        // warp w finishes row rb*8+w; lanes fetch different slices in parallel (fixed order)
+        double sum = 0.0;
+        if (o < p.O)
+            for (int k = lane; k < p.n_slices; k += 32) sum += __ldcg(p.partial + ((long long)g * p.n_slices + k) * p.O + o);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        if (o < p.O && lane == 0) {
+            long long dst = p.out_map ? (long long)p.out_map[(long long)g * p.O + o] : (long long)g * p.O + o;
             p.v[dst * p.v_stride] = sum;
             if (p.v_copy) p.v_copy[dst * p.v_copy_stride] = sum;
         }

@@ -61,7 +61,7 @@ def exchange_owned(field, owned, rank, gathered):
 
 class LazyESN(ESN):
     __slots__ = ("esn_chunks", "overlap", "persist", "boundary",
-                 "_grid", "_dims", "_maps", "_wout_blocks_host")
+                 "_grid", "_dims", "_maps", "_wout_blocks_host", "_p2p")
 
     @property
     def output_chunks(self):
@@ -101,6 +101,7 @@ class LazyESN(ESN):
         if sum(1 for d in self.overlap.values() if d > 0) > 2:
             raise NotImplementedError("LazyESN.__init__: cannot overlap more than 2 axes")
         self._grid = self._dims = self._maps = self._wout_blocks_host = None
+        self._p2p = None
 
     def __str__(self):
         bdy = "\n" + self._dictstr(self.boundary) if isinstance(self.boundary, dict) else str(self.boundary)
@@ -321,41 +322,69 @@ class LazyESN(ESN):
 
     def _predict_multi(self, lib, res, wout, G, g0, n_cells, t_in, t_fill, t_out, out_map, field, r, n_steps,
                        pred, scratch, nb, st):
-        """One process per GPU: every rank advances its slab of groups, then the ranks
-        all-gather the cells they own (NCCL over NVLink) -- the per-step neighbour exchange
-        that dask's `overlap` performs in the reference (lazyesn.py:235).
-
-        When every rank's cells form one contiguous range of the flat domain (slabs along the
-        first axis, the normal case) the all-gather runs in place on the field vector and the
-        readout kernel writes the trajectory of the owned cells directly; the full trajectory is
-        assembled with one all-gather at the end.  Otherwise an index-based exchange is used."""
+        """One process per GPU.  Every rank runs ONE persistent forecast kernel over its slab of groups;
+        the readout stores each predicted cell into the field buffer of every rank through
+        peer-mapped memory (NVLink P2P stores) and the ranks synchronise once per step on peer-mapped
+        flags -- the per-step neighbour exchange dask's `overlap` performs in the reference
+        (lazyesn.py:235), without leaving the kernel.  The trajectory of the owned cells is gathered
+        once at the end (NCCL)."""
         torch = _torch()
         import torch.distributed as dist
         rank, world = _dist()
         O = self.n_output
         dev = res.device
+        p2p = self._p2p_buffers(lib, n_cells, world, rank)
+        _lib.check(lib.xesn_memcpy_async(p2p["field"][0][rank], _ptr(field), 8 * n_cells, st))
+        field_ptrs = (ctypes.c_uint64 * (2 * world))(*[p2p["field"][par][k] for par in range(2) for k in range(world)])
+        flag_ptrs = (ctypes.c_uint64 * world)(*p2p["flags"])
         per = out_map.shape[0] // world * out_map.shape[1]
         owned_np = out_map.reshape(world, -1)
+        mine = torch.from_numpy(owned_np[rank].astype(np.int64)).to(dev)
+        pred[mine, 0] = field[mine]
+        _lib.check(lib.xesn_predict_p2p(res.handle, _ptr(wout), O, G, n_cells, _ptr(t_in), _ptr(t_fill), _ptr(t_out),
+                                        _ptr(r), n_steps, _ptr(pred), world, rank, p2p["steps"],
+                                        ctypes.cast(field_ptrs, ctypes.c_void_p), ctypes.cast(flag_ptrs, ctypes.c_void_p),
+                                        _ptr(scratch), nb, st))
+        p2p["steps"] += n_steps
+        # assemble the trajectory: every rank contributes the rows (cells) it owns
         contiguous = all(np.array_equal(np.sort(owned_np[k]), np.arange(k * per, (k + 1) * per)) for k in range(world))
-        nxt = field.clone()
-        ld = pred.stride(0)
         if contiguous:
             lo, hi = rank * per, (rank + 1) * per
-            pred[lo:hi, 0] = field[lo:hi]
-            for n in range(1, n_steps + 1):
-                _lib.check(lib.xesn_predict_step(res.handle, _ptr(wout), O, G, _ptr(t_in), _ptr(t_fill), _ptr(t_out),
-                                                 _ptr(field), _ptr(nxt), _ptr(r), pred.data_ptr() + 8 * n, ld,
-                                                 _ptr(scratch), nb, st))
-                dist.all_gather_into_tensor(nxt, nxt[lo:hi])
-                field, nxt = nxt, field
             dist.all_gather_into_tensor(pred, pred[lo:hi])
-            return
-        owned = torch.from_numpy(owned_np.astype(np.int64)).to(dev)
-        pred[:, 0] = field
-        gathered = torch.empty(tuple(owned.shape), dtype=torch.float64, device=dev)
-        for n in range(1, n_steps + 1):
-            _lib.check(lib.xesn_predict_step(res.handle, _ptr(wout), O, G, _ptr(t_in), _ptr(t_fill), _ptr(t_out),
-                                             _ptr(field), _ptr(nxt), _ptr(r), None, 0, _ptr(scratch), nb, st))
-            exchange_owned(nxt, owned, rank, gathered)
-            pred[:, n] = nxt
-            field, nxt = nxt, field
+        else:
+            owned = torch.from_numpy(owned_np.astype(np.int64)).to(dev)
+            rows = pred[mine].contiguous()
+            gathered = torch.empty((world,) + tuple(rows.shape), dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(gathered, rows)
+            pred[owned.reshape(-1)] = gathered.reshape(-1, rows.shape[-1])
+
+    def _p2p_buffers(self, lib, n_cells, world, rank):
+        """Peer-mapped field buffers (2 parities) and step flags of every rank, opened through CUDA
+        IPC handles exchanged with torch.distributed; cached per domain size."""
+        import torch.distributed as dist
+        if self._p2p is not None and self._p2p["n_cells"] == n_cells and self._p2p["world"] == world:
+            return self._p2p
+        mine = {}
+        handles = {}
+        for name, nbytes in (("f0", 8 * n_cells), ("f1", 8 * n_cells), ("flags", 256)):
+            ptr = ctypes.c_void_p()
+            h = (ctypes.c_uint8 * 64)()
+            _lib.check(lib.xesn_p2p_alloc(nbytes, ctypes.byref(ptr), ctypes.cast(h, ctypes.c_void_p)))
+            mine[name] = ptr.value
+            handles[name] = bytes(h)
+        everyone = [None] * world
+        dist.all_gather_object(everyone, handles)
+        field = [[0] * world, [0] * world]
+        flags = [0] * world
+        for k in range(world):
+            if k == rank:
+                field[0][k], field[1][k], flags[k] = mine["f0"], mine["f1"], mine["flags"]
+                continue
+            for name, slot in (("f0", (field[0], k)), ("f1", (field[1], k)), ("flags", (flags, k))):
+                ptr = ctypes.c_void_p()
+                buf = (ctypes.c_uint8 * 64).from_buffer_copy(everyone[k][name])
+                _lib.check(lib.xesn_p2p_open(ctypes.cast(buf, ctypes.c_void_p), ctypes.byref(ptr)))
+                slot[0][slot[1]] = ptr.value
+        dist.barrier()
+        self._p2p = {"n_cells": n_cells, "world": world, "field": field, "flags": flags, "steps": 0, "own": mine}
+        return self._p2p
