@@ -11,6 +11,7 @@ training needs no communication; during `predict` the ranks exchange the
 freshly predicted cells once per step.
 """
 import ctypes
+import os
 import warnings
 from functools import reduce
 
@@ -306,8 +307,13 @@ class LazyESN(ESN):
                                             _ptr(t_out), _ptr(field), _ptr(r), n_steps, _ptr(pred), _ptr(scratch),
                                             nb, st))
             else:
-                self._predict_multi(lib, res, wout, G, g0, n_cells, t_in, t_fill, t_out, out_map, field, r,
-                                    n_steps, pred, scratch, nb, st)
+                # latency-bound shapes: one persistent kernel per rank with the exchange inside (P2P);
+                # bandwidth-bound shapes (huge Win/Wout traffic per step): per-step launches + NCCL
+                small = (G * N * I * 8 <= (64 << 20) and world <= 8
+                         and os.environ.get("XESN_B200_EXCHANGE", "p2p") == "p2p")
+                multi = self._predict_multi if small else self._predict_multi_nccl
+                multi(lib, res, wout, G, g0, n_cells, t_in, t_fill, t_out, out_map, field, r,
+                      n_steps, pred, scratch, nb, st)
         return pred
 
     def _initial_field(self, y, n_spinup, dev):
@@ -388,3 +394,44 @@ class LazyESN(ESN):
         dist.barrier()
         self._p2p = {"n_cells": n_cells, "world": world, "field": field, "flags": flags, "steps": 0, "own": mine}
         return self._p2p
+
+    def _predict_multi_nccl(self, lib, res, wout, G, g0, n_cells, t_in, t_fill, t_out, out_map, field, r, n_steps,
+                       pred, scratch, nb, st):
+        """Per-step launches + NCCL (used for bandwidth-bound shapes).  Every rank advances its slab of groups, then the ranks
+        all-gather the cells they own (NCCL over NVLink) -- the per-step neighbour exchange
+        that dask's `overlap` performs in the reference (lazyesn.py:235).
+
+        When every rank's cells form one contiguous range of the flat domain (slabs along the
+        first axis, the normal case) the all-gather runs in place on the field vector and the
+        readout kernel writes the trajectory of the owned cells directly; the full trajectory is
+        assembled with one all-gather at the end.  Otherwise an index-based exchange is used."""
+        torch = _torch()
+        import torch.distributed as dist
+        rank, world = _dist()
+        O = self.n_output
+        dev = res.device
+        per = out_map.shape[0] // world * out_map.shape[1]
+        owned_np = out_map.reshape(world, -1)
+        contiguous = all(np.array_equal(np.sort(owned_np[k]), np.arange(k * per, (k + 1) * per)) for k in range(world))
+        nxt = field.clone()
+        ld = pred.stride(0)
+        if contiguous:
+            lo, hi = rank * per, (rank + 1) * per
+            pred[lo:hi, 0] = field[lo:hi]
+            for n in range(1, n_steps + 1):
+                _lib.check(lib.xesn_predict_step(res.handle, _ptr(wout), O, G, _ptr(t_in), _ptr(t_fill), _ptr(t_out),
+                                                 _ptr(field), _ptr(nxt), _ptr(r), pred.data_ptr() + 8 * n, ld,
+                                                 _ptr(scratch), nb, st))
+                dist.all_gather_into_tensor(nxt, nxt[lo:hi])
+                field, nxt = nxt, field
+            dist.all_gather_into_tensor(pred, pred[lo:hi])
+            return
+        owned = torch.from_numpy(owned_np.astype(np.int64)).to(dev)
+        pred[:, 0] = field
+        gathered = torch.empty(tuple(owned.shape), dtype=torch.float64, device=dev)
+        for n in range(1, n_steps + 1):
+            _lib.check(lib.xesn_predict_step(res.handle, _ptr(wout), O, G, _ptr(t_in), _ptr(t_fill), _ptr(t_out),
+                                             _ptr(field), _ptr(nxt), _ptr(r), None, 0, _ptr(scratch), nb, st))
+            exchange_owned(nxt, owned, rank, gathered)
+            pred[:, n] = nxt
+            field, nxt = nxt, field
