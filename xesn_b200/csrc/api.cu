@@ -399,7 +399,7 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
     }
     // accumulate: xesn/esn.py:502-513
     int team = 0, upt = 0;
-    const bool fuse = h->fused_enabled && (N % 2 == 0) && fused_recur_geometry(N, G, &team, &upt) == 0 &&
+    const bool fuse = h->fused_enabled && (N % 2 == 0) && fused_recur_geometry(N, G, fused_threads(h->gram_mode == 1), &team, &upt) == 0 &&
                       (long long)team * G < h->num_sms && T > n_spinup;
     if (fuse) {
         // software pipeline over chunks: launch c runs recurrence(c) || Gram(c-1) in one cooperative kernel

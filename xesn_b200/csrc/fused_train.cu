@@ -45,13 +45,15 @@ fused_chunk_kernel(RecurArgs rp, int rec_ctas, int team, GemmArgs gp, const int2
 
 // Gram role on the int8 tensor cores: tcgen05.mma kind::i8 on the digit planes written by the
 // recurrence role of the PREVIOUS launch (gram_i8.cuh).
+constexpr int FUSED_I8_THREADS = 512;  // 16 warps: twice the latency hiding for the recurrence role
+
 template <int UPT, bool WS>
-__global__ void __launch_bounds__(FUSED_THREADS, 1)
+__global__ void __launch_bounds__(FUSED_I8_THREADS, 1)
 fused_chunk_i8_kernel(RecurArgs rp, int rec_ctas, int team, gi8::GramI8Args gp, const int2* __restrict__ tiles,
                       int ntiles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     if ((int)blockIdx.x < rec_ctas) {
-        recur::recur_body<UPT, FUSED_THREADS, WS>(rp, blockIdx.x % team, team, blockIdx.x / team, smem_raw);
+        recur::recur_body<UPT, FUSED_I8_THREADS, WS>(rp, blockIdx.x % team, team, blockIdx.x / team, smem_raw);
         return;
     }
     const int worker = blockIdx.x - rec_ctas, nworkers = gridDim.x - rec_ctas;
@@ -61,7 +63,7 @@ fused_chunk_i8_kernel(RecurArgs rp, int rec_ctas, int team, gi8::GramI8Args gp, 
     gi8::gram_i8_setup(ctx, smem_raw);
     for (long long t = worker; t < total; t += nworkers) {
         const int2 ij = tiles[t % ntiles];
-        gi8::gram_i8_tile(ctx, gp, ij.x, ij.y, (int)(t / ntiles));
+        gi8::gram_i8_tile<FUSED_I8_THREADS>(ctx, gp, ij.x, ij.y, (int)(t / ntiles));
     }
     gi8::gram_i8_teardown(ctx);
 }
@@ -69,7 +71,7 @@ fused_chunk_i8_kernel(RecurArgs rp, int rec_ctas, int team, gi8::GramI8Args gp, 
 }  // namespace
 
 // team size / units per thread of the recurrence role for FUSED_THREADS-wide CTAs
-int fused_recur_geometry(int N, int n_groups, int* team_out, int* upt_out) {
+int fused_recur_geometry(int N, int n_groups, int threads, int* team_out, int* upt_out) {
     // The recurrence role wants many thin CTAs (its per-step cost grows with the units per CTA),
     // the Gram role wants the SMs.  Default: at most 512 units per thread block... per CTA 256 threads x
     // UPT units, the smallest UPT whose total CTA count stays within the cap (32 CTAs for one big
@@ -81,7 +83,7 @@ int fused_recur_geometry(int N, int n_groups, int* team_out, int* upt_out) {
     int best_team = -1, best_upt = 0;
     for (int upt = 1; upt <= 8; upt <<= 1) {
         if (force_upt && upt != force_upt) continue;
-        int team = (N + FUSED_THREADS * upt - 1) / (FUSED_THREADS * upt);
+        int team = (N + threads * upt - 1) / (threads * upt);
         if ((long long)team * n_groups > cap) continue;
         best_team = team, best_upt = upt;
         break;
@@ -153,6 +155,9 @@ int launch_fused_chunk(RecurArgs rp, int n_groups, int team, int upt, int max_sl
 
 namespace xesn {
 
+int fused_threads(int i8) { return i8 ? FUSED_I8_THREADS : FUSED_THREADS; }
+
+
 int launch_fused_chunk_i8(RecurArgs rp, int n_groups, int team, int upt, int max_slice_nnz,
                           const gi8::GramI8Args& gp, const int2* tiles, int ntiles, int num_sms, cudaStream_t stream) {
     const bool has_rec = rp.steps > 0;
@@ -190,7 +195,7 @@ int launch_fused_chunk_i8(RecurArgs rp, int n_groups, int team, int upt, int max
     XESN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     gi8::GramI8Args g = gp;
     void* args[] = {&rp, &rec_ctas, &team, &g, (void*)&tiles, &ntiles};
-    XESN_CUDA_OK(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(FUSED_THREADS), args, (size_t)smem, stream));
+    XESN_CUDA_OK(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(FUSED_I8_THREADS), args, (size_t)smem, stream));
     count_launch();
     return 0;
 }

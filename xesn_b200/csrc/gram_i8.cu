@@ -20,7 +20,7 @@ gram_i8_kernel(GramI8Args p, const int2* __restrict__ tiles, int ntiles) {
     const long long total = (long long)ntiles * p.batch;
     for (long long t = blockIdx.x; t < total; t += gridDim.x) {
         const int2 ij = tiles[t % ntiles];
-        gram_i8_tile(ctx, p, ij.x, ij.y, (int)(t / ntiles));
+        gram_i8_tile<THREADS>(ctx, p, ij.x, ij.y, (int)(t / ntiles));
     }
     gram_i8_teardown(ctx);
 }

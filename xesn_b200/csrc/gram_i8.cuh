@@ -165,33 +165,52 @@ __device__ __forceinline__ void gram_i8_teardown(GramI8Ctx& ctx) {
     }
 }
 
+// NC consecutive TMEM columns of this thread's lane (NC = 16 or 32)
+template <int NC>
+__device__ __forceinline__ void tmem_ld(unsigned taddr, int (&v)[NC]);
+template <>
+__device__ __forceinline__ void tmem_ld<32>(unsigned taddr, int (&v)[32]) { tmem_ld32(taddr, v); }
+template <>
+__device__ __forceinline__ void tmem_ld<16>(unsigned taddr, int (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
 // copy K-block kb of the A (rows m0.., 128 bytes) and B (rows n0.., 64 bytes) digit planes into stage s
+// NT = threads of the CTA taking part (256 or 512)
+template <int NT>
 __device__ __forceinline__ void gram_i8_load(const GramI8Ctx& ctx, const GramI8Args& p, const int8_t* planes, int s,
                                              int kb, int m0, int n0) {
     const int tid = threadIdx.x;
     const unsigned sa = ctx.stage_base + s * STAGE_BYTES;
     const unsigned sb = sa + A_BYTES;
     const long long row0 = (long long)kb * KB;
-    {   // A: thread -> (row kk, chunk c), loops over the 8 planes
-        const int c = tid & 7, kk = tid >> 3;
+    {   // A: 256 (row, chunk) slots per plane; thread -> slot tid & 255, planes a0, a0 + NT/256, ...
+        constexpr int PSTEP = NT / 256;
+        const int c = tid & 7, kk = (tid >> 3) & 31, a0 = tid >> 8;
         const int8_t* src = planes + (row0 + kk) * p.ldp + m0 + c * 16;
         const unsigned dst = sa + kk * 128 + ((c ^ (kk & 7)) << 4);
 #pragma unroll
-        for (int a = 0; a < NDIG; ++a) cp16(dst + a * A_PLANE, src + a * p.plane_stride);
+        for (int a = a0; a < NDIG; a += PSTEP) cp16(dst + a * A_PLANE, src + a * p.plane_stride);
     }
-    {   // B: 4 chunks per row; thread -> (row kk, chunk c, plane parity), loops over 4 plane pairs
-        const int c = tid & 3, kk = (tid >> 2) & 31, ap = tid >> 7;
+    {   // B: 128 slots per plane (4 chunks per row); thread -> slot tid & 127, planes a0, a0 + NT/128, ...
+        constexpr int PSTEP = NT / 128;
+        const int c = tid & 3, kk = (tid >> 2) & 31, a0 = tid >> 7;
         const int8_t* src = planes + (row0 + kk) * p.ldp + n0 + c * 16;
         const unsigned dst = sb + kk * 64 + ((c ^ ((kk >> 1) & 3)) << 4);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int a = 2 * i + ap;
-            cp16(dst + a * B_PLANE, src + a * p.plane_stride);
-        }
+        for (int a = a0; a < NDIG; a += PSTEP) cp16(dst + a * B_PLANE, src + a * p.plane_stride);
     }
 }
 
 // One 128 x 64 tile: rows m0 = 128*ti, columns n0 = 64*tj of batch entry bz.
+template <int NT>
 __device__ __forceinline__ void gram_i8_tile(GramI8Ctx& ctx, const GramI8Args& p, int ti, int tj, int bz) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = ti * TM, n0 = tj * TN;
@@ -201,7 +220,7 @@ __device__ __forceinline__ void gram_i8_tile(GramI8Ctx& ctx, const GramI8Args& p
     // prologue: fill up to STAGES-1 stages (stages are free: the previous tile waited for its last MMA)
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < nkb) gram_i8_load(ctx, p, planes, s, s, m0, n0);
+        if (s < nkb) gram_i8_load<NT>(ctx, p, planes, s, s, m0, n0);
         cp_commit();
     }
     for (int kb = 0; kb < nkb; ++kb) {
@@ -212,15 +231,14 @@ __device__ __forceinline__ void gram_i8_tile(GramI8Ctx& ctx, const GramI8Args& p
         if (tid == 0) {
             tc_fence_after();
             const unsigned sa = ctx.stage_base + s * STAGE_BYTES;
-            const unsigned sb = sa + A_BYTES;
+            const unsigned long long da0 = smem_desc(sa, 1024, 2);
+            const unsigned long long db0 = smem_desc(sa + A_BYTES, 512, 4);
 #pragma unroll
             for (int a = 0; a < NDIG; ++a) {
-                const unsigned long long da = smem_desc(sa + a * A_PLANE, 1024, 2);
 #pragma unroll
-                for (int b = 0; b + a < NDIG; ++b) {
-                    const unsigned long long db = smem_desc(sb + b * B_PLANE, 512, 4);
-                    mma_i8(ctx.tmem + (a + b) * TN, da, db, (kb > 0 || a > 0) ? 1u : 0u);
-                }
+                for (int b = 0; b + a < NDIG; ++b)
+                    mma_i8(ctx.tmem + (a + b) * TN, da0 + (unsigned long long)(a * (A_PLANE >> 4)),
+                           db0 + (unsigned long long)(b * (B_PLANE >> 4)), (kb > 0 || a > 0) ? 1u : 0u);
             }
             mma_commit(ctx.bar_done + 8 * s);
             if (kb == nkb - 1) mma_commit(ctx.bar_final);
@@ -235,7 +253,7 @@ __device__ __forceinline__ void gram_i8_tile(GramI8Ctx& ctx, const GramI8Args& p
                 ctx.done_phase ^= 1u << sn;
                 ctx.used &= ~(1u << sn);
             }
-            gram_i8_load(ctx, p, planes, sn, nk, m0, n0);
+            gram_i8_load<NT>(ctx, p, planes, sn, nk, m0, n0);
         }
         cp_commit();
     }
@@ -253,35 +271,36 @@ __device__ __forceinline__ void gram_i8_tile(GramI8Ctx& ctx, const GramI8Args& p
     ctx.used = 0;
     tc_fence_after();
 
-    // epilogue: lane quarter q of TMEM <-> rows m0 + 32q + lane; warps 4..7 take columns 32..63
-    const int q = warp & 3, half = warp >> 2;
+    // epilogue: lane quarter q of TMEM <-> rows m0 + 32q + lane; the NT/128 warps of a quarter split the 64 columns
+    constexpr int NC = TN / (NT / 128);
+    const int q = warp & 3, part = warp >> 2;
     const int m = m0 + q * 32 + lane;
-    double acc[32];
+    double acc[NC];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] = 0.0;
+    for (int j = 0; j < NC; ++j) acc[j] = 0.0;
     if (nkb > 0) {
 #pragma unroll
         for (int s = NDIG - 1; s >= 0; --s) {  // smallest weights first
-            int v[32];
-            tmem_ld32(ctx.tmem + ((unsigned)(q * 32) << 16) + s * TN + half * 32, v);
+            int v[NC];
+            tmem_ld<NC>(ctx.tmem + ((unsigned)(q * 32) << 16) + s * TN + part * NC, v);
             const double w = __longlong_as_double((long long)(1023 - 12 - 7 * s) << 52);  // 2^(-12-7s)
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] = fma((double)v[j], w, acc[j]);
+            for (int j = 0; j < NC; ++j) acc[j] = fma((double)v[j], w, acc[j]);
         }
     }
     if (m < p.N) {
-        double* g = p.G + (long long)bz * p.strideG + (long long)m * p.ldg + n0 + half * 32;
-        const int nmax = min(32, min(p.N, m + 1) - (n0 + half * 32));  // columns <= row only (lower triangle)
-        if (nmax == 32 && ((reinterpret_cast<uintptr_t>(g) & 15) == 0)) {
+        double* g = p.G + (long long)bz * p.strideG + (long long)m * p.ldg + n0 + part * NC;
+        const int nmax = min(NC, min(p.N, m + 1) - (n0 + part * NC));  // columns <= row only (lower triangle)
+        if (nmax == NC && ((reinterpret_cast<uintptr_t>(g) & 15) == 0)) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
+            for (int j = 0; j < NC; j += 2) {
                 double2 c = *reinterpret_cast<double2*>(g + j);
                 c.x += acc[j], c.y += acc[j + 1];
                 *reinterpret_cast<double2*>(g + j) = c;
             }
         } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
+            for (int j = 0; j < NC; ++j)
                 if (j < nmax) g[j] += acc[j];
         }
     }

@@ -64,7 +64,8 @@ int recur_cluster_size(int N);
 // units owned by one CTA of a team: ceil(N / team) rounded up to a multiple of 8 (vector stores)
 inline int recur_units_per_cta(int N, int team) { return ((N + team - 1) / team + 7) & ~7; }
 // fused recurrence(c) || Gram(c-1) chunk kernel (fused_train.cu)
-int fused_recur_geometry(int N, int n_groups, int* team_out, int* upt_out);
+int fused_threads(int i8);  // CTA width of the fused chunk kernel (256 FP64-Gram, 512 int8-Gram)
+int fused_recur_geometry(int N, int n_groups, int threads, int* team_out, int* upt_out);
 int launch_fused_chunk(RecurArgs rp, int n_groups, int team, int upt, int max_slice_nnz, const GemmArgs& gp,
                        const int2* tiles, int ntiles, int num_sms, cudaStream_t stream);
 namespace gi8 { struct GramI8Args; }
