@@ -59,13 +59,13 @@ fused_chunk_i8_kernel(RecurArgs rp, int rec_ctas, int team, gi8::GramI8Args gp, 
     const int worker = blockIdx.x - rec_ctas, nworkers = gridDim.x - rec_ctas;
     const long long total = (long long)ntiles * gp.batch;
     if (worker >= total) return;
-    gi8::GramI8Ctx ctx;
-    gi8::gram_i8_setup(ctx, smem_raw);
+    gi8::GramI8WsCtx ctx;
+    gi8::gram_i8_ws_setup<FUSED_I8_THREADS>(ctx, smem_raw);
     for (long long t = worker; t < total; t += nworkers) {
         const int2 ij = tiles[t % ntiles];
-        gi8::gram_i8_tile<FUSED_I8_THREADS>(ctx, gp, ij.x, ij.y, (int)(t / ntiles));
+        gi8::gram_i8_tile_ws<FUSED_I8_THREADS>(ctx, gp, ij.x, ij.y, (int)(t / ntiles));
     }
-    gi8::gram_i8_teardown(ctx);
+    gi8::gram_i8_ws_teardown<FUSED_I8_THREADS>(ctx);
 }
 
 }  // namespace
@@ -76,7 +76,7 @@ int fused_recur_geometry(int N, int n_groups, int threads, int* team_out, int* u
     // the Gram role wants the SMs.  Default: at most 512 units per thread block... per CTA 256 threads x
     // UPT units, the smallest UPT whose total CTA count stays within the cap (32 CTAs for one big
     // reservoir, 64 when many small reservoirs run side by side).  XESN_B200_REC_UPT / _REC_CAP override.
-    int cap = n_groups > 1 ? 64 : 32;
+    int cap = n_groups > 1 ? 64 : 16;
     int force_upt = 0;
     if (const char* e = getenv("XESN_B200_REC_CAP")) cap = atoi(e);
     if (const char* e = getenv("XESN_B200_REC_UPT")) force_upt = atoi(e);

@@ -24,6 +24,7 @@ struct RecurArgs {
     int smem_nnz;            // capacity (entries) of the shared-memory CSR slice
     int w_in_smem;
     int n_pad;               // N rounded up to even: size of the shared-memory state copy
+    int debug_no_exchange;   // timing experiments only: skip the refresh of the other CTAs' slices (wrong results)
 };
 
 struct StepArgs {

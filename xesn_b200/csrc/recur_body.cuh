@@ -231,7 +231,7 @@ __device__ __forceinline__ void recur_body(const RecurArgs& p, const unsigned c,
         for (int j = 0; j < UPT; ++j)
             if (j < nvalid) s_r[ubase + j] = r_cur[j];
         // ---- refresh the other CTAs' slices of r_{t+1} with coalesced polling loads ----
-        if (C > 1) {
+        if (C > 1 && !p.debug_no_exchange) {
             if (vec2) {
                 const int n2 = N >> 1;
                 for (int q0 = tid; q0 < n2; q0 += RC_THREADS * POLL_BATCH) {
