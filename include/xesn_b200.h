@@ -146,9 +146,6 @@ int xesn_gemm_f64(const double* a_dev, int64_t lda, const double* b_dev, int64_t
  * device code inside the fused chunk kernel).  Replaces xesn/esn.py:510. */
 int xesn_gram_i8(const double* states_dev, int64_t lds, int32_t n_rows, int32_t n_reservoir, double* gram_dev,
                  int64_t ldg, void* stream);
-/* same result through the 128 x 256-tile / four-pass variant of the kernel */
-int xesn_gram_i8_wide(const double* states_dev, int64_t lds, int32_t n_rows, int32_t n_reservoir, double* gram_dev,
-                      int64_t ldg, void* stream);
 /* readout v[g][o] = Wout[g][o][:] . r[g][:]   (xesn/esn.py:268, xesn/lazyesn.py:325-327) */
 int xesn_readout(const double* wout_dev, const double* r_dev, double* v_dev, int32_t n_reservoir,
                  int32_t n_output, int32_t n_groups, void* stream);

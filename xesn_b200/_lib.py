@@ -66,7 +66,6 @@ SIGNATURES = {
     "xesn_profile_enable": (C.c_int, [C.c_int32]),
     "xesn_profile_read": (C.c_int, [C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "xesn_gram_i8": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
-    "xesn_gram_i8_wide": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
     "xesn_readout": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
 }
 

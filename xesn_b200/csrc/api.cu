@@ -19,8 +19,6 @@ void gram_i8_tile_list(int N, std::vector<int2>& tiles);
 int launch_digitize(const double* states, long long lds, int n_rows, int N, int8_t* planes, long long ldp,
                     long long plane_stride, int rows_pad, cudaStream_t stream);
 int launch_gram_i8(const gi8::GramI8Args& a, const int2* tiles, int ntiles, int num_sms, cudaStream_t stream);
-void gram_i8_tile_list_wide(int N, std::vector<int2>& tiles);
-int launch_gram_i8_wide(const gi8::GramI8Args& a, const int2* tiles, int ntiles, int num_sms, cudaStream_t stream);
 
 static thread_local std::string g_error;
 static std::atomic<long long> g_launches{0};
@@ -787,8 +785,7 @@ int xesn_predict_p2p(xesn_reservoir* h, const double* wout, int32_t O, int32_t G
 
 // test / A-B entry: G (N x N, lower triangle) += S^T S for S = states [n_rows][N] through the int8
 // tensor-core path (digitise -> tcgen05 kind::i8 Gram).  Allocates its own scratch and synchronises.
-static int gram_i8_entry(const double* states, int64_t lds, int32_t n_rows, int32_t N, double* gram, int64_t ldg, void* stream,
-                         bool wide) {
+int xesn_gram_i8(const double* states, int64_t lds, int32_t n_rows, int32_t N, double* gram, int64_t ldg, void* stream) {
     XESN_REQUIRE(states && gram && n_rows > 0 && N > 0, "bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     int dev = 0;
@@ -802,32 +799,20 @@ static int gram_i8_entry(const double* states, int64_t lds, int32_t n_rows, int3
     int2* d_tiles = nullptr;
     XESN_CUDA_OK(cudaMalloc(&planes, (size_t)plane_stride * gi8::NDIG));
     std::vector<int2> tiles;
-    if (wide) gram_i8_tile_list_wide(N, tiles);
-    else gram_i8_tile_list(N, tiles);
+    gram_i8_tile_list(N, tiles);
     XESN_CUDA_OK(cudaMalloc(&d_tiles, sizeof(int2) * tiles.size()));
     XESN_CUDA_OK(cudaMemcpyAsync(d_tiles, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, st));
     int rc = launch_digitize(states, lds, n_rows, N, planes, ldp, plane_stride, rows_pad, st);
     gi8::GramI8Args a = {};
     a.planes = planes, a.ldp = ldp, a.plane_stride = plane_stride, a.group_stride = 0;
     a.K = rows_pad, a.N = N, a.G = gram, a.ldg = ldg, a.strideG = 0, a.batch = 1;
-    if (!rc)
-        rc = wide ? launch_gram_i8_wide(a, d_tiles, (int)tiles.size(), prop.multiProcessorCount, st)
-                  : launch_gram_i8(a, d_tiles, (int)tiles.size(), prop.multiProcessorCount, st);
+    if (!rc) rc = launch_gram_i8(a, d_tiles, (int)tiles.size(), prop.multiProcessorCount, st);
     cudaError_t e = cudaStreamSynchronize(st);
     cudaFree(planes);
     cudaFree(d_tiles);
     if (rc) return rc;
     XESN_CUDA_OK(e);
     return 0;
-}
-
-int xesn_gram_i8(const double* states, int64_t lds, int32_t n_rows, int32_t N, double* gram, int64_t ldg, void* stream) {
-    return gram_i8_entry(states, lds, n_rows, N, gram, ldg, stream, false);
-}
-// same through the 128 x 256 / four-pass variant
-int xesn_gram_i8_wide(const double* states, int64_t lds, int32_t n_rows, int32_t N, double* gram, int64_t ldg,
-                      void* stream) {
-    return gram_i8_entry(states, lds, n_rows, N, gram, ldg, stream, true);
 }
 
 int xesn_gemm_f64(const double* a, int64_t lda, const double* b, int64_t ldb, double* c, int64_t ldc, int32_t m,

@@ -59,13 +59,13 @@ fused_chunk_i8_kernel(RecurArgs rp, int rec_ctas, int team, gi8::GramI8Args gp, 
     const int worker = blockIdx.x - rec_ctas, nworkers = gridDim.x - rec_ctas;
     const long long total = (long long)ntiles * gp.batch;
     if (worker >= total) return;
-    gi8::GramI8WsCtx ctx;
-    gi8::gram_i8_ws_setup<FUSED_I8_THREADS>(ctx, smem_raw);
+    gi8::GramI8Ctx ctx;
+    gi8::gram_i8_setup(ctx, smem_raw);
     for (long long t = worker; t < total; t += nworkers) {
         const int2 ij = tiles[t % ntiles];
-        gi8::gram_i8_tile_ws<FUSED_I8_THREADS>(ctx, gp, ij.x, ij.y, (int)(t / ntiles));
+        gi8::gram_i8_tile<FUSED_I8_THREADS>(ctx, gp, ij.x, ij.y, (int)(t / ntiles));
     }
-    gi8::gram_i8_ws_teardown<FUSED_I8_THREADS>(ctx);
+    gi8::gram_i8_teardown(ctx);
 }
 
 }  // namespace

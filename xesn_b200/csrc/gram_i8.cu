@@ -15,25 +15,12 @@ using namespace gi8;
 __global__ void __launch_bounds__(THREADS, 1)
 gram_i8_kernel(GramI8Args p, const int2* __restrict__ tiles, int ntiles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    GramI8WsCtx ctx;
-    gram_i8_ws_setup<THREADS>(ctx, smem_raw);
-    const long long total = (long long)ntiles * p.batch;
-    for (long long t = blockIdx.x; t < total; t += gridDim.x) {
-        const int2 ij = tiles[t % ntiles];
-        gram_i8_tile_ws<THREADS>(ctx, p, ij.x, ij.y, (int)(t / ntiles));
-    }
-    gram_i8_ws_teardown<THREADS>(ctx);
-}
-
-__global__ void __launch_bounds__(512, 1)
-gram_i8_wide_kernel(GramI8Args p, const int2* __restrict__ tiles, int ntiles) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     GramI8Ctx ctx;
     gram_i8_setup(ctx, smem_raw);
     const long long total = (long long)ntiles * p.batch;
     for (long long t = blockIdx.x; t < total; t += gridDim.x) {
         const int2 ij = tiles[t % ntiles];
-        gram_i8_tile_wide<512>(ctx, p, ij.x, ij.y, (int)(t / ntiles));
+        gram_i8_tile<THREADS>(ctx, p, ij.x, ij.y, (int)(t / ntiles));
     }
     gram_i8_teardown(ctx);
 }
@@ -69,38 +56,6 @@ void gram_i8_tile_list(int N, std::vector<int2>& tiles) {
             for (int ti = sb; ti < ti_hi; ++ti)
                 if ((long long)tj * TN <= (long long)ti * TM + TM - 1 && tj * TN < N) tiles.push_back(make_int2(ti, tj));
     }
-}
-
-// same for the 128 x 256 tiles of the wide variant (ti: 128-row block, tj: 256-column block)
-void gram_i8_tile_list_wide(int N, std::vector<int2>& tiles) {
-    const int TI = (N + TM - 1) / TM, H = 16;
-    tiles.clear();
-    for (int sb = 0; sb < TI; sb += H) {
-        const int ti_hi = sb + H < TI ? sb + H : TI;
-        const int tj_hi = (ti_hi * TM + WN - 1) / WN;
-        for (int tj = 0; tj < tj_hi; ++tj)
-            for (int ti = sb; ti < ti_hi; ++ti)
-                if ((long long)tj * WN <= (long long)ti * TM + TM - 1 && tj * WN < N) tiles.push_back(make_int2(ti, tj));
-    }
-}
-
-int launch_gram_i8_wide(const gi8::GramI8Args& a, const int2* tiles, int ntiles, int num_sms, cudaStream_t stream) {
-    if (ntiles <= 0 || a.batch <= 0 || a.K <= 0) return 0;
-    if (a.K % KB) {
-        set_error("gram_i8: K=%d must be a multiple of %d (zero-padded rows)", a.K, KB);
-        return -1;
-    }
-    static bool attr = false;
-    if (!attr) {
-        XESN_CUDA_OK(cudaFuncSetAttribute(gram_i8_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM_BYTES));
-        attr = true;
-    }
-    long long total = (long long)ntiles * a.batch;
-    int grid = (int)(total < num_sms ? total : num_sms);
-    gram_i8_wide_kernel<<<grid, 512, W_SMEM_BYTES, stream>>>(a, tiles, ntiles);
-    XESN_CUDA_OK(cudaGetLastError());
-    count_launch();
-    return 0;
 }
 
 int launch_digitize(const double* states, long long lds, int n_rows, int N, int8_t* planes, long long ldp,

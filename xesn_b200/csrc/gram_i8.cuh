@@ -309,342 +309,6 @@ __device__ __forceinline__ void gram_i8_tile(GramI8Ctx& ctx, const GramI8Args& p
     __syncthreads();
 }
 
-// ================================================================================================
-// Warp-specialised pipeline for the 128 x 64 tile (same arithmetic as gram_i8_tile).
-//   warp 0 (one lane)   : waits for a full stage, issues its 36 tcgen05.mma, commits -> empty[stage]
-//   warps 1 .. NT/32-1  : producers: wait empty[stage], cp.async the K-block into the swizzled layout,
-//                         and once an OLDER block has landed (wait_group lag), fence.proxy.async and
-//                         arrive (one arrival per warp) on full[stage]
-// No CTA-wide barrier inside the K loop: ncu showed the synchronous version stalled mostly on its
-// per-K-block __syncthreads (barrier stall 9.8 per issue) with the tensor pipe 46 % busy.
-// ================================================================================================
-constexpr int WS_LAG = 2;  // a producer signals block kb-LAG while its copies of kb, kb-1 are still in flight
-
-struct GramI8WsCtx {
-    unsigned stage_base;
-    unsigned bar_full;    // STAGES mbarriers, count = producer warps
-    unsigned bar_empty;   // STAGES mbarriers, count = 1 (tcgen05.commit)
-    unsigned bar_final;   // count = 1
-    unsigned tmem;
-    unsigned it;          // K-blocks processed so far by this CTA (stage = it % STAGES, use = it / STAGES)
-    unsigned tiles_done;  // parity of bar_final
-};
-
-template <int NT>
-__device__ __forceinline__ void gram_i8_ws_setup(GramI8WsCtx& ctx, unsigned char* smem_raw) {
-    const unsigned raw = smem_u32(smem_raw);
-    ctx.stage_base = (raw + 1023u) & ~1023u;
-    const unsigned ctl = ctx.stage_base + STAGES * STAGE_BYTES;
-    ctx.bar_full = ctl;
-    ctx.bar_empty = ctl + 8 * STAGES;
-    ctx.bar_final = ctl + 16 * STAGES;
-    const unsigned tmem_slot = ctl + 16 * STAGES + 8;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(ctx.bar_full + 8 * s, NT / 32 - 1);
-            mbar_init(ctx.bar_empty + 8 * s, 1);
-        }
-        mbar_init(ctx.bar_final, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    }
-    if (threadIdx.x < 32) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(tmem_slot) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    asm volatile("ld.shared.b32 %0, [%1];\n" : "=r"(ctx.tmem) : "r"(tmem_slot) : "memory");
-    ctx.it = 0, ctx.tiles_done = 0;
-}
-
-template <int NT>
-__device__ __forceinline__ void gram_i8_ws_teardown(GramI8WsCtx& ctx) {
-    tc_fence_before();
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(ctx.tmem) : "memory");
-    }
-}
-
-__device__ __forceinline__ void mbar_arrive(unsigned bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
-}
-
-template <int NT>
-__device__ __forceinline__ void gram_i8_tile_ws(GramI8WsCtx& ctx, const GramI8Args& p, int ti, int tj, int bz) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int m0 = ti * TM, n0 = tj * TN;
-    const int8_t* planes = p.planes + (long long)bz * p.group_stride;
-    const int nkb = p.K / KB;
-    const unsigned it0 = ctx.it;
-    constexpr int NPROD = NT - 32;
-
-    if (warp == 0) {
-        // ---------------- MMA issuer ----------------
-        if (lane == 0) {
-            for (int kb = 0; kb < nkb; ++kb) {
-                const unsigned it = it0 + kb, s = it % STAGES, use = it / STAGES;
-                mbar_wait(ctx.bar_full + 8 * s, use & 1u);
-                tc_fence_after();
-                const unsigned sa = ctx.stage_base + s * STAGE_BYTES;
-                const unsigned long long da0 = smem_desc(sa, 1024, 2);
-                const unsigned long long db0 = smem_desc(sa + A_BYTES, 512, 4);
-#pragma unroll
-                for (int a = 0; a < NDIG; ++a) {
-#pragma unroll
-                    for (int b = 0; b + a < NDIG; ++b)
-                        mma_i8(ctx.tmem + (a + b) * TN, da0 + (unsigned long long)(a * (A_PLANE >> 4)),
-                               db0 + (unsigned long long)(b * (B_PLANE >> 4)), (kb > 0 || a > 0) ? 1u : 0u);
-                }
-                mma_commit(ctx.bar_empty + 8 * s);
-                if (kb == nkb - 1) mma_commit(ctx.bar_final);
-            }
-        }
-        __syncwarp();  // the other lanes of the issuer warp park here instead of spinning on the final barrier
-    } else {
-        // ---------------- producers ----------------
-        const int ptid = tid - 32;
-        for (int kb = 0; kb < nkb + WS_LAG; ++kb) {
-            if (kb < nkb) {
-                const unsigned it = it0 + kb, s = it % STAGES, use = it / STAGES;
-                if (use > 0) mbar_wait(ctx.bar_empty + 8 * s, (use - 1) & 1u);
-                const unsigned sa = ctx.stage_base + s * STAGE_BYTES;
-                const long long row0 = (long long)kb * KB;
-                for (int idx = ptid; idx < NDIG * (256 + 128); idx += NPROD) {
-                    if (idx < NDIG * 256) {
-                        const int a = idx >> 8, kk = (idx >> 3) & 31, c = idx & 7;
-                        cp16(sa + a * A_PLANE + kk * 128 + ((c ^ (kk & 7)) << 4),
-                             planes + a * p.plane_stride + (row0 + kk) * p.ldp + m0 + c * 16);
-                    } else {
-                        const int j = idx - NDIG * 256;
-                        const int a = j >> 7, kk = (j >> 2) & 31, c = j & 3;
-                        cp16(sa + A_BYTES + a * B_PLANE + kk * 64 + ((c ^ ((kk >> 1) & 3)) << 4),
-                             planes + a * p.plane_stride + (row0 + kk) * p.ldp + n0 + c * 16);
-                    }
-                }
-            }
-            cp_commit();  // (empty groups past the end keep the wait_group arithmetic uniform)
-            if (kb >= WS_LAG) {
-                cp_wait<WS_LAG>();     // this thread's copies of block kb-LAG have landed
-                fence_proxy_async();   // ... visible to the tensor core's async-proxy reads
-                __syncwarp();
-                if (lane == 0) mbar_arrive(ctx.bar_full + 8 * ((it0 + kb - WS_LAG) % STAGES));
-            }
-        }
-    }
-    ctx.it = it0 + nkb;
-
-    // ---------------- epilogue (all warps) ----------------
-    if (nkb > 0) {
-        mbar_wait(ctx.bar_final, ctx.tiles_done & 1u);
-        ctx.tiles_done++;
-    }
-    tc_fence_after();
-    constexpr int NC = TN / (NT / 128);
-    const int q = warp & 3, part = warp >> 2;
-    const int m = m0 + q * 32 + lane;
-    double acc[NC];
-#pragma unroll
-    for (int j = 0; j < NC; ++j) acc[j] = 0.0;
-    if (nkb > 0) {
-#pragma unroll
-        for (int s = NDIG - 1; s >= 0; --s) {  // smallest weights first
-            int v[NC];
-            tmem_ld<NC>(ctx.tmem + ((unsigned)(q * 32) << 16) + s * TN + part * NC, v);
-            const double w = __longlong_as_double((long long)(1023 - 12 - 7 * s) << 52);  // 2^(-12-7s)
-#pragma unroll
-            for (int j = 0; j < NC; ++j) acc[j] = fma((double)v[j], w, acc[j]);
-        }
-    }
-    if (m < p.N) {
-        double* g = p.G + (long long)bz * p.strideG + (long long)m * p.ldg + n0 + part * NC;
-        const int nmax = min(NC, min(p.N, m + 1) - (n0 + part * NC));  // columns <= row only (lower triangle)
-        if (nmax == NC && ((reinterpret_cast<uintptr_t>(g) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < NC; j += 2) {
-                double2 c = *reinterpret_cast<double2*>(g + j);
-                c.x += acc[j], c.y += acc[j + 1];
-                *reinterpret_cast<double2*>(g + j) = c;
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < NC; ++j)
-                if (j < nmax) g[j] += acc[j];
-        }
-    }
-    // all TMEM reads of this tile are done before the next tile's first MMA overwrites the accumulators
-    tc_fence_before();
-    __syncthreads();
-}
-
-// ================================================================================================
-// Wide variant: 128 x 256 tile, two levels resident in TMEM (2 x 256 columns), four passes over K.
-//
-// ncu on the 128 x 64 tile (profiles/gram_i8_r01_v3.txt): tensor pipe 46 % busy, the shared-memory
-// pipe 69 %: an M=128, N=64, K=32 MMA reads (128+64)*32 B = 6 KB of operands for 32 cycles of math
-// = 192 B/clk, more than the 128 B/clk shared memory delivers.  With N=256 an MMA reads 12 KB for
-// 128 cycles = 96 B/clk.  Eight int32 accumulators of 128 x 256 do not fit TMEM (512 columns), so the
-// levels are processed two at a time: pass p in {0,1,2,3} accumulates levels 2p and 2p+1 over the
-// whole K range using digit planes 0 .. 2p+1 only, then adds 2^(-12-7s) * P_s to the FP64 tile.
-// ================================================================================================
-constexpr int WN = 256;
-constexpr int WB_PLANE = KB * WN;                      // 8 KB per B plane per stage: [2 x 128-byte column block][32 rows][128 B]
-constexpr int W_TOTAL = 192 * 1024;                    // shared memory ring (all stages)
-constexpr int W_SMEM_BYTES = W_TOTAL + 1024 + 128;
-constexpr unsigned W_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((WN >> 3) << 17) |
-                             ((TM >> 4) << 24);
-
-__device__ __forceinline__ unsigned long long smem_desc_lbo(unsigned addr, unsigned lbo_bytes, unsigned sbo_bytes,
-                                                            unsigned layout_type) {
-    unsigned long long d = 0;
-    d |= (unsigned long long)((addr >> 4) & 0x3FFF);
-    d |= (unsigned long long)((lbo_bytes >> 4) & 0x3FFF) << 16;  // next 128-byte block along MN
-    d |= (unsigned long long)((sbo_bytes >> 4) & 0x3FFF) << 32;  // next group of 8 K rows
-    d |= (unsigned long long)(1) << 46;
-    d |= (unsigned long long)(layout_type & 7) << 61;
-    return d;
-}
-__device__ __forceinline__ void mma_i8_wide(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(tmem_d),
-        "l"(da), "l"(db), "r"(W_IDESC), "r"(accumulate), "r"(0u)
-        : "memory");
-}
-
-// planes 0..np-1 of K-block kb into the stage at shared address `st` (A then B; plane strides 4 KB / 8 KB)
-template <int NT>
-__device__ __forceinline__ void gram_i8_load_wide(unsigned st, int np, const GramI8Args& p, const int8_t* planes, int kb,
-                                                  int m0, int n0) {
-    const int tid = threadIdx.x;
-    const long long row0 = (long long)kb * KB;
-    const unsigned sb = st + np * A_PLANE;
-    {   // A: 256 (row, chunk) slots per plane
-        const int c = tid & 7, kk = (tid >> 3) & 31, a0 = tid >> 8;
-        const int8_t* src = planes + (row0 + kk) * p.ldp + m0 + c * 16;
-        const unsigned dst = st + kk * 128 + ((c ^ (kk & 7)) << 4);
-        for (int a = a0; a < np; a += NT / 256) cp16(dst + a * A_PLANE, src + a * p.plane_stride);
-    }
-    {   // B: 512 slots per plane: (column block mi, row kk, chunk c)
-        const int c = tid & 7, kk = (tid >> 3) & 31, mi = (tid >> 8) & 1, a0 = tid >> 9;
-        const int8_t* src = planes + (row0 + kk) * p.ldp + n0 + mi * 128 + c * 16;
-        const unsigned dst = sb + mi * (KB * 128) + kk * 128 + ((c ^ (kk & 7)) << 4);
-        constexpr int PSTEP = NT >= 512 ? NT / 512 : 1;
-        if (NT >= 512) {
-            for (int a = a0; a < np; a += PSTEP) cp16(dst + a * WB_PLANE, src + a * p.plane_stride);
-        } else {  // 256 threads: every thread covers both column blocks
-            for (int a = 0; a < np; ++a) {
-                cp16(dst + a * WB_PLANE, src + a * p.plane_stride);
-                cp16(dst + a * WB_PLANE + KB * 128, src + a * p.plane_stride + 128);
-            }
-        }
-    }
-}
-
-// One 128 x 256 tile: rows m0 = 128*ti, columns n0 = 256*tj of batch entry bz.
-template <int NT>
-__device__ __forceinline__ void gram_i8_tile_wide(GramI8Ctx& ctx, const GramI8Args& p, int ti, int tj, int bz) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int m0 = ti * TM, n0 = tj * WN;
-    const int8_t* planes = p.planes + (long long)bz * p.group_stride;
-    const int nkb = p.K / KB;
-    if (nkb == 0) return;
-    const int q = warp & 3, part = warp >> 2;
-    constexpr int PARTS = NT / 128;          // warps per lane quarter
-    constexpr int CPP = WN / PARTS;          // columns per warp (64 with 512 threads, 128 with 256)
-    const int m = m0 + q * 32 + lane;
-    double* grow = p.G + (long long)bz * p.strideG + (long long)m * p.ldg + n0 + part * CPP;
-
-    for (int pass = 0; pass < 4; ++pass) {
-        const int np = 2 * pass + 2;                         // digit planes 0 .. np-1
-        const int stage_bytes = np * (A_PLANE + WB_PLANE);
-        const int nst = min(4, W_TOTAL / stage_bytes);       // 4, 4, 2, 2 stages
-        // prologue
-        for (int s = 0; s < nst - 1; ++s) {
-            if (s < nkb) gram_i8_load_wide<NT>(ctx.stage_base + s * stage_bytes, np, p, planes, s, m0, n0);
-            cp_commit();
-        }
-        for (int kb = 0; kb < nkb; ++kb) {
-            const int s = kb % nst;
-            // this thread's copies of K-block kb have landed (groups committed so far: nst-1+kb, need group kb)
-            if (nst == 4) cp_wait<2>(); else cp_wait<0>();
-            fence_proxy_async();
-            __syncthreads();
-            if (tid == 0) {
-                tc_fence_after();
-                const unsigned sa = ctx.stage_base + s * stage_bytes;
-                const unsigned long long da0 = smem_desc(sa, 1024, 2);
-                const unsigned long long db0 = smem_desc_lbo(sa + np * A_PLANE, KB * 128, 1024, 2);
-                for (int lv = 0; lv < 2; ++lv) {
-                    const int sl = 2 * pass + lv;            // level = a + b
-                    for (int a = 0; a <= sl; ++a) {
-                        const int b = sl - a;
-                        mma_i8_wide(ctx.tmem + lv * WN, da0 + (unsigned long long)(a * (A_PLANE >> 4)),
-                                    db0 + (unsigned long long)(b * (WB_PLANE >> 4)), (kb > 0 || a > 0) ? 1u : 0u);
-                    }
-                }
-                mma_commit(ctx.bar_done + 8 * s);
-                if (kb == nkb - 1) mma_commit(ctx.bar_final);
-            }
-            ctx.used |= 1u << s;
-            const int nk = kb + nst - 1;
-            if (nk < nkb) {
-                const int sn = nk % nst;
-                if (ctx.used & (1u << sn)) {
-                    mbar_wait(ctx.bar_done + 8 * sn, (ctx.done_phase >> sn) & 1u);
-                    ctx.done_phase ^= 1u << sn;
-                    ctx.used &= ~(1u << sn);
-                }
-                gram_i8_load_wide<NT>(ctx.stage_base + sn * stage_bytes, np, p, planes, nk, m0, n0);
-            }
-            cp_commit();
-        }
-        cp_wait<0>();
-        mbar_wait(ctx.bar_final, ctx.final_phase);
-        ctx.final_phase ^= 1u;
-#pragma unroll
-        for (int s = 0; s < 4; ++s)
-            if (ctx.used & (1u << s)) {
-                mbar_wait(ctx.bar_done + 8 * s, (ctx.done_phase >> s) & 1u);
-                ctx.done_phase ^= 1u << s;
-            }
-        ctx.used = 0;
-        tc_fence_after();
-
-        // epilogue of the pass: G += 2^(-12-7*s0) P_s0 + 2^(-12-7*s1) P_s1, 16 columns at a time
-        const double w0 = __longlong_as_double((long long)(1023 - 12 - 7 * (2 * pass)) << 52);
-        const double w1 = __longlong_as_double((long long)(1023 - 12 - 7 * (2 * pass + 1)) << 52);
-        for (int c0 = 0; c0 < CPP; c0 += 16) {
-            int v0[16], v1[16];
-            const unsigned tbase = ctx.tmem + ((unsigned)(q * 32) << 16) + part * CPP + c0;
-            tmem_ld<16>(tbase, v0);
-            tmem_ld<16>(tbase + WN, v1);
-            if (m < p.N) {
-                const int col = n0 + part * CPP + c0;
-                const int nmax = min(16, min(p.N, m + 1) - col);  // columns <= row only (lower triangle)
-                double* g = grow + c0;
-                if (nmax == 16 && ((reinterpret_cast<uintptr_t>(g) & 15) == 0)) {
-#pragma unroll
-                    for (int j = 0; j < 16; j += 2) {
-                        double2 c = *reinterpret_cast<double2*>(g + j);
-                        c.x += fma((double)v1[j], w1, (double)v0[j] * w0);
-                        c.y += fma((double)v1[j + 1], w1, (double)v0[j + 1] * w0);
-                        *reinterpret_cast<double2*>(g + j) = c;
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (j < nmax) g[j] += fma((double)v1[j], w1, (double)v0[j] * w0);
-                }
-            }
-        }
-        tc_fence_before();
-        __syncthreads();
-    }
-}
-
 // ---- fixed-point image of a state: 8 balanced base-128 digits ----
 // q = rint(r * 2^55);  q + BIAS has seven non-negative base-128 digits (d_a + 64) and a signed top
 // digit, so every digit is a shift and a mask.  Returned packed: w03 = bytes (d0,d1,d2,d3) with d0
