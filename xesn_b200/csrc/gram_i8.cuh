@@ -36,6 +36,7 @@ constexpr int A_BYTES = NDIG * A_PLANE;        // 32 KB
 constexpr int STAGE_BYTES = NDIG * (A_PLANE + B_PLANE);  // 48 KB
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 128 /*barriers + tmem ptr*/;
 constexpr int THREADS = 256;
+constexpr int ISSUERS = 4;  // threads issuing tcgen05.mma (one per warp 0..3), levels split modulo ISSUERS
 
 struct GramI8Args {
     const int8_t* planes;   // [NDIG][rows][ldp]
@@ -142,8 +143,8 @@ __device__ __forceinline__ void gram_i8_setup(GramI8Ctx& ctx, unsigned char* sme
     ctx.bar_final = ctl + 8 * STAGES;
     const unsigned tmem_slot = ctl + 8 * STAGES + 8;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) mbar_init(ctx.bar_done + 8 * s, 1);
-        mbar_init(ctx.bar_final, 1);
+        for (int s = 0; s < STAGES; ++s) mbar_init(ctx.bar_done + 8 * s, ISSUERS);
+        mbar_init(ctx.bar_final, ISSUERS);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (threadIdx.x < 32) {
@@ -228,17 +229,22 @@ __device__ __forceinline__ void gram_i8_tile(GramI8Ctx& ctx, const GramI8Args& p
         cp_wait<STAGES - 2>();   // this thread's copies of K-block kb have landed
         fence_proxy_async();     // ... and are visible to the tensor core's (async proxy) reads
         __syncthreads();
-        if (tid == 0) {
+        // Four issuing threads (lane 0 of warps 0..3), each owning the levels a+b = w (mod 4): a single
+        // thread cannot issue one N=64 MMA (32 tensor-pipe cycles) every 32 cycles, which capped the
+        // pipe at 46 % (profiles/gram_i8_r01_v3.txt).  All MMAs of a level come from one thread, so the
+        // non-accumulating first MMA of a level still precedes the others in issue order.
+        if (lane == 0 && warp < ISSUERS) {
             tc_fence_after();
             const unsigned sa = ctx.stage_base + s * STAGE_BYTES;
             const unsigned long long da0 = smem_desc(sa, 1024, 2);
             const unsigned long long db0 = smem_desc(sa + A_BYTES, 512, 4);
 #pragma unroll
-            for (int a = 0; a < NDIG; ++a) {
+            for (int lv = 0; lv < NDIG; ++lv) {
+                if ((lv % ISSUERS) != warp) continue;
 #pragma unroll
-                for (int b = 0; b + a < NDIG; ++b)
-                    mma_i8(ctx.tmem + (a + b) * TN, da0 + (unsigned long long)(a * (A_PLANE >> 4)),
-                           db0 + (unsigned long long)(b * (B_PLANE >> 4)), (kb > 0 || a > 0) ? 1u : 0u);
+                for (int a = 0; a <= lv; ++a)
+                    mma_i8(ctx.tmem + lv * TN, da0 + (unsigned long long)(a * (A_PLANE >> 4)),
+                           db0 + (unsigned long long)((lv - a) * (B_PLANE >> 4)), (kb > 0 || a > 0) ? 1u : 0u);
             }
             mma_commit(ctx.bar_done + 8 * s);
             if (kb == nkb - 1) mma_commit(ctx.bar_final);
