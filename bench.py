@@ -378,8 +378,8 @@ def main():
             traffic = None
     i8 = fused and os.environ.get("XESN_B200_GRAM", "i8").lower() not in ("f64", "fp64", "dmma", "0")
     if i8:
-        # the Gram role runs on the int8 tensor cores: 36 digit-pair MMAs replace each FP64 FMA
-        int_ops = 36.0 * gram_flops            # 36 pairs x (2 ops per MAC) x N(N+1)/2 MACs per step
+        # the Gram role runs on the int8 tensor cores: 28 digit-pair MMAs replace each FP64 FMA
+        int_ops = 28.0 * gram_flops            # 28 pairs x (2 ops per MAC) x N(N+1)/2 MACs per step
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -401,7 +401,7 @@ def main():
             "ops_per_launch": int_ops / n_gram_launches,
             "fp64_equivalent_tflops": achieved, "fp64_dgemm_peak_tflops": peak_tf,
             "fp64_equivalent_frac_of_dgemm_peak": achieved / peak_tf if peak_tf else None,
-            "note": "achieved = 36 x N(N+1) x T int8 ops (the digit-pair MMAs of one triangle) / summed event time of "
+            "note": "achieved = 28 x N(N+1) x T int8 ops (the digit-pair MMAs of one triangle) / summed event time of "
                     "the fused launches; the same kernel hosts the recurrence on its other SMs and is currently "
                     "bounded by whichever role finishes last",
         }

@@ -351,7 +351,7 @@ static TrainLayout train_layout(xesn_reservoir* h, int O, int G, int chunk, int 
     // second drive / state-ring buffers: the fused chunk kernel runs recurrence(c) beside Gram(c-1)
     L.D2 = off, off += round_up((long long)G * chunk * h->N, 2);
     L.R2 = off, off += round_up((long long)G * (chunk + 1) * h->N, 2);
-    // int8 digit planes of the states, [G][8][round_up(chunk,32)][round_up(N,128)] bytes, double-buffered
+    // int8 digit planes of the states, [G][7][round_up(chunk,32)][round_up(N,128)] bytes, double-buffered
     L.ldp = round_up(h->N, 128);
     L.plane_stride = L.ldp * round_up(chunk, gi8::KB);
     const long long plane_doubles = round_up((long long)G * gi8::NDIG * L.plane_stride, 16) / 8;
@@ -375,6 +375,7 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
     XESN_REQUIRE(O > 0 && G > 0 && chunk > 0 && T >= 0 && n_spinup >= 0 && n_spinup <= T, "bad sizes");
     const int gu = (u->map_dev || u->zero_row_dev) ? 1 : 0, gy = (y->map_dev || y->zero_row_dev) ? 1 : 0;
     XESN_REQUIRE(scratch_bytes >= xesn_train_scratch_bytes(h, O, G, chunk, gu, gy), "scratch too small");
+    XESN_REQUIRE(chunk <= gi8::MAX_K, "chunk: at most 16384 time steps per chunk (int32 accumulators of the int8 Gram)");
     cudaStream_t st = (cudaStream_t)stream;
     const int N = h->N;
     const TrainLayout L = train_layout(h, O, G, chunk, gu, gy);
@@ -787,6 +788,7 @@ int xesn_predict_p2p(xesn_reservoir* h, const double* wout, int32_t O, int32_t G
 // tensor-core path (digitise -> tcgen05 kind::i8 Gram).  Allocates its own scratch and synchronises.
 int xesn_gram_i8(const double* states, int64_t lds, int32_t n_rows, int32_t N, double* gram, int64_t ldg, void* stream) {
     XESN_REQUIRE(states && gram && n_rows > 0 && N > 0, "bad arguments");
+    XESN_REQUIRE(n_rows <= gi8::MAX_K, "gram_i8: at most 16384 rows per call (int32 accumulators); accumulate in pieces");
     cudaStream_t st = (cudaStream_t)stream;
     int dev = 0;
     XESN_CUDA_OK(cudaGetDevice(&dev));

@@ -14,7 +14,10 @@
 // Tile order of the Gram role: a host-built list that walks the lower triangle in super-rows of
 // 12 tile rows, column by column, so the ~132 tiles in flight at any time touch about 12 + 11
 // operand panels (L2-resident) instead of ~130 distinct ones.
+#include <cuda.h>
+
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 #include "gemm_tile.cuh"
@@ -47,13 +50,33 @@ fused_chunk_kernel(RecurArgs rp, int rec_ctas, int team, GemmArgs gp, const int2
 // recurrence role of the PREVIOUS launch (gram_i8.cuh).
 constexpr int FUSED_I8_THREADS = 512;  // 16 warps: twice the latency hiding for the recurrence role
 
+#ifdef XESN_RECUR_TRACE
+static __device__ unsigned long long g_cta_ns[2 * 160 * 2];  // debug builds: start/end %globaltimer of every CTA
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define XESN_CTA_STAMP(i)                                                              \
+    do {                                                                               \
+        __syncthreads();                                                               \
+        if (threadIdx.x == 0 && blockIdx.x < 160 && ntiles > 0) g_cta_ns[(rec_ctas > 0 ? 0 : 320) + blockIdx.x * 2 + (i)] = globaltimer_ns(); \
+    } while (0)
+#else
+#define XESN_CTA_STAMP(i) \
+    do {                  \
+    } while (0)
+#endif
+
 template <int UPT, bool WS>
 __global__ void __launch_bounds__(FUSED_I8_THREADS, 1)
-fused_chunk_i8_kernel(RecurArgs rp, int rec_ctas, int team, gi8::GramI8Args gp, const int2* __restrict__ tiles,
-                      int ntiles) {
+fused_chunk_i8_kernel(RecurArgs rp, int rec_ctas, int team, gi8::GramI8Args gp, const __grid_constant__ CUtensorMap tmA,
+                      const __grid_constant__ CUtensorMap tmB, const int2* __restrict__ tiles, int ntiles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    XESN_CTA_STAMP(0);
     if ((int)blockIdx.x < rec_ctas) {
         recur::recur_body<UPT, FUSED_I8_THREADS, WS>(rp, blockIdx.x % team, team, blockIdx.x / team, smem_raw);
+        XESN_CTA_STAMP(1);
         return;
     }
     const int worker = blockIdx.x - rec_ctas, nworkers = gridDim.x - rec_ctas;
@@ -61,22 +84,22 @@ fused_chunk_i8_kernel(RecurArgs rp, int rec_ctas, int team, gi8::GramI8Args gp, 
     if (worker >= total) return;
     gi8::GramI8Ctx ctx;
     gi8::gram_i8_setup(ctx, smem_raw);
-    for (long long t = worker; t < total; t += nworkers) {
-        const int2 ij = tiles[t % ntiles];
-        gi8::gram_i8_tile<FUSED_I8_THREADS>(ctx, gp, ij.x, ij.y, (int)(t / ntiles));
-    }
+    gi8::gram_i8_run<FUSED_I8_THREADS>(ctx, gp, &tmA, &tmB, tiles, ntiles, worker, nworkers);
     gi8::gram_i8_teardown(ctx);
+    XESN_CTA_STAMP(1);
 }
 
 }  // namespace
 
 // team size / units per thread of the recurrence role for FUSED_THREADS-wide CTAs
 int fused_recur_geometry(int N, int n_groups, int threads, int* team_out, int* upt_out) {
-    // The recurrence role wants many thin CTAs (its per-step cost grows with the units per CTA),
-    // the Gram role wants the SMs.  Default: at most 512 units per thread block... per CTA 256 threads x
-    // UPT units, the smallest UPT whose total CTA count stays within the cap (32 CTAs for one big
-    // reservoir, 64 when many small reservoirs run side by side).  XESN_B200_REC_UPT / _REC_CAP override.
-    int cap = n_groups > 1 ? 64 : 16;
+    // The recurrence role wants many thin CTAs (its per-step cost grows with the units per CTA: the
+    // shared-memory gathers of W r are bank-conflict bound), the Gram role wants the SMs.  Default: `threads`
+    // x UPT units per CTA with the smallest UPT whose total CTA count stays within the cap (32 CTAs for one
+    // big reservoir, 64 when many small reservoirs run side by side).  Measured at N=16000 (ms per 2048-step
+    // chunk, recurrence / Gram role): 16 CTAs 10.7 / 6.8, 32 CTAs 6.9 / 7.7.
+    // XESN_B200_REC_UPT / _REC_CAP override.
+    int cap = n_groups > 1 ? 64 : 32;
     int force_upt = 0;
     if (const char* e = getenv("XESN_B200_REC_CAP")) cap = atoi(e);
     if (const char* e = getenv("XESN_B200_REC_UPT")) force_upt = atoi(e);
@@ -183,7 +206,7 @@ int launch_fused_chunk_i8(RecurArgs rp, int n_groups, int team, int upt, int max
         set_error("fused chunk: recurrence role needs %d CTAs, device has %d SMs", rec_ctas, num_sms);
         return -2;
     }
-    void (*kern)(RecurArgs, int, int, gi8::GramI8Args, const int2*, int);
+    void (*kern)(RecurArgs, int, int, gi8::GramI8Args, const CUtensorMap, const CUtensorMap, const int2*, int);
     if (w_in_smem)
         kern = upt == 1 ? fused_chunk_i8_kernel<1, true>
                         : (upt == 2 ? fused_chunk_i8_kernel<2, true>
@@ -194,10 +217,24 @@ int launch_fused_chunk_i8(RecurArgs rp, int n_groups, int team, int upt, int max
                                     : (upt == 4 ? fused_chunk_i8_kernel<4, false> : fused_chunk_i8_kernel<8, false>));
     XESN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     gi8::GramI8Args g = gp;
-    void* args[] = {&rp, &rec_ctas, &team, &g, (void*)&tiles, &ntiles};
+    alignas(64) CUtensorMap tm_a, tm_b;
+    memset(&tm_a, 0, sizeof(tm_a));
+    memset(&tm_b, 0, sizeof(tm_b));
+    if (ntiles > 0)
+        if (int rc = gram_i8_make_maps(g, &tm_a, &tm_b)) return rc;
+    void* args[] = {&rp, &rec_ctas, &team, &g, &tm_a, &tm_b, (void*)&tiles, &ntiles};
     XESN_CUDA_OK(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(FUSED_I8_THREADS), args, (size_t)smem, stream));
     count_launch();
     return 0;
 }
 
 }  // namespace xesn
+
+#ifdef XESN_RECUR_TRACE
+extern "C" int xesn_debug_cta_ns(unsigned long long* out) {
+    return (int)cudaMemcpyFromSymbol(out, xesn::g_cta_ns, sizeof(unsigned long long) * 2 * 160 * 2);
+}
+extern "C" int xesn_debug_trace_fused(long long* out) {
+    return (int)cudaMemcpyFromSymbol(out, xesn::recur::g_recur_trace, sizeof(long long) * 64 * 8);
+}
+#endif

@@ -1,6 +1,8 @@
 // Stand-alone launchers of the int8 (tcgen05) Gram accumulation: digitiser + persistent Gram kernel.
 // The production path runs the same device code as a role of the fused chunk kernel (fused_train.cu);
 // these entry points serve parity tests, A/B measurements and the non-fused fallback.
+#include <cuda.h>
+
 #include <vector>
 
 #include "common.cuh"
@@ -13,19 +15,16 @@ namespace {
 using namespace gi8;
 
 __global__ void __launch_bounds__(THREADS, 1)
-gram_i8_kernel(GramI8Args p, const int2* __restrict__ tiles, int ntiles) {
+gram_i8_kernel(GramI8Args p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const int2* __restrict__ tiles, int ntiles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     GramI8Ctx ctx;
     gram_i8_setup(ctx, smem_raw);
-    const long long total = (long long)ntiles * p.batch;
-    for (long long t = blockIdx.x; t < total; t += gridDim.x) {
-        const int2 ij = tiles[t % ntiles];
-        gram_i8_tile<THREADS>(ctx, p, ij.x, ij.y, (int)(t / ntiles));
-    }
+    gram_i8_run<THREADS>(ctx, p, &tmA, &tmB, tiles, ntiles, blockIdx.x, gridDim.x);
     gram_i8_teardown(ctx);
 }
 
-// states [rows][N] f64 (row stride lds) -> planes [8][rows_pad][ldp]; rows >= n_rows and columns >= N are zero
+// states [rows][N] f64 (row stride lds) -> planes [NDIG][rows_pad][ldp]; rows >= n_rows and columns >= N are zero
 __global__ void digitize_kernel(const double* __restrict__ states, long long lds, int n_rows, int N, int8_t* planes,
                                 long long ldp, long long plane_stride, int rows_pad) {
     const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -58,6 +57,50 @@ void gram_i8_tile_list(int N, std::vector<int2>& tiles) {
     }
 }
 
+// TMA descriptors of the digit planes seen as a 3-D byte tensor (N bytes, time steps, planes of all groups):
+// box A = 128 B x 32 steps x 7 planes (SWIZZLE_128B), box B = 64 B x 32 x 7 (SWIZZLE_64B)
+int gram_i8_make_maps(const gi8::GramI8Args& a, void* map_a, void* map_b) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        XESN_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) {
+            set_error("gram_i8: cuTensorMapEncodeTiled is not available in this driver");
+            return -3;
+        }
+        encode = (EncodeFn)fn;
+    }
+    if (a.batch > 1 && a.group_stride != (long long)NDIG * a.plane_stride) {
+        set_error("gram_i8: groups must be stored back to back (group stride = %d planes)", NDIG);
+        return -1;
+    }
+    if ((a.ldp % 16) || (a.plane_stride % 16) || (reinterpret_cast<uintptr_t>(a.planes) & 15)) {
+        set_error("gram_i8: digit planes must be 16-byte aligned with row and plane pitches that are multiples of 16");
+        return -1;
+    }
+    const cuuint64_t gdim[3] = {(cuuint64_t)a.ldp, (cuuint64_t)a.K, (cuuint64_t)NDIG * (cuuint64_t)a.batch};
+    const cuuint64_t gstride[2] = {(cuuint64_t)a.ldp, (cuuint64_t)a.plane_stride};
+    const cuuint32_t estride[3] = {1, 1, 1};
+    const cuuint32_t box_a[3] = {128, (cuuint32_t)KB, (cuuint32_t)NDIG};
+    const cuuint32_t box_b[3] = {64, (cuuint32_t)KB, (cuuint32_t)NDIG};
+    void* base = const_cast<int8_t*>(a.planes);
+    CUresult r1 = encode((CUtensorMap*)map_a, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, gdim, gstride, box_a, estride,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r2 = encode((CUtensorMap*)map_b, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, gdim, gstride, box_b, estride,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) {
+        set_error("gram_i8: cuTensorMapEncodeTiled failed (%d, %d)", (int)r1, (int)r2);
+        return -3;
+    }
+    return 0;
+}
+
 int launch_digitize(const double* states, long long lds, int n_rows, int N, int8_t* planes, long long ldp,
                     long long plane_stride, int rows_pad, cudaStream_t stream) {
     dim3 grid((unsigned)((ldp + 255) / 256), (unsigned)rows_pad);
@@ -69,6 +112,10 @@ int launch_digitize(const double* states, long long lds, int n_rows, int N, int8
 
 int launch_gram_i8(const gi8::GramI8Args& a, const int2* tiles, int ntiles, int num_sms, cudaStream_t stream) {
     if (ntiles <= 0 || a.batch <= 0 || a.K <= 0) return 0;
+    if (a.K > MAX_K) {
+        set_error("gram_i8: K=%d exceeds %d steps per launch (int32 accumulators)", a.K, MAX_K);
+        return -1;
+    }
     if (a.K % KB) {
         set_error("gram_i8: K=%d must be a multiple of %d (zero-padded rows)", a.K, KB);
         return -1;
@@ -78,9 +125,11 @@ int launch_gram_i8(const gi8::GramI8Args& a, const int2* tiles, int ntiles, int 
         XESN_CUDA_OK(cudaFuncSetAttribute(gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr = true;
     }
+    alignas(64) CUtensorMap tm_a, tm_b;
+    if (int rc = gram_i8_make_maps(a, &tm_a, &tm_b)) return rc;
     long long total = (long long)ntiles * a.batch;
     int grid = (int)(total < num_sms ? total : num_sms);
-    gram_i8_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(a, tiles, ntiles);
+    gram_i8_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(a, tm_a, tm_b, tiles, ntiles);
     XESN_CUDA_OK(cudaGetLastError());
     count_launch();
     return 0;

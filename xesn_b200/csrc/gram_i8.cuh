@@ -1,42 +1,46 @@
-// Error-free Gram accumulation on the 5th-gen tensor cores (tcgen05, kind::i8) -- device side.
+// Gram accumulation on the 5th-gen tensor cores (tcgen05, kind::i8) from fixed-point digit planes -- device side.
 //
 // FP64 has no tcgen05 kind; DMMA tops out at 37 TFLOP/s.  But reservoir states are bounded,
-// |r| <= 1 (tanh + convex leak), so they have an exact fixed-point image
-//       q = rint(r * 2^55)  =  sum_{a=0..7} d_a * 128^(7-a),   d_a in [-64, 64]  (balanced base 128)
+// |r| <= 1 (tanh + convex leak), so they have a fixed-point image
+//       q = rint(r * 2^54)  =  sum_{a=0..6} d_a * 256^(6-a),   d_a in [-128, 127]  (balanced base 256)
 // and the Gram matrix  sum_t r_i r_j  splits into integer matrix products of the digit planes
-//       sum_t r_i(t) r_j(t)  =  sum_{a,b} 2^(-12-7(a+b)) * sum_t d_a,i(t) d_b,j(t).
+//       sum_t r_i(t) r_j(t)  =  sum_{a,b} 2^(-12-8(a+b)) * sum_t d_a,i(t) d_b,j(t).
 // Every plane product is an int8 x int8 -> int32 GEMM that the tensor cores compute EXACTLY
-// (|d| <= 64, K <= 2^17 steps per chunk keeps the int32 sums below 2^31 even with 8 pairs per
-// accumulator).  Pairs with a+b = s share one TMEM accumulator (same weight 2^(-12-7s)); pairs with
-// a+b >= 8 are dropped (< 2^-68 per product).  The only roundings are the fixed-point image itself
-// (2^-56 absolute, below FP64's own resolution for |r| > 2^-3) and the eight FP64 adds that
-// combine the levels -- tighter than a DGEMM whose every FMA rounds.  36 int8 MMAs replace the
-// FP64 FMAs: 36 * 2 N^2 K int-ops at 4.5 Pop/s vs 2 N^2 K flops at 37 TFLOP/s.
+// (|d| <= 128, at most 7 pairs per accumulator: K <= 16384 steps per launch keeps the int32 sums below
+// 2^31).  Pairs with a+b = s share one TMEM accumulator (same weight 2^(-12-8s)); the 28 pairs with
+// a+b <= 6 are kept.  Roundings: the fixed-point image (2^-55 absolute: exact for |r| >= 2^-2 given
+// FP64's own spacing), the dropped pairs (a+b >= 7: below 2^-51 per product in the worst case, ~2^-54
+// typical, zero-mean) and the seven FP64 adds that combine the levels -- the same order as the
+// rounding of each FP64 product in a DGEMM, and exact when the states live on a 2^-42 grid.
+// 28 int8 MMAs replace the FP64 FMAs: 28 * 2 N^2 K int-ops at 4.5 Pop/s vs 2 N^2 K flops at 37 TFLOP/s.
+// (First version: 8 balanced base-128 digits, 36 pairs, 8 levels = all of TMEM; base 256 needs 22 % fewer
+// MMAs and one plane less for the same 2^-55..2^-56 resolution.)
 //
-// Data layout: digit planes [8][rows][ldp] int8, row = time step, ldp >= N rounded up to 128:
+// Data layout: digit planes [7][rows][ldp] int8, row = time step, ldp >= N rounded up to 128:
 // MN-major operands for BOTH sides of R^T R, read straight by tcgen05.mma (a_major = b_major = MN).
 // The recurrence writes the digits of a state next to the FP64 value, so no transpose or
 // re-quantisation pass exists.
 //
-// Tile: 128 (M) x 64 (N) outputs, K-block = 32 time steps.  TMEM: 8 levels x 64 columns = 512.
-// Shared memory per stage: A 8 planes x 32 rows x 128 B (SWIZZLE_128B) + B 8 x 32 x 64 B
-// (SWIZZLE_64B) = 48 KB, 4 stages.  All 256 threads copy with cp.async (16 B chunks straight into
-// the swizzled position), one thread issues the 36 MMAs of a K-block and commits to an mbarrier.
+// Tile: 128 (M) x 64 (N) outputs, K-block = 32 time steps.  TMEM: 7 levels x 64 columns = 448 of 512.
+// Shared memory per stage: A 7 planes x 32 rows x 128 B (SWIZZLE_128B) + B 7 x 32 x 64 B
+// (SWIZZLE_64B) = 42 KB, 5 stages.  All threads copy with cp.async (16 B chunks straight into
+// the swizzled position), four threads issue the 28 MMAs of a K-block and commit to an mbarrier.
 #pragma once
 #include "common.cuh"
 
 namespace xesn {
 namespace gi8 {
 
-constexpr int TM = 128, TN = 64, KB = 32, NDIG = 8;
-constexpr int STAGES = 4;
+constexpr int TM = 128, TN = 64, KB = 32, NDIG = 7;
+constexpr int STAGES = 5;
+constexpr int MAX_K = 16384;  // int32 accumulators: 7 pairs x 2^14 x K < 2^31
 constexpr int A_PLANE = KB * 128;              // bytes per plane per stage (A)
 constexpr int B_PLANE = KB * 64;               // (B)
-constexpr int A_BYTES = NDIG * A_PLANE;        // 32 KB
-constexpr int STAGE_BYTES = NDIG * (A_PLANE + B_PLANE);  // 48 KB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 128 /*barriers + tmem ptr*/;
-constexpr int THREADS = 256;
-constexpr int ISSUERS = 4;  // threads issuing tcgen05.mma (one per warp 0..3), levels split modulo ISSUERS
+constexpr int A_BYTES = NDIG * A_PLANE;        // 28 KB
+constexpr int STAGE_BYTES = NDIG * (A_PLANE + B_PLANE);  // 42 KB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers + tmem ptr*/;
+constexpr int THREADS = 512;
+constexpr int ISSUERS = 4;  // threads issuing tcgen05.mma (one per warp 0..3): levels {0,6}, {1,5}, {2,4}, {3}
 
 struct GramI8Args {
     const int8_t* planes;   // [NDIG][rows][ldp]
@@ -126,12 +130,11 @@ __device__ __forceinline__ void tmem_ld32(unsigned taddr, int (&v)[32]) {
 // Per-CTA state of the Gram role (lives across tiles of a persistent loop).
 struct GramI8Ctx {
     unsigned stage_base;   // shared address of stage 0 (1024-byte aligned)
-    unsigned bar_done;     // STAGES mbarriers: MMAs that read the stage have completed
-    unsigned bar_final;    // all MMAs of the tile have completed
+    unsigned bar_full;     // STAGES mbarriers: the TMA boxes of the stage have landed
+    unsigned bar_empty;    // STAGES mbarriers: the MMAs that read the stage have completed
+    unsigned bar_tfull;    // all MMAs of the tile have completed: accumulators ready for the epilogue
+    unsigned bar_tempty;   // the epilogue has read the accumulators
     unsigned tmem;         // TMEM base address (512 columns)
-    unsigned done_phase;   // bit s: parity to wait for on bar_done[s]
-    unsigned final_phase;
-    unsigned used;         // bit s: stage s has outstanding MMAs (bar_done must be waited before refill)
 };
 
 // one warp allocates all 512 TMEM columns; every thread learns the base address
@@ -139,12 +142,18 @@ __device__ __forceinline__ void gram_i8_setup(GramI8Ctx& ctx, unsigned char* sme
     const unsigned raw = smem_u32(smem_raw);
     ctx.stage_base = (raw + 1023u) & ~1023u;
     const unsigned ctl = ctx.stage_base + STAGES * STAGE_BYTES;
-    ctx.bar_done = ctl;            // 8 bytes each
-    ctx.bar_final = ctl + 8 * STAGES;
-    const unsigned tmem_slot = ctl + 8 * STAGES + 8;
+    ctx.bar_full = ctl;            // 8 bytes each
+    ctx.bar_empty = ctl + 8 * STAGES;
+    ctx.bar_tfull = ctl + 16 * STAGES;
+    ctx.bar_tempty = ctl + 16 * STAGES + 8;
+    const unsigned tmem_slot = ctl + 16 * STAGES + 16;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) mbar_init(ctx.bar_done + 8 * s, ISSUERS);
-        mbar_init(ctx.bar_final, ISSUERS);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(ctx.bar_full + 8 * s, 1);
+            mbar_init(ctx.bar_empty + 8 * s, ISSUERS);
+        }
+        mbar_init(ctx.bar_tfull, ISSUERS);
+        mbar_init(ctx.bar_tempty, 8 /* EPI_WARPS */);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (threadIdx.x < 32) {
@@ -155,7 +164,6 @@ __device__ __forceinline__ void gram_i8_setup(GramI8Ctx& ctx, unsigned char* sme
     __syncthreads();
     tc_fence_after();
     asm volatile("ld.shared.b32 %0, [%1];\n" : "=r"(ctx.tmem) : "r"(tmem_slot) : "memory");
-    ctx.done_phase = 0, ctx.final_phase = 0, ctx.used = 0;
 }
 
 __device__ __forceinline__ void gram_i8_teardown(GramI8Ctx& ctx) {
@@ -183,163 +191,158 @@ __device__ __forceinline__ void tmem_ld<16>(unsigned taddr, int (&v)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
 
-// copy K-block kb of the A (rows m0.., 128 bytes) and B (rows n0.., 64 bytes) digit planes into stage s
-// NT = threads of the CTA taking part (256 or 512)
-template <int NT>
-__device__ __forceinline__ void gram_i8_load(const GramI8Ctx& ctx, const GramI8Args& p, const int8_t* planes, int s,
-                                             int kb, int m0, int n0) {
-    const int tid = threadIdx.x;
-    const unsigned sa = ctx.stage_base + s * STAGE_BYTES;
-    const unsigned sb = sa + A_BYTES;
-    const long long row0 = (long long)kb * KB;
-    {   // A: 256 (row, chunk) slots per plane; thread -> slot tid & 255, planes a0, a0 + NT/256, ...
-        constexpr int PSTEP = NT / 256;
-        const int c = tid & 7, kk = (tid >> 3) & 31, a0 = tid >> 8;
-        const int8_t* src = planes + (row0 + kk) * p.ldp + m0 + c * 16;
-        const unsigned dst = sa + kk * 128 + ((c ^ (kk & 7)) << 4);
-#pragma unroll
-        for (int a = a0; a < NDIG; a += PSTEP) cp16(dst + a * A_PLANE, src + a * p.plane_stride);
-    }
-    {   // B: 128 slots per plane (4 chunks per row); thread -> slot tid & 127, planes a0, a0 + NT/128, ...
-        constexpr int PSTEP = NT / 128;
-        const int c = tid & 3, kk = (tid >> 2) & 31, a0 = tid >> 7;
-        const int8_t* src = planes + (row0 + kk) * p.ldp + n0 + c * 16;
-        const unsigned dst = sb + kk * 64 + ((c ^ ((kk >> 1) & 3)) << 4);
-#pragma unroll
-        for (int a = a0; a < NDIG; a += PSTEP) cp16(dst + a * B_PLANE, src + a * p.plane_stride);
-    }
+// ---- TMA + mbarrier helpers -----------------------------------------------------------------
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+// one box of the digit-plane tensor (bytes along N, time steps, planes) -> shared memory, swizzled by the TMA unit
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const void* tmap, int c0, int c1, int c2, unsigned bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(dst),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+        : "memory");
 }
 
-// One 128 x 64 tile: rows m0 = 128*ti, columns n0 = 64*tj of batch entry bz.
+// Persistent Gram role of one CTA (512 threads), warp-specialised:
+//   warp 4 lane 0      producer: one TMA box per operand and K-block (A: 7 planes x 32 steps x 128 B, SWIZZLE_128B;
+//                      B: 7 x 32 x 64 B, SWIZZLE_64B) into a STAGES-deep ring, completion on full[s]
+//   warps 0..3 lane 0  MMA issuers (levels {0,6}, {1,5}, {2,4}, {3}): wait full[s], issue, tcgen05.commit -> empty[s];
+//                      after the last K-block of a tile commit -> tmem_full
+//   warps 8..15        epilogue: wait tmem_full, tcgen05.ld the 7 levels, combine in FP64, release TMEM
+//                      (tmem_empty) and only then read-modify-write G, so the next tile's MMAs overlap the
+//                      global-memory part of the epilogue
+// The first version refilled the ring with cp.async from every thread and ran bulk-synchronously (wait copies,
+// __syncthreads, issue, wait MMAs, refill): ncu showed half of all stall samples at that barrier and the
+// tensor pipe idle 44 % of the time, because the issuing threads block while the MMA queue is full and
+// nothing else overlaps with it.  Here loads, issue and epilogue only meet at mbarriers.
+constexpr int EPI_WARP0 = 8, EPI_WARPS = 8, PRODUCER_WARP = 4;
+
 template <int NT>
-__device__ __forceinline__ void gram_i8_tile(GramI8Ctx& ctx, const GramI8Args& p, int ti, int tj, int bz) {
+__device__ __forceinline__ void gram_i8_run(GramI8Ctx& ctx, const GramI8Args& p, const void* tmA, const void* tmB,
+                                            const int2* __restrict__ tiles, int ntiles, long long worker,
+                                            long long nworkers) {
+    static_assert(NT == 512, "the Gram role is laid out for 16 warps");
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int m0 = ti * TM, n0 = tj * TN;
-    const int8_t* planes = p.planes + (long long)bz * p.group_stride;
     const int nkb = p.K / KB;
+    const long long total = (long long)ntiles * p.batch;
 
-    // prologue: fill up to STAGES-1 stages (stages are free: the previous tile waited for its last MMA)
+    if (warp == PRODUCER_WARP) {
+        if (lane == 0) {
+            unsigned it = 0;
+            for (long long t = worker; t < total; t += nworkers) {
+                const int2 ij = tiles[t % ntiles];
+                const int bz = (int)(t / ntiles);
+                const int m0 = ij.x * TM, n0 = ij.y * TN;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const unsigned s = it % STAGES, use = it / STAGES;
+                    mbar_wait(ctx.bar_empty + 8 * s, (use & 1u) ^ 1u);
+                    const unsigned sa = ctx.stage_base + s * STAGE_BYTES;
+                    mbar_expect_tx(ctx.bar_full + 8 * s, STAGE_BYTES);
+                    tma_load_3d(sa, tmA, m0, kb * KB, bz * NDIG, ctx.bar_full + 8 * s);
+                    tma_load_3d(sa + A_BYTES, tmB, n0, kb * KB, bz * NDIG, ctx.bar_full + 8 * s);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp < ISSUERS) {
+        if (lane == 0) {
+            unsigned it = 0, tc = 0;
+            for (long long t = worker; t < total; t += nworkers, ++tc) {
+                mbar_wait(ctx.bar_tempty, (tc & 1u) ^ 1u);  // the epilogue has drained the previous tile's accumulators
+                tc_fence_after();
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const unsigned s = it % STAGES, use = it / STAGES;
+                    mbar_wait(ctx.bar_full + 8 * s, use & 1u);
+                    tc_fence_after();
+                    const unsigned sa = ctx.stage_base + s * STAGE_BYTES;
+                    const unsigned long long da0 = smem_desc(sa, 1024, 2);
+                    const unsigned long long db0 = smem_desc(sa + A_BYTES, 512, 4);
 #pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < nkb) gram_i8_load<NT>(ctx, p, planes, s, s, m0, n0);
-        cp_commit();
-    }
-    for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        cp_wait<STAGES - 2>();   // this thread's copies of K-block kb have landed
-        fence_proxy_async();     // ... and are visible to the tensor core's (async proxy) reads
-        __syncthreads();
-        // Four issuing threads (lane 0 of warps 0..3), each owning the levels a+b = w (mod 4): a single
-        // thread cannot issue one N=64 MMA (32 tensor-pipe cycles) every 32 cycles, which capped the
-        // pipe at 46 % (profiles/gram_i8_r01_v3.txt).  All MMAs of a level come from one thread, so the
-        // non-accumulating first MMA of a level still precedes the others in issue order.
-        if (lane == 0 && warp < ISSUERS) {
+                    for (int lv = 0; lv < NDIG; ++lv) {
+                        if ((lv <= 3 ? lv : 6 - lv) != warp) continue;
+#pragma unroll
+                        for (int a = 0; a <= lv; ++a)
+                            mma_i8(ctx.tmem + lv * TN, da0 + (unsigned long long)(a * (A_PLANE >> 4)),
+                                   db0 + (unsigned long long)((lv - a) * (B_PLANE >> 4)), (kb > 0 || a > 0) ? 1u : 0u);
+                    }
+                    mma_commit(ctx.bar_empty + 8 * s);  // stage s may be refilled once these MMAs have read it
+                }
+                mma_commit(ctx.bar_tfull);
+            }
+        }
+        __syncwarp();
+    } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + EPI_WARPS) {
+        // lane quarter q of TMEM <-> rows m0 + 32q + lane; the two warps of a quarter split the 64 columns
+        constexpr int NC = TN / (EPI_WARPS / 4);
+        const int q = warp & 3, part = (warp - EPI_WARP0) >> 2;
+        unsigned tc = 0;
+        for (long long t = worker; t < total; t += nworkers, ++tc) {
+            const int2 ij = tiles[t % ntiles];
+            const int bz = (int)(t / ntiles);
+            const int m0 = ij.x * TM, n0 = ij.y * TN;
+            mbar_wait(ctx.bar_tfull, tc & 1u);
             tc_fence_after();
-            const unsigned sa = ctx.stage_base + s * STAGE_BYTES;
-            const unsigned long long da0 = smem_desc(sa, 1024, 2);
-            const unsigned long long db0 = smem_desc(sa + A_BYTES, 512, 4);
+            double acc[NC];
 #pragma unroll
-            for (int lv = 0; lv < NDIG; ++lv) {
-                if ((lv % ISSUERS) != warp) continue;
+            for (int j = 0; j < NC; ++j) acc[j] = 0.0;
 #pragma unroll
-                for (int a = 0; a <= lv; ++a)
-                    mma_i8(ctx.tmem + lv * TN, da0 + (unsigned long long)(a * (A_PLANE >> 4)),
-                           db0 + (unsigned long long)((lv - a) * (B_PLANE >> 4)), (kb > 0 || a > 0) ? 1u : 0u);
+            for (int s = NDIG - 1; s >= 0; --s) {  // smallest weights first
+                int v[NC];
+                tmem_ld<NC>(ctx.tmem + ((unsigned)(q * 32) << 16) + s * TN + part * NC, v);
+                const double w = __longlong_as_double((long long)(1023 - 12 - 8 * s) << 52);  // 2^(-12-8s)
+#pragma unroll
+                for (int j = 0; j < NC; ++j) acc[j] = fma((double)v[j], w, acc[j]);
             }
-            mma_commit(ctx.bar_done + 8 * s);
-            if (kb == nkb - 1) mma_commit(ctx.bar_final);
-        }
-        ctx.used |= 1u << s;
-        // refill the stage that K-block kb-1 used, once its MMAs are done
-        const int nk = kb + STAGES - 1;
-        if (nk < nkb) {
-            const int sn = nk % STAGES;
-            if (ctx.used & (1u << sn)) {
-                mbar_wait(ctx.bar_done + 8 * sn, (ctx.done_phase >> sn) & 1u);
-                ctx.done_phase ^= 1u << sn;
-                ctx.used &= ~(1u << sn);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ctx.bar_tempty);  // accumulators may be overwritten by the next tile
+            const int m = m0 + q * 32 + lane;
+            if (m < p.N) {
+                double* g = p.G + (long long)bz * p.strideG + (long long)m * p.ldg + n0 + part * NC;
+                const int nmax = min(NC, min(p.N, m + 1) - (n0 + part * NC));  // columns <= row only (lower triangle)
+                if (nmax == NC && ((reinterpret_cast<uintptr_t>(g) & 15) == 0)) {
+#pragma unroll
+                    for (int j = 0; j < NC; j += 2) {
+                        double2 c = *reinterpret_cast<double2*>(g + j);
+                        c.x += acc[j], c.y += acc[j + 1];
+                        *reinterpret_cast<double2*>(g + j) = c;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < NC; ++j)
+                        if (j < nmax) g[j] += acc[j];
+                }
             }
-            gram_i8_load<NT>(ctx, p, planes, sn, nk, m0, n0);
-        }
-        cp_commit();
-    }
-    cp_wait<0>();
-    // drain: every stage's MMAs have completed once the final commit fires
-    mbar_wait(ctx.bar_final, ctx.final_phase);
-    ctx.final_phase ^= 1u;
-    // keep the per-stage barrier phases in step: each outstanding commit has completed by now
-#pragma unroll
-    for (int s = 0; s < STAGES; ++s)
-        if (ctx.used & (1u << s)) {
-            mbar_wait(ctx.bar_done + 8 * s, (ctx.done_phase >> s) & 1u);
-            ctx.done_phase ^= 1u << s;
-        }
-    ctx.used = 0;
-    tc_fence_after();
-
-    // epilogue: lane quarter q of TMEM <-> rows m0 + 32q + lane; the NT/128 warps of a quarter split the 64 columns
-    constexpr int NC = TN / (NT / 128);
-    const int q = warp & 3, part = warp >> 2;
-    const int m = m0 + q * 32 + lane;
-    double acc[NC];
-#pragma unroll
-    for (int j = 0; j < NC; ++j) acc[j] = 0.0;
-    if (nkb > 0) {
-#pragma unroll
-        for (int s = NDIG - 1; s >= 0; --s) {  // smallest weights first
-            int v[NC];
-            tmem_ld<NC>(ctx.tmem + ((unsigned)(q * 32) << 16) + s * TN + part * NC, v);
-            const double w = __longlong_as_double((long long)(1023 - 12 - 7 * s) << 52);  // 2^(-12-7s)
-#pragma unroll
-            for (int j = 0; j < NC; ++j) acc[j] = fma((double)v[j], w, acc[j]);
         }
     }
-    if (m < p.N) {
-        double* g = p.G + (long long)bz * p.strideG + (long long)m * p.ldg + n0 + part * NC;
-        const int nmax = min(NC, min(p.N, m + 1) - (n0 + part * NC));  // columns <= row only (lower triangle)
-        if (nmax == NC && ((reinterpret_cast<uintptr_t>(g) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < NC; j += 2) {
-                double2 c = *reinterpret_cast<double2*>(g + j);
-                c.x += acc[j], c.y += acc[j + 1];
-                *reinterpret_cast<double2*>(g + j) = c;
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < NC; ++j)
-                if (j < nmax) g[j] += acc[j];
-        }
-    }
-    // all TMEM reads of this tile are done before the next tile's first MMA overwrites the accumulators
-    tc_fence_before();
-    __syncthreads();
 }
 
-// ---- fixed-point image of a state: 8 balanced base-128 digits ----
-// q = rint(r * 2^55);  q + BIAS has seven non-negative base-128 digits (d_a + 64) and a signed top
-// digit, so every digit is a shift and a mask.  Returned packed: w03 = bytes (d0,d1,d2,d3) with d0
-// (most significant digit) in the lowest byte, w47 = (d4,d5,d6,d7).
+// ---- fixed-point image of a state: 7 balanced base-256 digits ----
+// q = rint(r * 2^54);  q + BIAS has six non-negative base-256 digits (d_a + 128) and a signed top
+// digit (|q| <= 2^54 keeps it within +-65), so every digit is a byte of q + BIAS with its top bit flipped.
+// Returned packed: w03 = bytes (d0,d1,d2,d3) with d0 (most significant digit) in the lowest byte,
+// w47 = (d4,d5,d6,0).
 __device__ __forceinline__ void state_digit_words(double r, unsigned& w03, unsigned& w47) {
     // |r| <= 1; non-finite states (diverged runs) are mapped to 0 here, the FP64 ring keeps them
-    long long q = (fabs(r) <= 1.0) ? __double2ll_rn(r * 36028797018963968.0 /* 2^55 */) : 0;
-    constexpr long long BIAS = 64LL * (1LL + (1LL << 7) + (1LL << 14) + (1LL << 21) + (1LL << 28) + (1LL << 35) + (1LL << 42));
+    long long q = (fabs(r) <= 1.0) ? __double2ll_rn(r * 18014398509481984.0 /* 2^54 */) : 0;
+    constexpr long long BIAS = 128LL * (1LL + (1LL << 8) + (1LL << 16) + (1LL << 24) + (1LL << 32) + (1LL << 40));
     q += BIAS;
     const unsigned lo = (unsigned)q, hi = (unsigned)((unsigned long long)q >> 32);
-    const unsigned e7 = lo & 127u, e6 = (lo >> 7) & 127u, e5 = (lo >> 14) & 127u, e4 = (lo >> 21) & 127u;
-    const unsigned e3 = __funnelshift_r(lo, hi, 28) & 127u, e2 = (hi >> 3) & 127u, e1 = (hi >> 10) & 127u;
-    const unsigned e0 = (unsigned)(((int)hi) >> 17) + 64u;  // signed top digit, biased like the others
-    w03 = __vsub4(e0 | (e1 << 8) | (e2 << 16) | (e3 << 24), 0x40404040u);
-    w47 = __vsub4(e4 | (e5 << 8) | (e6 << 16) | (e7 << 24), 0x40404040u);
+    // bytes of q + BIAS, least significant first: lo = (b0,b1,b2,b3), hi = (b4,b5,top,sign); digit d_a = byte 6-a
+    const unsigned x03 = __byte_perm(lo, hi, 0x3456);  // (top, b5, b4, b3)
+    const unsigned x47 = __byte_perm(lo, hi, 0x7012);  // (b2, b1, b0, sign byte -> cleared below)
+    w03 = x03 ^ 0x80808000u;                           // flip the bias bit of b5, b4, b3; the top digit is signed as is
+    w47 = (x47 & 0x00FFFFFFu) ^ 0x00808080u;
 }
 
 __device__ __forceinline__ void state_digits(double r, signed char (&d)[NDIG]) {
     unsigned w03, w47;
     state_digit_words(r, w03, w47);
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        d[a] = (signed char)((w03 >> (8 * a)) & 255u);
-        d[a + 4] = (signed char)((w47 >> (8 * a)) & 255u);
-    }
+    for (int a = 0; a < NDIG; ++a) d[a] = (signed char)(((a < 4 ? w03 : w47) >> (8 * (a & 3))) & 255u);
 }
 
 }  // namespace gi8

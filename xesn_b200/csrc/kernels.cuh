@@ -12,7 +12,7 @@ struct RecurArgs {
     long long drive_group_stride;
     double* states;          // [G][steps+1][N] ring: row 0 <- carry, rows 1..steps written (pre-filled "unset")
     long long state_group_stride;
-    signed char* planes;     // optional [G][8][rows][ldp] int8 digit planes of the states (gram_i8.cuh); rows 0..steps-1
+    signed char* planes;     // optional [G][7][rows][ldp] int8 digit planes of the states (gram_i8.cuh); rows 0..steps-1
     long long ldp, plane_stride, plane_group_stride;
     int* status;             // device int, set to 1 if a poll timed out (co-residency lost: never expected)
     double* carry;           // [G][N] state entering the chunk; overwritten with the state leaving it
@@ -71,6 +71,7 @@ int launch_fused_chunk(RecurArgs rp, int n_groups, int team, int upt, int max_sl
                        const int2* tiles, int ntiles, int num_sms, cudaStream_t stream);
 namespace gi8 { struct GramI8Args; }
 // same, with the Gram role on the int8 tensor cores (tcgen05 kind::i8) reading digit planes
+int gram_i8_make_maps(const gi8::GramI8Args& a, void* map_a, void* map_b);  // two CUtensorMap (64-byte aligned)
 int launch_fused_chunk_i8(RecurArgs rp, int n_groups, int team, int upt, int max_slice_nnz,
                           const gi8::GramI8Args& gp, const int2* tiles, int ntiles, int num_sms, cudaStream_t stream);
 int launch_step_update(const StepArgs& a, int n_groups, cudaStream_t stream);

@@ -8,6 +8,23 @@
 namespace xesn {
 namespace recur {
 
+#ifdef XESN_RECUR_TRACE
+// debug builds only: per-CTA cycle sums of the four phases of a step (thread 0's view)
+static __device__ long long g_recur_trace[64 * 8];
+#define XESN_TRACE_MARK(i)                         \
+    do {                                           \
+        if (tid == 0) {                            \
+            const long long now_ = clock64();      \
+            tr_sum[i] += now_ - tr_last;           \
+            tr_last = now_;                        \
+        }                                          \
+    } while (0)
+#else
+#define XESN_TRACE_MARK(i) \
+    do {                   \
+    } while (0)
+#endif
+
 constexpr int KMAX = 16;  // gathers issued back-to-back before the first FMA
 
 __device__ __forceinline__ double ld_cg(const double* p) {
@@ -58,7 +75,20 @@ __device__ __forceinline__ double leaky(double pre, double r_old, double alpha, 
 // scope compiles to MEMBAR.ALL.GPU per warp: 6.4 us per step in the first version).
 constexpr long long UNSET_BITS = -1LL;
 constexpr int SPIN_LIMIT = 1 << 22;  // ~1-2 s of polling, then the run is flagged as failed
-constexpr int POLL_BATCH = 16;       // 16-byte pieces in flight per thread while refreshing the copy
+// 16-byte pieces in flight per thread while refreshing the copy (64 KB per CTA either way)
+template <int RC_THREADS>
+struct PollCfg {
+    static constexpr int BATCH = RC_THREADS <= 256 ? 16 : 8;
+};
+
+// The first KREG entries of every owned row of W live in REGISTERS for the whole chunk (value and
+// byte offset into the shared state copy): they never change, and reading them from the CSR slice in
+// shared memory cost more wavefronts (thread-strided -> bank conflicts) than the state gathers themselves:
+// ncu, N=16000: 3200 shared wavefronts per step per CTA for the row dot, of which ~800 are the gathers.
+template <int UPT, int RC_THREADS>
+struct RowRegs {
+    static constexpr int K = RC_THREADS <= 256 ? (UPT <= 4 ? 8 : 4) : (UPT <= 2 ? 8 : (UPT == 4 ? 4 : 2));
+};
 
 __device__ __forceinline__ double2 ld_flag2(const double* p) {
     double2 v;
@@ -186,6 +216,33 @@ __device__ __forceinline__ void recur_body(const RecurArgs& p, const unsigned c,
         r_cur[j] = ok ? carry[unit] : 0.0;
         d_next[j] = (ok && p.steps > 0) ? drive[unit] : 0.0;
     }
+    // register-resident head of each owned row
+    constexpr int KREG = RowRegs<UPT, RC_THREADS>::K;
+    constexpr int POLL_BATCH = PollCfg<RC_THREADS>::BATCH;
+    const unsigned s_r_addr = (unsigned)__cvta_generic_to_shared(s_r);
+    double hv[UPT][KREG];
+    int ho[UPT][KREG];
+#pragma unroll
+    for (int j = 0; j < UPT; ++j)
+#pragma unroll
+        for (int k = 0; k < KREG; ++k) {
+            const bool in = k < row_len[j];
+            hv[j][k] = in ? p.values[row_lo[j] + k] : 0.0;
+            ho[j][k] = in ? p.indices[row_lo[j] + k] * (int)sizeof(double) : 0;
+        }
+    // pieces of the state copy this thread refreshes per polling round (own slice excluded); constant over
+    // the chunk, packed POLL_BATCH bits per round when all rounds fit one word
+    const int n2_all = N >> 1;
+    const int poll_rounds = (n2_all + RC_THREADS * POLL_BATCH - 1) / (RC_THREADS * POLL_BATCH);
+    const bool packed_masks = poll_rounds * POLL_BATCH <= 32;
+    unsigned mine_all = 0;
+    if (packed_masks)
+        for (int it = 0; it < poll_rounds; ++it)
+#pragma unroll
+            for (int b = 0; b < POLL_BATCH; ++b) {
+                const int q = tid + (it * POLL_BATCH + b) * RC_THREADS;
+                if ((q < n2_all) && !(2 * q >= u0 && 2 * q + 1 < u1)) mine_all |= 1u << (it * POLL_BATCH + b);
+            }
     put_states<UPT>(states + ubase, r_cur, nvalid);  // row 0 = state entering the chunk (read by the Gram kernel)
     if (digits && p.steps > 0) put_digits<UPT>(digits, p, 0, ubase, r_cur, nvalid);
     const double alpha = p.alpha, oma = 1.0 - p.alpha;
@@ -193,32 +250,96 @@ __device__ __forceinline__ void recur_body(const RecurArgs& p, const unsigned c,
     bool aborted = false;
     __syncthreads();
 
+#ifdef XESN_RECUR_TRACE
+    long long tr_sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tr_last = clock64();
+#endif
     for (int t = 0; t < p.steps; ++t) {
         double* r_next = states + (long long)(t + 1) * N;
         // ---- my units: W r_t from the shared copy, tanh, leak; publish to the ring ----
         // (branch-free over the UPT units so their dependent chains interleave)
         double pre[UPT];
+        // all UPT*KREG gathers are issued back to back (volatile asm keeps them batched: left to itself the
+        // compiler serialises load/use pairs to save registers and the phase becomes 16 shared-memory round
+        // trips); padding entries read offset 0 and are masked out of the arithmetic
+        double gth[UPT][KREG], hsum[UPT];
+#pragma unroll
+        for (int j = 0; j < UPT; ++j)
+#pragma unroll
+            for (int k = 0; k < KREG; ++k)
+                asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(gth[j][k]) : "r"(s_r_addr + (unsigned)ho[j][k]));
 #pragma unroll
         for (int j = 0; j < UPT; ++j) {
             double acc = 0.0;
-            if (WS) {
-                const int* of = s_off + (row_lo[j] - slice_lo);
-                const double* vl = s_val + (row_lo[j] - slice_lo);
-#pragma unroll 4
-                for (int k = 0; k < row_len[j]; ++k)
-                    acc = __dadd_rn(acc, __dmul_rn(vl[k], *reinterpret_cast<const double*>(
-                                                              reinterpret_cast<const char*>(s_r) + of[k])));
-            } else {
-                const int* ix = p.indices + row_lo[j];
-                const double* vl = p.values + row_lo[j];
-#pragma unroll 4
-                for (int k = 0; k < row_len[j]; ++k) acc = __dadd_rn(acc, __dmul_rn(__ldg(vl + k), s_r[__ldg(ix + k)]));
+#pragma unroll
+            for (int k = 0; k < KREG; ++k)
+                if (k < row_len[j]) acc = __dadd_rn(acc, __dmul_rn(hv[j][k], gth[j][k]));
+            hsum[j] = acc;
+        }
+        // long rows: the next KTAIL entries are staged together (offsets and values from the CSR slice, then
+        // the gathers) so the longest row of the warp costs one more round of loads, not one per entry
+        bool any_long = false;
+#pragma unroll
+        for (int j = 0; j < UPT; ++j) any_long |= row_len[j] > KREG;
+        if (__any_sync(0xffffffffu, any_long)) {
+            constexpr int KTAIL = 4;
+            int to[UPT][KTAIL];
+            double tv[UPT][KTAIL], tg[UPT][KTAIL];
+#pragma unroll
+            for (int j = 0; j < UPT; ++j)
+#pragma unroll
+                for (int k = 0; k < KTAIL; ++k) {
+                    const bool in = KREG + k < row_len[j];
+                    const int e = row_lo[j] + KREG + k;
+                    if (WS) {
+                        to[j][k] = in ? s_off[e - slice_lo] : 0;
+                        tv[j][k] = in ? s_val[e - slice_lo] : 0.0;
+                    } else {
+                        to[j][k] = in ? __ldg(p.indices + e) * (int)sizeof(double) : 0;
+                        tv[j][k] = in ? __ldg(p.values + e) : 0.0;
+                    }
+                }
+#pragma unroll
+            for (int j = 0; j < UPT; ++j)
+#pragma unroll
+                for (int k = 0; k < KTAIL; ++k)
+                    tg[j][k] = (KREG + k < row_len[j])
+                                   ? *reinterpret_cast<const double*>(reinterpret_cast<const char*>(s_r) + to[j][k])
+                                   : 0.0;
+#pragma unroll
+            for (int j = 0; j < UPT; ++j) {
+                double acc = hsum[j];
+#pragma unroll
+                for (int k = 0; k < KTAIL; ++k)
+                    if (KREG + k < row_len[j]) acc = __dadd_rn(acc, __dmul_rn(tv[j][k], tg[j][k]));
+                if (row_len[j] > KREG + KTAIL) {  // very rare: the rest one by one
+                    if (WS) {
+                        const int* of = s_off + (row_lo[j] - slice_lo);
+                        const double* vl = s_val + (row_lo[j] - slice_lo);
+                        for (int k = KREG + KTAIL; k < row_len[j]; ++k)
+                            acc = __dadd_rn(acc, __dmul_rn(vl[k], *reinterpret_cast<const double*>(
+                                                                      reinterpret_cast<const char*>(s_r) + of[k])));
+                    } else {
+                        const int* ix = p.indices + row_lo[j];
+                        const double* vl = p.values + row_lo[j];
+                        for (int k = KREG + KTAIL; k < row_len[j]; ++k)
+                            acc = __dadd_rn(acc, __dmul_rn(__ldg(vl + k), s_r[__ldg(ix + k)]));
+                    }
+                }
+                hsum[j] = acc;
             }
-            pre[j] = __dadd_rn(acc, d_next[j]);
         }
 #pragma unroll
+        for (int j = 0; j < UPT; ++j) {
+            double acc = hsum[j];
+            pre[j] = __dadd_rn(acc, d_next[j]);
+        }
+        XESN_TRACE_MARK(4);
+#pragma unroll
         for (int j = 0; j < UPT; ++j) r_cur[j] = leaky(pre[j], r_cur[j], alpha, oma);
+        XESN_TRACE_MARK(5);
         put_states<UPT>(r_next + ubase, r_cur, nvalid);
+        XESN_TRACE_MARK(6);
         // fixed-point digit planes for the int8 tensor-core Gram: row t+1 pairs with y(t0+t+1);
         // the state leaving the chunk (row `steps`) belongs to the next chunk's row 0
         if (digits && t + 1 < p.steps) put_digits<UPT>(digits, p, t + 1, ubase, r_cur, nvalid);
@@ -226,7 +347,9 @@ __device__ __forceinline__ void recur_body(const RecurArgs& p, const unsigned c,
 #pragma unroll
         for (int j = 0; j < UPT; ++j)
             if (j < nvalid) d_next[j] = __ldg(drive + (long long)(t + 1) * N + ubase + j);
+        XESN_TRACE_MARK(0);
         __syncthreads();  // every gather of r_t is done: the shared copy may be overwritten
+        XESN_TRACE_MARK(1);
 #pragma unroll
         for (int j = 0; j < UPT; ++j)
             if (j < nvalid) s_r[ubase + j] = r_cur[j];
@@ -234,14 +357,19 @@ __device__ __forceinline__ void recur_body(const RecurArgs& p, const unsigned c,
         if (C > 1 && !p.debug_no_exchange) {
             if (vec2) {
                 const int n2 = N >> 1;
-                for (int q0 = tid; q0 < n2; q0 += RC_THREADS * POLL_BATCH) {
+                int it = 0;
+                for (int q0 = tid; q0 < n2; q0 += RC_THREADS * POLL_BATCH, ++it) {
                     double2 v[POLL_BATCH];
                     unsigned pending = 0;  // bit b: piece b still has an unset half
+                    if (packed_masks) {
+                        pending = (mine_all >> (it * POLL_BATCH)) & ((1u << POLL_BATCH) - 1u);
+                    } else {
 #pragma unroll
-                    for (int b = 0; b < POLL_BATCH; ++b) {
-                        const int q = q0 + b * RC_THREADS;
-                        // pieces lying entirely inside my own slice are already in the copy
-                        if ((q < n2) && !(2 * q >= u0 && 2 * q + 1 < u1)) pending |= 1u << b;
+                        for (int b = 0; b < POLL_BATCH; ++b) {
+                            const int q = q0 + b * RC_THREADS;
+                            // pieces lying entirely inside my own slice are already in the copy
+                            if ((q < n2) && !(2 * q >= u0 && 2 * q + 1 < u1)) pending |= 1u << b;
+                        }
                     }
                     const unsigned mine = pending;
                     int spins = 0;
@@ -271,8 +399,14 @@ __device__ __forceinline__ void recur_body(const RecurArgs& p, const unsigned c,
                 }
             }
         }
+        XESN_TRACE_MARK(2);
         __syncthreads();
+        XESN_TRACE_MARK(3);
     }
+#ifdef XESN_RECUR_TRACE
+    if (tid == 0 && c < 64)
+        for (int i = 0; i < 8; ++i) g_recur_trace[c * 8 + i] = tr_sum[i];
+#endif
 #pragma unroll
     for (int j = 0; j < UPT; ++j)
         if (j < nvalid) p.carry[(long long)g * N + ubase + j] = r_cur[j];

@@ -17,6 +17,8 @@
 //     HBM-streaming batched GEMV, one warp per output row, scattered straight into the field.
 // K5  gather kernels      : halo construction (dask overlap, lazyesn.py:166,200,235) as an index
 //     gather with NaN->0 masking (lazyesn.py:287-289,362-364).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -36,6 +38,15 @@ __global__ void __launch_bounds__(RC_THREADS, 1) recur_forced_kernel(RecurArgs p
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned C = cluster_nctarank();
     recur_body<UPT, RC_THREADS, WS>(p, cluster_ctarank(), C, blockIdx.x / C, smem_raw);
+}
+
+// experimental geometry: 256 threads x 4 units with twice the registers per thread
+constexpr int RC_THREADS_NARROW = 256;
+template <int UPT, bool WS>
+__global__ void __launch_bounds__(RC_THREADS_NARROW, 1) recur_forced_narrow_kernel(RecurArgs p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const unsigned C = cluster_nctarank();
+    recur_body<UPT, RC_THREADS_NARROW, WS>(p, cluster_ctarank(), C, blockIdx.x / C, smem_raw);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -255,12 +266,17 @@ int launch_recur_forced(RecurArgs a, int n_groups, int max_slice_nnz, cudaStream
         kern = upt == 1 ? recur_forced_kernel<1, true> : (upt == 2 ? recur_forced_kernel<2, true> : recur_forced_kernel<4, true>);
     else
         kern = upt == 1 ? recur_forced_kernel<1, false> : (upt == 2 ? recur_forced_kernel<2, false> : recur_forced_kernel<4, false>);
+    int threads = RC_THREADS;
+    if (getenv("XESN_B200_REC_NARROW") && upt == 2) {
+        kern = a.w_in_smem ? recur_forced_narrow_kernel<4, true> : recur_forced_narrow_kernel<4, false>;
+        threads = RC_THREADS_NARROW;
+    }
     XESN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
     if (C > 8) XESN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
 
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(C * n_groups));
-    cfg.blockDim = dim3(RC_THREADS);
+    cfg.blockDim = dim3((unsigned)threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -340,3 +356,9 @@ int launch_gather_series(const double* src, long long ld_src, long long t0, cons
 }
 
 }  // namespace xesn
+
+#ifdef XESN_RECUR_TRACE
+extern "C" int xesn_debug_trace(long long* out) {
+    return (int)cudaMemcpyFromSymbol(out, xesn::recur::g_recur_trace, sizeof(long long) * 64 * 8);
+}
+#endif
