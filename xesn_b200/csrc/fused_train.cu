@@ -16,6 +16,7 @@
 // operand panels (L2-resident) instead of ~130 distinct ones.
 #include <cuda.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
@@ -95,11 +96,11 @@ fused_chunk_i8_kernel(RecurArgs rp, int rec_ctas, int team, gi8::GramI8Args gp, 
 int fused_recur_geometry(int N, int n_groups, int threads, int* team_out, int* upt_out) {
     // The recurrence role wants many thin CTAs (its per-step cost grows with the units per CTA: the
     // shared-memory gathers of W r are bank-conflict bound), the Gram role wants the SMs.  Default: `threads`
-    // x UPT units per CTA with the smallest UPT whose total CTA count stays within the cap (32 CTAs for one
-    // big reservoir, 64 when many small reservoirs run side by side).  Measured at N=16000 (ms per 2048-step
-    // chunk, recurrence / Gram role): 16 CTAs 10.7 / 6.8, 32 CTAs 6.9 / 7.7.
-    // XESN_B200_REC_UPT / _REC_CAP override.
-    int cap = n_groups > 1 ? 64 : 32;
+    // x UPT units per CTA with the smallest UPT whose total CTA count stays within the cap (48 CTAs for one
+    // big reservoir, 64 when many small reservoirs run side by side).  Measured at N=16000 with the first TMA
+    // Gram role (ms per 2048-step chunk, recurrence / Gram role): 16 CTAs 10.7 / 6.8, 32 CTAs 6.9 / 7.7.
+    // XESN_B200_REC_UPT / _REC_CAP / _REC_TEAM override.
+    int cap = n_groups > 1 ? 64 : 48;
     int force_upt = 0;
     if (const char* e = getenv("XESN_B200_REC_CAP")) cap = atoi(e);
     if (const char* e = getenv("XESN_B200_REC_UPT")) force_upt = atoi(e);
@@ -112,6 +113,17 @@ int fused_recur_geometry(int N, int n_groups, int threads, int* team_out, int* u
         break;
     }
     if (best_team < 0) return -2;
+    // one big reservoir: ~400 units per CTA instead of one per thread (40 CTAs at N=16000: measured 67.7 ms of
+    // fused kernels per 20000 steps against 71.5 with 32 CTAs and 66.8 with 48)
+    int want_team = 0;
+    if (n_groups == 1 && best_upt == 1 && !force_upt) want_team = std::min(cap, (N + 399) / 400);
+    if (const char* e = getenv("XESN_B200_REC_TEAM")) want_team = atoi(e);  // experiments: any team size
+    if (want_team > best_team && (long long)want_team * n_groups <= 96) {
+        const int upc = recur_units_per_cta(N, want_team);
+        int upt = (upc + threads - 1) / threads;
+        upt = upt <= 1 ? 1 : (upt <= 2 ? 2 : (upt <= 4 ? 4 : 8));
+        if ((long long)threads * upt >= upc) best_team = want_team, best_upt = upt;
+    }
     *team_out = best_team, *upt_out = best_upt;
     return 0;
 }

@@ -40,7 +40,7 @@ constexpr int A_BYTES = NDIG * A_PLANE;        // 28 KB
 constexpr int STAGE_BYTES = NDIG * (A_PLANE + B_PLANE);  // 42 KB
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers + tmem ptr*/;
 constexpr int THREADS = 512;
-constexpr int ISSUERS = 4;  // threads issuing tcgen05.mma (one per warp 0..3): levels {0,6}, {1,5}, {2,4}, {3}
+constexpr int ISSUERS = 1;  // one thread issues the 10 (wide) MMAs of a K-block
 
 struct GramI8Args {
     const int8_t* planes;   // [NDIG][rows][ldp]
@@ -85,10 +85,13 @@ __device__ __forceinline__ void cp_wait() {
 }
 
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): MN-major, swizzled, sm_100 version
-__device__ __forceinline__ unsigned long long smem_desc(unsigned addr, unsigned sbo_bytes, unsigned layout_type) {
+// canonical MN-major layout (16-byte units): ((atom,n),(8,k)) : ((1,LBO),(atom,SBO)) -- LBO = distance between
+// swizzle atoms along MN (here: between the stacked digit planes of B), SBO = between groups of 8 K rows
+__device__ __forceinline__ unsigned long long smem_desc(unsigned addr, unsigned sbo_bytes, unsigned layout_type,
+                                                        unsigned lbo_bytes = 16) {
     unsigned long long d = 0;
     d |= (unsigned long long)((addr >> 4) & 0x3FFF);          // start address
-    d |= (unsigned long long)(1) << 16;                         // leading byte offset (unused: one MN block)
+    d |= (unsigned long long)((lbo_bytes >> 4) & 0x3FFF) << 16;  // leading byte offset
     d |= (unsigned long long)((sbo_bytes >> 4) & 0x3FFF) << 32;  // stride byte offset: next group of 8 K rows
     d |= (unsigned long long)(1) << 46;                         // descriptor version (Blackwell)
     d |= (unsigned long long)(layout_type & 7) << 61;           // 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
@@ -96,16 +99,18 @@ __device__ __forceinline__ unsigned long long smem_desc(unsigned addr, unsigned 
 }
 
 // kind::i8 instruction descriptor (cute::UMMA::InstrDescriptor): S32 accumulate, signed 8-bit A and B,
-// both MN-major, M = 128, N = 64
-constexpr unsigned IDESC = (2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((TN >> 3) << 17) |
-                           ((TM >> 4) << 24);
+// both MN-major, M = 128, N = n (multiple of 16, <= 256)
+__host__ __device__ constexpr unsigned idesc_n(int n) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((unsigned)(n >> 3) << 17) | ((TM >> 4) << 24);
+}
 
-__device__ __forceinline__ void mma_i8(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned accumulate) {
+__device__ __forceinline__ void mma_i8(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned idesc,
+                                       unsigned accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(tmem_d),
-        "l"(da), "l"(db), "r"(IDESC), "r"(accumulate), "r"(0u)
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u)
         : "memory");
 }
 __device__ __forceinline__ void mma_commit(unsigned bar) {
@@ -209,7 +214,7 @@ __device__ __forceinline__ void tma_load_3d(unsigned dst, const void* tmap, int 
 // Persistent Gram role of one CTA (512 threads), warp-specialised:
 //   warp 4 lane 0      producer: one TMA box per operand and K-block (A: 7 planes x 32 steps x 128 B, SWIZZLE_128B;
 //                      B: 7 x 32 x 64 B, SWIZZLE_64B) into a STAGES-deep ring, completion on full[s]
-//   warps 0..3 lane 0  MMA issuers (levels {0,6}, {1,5}, {2,4}, {3}): wait full[s], issue, tcgen05.commit -> empty[s];
+//   warp 0 lane 0      MMA issuer: wait full[s], issue the 10 MMAs of the K-block, tcgen05.commit -> empty[s];
 //                      after the last K-block of a tile commit -> tmem_full
 //   warps 8..15        epilogue: wait tmem_full, tcgen05.ld the 7 levels, combine in FP64, release TMEM
 //                      (tmem_empty) and only then read-modify-write G, so the next tile's MMAs overlap the
@@ -259,14 +264,20 @@ __device__ __forceinline__ void gram_i8_run(GramI8Ctx& ctx, const GramI8Args& p,
                     tc_fence_after();
                     const unsigned sa = ctx.stage_base + s * STAGE_BYTES;
                     const unsigned long long da0 = smem_desc(sa, 1024, 2);
-                    const unsigned long long db0 = smem_desc(sa + A_BYTES, 512, 4);
+                    const unsigned long long db0 = smem_desc(sa + A_BYTES, 512, 4, B_PLANE);
+                    // A plane a meets B planes 0..6-a, whose products belong to the CONSECUTIVE levels a..6:
+                    // the B planes are stacked along N (descriptor LBO = plane pitch), so one MMA of width
+                    // 64*(7-a) (split at the 256-column instruction limit) writes all of them -- 10 MMAs
+                    // instead of 28, and the A plane is read from shared memory once or twice instead of 7-a times
 #pragma unroll
-                    for (int lv = 0; lv < NDIG; ++lv) {
-                        if ((lv <= 3 ? lv : 6 - lv) != warp) continue;
+                    for (int a = 0; a < NDIG; ++a) {
 #pragma unroll
-                        for (int a = 0; a <= lv; ++a)
-                            mma_i8(ctx.tmem + lv * TN, da0 + (unsigned long long)(a * (A_PLANE >> 4)),
-                                   db0 + (unsigned long long)((lv - a) * (B_PLANE >> 4)), (kb > 0 || a > 0) ? 1u : 0u);
+                        for (int b0 = 0; b0 < NDIG - a; b0 += 4) {
+                            const int nb = (NDIG - a - b0) < 4 ? (NDIG - a - b0) : 4;  // B planes b0 .. b0+nb-1
+                            mma_i8(ctx.tmem + (a + b0) * TN, da0 + (unsigned long long)(a * (A_PLANE >> 4)),
+                                   db0 + (unsigned long long)(b0 * (B_PLANE >> 4)), idesc_n(nb * TN),
+                                   (kb > 0 || a > 0) ? 1u : 0u);
+                        }
                     }
                     mma_commit(ctx.bar_empty + 8 * s);  // stage s may be refilled once these MMAs have read it
                 }

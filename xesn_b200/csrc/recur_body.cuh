@@ -76,9 +76,9 @@ __device__ __forceinline__ double leaky(double pre, double r_old, double alpha, 
 constexpr long long UNSET_BITS = -1LL;
 constexpr int SPIN_LIMIT = 1 << 22;  // ~1-2 s of polling, then the run is flagged as failed
 // 16-byte pieces in flight per thread while refreshing the copy (64 KB per CTA either way)
-template <int RC_THREADS>
+template <int RC_THREADS, int UPT>
 struct PollCfg {
-    static constexpr int BATCH = RC_THREADS <= 256 ? 16 : 8;
+    static constexpr int BATCH = RC_THREADS <= 256 ? 16 : 8;  // measured at 512 threads, N=16000: 4 and 16 are both slower
 };
 
 // The first KREG entries of every owned row of W live in REGISTERS for the whole chunk (value and
@@ -218,7 +218,7 @@ __device__ __forceinline__ void recur_body(const RecurArgs& p, const unsigned c,
     }
     // register-resident head of each owned row
     constexpr int KREG = RowRegs<UPT, RC_THREADS>::K;
-    constexpr int POLL_BATCH = PollCfg<RC_THREADS>::BATCH;
+    constexpr int POLL_BATCH = PollCfg<RC_THREADS, UPT>::BATCH;
     const unsigned s_r_addr = (unsigned)__cvta_generic_to_shared(s_r);
     double hv[UPT][KREG];
     int ho[UPT][KREG];
