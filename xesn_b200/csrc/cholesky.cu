@@ -13,6 +13,8 @@
 //   3. trailing update   : A_22 -= L_21 L_21^T (lower tiles) -> DMMA GEMM
 // The two triangular solves with the (O x N) right-hand side are also pure GEMM sweeps that
 // use the stored diagonal-block inverses, so >99% of the flops run on the tensor pipe.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -173,10 +175,25 @@ int launch_add_diag(double* A, long long lda, long long strideA, int n, int batc
     return 0;
 }
 
-// workspace: Linv blocks, nblk * NB*NB doubles per matrix
+long long syrk_i8_workspace_bytes(int n, int K);
+int launch_syrk_i8(const double* L, long long ldl, double* C, long long ldc, int n, int K, void* work, int num_sms,
+                   cudaStream_t stream);
+
+// The big trailing updates run on the int8 tensor cores (row-scaled 8-digit fixed point, gram_i8.cu) when there
+// is one large matrix; XESN_B200_SOLVE_I8=0 keeps them on the FP64 DMMA GEMM.
+static bool solve_uses_i8(int n, int batch) {
+    const char* e = getenv("XESN_B200_SOLVE_I8");
+    const bool on = !(e && e[0] == '0');
+    return on && batch == 1 && n >= 2048;
+}
+constexpr int I8_MIN_TRAIL = 1024;  // smaller trailing matrices stay on DMMA
+
+// workspace: Linv blocks, nblk * NB*NB doubles per matrix (+ the digit planes of one outer panel)
 long long cholesky_workspace_doubles(int n, int batch) {
     long long nblk = (n + NB - 1) / NB;
-    return nblk * NB * NB * (long long)batch;
+    long long d = nblk * NB * NB * (long long)batch;
+    if (solve_uses_i8(n, batch)) d += 32 + (syrk_i8_workspace_bytes(n, 512) + 7) / 8;
+    return d;
 }
 
 int launch_cholesky_solve_ws(double* A, long long lda, long long strideA, double* B, long long ldb, long long strideB,
@@ -276,7 +293,19 @@ int launch_cholesky_solve_ws(double* A, long long lda, long long strideA, double
         }
         // T(J) on the caller's stream: everything right of the next panel (lower tiles)
         XESN_CUDA_OK(cudaStreamWaitEvent(stream, ev_panel[it & 1], 0));
-        if (n - Jend2 > 0) {
+        if (n - Jend2 >= I8_MIN_TRAIL && solve_uses_i8(n, batch) && (Jend - J) % 32 == 0) {
+            static int num_sms = 0;
+            if (!num_sms) {
+                int dev = 0;
+                XESN_CUDA_OK(cudaGetDevice(&dev));
+                XESN_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+            }
+            double* w8 = work + strideLinv * batch;
+            w8 = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(w8) + 255) & ~(uintptr_t)255);
+            if ((rc = launch_syrk_i8(A + (long long)Jend2 * lda + J, lda, A + (long long)Jend2 * lda + Jend2, lda, n - Jend2,
+                                     Jend - J, w8, num_sms, stream)))
+                return rc;
+        } else if (n - Jend2 > 0) {
             GemmArgs t = {};
             t.A = A + (long long)Jend2 * lda + J, t.lda = lda, t.strideA = strideA;
             t.B = t.A, t.ldb = lda, t.strideB = strideA;

@@ -32,13 +32,20 @@ namespace xesn {
 namespace gi8 {
 
 constexpr int TM = 128, TN = 64, KB = 32, NDIG = 7;
-constexpr int STAGES = 5;
-constexpr int MAX_K = 16384;  // int32 accumulators: 7 pairs x 2^14 x K < 2^31
+constexpr int NDIG_WIDE = 8;  // 8 digits (2^-63 of the row scale): the trailing updates of the ridge solve (cholesky.cu)
+constexpr int MAX_K = 16384;  // int32 accumulators: 8 pairs x 2^14 x K < 2^31
 constexpr int A_PLANE = KB * 128;              // bytes per plane per stage (A)
 constexpr int B_PLANE = KB * 64;               // (B)
-constexpr int A_BYTES = NDIG * A_PLANE;        // 28 KB
-constexpr int STAGE_BYTES = NDIG * (A_PLANE + B_PLANE);  // 42 KB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers + tmem ptr*/;
+// shared-memory ring of an ND-digit pipeline: 7 digits -> 42 KB stages x 5, 8 digits -> 48 KB x 4
+template <int ND>
+struct Ring {
+    static constexpr int A_BYTES = ND * A_PLANE;
+    static constexpr int STAGE_BYTES = ND * (A_PLANE + B_PLANE);
+    static constexpr int STAGES = ND <= 7 ? 5 : 4;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers + tmem ptr*/;
+};
+constexpr int SMEM_BYTES = Ring<NDIG_WIDE>::SMEM_BYTES > Ring<NDIG>::SMEM_BYTES ? Ring<NDIG_WIDE>::SMEM_BYTES
+                                                                                : Ring<NDIG>::SMEM_BYTES;
 constexpr int THREADS = 512;
 constexpr int ISSUERS = 1;  // one thread issues the 10 (wide) MMAs of a K-block
 
@@ -53,6 +60,9 @@ struct GramI8Args {
     long long ldg;
     long long strideG;
     int batch;
+    int ndig;               // digit planes per group (NDIG or NDIG_WIDE); 0 = NDIG
+    const double* scale;    // nullptr: G += P^T P.  Else the planes hold rows scaled by 1/scale[i] and the
+                            // tile update is  G[m][n] -= scale[m] * scale[n] * (P^T P)[m][n]   (SYRK of the solve)
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -143,7 +153,9 @@ struct GramI8Ctx {
 };
 
 // one warp allocates all 512 TMEM columns; every thread learns the base address
+template <int ND = NDIG>
 __device__ __forceinline__ void gram_i8_setup(GramI8Ctx& ctx, unsigned char* smem_raw) {
+    constexpr int STAGES = Ring<ND>::STAGES, STAGE_BYTES = Ring<ND>::STAGE_BYTES;
     const unsigned raw = smem_u32(smem_raw);
     ctx.stage_base = (raw + 1023u) & ~1023u;
     const unsigned ctl = ctx.stage_base + STAGES * STAGE_BYTES;
@@ -225,11 +237,23 @@ __device__ __forceinline__ void tma_load_3d(unsigned dst, const void* tmap, int 
 // nothing else overlaps with it.  Here loads, issue and epilogue only meet at mbarriers.
 constexpr int EPI_WARP0 = 8, EPI_WARPS = 8, PRODUCER_WARP = 4;
 
-template <int NT>
+// tile t of the lower triangle: from the host-built list, or (tiles == nullptr) row by row, tile row ti holding
+// the column tiles 0 .. 2 ti + 1
+__device__ __forceinline__ int2 tile_of(const int2* __restrict__ tiles, long long t) {
+    if (tiles) return tiles[t];
+    int ti = (int)((sqrt(4.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((long long)ti * (ti + 1) > t) --ti;
+    while ((long long)(ti + 1) * (ti + 2) <= t) ++ti;
+    return make_int2(ti, (int)(t - (long long)ti * (ti + 1)));
+}
+
+template <int NT, int ND = NDIG>
 __device__ __forceinline__ void gram_i8_run(GramI8Ctx& ctx, const GramI8Args& p, const void* tmA, const void* tmB,
                                             const int2* __restrict__ tiles, int ntiles, long long worker,
                                             long long nworkers) {
     static_assert(NT == 512, "the Gram role is laid out for 16 warps");
+    constexpr int NDIG = ND;  // shadows the 7-digit default inside this function
+    constexpr int STAGES = Ring<ND>::STAGES, STAGE_BYTES = Ring<ND>::STAGE_BYTES, A_BYTES = Ring<ND>::A_BYTES;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nkb = p.K / KB;
     const long long total = (long long)ntiles * p.batch;
@@ -238,7 +262,7 @@ __device__ __forceinline__ void gram_i8_run(GramI8Ctx& ctx, const GramI8Args& p,
         if (lane == 0) {
             unsigned it = 0;
             for (long long t = worker; t < total; t += nworkers) {
-                const int2 ij = tiles[t % ntiles];
+                const int2 ij = tile_of(tiles, t % ntiles);
                 const int bz = (int)(t / ntiles);
                 const int m0 = ij.x * TM, n0 = ij.y * TN;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
@@ -291,7 +315,7 @@ __device__ __forceinline__ void gram_i8_run(GramI8Ctx& ctx, const GramI8Args& p,
         const int q = warp & 3, part = (warp - EPI_WARP0) >> 2;
         unsigned tc = 0;
         for (long long t = worker; t < total; t += nworkers, ++tc) {
-            const int2 ij = tiles[t % ntiles];
+            const int2 ij = tile_of(tiles, t % ntiles);
             const int bz = (int)(t / ntiles);
             const int m0 = ij.x * TM, n0 = ij.y * TN;
             mbar_wait(ctx.bar_tfull, tc & 1u);
@@ -311,6 +335,11 @@ __device__ __forceinline__ void gram_i8_run(GramI8Ctx& ctx, const GramI8Args& p,
             __syncwarp();
             if (lane == 0) mbar_arrive(ctx.bar_tempty);  // accumulators may be overwritten by the next tile
             const int m = m0 + q * 32 + lane;
+            if (p.scale) {
+                const double sm = (m < p.N) ? -p.scale[m] : 0.0;
+#pragma unroll
+                for (int j = 0; j < NC; ++j) acc[j] *= sm * __ldg(p.scale + n0 + part * NC + j);  // powers of two: exact
+            }
             if (m < p.N) {
                 double* g = p.G + (long long)bz * p.strideG + (long long)m * p.ldg + n0 + part * NC;
                 const int nmax = min(NC, min(p.N, m + 1) - (n0 + part * NC));  // columns <= row only (lower triangle)
