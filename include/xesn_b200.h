@@ -86,7 +86,11 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
                           int32_t n_groups, int64_t n_time, int64_t n_spinup, int32_t chunk,
                           double* gram_dev, double* wout_dev, void* scratch_dev, int64_t scratch_bytes,
                           void* stream);
-/* (R R^T + beta I) solve: xesn/esn.py:516-520.  beta_dev: [G] or NULL (then beta_scalar is used). */
+/* (R R^T + beta I) solve: xesn/esn.py:516-520.  beta_dev: [G] or NULL (then beta_scalar is used).
+ *      Blocked Cholesky; for one large system the trailing updates run on the int8 tensor cores (row-scaled
+ *      8-digit fixed point, XESN_B200_SOLVE_I8=0 keeps FP64 DMMA).  Layout hint: with n_groups == 1 and
+ *      wout_dev == gram_dev + N*N (readout rows stored right below the Gram matrix) the forward substitution
+ *      is folded into the factorisation. */
 int xesn_ridge_solve(xesn_reservoir* h, int32_t n_output, int32_t n_groups, const double* beta_dev,
                      double beta_scalar, double* gram_dev, double* wout_dev, int32_t* info_dev,
                      void* scratch_dev, int64_t scratch_bytes, void* stream);

@@ -314,12 +314,14 @@ def test_readout_linearity_full_size(torch, lib):
     assert float((outs[2] - (outs[0] + 2.0 * outs[1])).abs().max()) < 1e-10
 
 
-def test_ridge_normal_equations_full_size(torch):
-    """Property at N=4000 (31+ Cholesky panels, partial last block): the returned readout
-    satisfies Wout (R R^T + beta I) = Y R^T for a Gram matrix rebuilt from the stored states."""
+@pytest.mark.parametrize("N", [4000 + 37, 4096 + 3 * 128 + 37])
+def test_ridge_normal_equations_full_size(torch, N):
+    """Property at N~4000 (31+ Cholesky panels, partial last block; int8 trailing updates, right-hand sides
+    folded into the factorisation; the larger size also takes the 512-wide inverse sweep with a ragged tail):
+    the returned readout satisfies Wout (R R^T + beta I) = Y R^T for a Gram matrix rebuilt from the stored states."""
     from xesn_b200 import _lib
     from xesn_b200.synthetic import lorenz96
-    N, T = 4000 + 37, 700
+    T = 700
     data = lorenz96(8, T)
     esn = make_esn(8, 8, N, beta=1e-3)
     esn.train(data, n_spinup=0)

@@ -364,7 +364,7 @@ static TrainLayout train_layout(xesn_reservoir* h, int O, int G, int chunk, int 
 int64_t xesn_train_scratch_bytes(xesn_reservoir* h, int32_t O, int32_t G, int32_t chunk, int32_t gu, int32_t gy) {
     if (!h || chunk <= 0) return -1;
     long long train = train_layout(h, O, G, chunk, gu, gy).total;
-    long long solve = cholesky_workspace_doubles(h->N, G);
+    long long solve = cholesky_workspace_doubles(h->N, O, G);
     return (train > solve ? train : solve) * 8 + 256;
 }
 
@@ -544,7 +544,7 @@ int xesn_set_fused(xesn_reservoir* h, int32_t on) {
 int xesn_ridge_solve(xesn_reservoir* h, int32_t O, int32_t G, const double* beta_dev, double beta_scalar, double* gram,
                      double* wout, int32_t* info, void* scratch, int64_t scratch_bytes, void* stream) {
     XESN_REQUIRE(h && gram && wout && info && scratch, "null pointer");
-    XESN_REQUIRE(scratch_bytes >= cholesky_workspace_doubles(h->N, G) * 8, "scratch too small");
+    XESN_REQUIRE(scratch_bytes >= cholesky_workspace_doubles(h->N, O, G) * 8, "scratch too small");
     cudaStream_t st = (cudaStream_t)stream;
     const int N = h->N;
     ProfScope prof(PROF_SOLVE, st);

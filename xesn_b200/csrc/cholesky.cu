@@ -22,6 +22,9 @@ namespace xesn {
 namespace {
 
 constexpr int NB = 128;
+constexpr int I8_MIN_TRAIL = 1024;  // smaller trailing matrices stay on DMMA
+constexpr int FOLD_MAX_RHS = 256;   // right-hand-side rows that may ride along with the factorisation
+constexpr int WB = 512;             // width of the explicit inverses used by the backward sweep
 constexpr int LDS = NB + 1;
 constexpr int PD_THREADS = 256;  // 16 x 16 threads, thread (ty,tx) owns entries (ty+16a, tx+16b), a,b < 8
 constexpr int PD_SMEM = (NB * LDS + 4 * NB) * (int)sizeof(double) + 16;
@@ -157,6 +160,14 @@ potrf_diag_kernel(double* A, long long lda, long long strideA, int j0, int nbj, 
         }
 }
 
+// the four 128 x 128 inverses of a full 512 block -> its diagonal positions in the 512 x 512 inverse
+__global__ void copy_diag_blocks_kernel(const double* __restrict__ linv, double* __restrict__ winv) {
+    const int jb = blockIdx.x;  // 128-block index; belongs to wide block jb / 4, slot jb % 4
+    const double* src = linv + (long long)jb * NB * NB;
+    double* dst = winv + (long long)(jb >> 2) * WB * WB + (long long)(jb & 3) * NB * (WB + 1);
+    for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) dst[(e >> 7) * WB + (e & 127)] = src[e];
+}
+
 __global__ void add_diag_kernel(double* A, long long lda, long long strideA, int n, const double* beta, double beta_scalar) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -176,8 +187,8 @@ int launch_add_diag(double* A, long long lda, long long strideA, int n, int batc
 }
 
 long long syrk_i8_workspace_bytes(int n, int K);
-int launch_syrk_i8(const double* L, long long ldl, double* C, long long ldc, int n, int K, void* work, int num_sms,
-                   cudaStream_t stream);
+int launch_syrk_i8(const double* L, long long ldl, double* C, long long ldc, int n, int ncols, int K, void* work,
+                   int num_sms, cudaStream_t stream);
 
 // The big trailing updates run on the int8 tensor cores (row-scaled 8-digit fixed point, gram_i8.cu) when there
 // is one large matrix; XESN_B200_SOLVE_I8=0 keeps them on the FP64 DMMA GEMM.
@@ -186,13 +197,15 @@ static bool solve_uses_i8(int n, int batch) {
     const bool on = !(e && e[0] == '0');
     return on && batch == 1 && n >= 2048;
 }
-constexpr int I8_MIN_TRAIL = 1024;  // smaller trailing matrices stay on DMMA
+// inverses of the full WB x WB diagonal blocks + one 256 x 256 temporary per block
+static long long wide_inverse_doubles(int n) { return (long long)(n / WB) * (WB * WB + 256 * 256) + 64; }
 
 // workspace: Linv blocks, nblk * NB*NB doubles per matrix (+ the digit planes of one outer panel)
-long long cholesky_workspace_doubles(int n, int batch) {
+long long cholesky_workspace_doubles(int n, int nrhs, int batch) {
     long long nblk = (n + NB - 1) / NB;
     long long d = nblk * NB * NB * (long long)batch;
-    if (solve_uses_i8(n, batch)) d += 32 + (syrk_i8_workspace_bytes(n, 512) + 7) / 8;
+    if (solve_uses_i8(n, batch)) d += 32 + (syrk_i8_workspace_bytes(n + FOLD_MAX_RHS, 512) + 7) / 8;
+    if (batch == 1 && n >= 4096) d += wide_inverse_doubles(n) + (long long)nrhs * WB;
     return d;
 }
 
@@ -215,6 +228,11 @@ int launch_cholesky_solve_ws(double* A, long long lda, long long strideA, double
     // kernels that factors panel J+1 runs on a second, high-priority stream while T(J) still occupies
     // the GPU on the caller's stream.
     const int OUTER = n >= 4096 ? 512 : (n >= 1024 ? 256 : NB);
+    // FOLD: when the right-hand sides are stored as the rows n .. n+nrhs-1 of the same array (B = A + n*lda),
+    // every panel operation simply runs over nrhs more rows, which turns B into Z = B L^-T on the way:
+    // the forward sweep (125 dependent pairs of small launches at n = 16000) disappears.
+    const bool fold = batch == 1 && nrhs <= FOLD_MAX_RHS && ldb == lda && B == A + (long long)n * lda;
+    const int xr = fold ? nrhs : 0;
     static cudaStream_t side = nullptr;
     static cudaEvent_t ev_panel[2] = {nullptr, nullptr}, ev_trail[2] = {nullptr, nullptr}, ev_fork = nullptr;
     if (!side) {
@@ -238,7 +256,7 @@ int launch_cholesky_solve_ws(double* A, long long lda, long long strideA, double
             potrf_diag_kernel<<<batch, PD_THREADS, PD_SMEM, s>>>(A, lda, strideA, j0, nbj, Linv_j, strideLinv, info);
             XESN_CUDA_OK(cudaGetLastError());
             count_launch();
-            const int rest = n - j0 - nbj;
+            const int rest = n - j0 - nbj + xr;
             if (rest <= 0) break;
             GemmArgs g = {};
             // panel: L_ij = A_ij * inv(L_jj)^T   (in place: a tile reads only the rows it writes)
@@ -260,7 +278,7 @@ int launch_cholesky_solve_ws(double* A, long long lda, long long strideA, double
                 u.A = A + (long long)j1 * lda + j0, u.lda = lda, u.strideA = strideA;
                 u.B = A + (long long)j1 * lda + j0, u.ldb = lda, u.strideB = strideA;
                 u.C = A + (long long)j1 * lda + j1, u.ldc = lda, u.strideC = strideA;
-                u.M = n - j1, u.N = pw, u.K = nbj;
+                u.M = n - j1 + xr, u.N = pw, u.K = nbj;
                 u.batch = batch, u.alpha = -1.0, u.beta = 1.0;
                 u.flags = GEMM_A_KMAJOR | GEMM_B_KMAJOR;
                 rc = launch_gemm_f64(u, s);
@@ -286,7 +304,7 @@ int launch_cholesky_solve_ws(double* A, long long lda, long long strideA, double
             u.A = A + (long long)Jend * lda + J, u.lda = lda, u.strideA = strideA;
             u.B = A + (long long)Jend * lda + J, u.ldb = lda, u.strideB = strideA;
             u.C = A + (long long)Jend * lda + Jend, u.ldc = lda, u.strideC = strideA;
-            u.M = n - Jend, u.N = Jend2 - Jend, u.K = Jend - J;
+            u.M = n - Jend + xr, u.N = Jend2 - Jend, u.K = Jend - J;
             u.batch = batch, u.alpha = -1.0, u.beta = 1.0;
             u.flags = GEMM_A_KMAJOR | GEMM_B_KMAJOR;
             if ((rc = launch_gemm_f64(u, side))) return rc;
@@ -302,10 +320,20 @@ int launch_cholesky_solve_ws(double* A, long long lda, long long strideA, double
             }
             double* w8 = work + strideLinv * batch;
             w8 = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(w8) + 255) & ~(uintptr_t)255);
-            if ((rc = launch_syrk_i8(A + (long long)Jend2 * lda + J, lda, A + (long long)Jend2 * lda + Jend2, lda, n - Jend2,
-                                     Jend - J, w8, num_sms, stream)))
+            if ((rc = launch_syrk_i8(A + (long long)Jend2 * lda + J, lda, A + (long long)Jend2 * lda + Jend2, lda,
+                                     n - Jend2 + xr, n - Jend2, Jend - J, w8, num_sms, stream)))
                 return rc;
         } else if (n - Jend2 > 0) {
+            if (xr) {  // right-hand-side rows: B[:, Jend2:] -= Z[:, J:Jend] L[Jend2:, J:Jend]^T
+                GemmArgs t = {};
+                t.A = A + (long long)n * lda + J, t.lda = lda, t.strideA = strideA;
+                t.B = A + (long long)Jend2 * lda + J, t.ldb = lda, t.strideB = strideA;
+                t.C = A + (long long)n * lda + Jend2, t.ldc = lda, t.strideC = strideA;
+                t.M = xr, t.N = n - Jend2, t.K = Jend - J;
+                t.batch = batch, t.alpha = -1.0, t.beta = 1.0;
+                t.flags = GEMM_A_KMAJOR | GEMM_B_KMAJOR;
+                if ((rc = launch_gemm_f64(t, stream))) return rc;
+            }
             GemmArgs t = {};
             t.A = A + (long long)Jend2 * lda + J, t.lda = lda, t.strideA = strideA;
             t.B = t.A, t.ldb = lda, t.strideB = strideA;
@@ -324,7 +352,7 @@ int launch_cholesky_solve_ws(double* A, long long lda, long long strideA, double
     XESN_CUDA_OK(cudaStreamWaitEvent(stream, ev_panel[it & 1], 0));
 
     // ---- forward sweep:  Z L^T = B   (B is nrhs x n, row-major: every row is one right-hand side) ----
-    for (int jb = 0; jb < nblk; ++jb) {
+    for (int jb = 0; jb < nblk && !fold; ++jb) {
         const int j0 = jb * NB;
         const int nbj = min(NB, n - j0);
         double* Linv_j = work + (long long)jb * NB * NB;
@@ -351,7 +379,50 @@ int launch_cholesky_solve_ws(double* A, long long lda, long long strideA, double
     }
 
     // ---- backward sweep:  X L = Z ----
-    for (int jb = nblk - 1; jb >= 0; --jb) {
+    // Big single systems: explicit inverses of the full 512 x 512 diagonal blocks are assembled from the 128-wide
+    // ones (inv [[P,0],[C,Q]] = [[P^-1,0],[-Q^-1 C P^-1, Q^-1]], two batched levels), so the sweep is 2 launches per
+    // 512 columns instead of 2 per 128 -- the chain of dependent small launches was 6 of the solve's 54 ms.
+    const int n_wide = (batch == 1 && n >= 4096) ? n / WB : 0;  // full WB blocks [0, n_wide*WB)
+    double *Winv = nullptr, *Xtmp = nullptr;
+    if (n_wide > 0) {
+        double* wbase = work + strideLinv * batch;
+        if (solve_uses_i8(n, batch)) wbase += 32 + (syrk_i8_workspace_bytes(n + FOLD_MAX_RHS, 512) + 7) / 8;
+        Winv = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(wbase) + 255) & ~(uintptr_t)255);
+        double* Tmp = Winv + (long long)n_wide * WB * WB;
+        Xtmp = Tmp + (long long)n_wide * 256 * 256;
+        XESN_CUDA_OK(cudaMemsetAsync(Winv, 0, sizeof(double) * (size_t)n_wide * WB * WB, stream));
+        // diagonal 128-blocks
+        copy_diag_blocks_kernel<<<dim3(4 * n_wide), 256, 0, stream>>>(work, Winv);
+        XESN_CUDA_OK(cudaGetLastError());
+        count_launch();
+        auto level = [&](int h, int slot_count) -> int {
+            // h = half size (128 or 256); slot s places the pair at rows/cols s*2h inside the 512 block
+            for (int sl = 0; sl < slot_count; ++sl) {
+                const long long o = (long long)sl * 2 * h;  // offset of the pair inside the block
+                GemmArgs g = {};  // Tmp = C * inv(P)
+                g.A = A + (o + h) * lda + o, g.lda = lda, g.strideA = (long long)WB * (lda + 1);
+                g.B = Winv + o * WB + o, g.ldb = WB, g.strideB = (long long)WB * WB;
+                g.C = Tmp, g.ldc = h, g.strideC = 256 * 256;
+                g.M = h, g.N = h, g.K = h, g.batch = n_wide, g.alpha = 1.0, g.beta = 0.0;
+                g.flags = GEMM_A_KMAJOR;
+                int rc = launch_gemm_f64(g, stream);
+                if (rc) return rc;
+                GemmArgs w = {};  // W = -inv(Q) * Tmp
+                w.A = Winv + (o + h) * WB + (o + h), w.lda = WB, w.strideA = (long long)WB * WB;
+                w.B = Tmp, w.ldb = h, w.strideB = 256 * 256;
+                w.C = Winv + (o + h) * WB + o, w.ldc = WB, w.strideC = (long long)WB * WB;
+                w.M = h, w.N = h, w.K = h, w.batch = n_wide, w.alpha = -1.0, w.beta = 0.0;
+                w.flags = GEMM_A_KMAJOR;
+                rc = launch_gemm_f64(w, stream);
+                if (rc) return rc;
+            }
+            return 0;
+        };
+        if ((rc = level(NB, 2))) return rc;
+        if ((rc = level(2 * NB, 1))) return rc;
+    }
+    // columns beyond the full wide blocks (and everything when there are none): 128-wide steps
+    for (int jb = nblk - 1; jb >= 0 && jb * NB >= n_wide * WB; --jb) {
         const int j0 = jb * NB;
         const int nbj = min(NB, n - j0);
         double* Linv_j = work + (long long)jb * NB * NB;
@@ -371,6 +442,28 @@ int launch_cholesky_solve_ws(double* A, long long lda, long long strideA, double
         u.C = B, u.ldc = ldb, u.strideC = strideB;
         u.M = nrhs, u.N = j0, u.K = nbj;
         u.batch = batch, u.alpha = -1.0, u.beta = 1.0;
+        u.flags = GEMM_A_KMAJOR;
+        rc = launch_gemm_f64(u, stream);
+        if (rc) return rc;
+    }
+    for (int J = n_wide - 1; J >= 0; --J) {
+        const int j0 = J * WB;
+        GemmArgs g = {};  // X_J = Z_J * inv(L_JJ)   (four column tiles read all of Z_J: not in place)
+        g.A = B + j0, g.lda = ldb, g.strideA = strideB;
+        g.B = Winv + (long long)J * WB * WB, g.ldb = WB, g.strideB = 0;
+        g.C = Xtmp, g.ldc = WB, g.strideC = 0;
+        g.M = nrhs, g.N = WB, g.K = WB, g.batch = 1, g.alpha = 1.0, g.beta = 0.0;
+        g.flags = GEMM_A_KMAJOR;
+        int rc = launch_gemm_f64(g, stream);
+        if (rc) return rc;
+        XESN_CUDA_OK(cudaMemcpy2DAsync(B + j0, sizeof(double) * ldb, Xtmp, sizeof(double) * WB, sizeof(double) * WB, nrhs,
+                                       cudaMemcpyDeviceToDevice, stream));
+        if (j0 == 0) break;
+        GemmArgs u = {};  // Z[:, :j0] -= X_J * L[j0:j0+WB, :j0]
+        u.A = Xtmp, u.lda = WB, u.strideA = 0;
+        u.B = A + (long long)j0 * lda, u.ldb = lda, u.strideB = strideA;
+        u.C = B, u.ldc = ldb, u.strideC = strideB;
+        u.M = nrhs, u.N = j0, u.K = WB, u.batch = 1, u.alpha = -1.0, u.beta = 1.0;
         u.flags = GEMM_A_KMAJOR;
         rc = launch_gemm_f64(u, stream);
         if (rc) return rc;

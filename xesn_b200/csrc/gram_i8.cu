@@ -228,8 +228,9 @@ long long syrk_i8_workspace_bytes(int n, int K) {
     return NDIG_WIDE * kp * ldp + 256 + 8 * ldp;
 }
 
-int launch_syrk_i8(const double* L, long long ldl, double* C, long long ldc, int n, int K, void* work, int num_sms,
-                   cudaStream_t stream) {
+// ncols < n: only the first ncols columns of C exist (the rows beyond them are right-hand-side rows carried along).
+int launch_syrk_i8(const double* L, long long ldl, double* C, long long ldc, int n, int ncols, int K, void* work,
+                   int num_sms, cudaStream_t stream) {
     if (n <= 0 || K <= 0) return 0;
     const long long ldp = (n + 127) / 128 * 128, kp = (K + KB - 1) / KB * KB;
     int8_t* planes = reinterpret_cast<int8_t*>(work);
@@ -249,7 +250,7 @@ int launch_syrk_i8(const double* L, long long ldl, double* C, long long ldc, int
     GramI8Args a = {};
     a.planes = planes, a.ldp = ldp, a.plane_stride = ldp * kp, a.group_stride = 0;
     a.K = (int)kp, a.N = n, a.G = C, a.ldg = ldc, a.strideG = 0, a.batch = 1;
-    a.ndig = NDIG_WIDE, a.scale = scale;
+    a.ndig = NDIG_WIDE, a.scale = scale, a.ncols = ncols;
     const int TI = (n + TM - 1) / TM;
     return launch_gram_i8(a, nullptr, TI * (TI + 1), num_sms, stream);
 }

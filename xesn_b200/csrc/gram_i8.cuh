@@ -60,6 +60,7 @@ struct GramI8Args {
     long long ldg;
     long long strideG;
     int batch;
+    int ncols;              // columns of G that exist (0 = N): rows may extend beyond them (solve: appended rhs rows)
     int ndig;               // digit planes per group (NDIG or NDIG_WIDE); 0 = NDIG
     const double* scale;    // nullptr: G += P^T P.  Else the planes hold rows scaled by 1/scale[i] and the
                             // tile update is  G[m][n] -= scale[m] * scale[n] * (P^T P)[m][n]   (SYRK of the solve)
@@ -342,7 +343,8 @@ __device__ __forceinline__ void gram_i8_run(GramI8Ctx& ctx, const GramI8Args& p,
             }
             if (m < p.N) {
                 double* g = p.G + (long long)bz * p.strideG + (long long)m * p.ldg + n0 + part * NC;
-                const int nmax = min(NC, min(p.N, m + 1) - (n0 + part * NC));  // columns <= row only (lower triangle)
+                const int ncols = p.ncols ? p.ncols : p.N;
+                const int nmax = min(NC, min(ncols, m + 1) - (n0 + part * NC));  // columns <= row only (lower triangle)
                 if (nmax == NC && ((reinterpret_cast<uintptr_t>(g) & 15) == 0)) {
 #pragma unroll
                     for (int j = 0; j < NC; j += 2) {

@@ -118,7 +118,7 @@ int launch_predict_loop(const PredictLoopArgs& a, int num_sms, cudaStream_t stre
 // In-place blocked Cholesky of the lower triangle of `batch` SPD matrices A[b] (n x n, row-major,
 // leading dimension lda), then X = A^{-1} B for B[b] (n x nrhs, row-major, ldb) in place.
 // info[b] = 0 on success, k>0 if the leading minor of order k is not positive definite.
-long long cholesky_workspace_doubles(int n, int batch);
+long long cholesky_workspace_doubles(int n, int nrhs, int batch);
 int launch_cholesky_solve_ws(double* A, long long lda, long long strideA, double* B, long long ldb, long long strideB,
                              int n, int nrhs, int batch, int* info, double* work, cudaStream_t stream);
 int launch_add_diag(double* A, long long lda, long long strideA, int n, int batch, const double* beta_dev,

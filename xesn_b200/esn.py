@@ -313,8 +313,14 @@ class ESN:
         with torch.cuda.device(res.device):
             nbytes = lib.xesn_train_scratch_bytes(res.handle, O, G, chunk, gu, gy)
             scratch = torch.empty(nbytes, dtype=torch.uint8, device=res.device)
-            gram = torch.empty((G, N, N), dtype=torch.float64, device=res.device)
-            wout = torch.empty((G, O, N), dtype=torch.float64, device=res.device)
+            if G == 1:
+                # readout rows stored right below the Gram matrix: the solve then carries them through the
+                # factorisation as extra rows and needs no forward substitution (include/xesn_b200.h)
+                both = torch.empty((N + O, N), dtype=torch.float64, device=res.device)
+                gram, wout = both[:N].view(1, N, N), both[N:].view(1, O, N)
+            else:
+                gram = torch.empty((G, N, N), dtype=torch.float64, device=res.device)
+                wout = torch.empty((G, O, N), dtype=torch.float64, device=res.device)
             info = torch.zeros(G, dtype=torch.int32, device=res.device)
             st = self._stream()
             _lib.check(lib.xesn_train_accumulate(
@@ -323,6 +329,9 @@ class ESN:
             _lib.check(lib.xesn_ridge_solve(
                 res.handle, O, G, None, float(self.tikhonov_parameter), _ptr(gram), _ptr(wout), _ptr(info),
                 _ptr(scratch), nbytes, st))
+            if G == 1:
+                wout = wout.clone()  # do not keep the 8 N^2 bytes of the Gram matrix alive through a view
+                del gram, both
         self.last_info = info
         del keepalive
         return wout
