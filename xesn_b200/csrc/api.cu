@@ -105,6 +105,7 @@ struct xesn_reservoir {
     int n_tiles_i8 = 0;
     int gram_mode = 1;  // 0 = FP64 DMMA, 1 = error-free int8 on tcgen05
     int fused_enabled = 1;
+    int recur_pull = 0;  // 1 = pull-model recurrence (pull_body.cuh), 0 = team model (recur_body.cuh)
 };
 
 extern "C" {
@@ -169,6 +170,7 @@ int xesn_reservoir_create(xesn_reservoir** out, int device, int32_t N, int32_t I
     XESN_CUDA_OK(cudaMalloc(&h->d_bar, 2 * sizeof(unsigned)));
     XESN_CUDA_OK(cudaMemset(h->d_bar, 0, 2 * sizeof(unsigned)));
     if (const char* e = getenv("XESN_B200_PREDICT")) h->persistent_predict = strcmp(e, "steps") != 0;
+    if (const char* e = getenv("XESN_B200_RECUR")) h->recur_pull = strcmp(e, "pull") == 0;
     XESN_CUDA_OK(cudaMemcpy(h->d_indptr, indptr, sizeof(int) * (N + 1), cudaMemcpyHostToDevice));
     if (nnz) {
         XESN_CUDA_OK(cudaMemcpy(h->d_indices, indices, sizeof(int) * nnz, cudaMemcpyHostToDevice));
@@ -274,6 +276,13 @@ static int drive_gemm(xesn_reservoir* h, const double* ubase, long long ldu, lon
     return launch_gemm_f64(g, st);
 }
 
+// teacher-forced recurrence without a Gram role (spin-up, forced runs)
+static int forced_launch(xesn_reservoir* h, const RecurArgs& r, int G, cudaStream_t st) {
+    int upc = 0, upt = 0;
+    if (h->recur_pull && pull_geometry(h->N, G, h->num_sms, &upc, &upt) == 0) return launch_pull_forced(r, G, h->num_sms, st);
+    return launch_recur_forced(r, G, h->max_slice_nnz, st);
+}
+
 static RecurArgs recur_args(xesn_reservoir* h) {
     RecurArgs r = {};
     r.indptr = h->d_indptr, r.indices = h->d_indices, r.values = h->d_values;
@@ -325,7 +334,7 @@ int xesn_forced_run(xesn_reservoir* h, const xesn_series* u, int64_t t0, int32_t
         } else {
             r.states = pp, r.state_group_stride = (long long)(m + 1) * N;
         }
-        rc = launch_recur_forced(r, G, h->max_slice_nnz, st);
+        rc = forced_launch(h, r, G, st);
         if (rc) return rc;
     }
     return 0;
@@ -397,17 +406,20 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
         RecurArgs r = recur_args(h);
         r.drive = D, r.drive_group_stride = (long long)m * N, r.steps = m, r.carry = carry;
         r.states = R, r.state_group_stride = (long long)(m + 1) * N;
-        if ((rc = launch_recur_forced(r, G, h->max_slice_nnz, st))) return rc;
+        if ((rc = forced_launch(h, r, G, st))) return rc;
     }
     // accumulate: xesn/esn.py:502-513
     int team = 0, upt = 0;
-    const bool fuse = h->fused_enabled && (N % 2 == 0) && fused_recur_geometry(N, G, fused_threads(h->gram_mode == 1), &team, &upt) == 0 &&
-                      (long long)team * G < h->num_sms && T > n_spinup;
+    int pull_upc = 0, pull_upt = 0;
+    const bool pull = h->recur_pull && h->gram_mode == 1 && pull_geometry(N, G, h->num_sms, &pull_upc, &pull_upt) == 0;
+    const bool fuse = h->fused_enabled && (N % 2 == 0) && T > n_spinup &&
+                      (pull || (fused_recur_geometry(N, G, fused_threads(h->gram_mode == 1), &team, &upt) == 0 &&
+                                (long long)team * G < h->num_sms));
     if (fuse) {
         // software pipeline over chunks: launch c runs recurrence(c) || Gram(c-1) in one cooperative kernel
-        const int upc = recur_units_per_cta(N, team);
+        const int upc = pull ? N : recur_units_per_cta(N, team);
         int slice_nnz = 0;
-        for (int c = 0; c < team; ++c) {
+        for (int c = 0; c < (pull ? 0 : team); ++c) {
             const int lo = c * upc < N ? c * upc : N, hi = (c + 1) * upc < N ? (c + 1) * upc : N;
             slice_nnz = std::max(slice_nnz, h->h_indptr[hi] - h->h_indptr[lo]);
         }
@@ -467,8 +479,9 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
             }
             {
                 ProfScope prof(PROF_FUSED, st);
-                rc = i8 ? launch_fused_chunk_i8(r, G, team, upt, slice_nnz, g8, h->d_tiles_i8, ntiles, h->num_sms, st)
-                        : launch_fused_chunk(r, G, team, upt, slice_nnz, g, h->d_tiles, ntiles, h->num_sms, st);
+                rc = pull ? launch_fused_pull_i8(r, G, g8, h->d_tiles_i8, ntiles, h->num_sms, st)
+                     : i8 ? launch_fused_chunk_i8(r, G, team, upt, slice_nnz, g8, h->d_tiles_i8, ntiles, h->num_sms, st)
+                          : launch_fused_chunk(r, G, team, upt, slice_nnz, g, h->d_tiles, ntiles, h->num_sms, st);
                 if (rc) return rc;
             }
             if (c >= 1) {
@@ -501,7 +514,7 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
         r.states = R, r.state_group_stride = rgs;
         {
             ProfScope prof(PROF_RECUR, st);
-            if ((rc = launch_recur_forced(r, G, h->max_slice_nnz, st))) return rc;
+            if ((rc = forced_launch(h, r, G, st))) return rc;
         }
         // rbar += R^T R  (rows 0..m-1: the state that has seen u(..t-1) pairs with y(t))
         GemmArgs g = {};
@@ -531,6 +544,14 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
 int xesn_set_gram_mode(xesn_reservoir* h, int32_t mode) {
     XESN_REQUIRE(h && (mode == 0 || mode == 1), "bad arguments");
     h->gram_mode = mode;
+    return 0;
+}
+
+// 0 = team-model recurrence (shared-memory state copy per CTA), 1 = pull model (every thread polls the states
+// its rows need; the recurrence rides on the idle warps of the Gram CTAs)
+int xesn_set_recur_mode(xesn_reservoir* h, int32_t mode) {
+    XESN_REQUIRE(h && (mode == 0 || mode == 1), "bad arguments");
+    h->recur_pull = mode;
     return 0;
 }
 

@@ -25,6 +25,7 @@
 #include "gram_i8.cuh"
 #include "kernels.cuh"
 #include "recur_body.cuh"
+#include "pull_body.cuh"
 
 namespace xesn {
 namespace {
@@ -88,6 +89,36 @@ fused_chunk_i8_kernel(RecurArgs rp, int rec_ctas, int team, gi8::GramI8Args gp, 
     gi8::gram_i8_run<FUSED_I8_THREADS>(ctx, gp, &tmA, &tmB, tiles, ntiles, worker, nworkers);
     gi8::gram_i8_teardown(ctx);
     XESN_CTA_STAMP(1);
+}
+
+
+// Pull-model fusion: no SM specialisation.  EVERY CTA runs the Gram role (producer warp 4, issuer warp 0,
+// epilogue warps 8..15 -- gram_i8.cuh) and its otherwise idle warps 1-3 and 5-7 run the recurrence of
+// ~(G N / 148) units in the pull model (pull_body.cuh): the Gram role gets all 148 tensor cores, the
+// recurrence all 148 L1s, and neither needs a barrier with the other.
+template <int UPT>
+__global__ void __launch_bounds__(FUSED_I8_THREADS, 1)
+fused_pull_i8_kernel(RecurArgs rp, int n_groups, gi8::GramI8Args gp, const __grid_constant__ CUtensorMap tmA,
+                     const __grid_constant__ CUtensorMap tmB, const int2* __restrict__ tiles, int ntiles) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long total = (long long)ntiles * gp.batch;
+    const bool has_gram = (long long)blockIdx.x < total;  // uniform per CTA
+    gi8::GramI8Ctx ctx;
+    if (has_gram) gi8::gram_i8_setup(ctx, smem_raw);
+    const bool rec_warp = (warp >= 1 && warp <= 3) || (warp >= 5 && warp <= 7);
+    if (rec_warp) {
+        if (rp.steps > 0) recur::pull_body<UPT>(rp, n_groups, (warp < 4 ? warp - 1 : warp - 2) * 32 + lane, blockIdx.x);
+    } else if (has_gram) {
+        gi8::gram_i8_run<FUSED_I8_THREADS>(ctx, gp, &tmA, &tmB, tiles, ntiles, blockIdx.x, gridDim.x);
+    }
+    if (has_gram) gi8::gram_i8_teardown(ctx);
+}
+
+// stand-alone pull recurrence (spin-up, forced runs): PULL_THREADS-wide CTAs, one per SM, all co-resident
+template <int UPT>
+__global__ void __launch_bounds__(recur::PULL_THREADS, 1) pull_forced_kernel(RecurArgs rp, int n_groups) {
+    recur::pull_body<UPT>(rp, n_groups, threadIdx.x, blockIdx.x);
 }
 
 }  // namespace
@@ -236,6 +267,76 @@ int launch_fused_chunk_i8(RecurArgs rp, int n_groups, int team, int upt, int max
         if (int rc = gram_i8_make_maps(g, &tm_a, &tm_b)) return rc;
     void* args[] = {&rp, &rec_ctas, &team, &g, &tm_a, &tm_b, (void*)&tiles, &ntiles};
     XESN_CUDA_OK(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(FUSED_I8_THREADS), args, (size_t)smem, stream));
+    count_launch();
+    return 0;
+}
+
+
+// units per CTA (multiple of 8) and units per thread of the pull-model recurrence spread over n_ctas CTAs
+int pull_geometry(int N, int n_groups, int n_ctas, int* upc_out, int* upt_out) {
+    const long long total = (long long)N * n_groups;
+    const long long upc = (((total + n_ctas - 1) / n_ctas) + 7) & ~7LL;
+    for (int upt = 1; upt <= 8; upt <<= 1) {
+        if (N % upt) break;
+        if ((long long)recur::PULL_THREADS * upt >= upc) {
+            *upc_out = (int)upc, *upt_out = upt;
+            return 0;
+        }
+    }
+    return -2;
+}
+
+static int prefill_ring(const RecurArgs& rp, int n_groups, cudaStream_t stream) {
+    XESN_CUDA_OK(cudaMemset2DAsync(rp.states, sizeof(double) * rp.state_group_stride, 0xFF,
+                                   sizeof(double) * (size_t)(rp.steps + 1) * rp.N, n_groups, stream));
+    return 0;
+}
+
+int launch_pull_forced(RecurArgs rp, int n_groups, int num_sms, cudaStream_t stream) {
+    if (rp.steps <= 0) return 0;
+    int upc = 0, upt = 0;
+    if (pull_geometry(rp.N, n_groups, num_sms, &upc, &upt)) {
+        set_error("pull recurrence: %d x %d units do not fit %d CTAs", n_groups, rp.N, num_sms);
+        return -2;
+    }
+    rp.units_per_cta = upc;
+    if (int rc = prefill_ring(rp, n_groups, stream)) return rc;
+    const long long total = (long long)rp.N * n_groups;
+    int grid = (int)((total + upc - 1) / upc);
+    void (*kern)(RecurArgs, int) = upt == 1 ? pull_forced_kernel<1>
+                                            : (upt == 2 ? pull_forced_kernel<2>
+                                                        : (upt == 4 ? pull_forced_kernel<4> : pull_forced_kernel<8>));
+    void* args[] = {&rp, &n_groups};
+    XESN_CUDA_OK(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(recur::PULL_THREADS), args, 0, stream));
+    count_launch();
+    return 0;
+}
+
+// rp.steps == 0 -> no recurrence; ntiles == 0 -> no Gram role
+int launch_fused_pull_i8(RecurArgs rp, int n_groups, const gi8::GramI8Args& gp, const int2* tiles, int ntiles,
+                         int num_sms, cudaStream_t stream) {
+    int upc = 0, upt = 0;
+    if (pull_geometry(rp.N, n_groups, num_sms, &upc, &upt)) {
+        set_error("pull recurrence: %d x %d units do not fit %d CTAs", n_groups, rp.N, num_sms);
+        return -2;
+    }
+    rp.units_per_cta = upc;
+    if (rp.steps > 0)
+        if (int rc = prefill_ring(rp, n_groups, stream)) return rc;
+    if (rp.steps <= 0 && ntiles == 0) return 0;
+    void (*kern)(RecurArgs, int, gi8::GramI8Args, const CUtensorMap, const CUtensorMap, const int2*, int) =
+        upt == 1 ? fused_pull_i8_kernel<1>
+                 : (upt == 2 ? fused_pull_i8_kernel<2> : (upt == 4 ? fused_pull_i8_kernel<4> : fused_pull_i8_kernel<8>));
+    XESN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    gi8::GramI8Args g = gp;
+    alignas(64) CUtensorMap tm_a, tm_b;
+    memset(&tm_a, 0, sizeof(tm_a));
+    memset(&tm_b, 0, sizeof(tm_b));
+    if (ntiles > 0)
+        if (int rc = gram_i8_make_maps(g, &tm_a, &tm_b)) return rc;
+    void* args[] = {&rp, &n_groups, &g, &tm_a, &tm_b, (void*)&tiles, &ntiles};
+    XESN_CUDA_OK(cudaLaunchCooperativeKernel((void*)kern, dim3(num_sms), dim3(FUSED_I8_THREADS), args,
+                                             (size_t)gi8::SMEM_BYTES, stream));
     count_launch();
     return 0;
 }

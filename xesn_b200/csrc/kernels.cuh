@@ -74,6 +74,11 @@ namespace gi8 { struct GramI8Args; }
 int gram_i8_make_maps(const gi8::GramI8Args& a, void* map_a, void* map_b);  // two CUtensorMap (64-byte aligned)
 int launch_fused_chunk_i8(RecurArgs rp, int n_groups, int team, int upt, int max_slice_nnz,
                           const gi8::GramI8Args& gp, const int2* tiles, int ntiles, int num_sms, cudaStream_t stream);
+// pull-model recurrence (pull_body.cuh): spread over all SMs, beside the Gram role in every CTA
+int pull_geometry(int N, int n_groups, int n_ctas, int* upc_out, int* upt_out);
+int launch_pull_forced(RecurArgs rp, int n_groups, int num_sms, cudaStream_t stream);
+int launch_fused_pull_i8(RecurArgs rp, int n_groups, const gi8::GramI8Args& gp, const int2* tiles, int ntiles,
+                         int num_sms, cudaStream_t stream);
 int launch_step_update(const StepArgs& a, int n_groups, cudaStream_t stream);
 int readout_slices(int N, int O, int n_groups);
 int launch_readout(ReadoutArgs a, int n_groups, cudaStream_t stream);
