@@ -164,8 +164,9 @@ int64_t xesn_launch_count(void);
  * SM-specialised kernel; xesn_set_fused(h, 0) falls back to separate launches (A/B measurements). */
 int xesn_set_fused(xesn_reservoir* h, int32_t on);
 /* Recurrence engine: 0 = team model (a team of CTAs per reservoir, full state copy in shared memory),
- * 1 = pull model (every thread polls exactly the states its rows of W need; spread over all SMs and, during
- * training, run by the idle warps of the Gram CTAs).  Same arithmetic, same results. */
+ * 1 (default) = pull model (every thread polls exactly the states its rows of W need, spread over all SMs) for
+ * forced runs and spin-up, team model inside the fused training kernel, 2 = pull model there too (run by the
+ * idle warps of the Gram CTAs).  Same arithmetic, bitwise the same results. */
 int xesn_set_recur_mode(xesn_reservoir* h, int32_t mode);
 /* Gram accumulation engine of the fused pipeline: 1 (default) = error-free int8 digit planes on the
  * tcgen05 tensor cores, 0 = FP64 DMMA. */

@@ -90,7 +90,7 @@ struct xesn_reservoir {
     double* d_win = nullptr;
     double* d_bias = nullptr;
     int* d_status = nullptr;
-    unsigned* d_bar = nullptr;  // grid barrier words of the persistent forecast kernel
+    unsigned* d_bar = nullptr;  // [0..1] grid barrier words of the persistent forecast kernel, [2] hint counter of the pull recurrence
     int persistent_predict = 1;
     double* d_ro_partial = nullptr;
     int* d_ro_counters = nullptr;
@@ -105,7 +105,9 @@ struct xesn_reservoir {
     int n_tiles_i8 = 0;
     int gram_mode = 1;  // 0 = FP64 DMMA, 1 = error-free int8 on tcgen05
     int fused_enabled = 1;
-    int recur_pull = 0;  // 1 = pull-model recurrence (pull_body.cuh), 0 = team model (recur_body.cuh)
+    // recurrence engine: 0 = team model everywhere (recur_body.cuh), 1 = pull model (pull_body.cuh) for forced runs and
+    // spin-up, team model inside the fused training kernel (default: measured fastest), 2 = pull model everywhere
+    int recur_pull = 1;
 };
 
 extern "C" {
@@ -167,10 +169,14 @@ int xesn_reservoir_create(xesn_reservoir** out, int device, int32_t N, int32_t I
     XESN_CUDA_OK(cudaMalloc(&h->d_bias, sizeof(double) * N));
     XESN_CUDA_OK(cudaMalloc(&h->d_status, sizeof(int)));
     XESN_CUDA_OK(cudaMemset(h->d_status, 0, sizeof(int)));
-    XESN_CUDA_OK(cudaMalloc(&h->d_bar, 2 * sizeof(unsigned)));
-    XESN_CUDA_OK(cudaMemset(h->d_bar, 0, 2 * sizeof(unsigned)));
-    if (const char* e = getenv("XESN_B200_PREDICT")) h->persistent_predict = strcmp(e, "steps") != 0;
-    if (const char* e = getenv("XESN_B200_RECUR")) h->recur_pull = strcmp(e, "pull") == 0;
+    XESN_CUDA_OK(cudaMalloc(&h->d_bar, 4 * sizeof(unsigned)));
+    XESN_CUDA_OK(cudaMemset(h->d_bar, 0, 4 * sizeof(unsigned)));
+    // forecast engine: 1 = barrier-free pull kernel for a single reservoir (else the barrier kernel), 2 = always the
+    // persistent kernel with grid barriers, 0 = one launch per phase and step
+    if (const char* e = getenv("XESN_B200_PREDICT"))
+        h->persistent_predict = strcmp(e, "steps") == 0 ? 0 : (strcmp(e, "barrier") == 0 ? 2 : 1);
+    if (const char* e = getenv("XESN_B200_RECUR"))
+        h->recur_pull = strcmp(e, "pull") == 0 ? 2 : (strcmp(e, "team") == 0 ? 0 : 1);
     XESN_CUDA_OK(cudaMemcpy(h->d_indptr, indptr, sizeof(int) * (N + 1), cudaMemcpyHostToDevice));
     if (nnz) {
         XESN_CUDA_OK(cudaMemcpy(h->d_indices, indices, sizeof(int) * nnz, cudaMemcpyHostToDevice));
@@ -288,6 +294,8 @@ static RecurArgs recur_args(xesn_reservoir* h) {
     r.indptr = h->d_indptr, r.indices = h->d_indices, r.values = h->d_values;
     r.N = h->N, r.alpha = h->alpha, r.smem_nnz = h->max_slice_nnz, r.status = h->d_status;
     r.debug_no_exchange = getenv("XESN_B200_DEBUG_NO_EXCHANGE") != nullptr;
+    r.hint = getenv("XESN_B200_NO_HINT") ? nullptr : h->d_bar + 2;
+    if (const char* e = getenv("XESN_B200_POLL_SLEEP1")) r.poll_sleep_retry = atoi(e);
     return r;
 }
 
@@ -411,7 +419,7 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
     // accumulate: xesn/esn.py:502-513
     int team = 0, upt = 0;
     int pull_upc = 0, pull_upt = 0;
-    const bool pull = h->recur_pull && h->gram_mode == 1 && pull_geometry(N, G, h->num_sms, &pull_upc, &pull_upt) == 0;
+    const bool pull = h->recur_pull == 2 && h->gram_mode == 1 && pull_geometry(N, G, h->num_sms, &pull_upc, &pull_upt) == 0;
     const bool fuse = h->fused_enabled && (N % 2 == 0) && T > n_spinup &&
                       (pull || (fused_recur_geometry(N, G, fused_threads(h->gram_mode == 1), &team, &upt) == 0 &&
                                 (long long)team * G < h->num_sms));
@@ -548,9 +556,10 @@ int xesn_set_gram_mode(xesn_reservoir* h, int32_t mode) {
 }
 
 // 0 = team-model recurrence (shared-memory state copy per CTA), 1 = pull model (every thread polls the states
-// its rows need; the recurrence rides on the idle warps of the Gram CTAs)
+// its rows need) for forced runs / spin-up only, 2 = pull model also inside the fused training kernel (the
+// recurrence rides on the idle warps of the Gram CTAs)
 int xesn_set_recur_mode(xesn_reservoir* h, int32_t mode) {
-    XESN_REQUIRE(h && (mode == 0 || mode == 1), "bad arguments");
+    XESN_REQUIRE(h && mode >= 0 && mode <= 2, "bad arguments");
     h->recur_pull = mode;
     return 0;
 }
@@ -665,9 +674,20 @@ static PredictLoopArgs predict_loop_args(xesn_reservoir* h, const double* wout, 
     return a;
 }
 
+// steps per launch of the barrier-free forecast kernel (bounds its rings: (257 N + 256 x 148 x O) x 8 bytes)
+constexpr int PULL_PREDICT_CHUNK = 256;
+
+static bool predict_pull_eligible(xesn_reservoir* h, int O, int G, long long n_cells, int* upc, int* n_ctas) {
+    return h->persistent_predict == 1 && G == 1 && n_cells > 0 &&
+           predict_pull_geometry(h->N, h->I, O, n_cells, h->num_sms, upc, n_ctas);
+}
+
 int64_t xesn_predict_scratch_bytes(xesn_reservoir* h, int32_t O, int32_t G, int64_t n_cells) {
     if (!h) return -1;
     long long d = round_up((long long)G * h->I, 2) + 2 * round_up((long long)G * h->N, 2) + round_up(n_cells, 2);
+    int upc = 0, n_ctas = 0;
+    if (predict_pull_eligible(h, O, G, n_cells, &upc, &n_ctas))
+        d += (long long)(PULL_PREDICT_CHUNK + 1) * h->N + (long long)PULL_PREDICT_CHUNK * (n_ctas + 1) * O;
     return d * 8 + 256;
 }
 
@@ -715,6 +735,26 @@ int xesn_predict(xesn_reservoir* h, const double* wout, int32_t O, int32_t G, in
 
     double* rbuf[2] = {r, r_alt};
     double* fbuf[2] = {field, field_alt};
+    int pp_upc = 0, pp_ctas = 0;
+    if (predict_pull_eligible(h, O, G, n_cells, &pp_upc, &pp_ctas)) {
+        // one reservoir: barrier-free forecast kernel, PULL_PREDICT_CHUNK steps per launch
+        PredictPullArgs a = {};
+        a.indptr = h->d_indptr, a.indices = h->d_indices, a.values = h->d_values;
+        a.Win = h->d_win, a.bias = h->d_bias, a.Wout = wout;
+        a.in_map = in_map, a.fill = fill, a.out_map = out_map;
+        a.field = field, a.r = r;
+        a.r_ring = field_alt + round_up(n_cells, 2);
+        a.part_ring = a.r_ring + (long long)(PULL_PREDICT_CHUNK + 1) * N;
+        a.v_ring = a.part_ring + (long long)PULL_PREDICT_CHUNK * pp_ctas * O;
+        a.pred = pred, a.ldp = ldp, a.n_cells = n_cells;
+        a.N = N, a.I = I, a.O = O, a.alpha = h->alpha, a.upc = pp_upc, a.n_ctas = pp_ctas;
+        a.hint = h->d_bar + 2, a.status = h->d_status;
+        for (int s0 = 0; s0 < n_steps; s0 += PULL_PREDICT_CHUNK) {
+            a.col0 = s0, a.steps = std::min(PULL_PREDICT_CHUNK, n_steps - s0);
+            if ((rc = launch_predict_pull(a, st))) return rc;
+        }
+        return 0;
+    }
     if (predict_loop_eligible(h, G)) {
         PredictLoopArgs a = predict_loop_args(h, wout, O, G, in_map, fill, out_map, fbuf, rbuf, pred, ldp, n_steps, S);
         if ((rc = launch_predict_loop(a, h->num_sms, st))) return rc;

@@ -101,6 +101,9 @@ __global__ void __launch_bounds__(FUSED_I8_THREADS, 1)
 fused_pull_i8_kernel(RecurArgs rp, int n_groups, gi8::GramI8Args gp, const __grid_constant__ CUtensorMap tmA,
                      const __grid_constant__ CUtensorMap tmB, const int2* __restrict__ tiles, int ntiles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_sync[2];
+    if (threadIdx.x < 2) s_sync[threadIdx.x] = 0;
+    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long total = (long long)ntiles * gp.batch;
     const bool has_gram = (long long)blockIdx.x < total;  // uniform per CTA
@@ -108,7 +111,7 @@ fused_pull_i8_kernel(RecurArgs rp, int n_groups, gi8::GramI8Args gp, const __gri
     if (has_gram) gi8::gram_i8_setup(ctx, smem_raw);
     const bool rec_warp = (warp >= 1 && warp <= 3) || (warp >= 5 && warp <= 7);
     if (rec_warp) {
-        if (rp.steps > 0) recur::pull_body<UPT>(rp, n_groups, (warp < 4 ? warp - 1 : warp - 2) * 32 + lane, blockIdx.x);
+        if (rp.steps > 0) recur::pull_body<UPT>(rp, n_groups, (warp < 4 ? warp - 1 : warp - 2) * 32 + lane, blockIdx.x, s_sync);
     } else if (has_gram) {
         gi8::gram_i8_run<FUSED_I8_THREADS>(ctx, gp, &tmA, &tmB, tiles, ntiles, blockIdx.x, gridDim.x);
     }
@@ -118,7 +121,10 @@ fused_pull_i8_kernel(RecurArgs rp, int n_groups, gi8::GramI8Args gp, const __gri
 // stand-alone pull recurrence (spin-up, forced runs): PULL_THREADS-wide CTAs, one per SM, all co-resident
 template <int UPT>
 __global__ void __launch_bounds__(recur::PULL_THREADS, 1) pull_forced_kernel(RecurArgs rp, int n_groups) {
-    recur::pull_body<UPT>(rp, n_groups, threadIdx.x, blockIdx.x);
+    __shared__ int s_sync[2];
+    if (threadIdx.x < 2) s_sync[threadIdx.x] = 0;
+    __syncthreads();
+    recur::pull_body<UPT>(rp, n_groups, threadIdx.x, blockIdx.x, s_sync);
 }
 
 }  // namespace
@@ -286,7 +292,10 @@ int pull_geometry(int N, int n_groups, int n_ctas, int* upc_out, int* upt_out) {
     return -2;
 }
 
-static int prefill_ring(const RecurArgs& rp, int n_groups, cudaStream_t stream) {
+static int prefill_ring(RecurArgs& rp, int n_groups, cudaStream_t stream) {
+    const long long total = (long long)rp.N * n_groups;
+    rp.n_active_ctas = (int)((total + rp.units_per_cta - 1) / rp.units_per_cta);
+    if (rp.hint) XESN_CUDA_OK(cudaMemsetAsync(rp.hint, 0, sizeof(unsigned), stream));
     XESN_CUDA_OK(cudaMemset2DAsync(rp.states, sizeof(double) * rp.state_group_stride, 0xFF,
                                    sizeof(double) * (size_t)(rp.steps + 1) * rp.N, n_groups, stream));
     return 0;
@@ -295,6 +304,7 @@ static int prefill_ring(const RecurArgs& rp, int n_groups, cudaStream_t stream) 
 int launch_pull_forced(RecurArgs rp, int n_groups, int num_sms, cudaStream_t stream) {
     if (rp.steps <= 0) return 0;
     int upc = 0, upt = 0;
+    if (const char* e = getenv("XESN_B200_PULL_CTAS")) num_sms = std::min(num_sms, std::max(1, atoi(e)));  // experiments
     if (pull_geometry(rp.N, n_groups, num_sms, &upc, &upt)) {
         set_error("pull recurrence: %d x %d units do not fit %d CTAs", n_groups, rp.N, num_sms);
         return -2;
@@ -327,7 +337,7 @@ int launch_fused_pull_i8(RecurArgs rp, int n_groups, const gi8::GramI8Args& gp, 
     void (*kern)(RecurArgs, int, gi8::GramI8Args, const CUtensorMap, const CUtensorMap, const int2*, int) =
         upt == 1 ? fused_pull_i8_kernel<1>
                  : (upt == 2 ? fused_pull_i8_kernel<2> : (upt == 4 ? fused_pull_i8_kernel<4> : fused_pull_i8_kernel<8>));
-    XESN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    XESN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gi8::SMEM_BYTES));
     gi8::GramI8Args g = gp;
     alignas(64) CUtensorMap tm_a, tm_b;
     memset(&tm_a, 0, sizeof(tm_a));

@@ -25,6 +25,9 @@ struct RecurArgs {
     int w_in_smem;
     int n_pad;               // N rounded up to even: size of the shared-memory state copy
     int debug_no_exchange;   // timing experiments only: skip the refresh of the other CTAs' slices (wrong results)
+    int poll_sleep_retry;    // pull model, experiments: nanoseconds to sleep between polls
+    unsigned* hint;          // pull model: device counter of CTAs that have published their part of a row (zeroed per launch)
+    int n_active_ctas;       // filled by the launcher
 };
 
 struct StepArgs {
@@ -118,6 +121,36 @@ struct PredictLoopArgs {
     unsigned* peer_flags[XESN_MAX_WORLD];    // [rank] -> that rank's flag array (one entry per source rank)
 };
 int launch_predict_loop(const PredictLoopArgs& a, int num_sms, cudaStream_t stream);
+
+// ---- barrier-free closed loop of one reservoir (predict_pull.cu) --------------------------------
+struct PredictPullArgs {
+    const int* indptr;
+    const int* indices;
+    const double* values;
+    const double* Win;      // [N][I]
+    const double* bias;
+    const double* Wout;     // [O][N]
+    const int* in_map;      // [I] cell index or -1-k -> fill[k]
+    const double* fill;
+    const int* out_map;     // [O] cell index (nullptr: o)
+    double* field;          // [n_cells] in: field entering the launch, out: field after `steps` steps
+    double* r;              // [N] in/out
+    double* r_ring;         // [steps+1][N]        pre-filled "unset" by the launcher
+    double* part_ring;      // [steps][O][n_ctas]  pre-filled "unset" by the launcher
+    double* v_ring;         // [steps][O]          pre-filled "unset" by the launcher
+    double* pred;           // [n_cells][ldp]; column col0 + n written for n = 1..steps
+    long long ldp;
+    long long n_cells;
+    int col0;
+    int N, I, O, steps;
+    double alpha;
+    int upc, n_ctas;        // units per CTA, CTAs
+    unsigned* hint;
+    int* status;
+};
+size_t predict_pull_smem(int I, int O, int upc, long long n_cells, int n_ctas);
+bool predict_pull_geometry(int N, int I, int O, long long n_cells, int num_sms, int* upc_out, int* n_ctas_out);
+int launch_predict_pull(PredictPullArgs a, cudaStream_t stream);
 
 // ---- ridge solve (cholesky.cu) ---------------------------------------------------------------
 // In-place blocked Cholesky of the lower triangle of `batch` SPD matrices A[b] (n x n, row-major,
