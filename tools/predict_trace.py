@@ -28,4 +28,4 @@ except AttributeError:
 a = np.array(buf[:], dtype=np.float64).reshape(64, 8) / STEPS
 print("cycles per step: [0]hint wait | [1]gathers issue + contributions | [2]input vector | [3]gather wait + dot | [4]Win u, tanh, store | [5]readout part")
 for name, v in (("mean", a.mean(0)), ("min", a.min(0)), ("max", a.max(0))):
-    print(f"   {name:5s} " + " ".join(f"{x:8.1f}" for x in v[:6]) + f"   total {v[:6].sum():8.0f}")
+    print(f"   {name:5s} " + " ".join(f"{x:8.1f}" for x in v[:5]) + f"   total {v[:5].sum():8.0f}   | thread 128: v poll {v[5]:8.1f}, hint wait {v[6]:8.1f} cycles, {v[7]:6.1f} spins")

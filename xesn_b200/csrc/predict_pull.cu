@@ -3,15 +3,20 @@
 //      for n = 1 .. n_steps:   r <- update(r, v);   v <- Wout r
 //
 // predict_loop.cu separates the update and the readout of a step by two software grid barriers
-// (13 us per step at N=16000).  Here the step has no barrier at all.  The reservoir is spread over all
+// (13 us per step at N=16000).  Here the step has no grid barrier.  The reservoir is spread over all
 // SMs (~N/148 units per CTA, one unit per thread).  A CTA keeps its rows of Win and its COLUMNS of Wout in
-// shared memory, so after updating its units it can form its contribution to the readout,
+// shared memory, so after updating its units it forms its contribution to every output,
 //      part_c[o] = sum_{i in slice c} Wout[o][i] r[i],
-// right away and publish it next to its slice of r.  Both travel through rings in global memory that are
-// pre-filled with the "unset" pattern (the data is its own flag, recur_body.cuh), gated by the relaxed
-// hint counter of pull_body.cuh so that nobody polls before the row is probably complete.  Every CTA
-// then adds the contributions of all CTAs in the same fixed order (bitwise the same v everywhere) and
-// gathers exactly the states its rows of W need.  Per step: one L2 hop instead of two grid barriers.
+// and publishes it next to its slice of r.  Output o is finished by ONE dedicated reducer warp (CTA
+// o % n_ctas) that adds the contributions of all CTAs in a fixed order and publishes v[o].  Everything
+// travels through rings in global memory pre-filled with the "unset" pattern (the data is its own flag,
+// recur_body.cuh); the many consumers of v are gated by the relaxed hint counter of pull_body.cuh (one
+// word polled by one thread per CTA), the few reducer warps poll the contributions themselves.
+// Measured on B200 (tools/micro/pingpong.cu): one store -> poll hop between SMs costs ~800 cycles, so a step
+// is two hops (contributions -> reducer -> everyone) plus the arithmetic, instead of two grid barriers.
+//
+// Warp roles (512 threads): warps 0-3 own the units, warps 4-11 compute the contributions, warps 12-15 are
+// reducers (free-running: they never join the CTA barriers of the other twelve).
 #include <algorithm>
 
 #include "common.cuh"
@@ -24,10 +29,14 @@ namespace {
 using namespace recur;
 
 constexpr int PP_THREADS = 512;
-constexpr int PP_WARPS = PP_THREADS / 32;
-constexpr int PP_UNITS = 128;  // unit threads per CTA (warps 0..3), one unit each; the other warps help with the readout
+constexpr int PP_UNITS = 128;         // warps 0..3, one unit per thread
+constexpr int PP_CONTRIB_WARP0 = 4, PP_CONTRIB_WARPS = 8;
+constexpr int PP_RED_WARP0 = 12, PP_RED_WARPS = 4;
+constexpr int PP_MAIN_THREADS = PP_RED_WARP0 * 32;  // 384 threads meet at named barrier 1
 constexpr int PP_KREG = 12;
 constexpr int PP_KTAIL = 4;
+
+__device__ __forceinline__ void main_barrier() { asm volatile("bar.sync 1, %0;\n" ::"n"(PP_MAIN_THREADS) : "memory"); }
 
 __device__ __forceinline__ double poll_value(const double* p, int* status, bool& aborted) {
     double v = ld_flag(p);
@@ -38,6 +47,7 @@ __device__ __forceinline__ double poll_value(const double* p, int* status, bool&
     }
     return v;
 }
+__device__ __forceinline__ double nan_to_zero(double x) { return (x != x) ? 0.0 : x; }
 
 __global__ void __launch_bounds__(PP_THREADS, 1) predict_pull_kernel(PredictPullArgs p) {
     extern __shared__ __align__(16) double smem[];
@@ -48,18 +58,74 @@ __global__ void __launch_bounds__(PP_THREADS, 1) predict_pull_kernel(PredictPull
     const int ldw = I + 1 + (I & 1);  // odd row pitch (in doubles): conflict-free reads of one row per lane
     double* s_win = smem;                          // [upc][ldw]
     double* s_wout = s_win + (size_t)upc * ldw;    // [O][upc]
-    double* s_field = s_wout + (size_t)O * upc;    // [n_cells]
-    double* s_u = s_field + p.n_cells;             // [I]
+    double* s_u0 = s_wout + (size_t)O * upc;       // [I] inputs that never change (and all inputs of step 1)
+    double* s_u = s_u0 + I;                        // [I]
     double* s_rnew = s_u + I;                      // [upc]
+    int* s_src = reinterpret_cast<int*>(s_rnew + upc);  // [I] output that feeds input k, or -1 (static input)
 
     for (int e = tid; e < nu * I; e += PP_THREADS) s_win[(e / I) * ldw + (e % I)] = p.Win[(long long)(u0 + e / I) * I + e % I];
     for (int e = tid; e < O * upc; e += PP_THREADS) {
         const int o = e / upc, il = e % upc;
         s_wout[e] = il < nu ? p.Wout[(long long)o * N + u0 + il] : 0.0;
     }
-    for (int e = tid; e < p.n_cells; e += PP_THREADS) s_field[e] = p.field[e];
+    // input k reads cell in_map[k] of the field (or a boundary fill value); the cell is rewritten every step by the
+    // output o with out_map[o] == cell, if there is one (NaN -> 0 as in lazyesn.py:362-364)
+    for (int k = tid; k < I; k += PP_THREADS) {
+        const int m = p.in_map[k];
+        int src = -1;
+        if (m >= 0)
+            for (int o = 0; o < O; ++o)
+                if ((p.out_map ? p.out_map[o] : o) == m) src = o;
+        s_src[k] = src;
+        s_u0[k] = nan_to_zero(m >= 0 ? p.field[m] : p.fill[-1 - m]);
+    }
 
-    // ---- per-unit constants (warps 0..3) ----
+    const double alpha = p.alpha, oma = 1.0 - p.alpha;
+    bool aborted = false;
+    __syncthreads();
+
+    // ================= reducer warps: v_n[o] = sum over the CTAs of part[n][o][cta] =================
+    if (warp >= PP_RED_WARP0) {
+        const int red_o = c + (warp - PP_RED_WARP0) * p.n_ctas;
+        if (red_o >= O) return;
+        const long long cell = p.out_map ? (long long)p.out_map[red_o] : (long long)red_o;
+        constexpr int RB = 5;  // 160 CTAs at most
+        for (int n = 1; n <= p.steps; ++n) {
+            const double* row = p.part_ring + ((long long)(n - 1) * O + red_o) * p.n_ctas;
+            double v[RB];
+            unsigned pend = 0;
+#pragma unroll
+            for (int b = 0; b < RB; ++b) {
+                v[b] = 0.0;
+                if (b * 32 + lane < p.n_ctas) pend |= 1u << b;
+            }
+            int spins = 0;
+            while (true) {
+#pragma unroll
+                for (int b = 0; b < RB; ++b)
+                    if (pend & (1u << b)) v[b] = ld_flag(row + b * 32 + lane);
+#pragma unroll
+                for (int b = 0; b < RB; ++b)
+                    if ((pend & (1u << b)) && !unset(v[b])) pend &= ~(1u << b);
+                if (!pend || aborted) break;
+                aborted = poll_expired(spins, p.status);
+            }
+            double sum = 0.0;
+#pragma unroll
+            for (int b = 0; b < RB; ++b) sum += v[b];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+            if (lane == 0) {
+                st_flag(p.v_ring + (long long)(n - 1) * O + red_o, sum);
+                add_hint(p.hint);
+                p.pred[cell * p.ldp + p.col0 + n] = sum;
+                if (n == p.steps) p.field[cell] = sum;
+            }
+        }
+        return;
+    }
+
+    // ================= the other twelve warps =================
     const bool owner = tid < PP_UNITS && tid < nu;
     const int unit = u0 + tid;
     int row_lo = 0, row_len = 0;
@@ -81,40 +147,36 @@ __global__ void __launch_bounds__(PP_THREADS, 1) predict_pull_kernel(PredictPull
         if (in) head_mask |= 1u << k;
     }
     if (owner) st_flag(p.r_ring + unit, r_cur);  // row 0 = state after spin-up
-    // output o is reduced by the LAST warps of CTA o % n_ctas (the first warps own the units)
-    const int red_o = c + (PP_WARPS - 1 - warp) * p.n_ctas;
-    const bool reducer = warp >= PP_UNITS / 32 && red_o < O;
-    const long long red_cell = reducer ? (p.out_map ? (long long)p.out_map[red_o] : (long long)red_o) : 0;
-    const double alpha = p.alpha, oma = 1.0 - p.alpha;
-    bool aborted = false;
 #ifdef XESN_RECUR_TRACE
     long long tr_sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    long long tr_last = clock64();
+    long long tr_last = trace_clock();
 #endif
-    __syncthreads();
 
-    // step n consumes row n-1 of the state ring and v_{n-1} (the field of step 0 is the initial condition); one
-    // extra pass (n = steps + 1) only fetches the last readout so that CTA 0 can store the final field
-    for (int n = 1; n <= p.steps + 1; ++n) {
-        const bool last = n == p.steps + 1;
-        if (last && c != 0) break;
-        XESN_TRACE_MARK(5);  // [5] readout contribution, publish, (reducer warps: the sum) of the previous step
-        // the hint counts the published outputs: O per step.  Complete => every CTA has published its contribution
-        // to every output, which it does after storing its slice of r
-        if (n >= 2 && tid == 0) {
+    for (int n = 1; n <= p.steps; ++n) {
+        XESN_TRACE_MARK(4);  // owners: idle while the contributions are formed (added to [4])
+        // the hint counts published outputs, O per step: complete => every CTA has published its contribution to
+        // every output, which it does after storing its slice of r
+        if (n >= 2 && tid == PP_CONTRIB_WARP0 * 32) {
             const unsigned target = (unsigned)O * (unsigned)(n - 1);
             int spins = 0;
+#ifdef XESN_RECUR_TRACE
+            const long long h0 = trace_clock();
+#endif
             while (ld_hint(p.hint) < target)
                 if (++spins > HINT_SPIN_LIMIT) break;
+#ifdef XESN_RECUR_TRACE
+            tr_sum[6] += trace_clock() - h0;
+            tr_sum[7] += spins;
+#endif
         }
-        __syncthreads();
+        main_barrier();
         XESN_TRACE_MARK(0);  // [0] hint wait
         const double* r_prev = p.r_ring + (long long)(n - 1) * N;
 
-        // (1) gathers of W r in flight first
+        // (1) owners: gathers of W r in flight; contribution warps: the input vector from v_{n-1}
         double gth[PP_KREG], tg[PP_KTAIL], tv[PP_KTAIL];
         int ti[PP_KTAIL];
-        unsigned pend = (owner && !last) ? head_mask : 0u, tpend = 0;
+        unsigned pend = owner ? head_mask : 0u, tpend = 0;
         if (pend && row_len > PP_KREG) {
 #pragma unroll
             for (int k = 0; k < PP_KTAIL; ++k) {
@@ -133,28 +195,24 @@ __global__ void __launch_bounds__(PP_THREADS, 1) predict_pull_kernel(PredictPull
             for (int k = 0; k < PP_KTAIL; ++k)
                 if (tpend & (1u << k)) tg[k] = ld_flag(r_prev + ti[k]);
         }
-
-        // (2) v_{n-1} into the field
-        if (n >= 2) {
-            for (int o = tid; o < O; o += PP_THREADS) {
-                const double v = poll_value(p.v_ring + (long long)(n - 2) * O + o, p.status, aborted);
-                s_field[p.out_map ? p.out_map[o] : o] = v;
+        if (warp >= PP_CONTRIB_WARP0) {
+#ifdef XESN_RECUR_TRACE
+            const long long v0 = trace_clock();
+#endif
+            for (int k = tid - PP_CONTRIB_WARP0 * 32; k < I; k += PP_CONTRIB_WARPS * 32) {
+                const int src = s_src[k];
+                s_u[k] = (n == 1 || src < 0)
+                             ? s_u0[k]
+                             : nan_to_zero(poll_value(p.v_ring + (long long)(n - 2) * O + src, p.status, aborted));
             }
-            __syncthreads();
+#ifdef XESN_RECUR_TRACE
+            tr_sum[5] += trace_clock() - v0;
+#endif
         }
-        if (last) break;
-        XESN_TRACE_MARK(1);  // [1] issue gathers + fetch v
+        main_barrier();
+        XESN_TRACE_MARK(1);  // [1] issue gathers, input vector
 
-        // (3) input vector of the step: gathered from the field, NaN -> 0 (lazyesn.py:362-364 for masked inputs)
-        for (int k = tid; k < I; k += PP_THREADS) {
-            const int m = __ldg(p.in_map + k);
-            const double x = (m >= 0) ? s_field[m] : __ldg(p.fill + (-1 - m));
-            s_u[k] = (x != x) ? 0.0 : x;
-        }
-        __syncthreads();
-        XESN_TRACE_MARK(2);  // [2] input vector
-
-        // (4) update of the owned unit
+        // (2) update of the owned unit
         if (owner) {
             int spins = 0;
             while (true) {
@@ -207,77 +265,57 @@ __global__ void __launch_bounds__(PP_THREADS, 1) predict_pull_kernel(PredictPull
         } else if (tid < upc) {
             s_rnew[tid] = 0.0;
         }
-        __syncthreads();
+        main_barrier();
         XESN_TRACE_MARK(4);  // [4] Win u + tanh + store + barrier
 
-        // (5) this CTA's contribution to every output: warp w takes outputs w, w+16, ...; lanes stride over the units.
-        // part_ring[step][o][cta]: the reducer of output o reads one contiguous row
-        {
+        // (3) contribution warps: this CTA's share of every output; warp w takes outputs w, w+8, ..., four at a
+        // time, lanes stride over the units.  part_ring[step][o][cta]: a reducer reads one contiguous row
+        if (warp >= PP_CONTRIB_WARP0) {
             double* part = p.part_ring + (long long)(n - 1) * O * p.n_ctas + c;
-            for (int o0 = 0; o0 < O; o0 += PP_WARPS * 4) {
-                double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int o0 = warp - PP_CONTRIB_WARP0; o0 < O; o0 += 4 * PP_CONTRIB_WARPS) {
+                const double* w0 = s_wout + (size_t)o0 * upc;
+                const double* w1 = s_wout + (size_t)min(o0 + PP_CONTRIB_WARPS, O - 1) * upc;
+                const double* w2 = s_wout + (size_t)min(o0 + 2 * PP_CONTRIB_WARPS, O - 1) * upc;
+                const double* w3 = s_wout + (size_t)min(o0 + 3 * PP_CONTRIB_WARPS, O - 1) * upc;
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
                 for (int il = lane; il < upc; il += 32) {
                     const double rv = s_rnew[il];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int o = o0 + j * PP_WARPS + warp;
-                        if (o < O) acc[j] = fma(s_wout[(size_t)o * upc + il], rv, acc[j]);
-                    }
+                    a0 = fma(w0[il], rv, a0);
+                    a1 = fma(w1[il], rv, a1);
+                    a2 = fma(w2[il], rv, a2);
+                    a3 = fma(w3[il], rv, a3);
                 }
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], off);
-                if (lane == 0)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int o = o0 + j * PP_WARPS + warp;
-                        if (o < O) st_flag(part + (long long)o * p.n_ctas, acc[j]);
-                    }
-            }
-        }
-        // (6) reducer warps: v_n[o] = sum over the CTAs, fixed order; few warps poll, so they poll the data itself
-        if (reducer) {
-            const double* row = p.part_ring + ((long long)(n - 1) * O + red_o) * p.n_ctas;
-            double sum = 0.0;
-            for (int cb = 0; cb < p.n_ctas; cb += 32 * 8) {
-                double v[8];
-#pragma unroll
-                for (int b = 0; b < 8; ++b) {
-                    const int cc = cb + b * 32 + lane;
-                    v[b] = cc < p.n_ctas ? ld_flag(row + cc) : 0.0;
+                for (int off = 16; off > 0; off >>= 1) {
+                    a0 += __shfl_xor_sync(0xffffffffu, a0, off);
+                    a1 += __shfl_xor_sync(0xffffffffu, a1, off);
+                    a2 += __shfl_xor_sync(0xffffffffu, a2, off);
+                    a3 += __shfl_xor_sync(0xffffffffu, a3, off);
                 }
-#pragma unroll
-                for (int b = 0; b < 8; ++b) {
-                    const int cc = cb + b * 32 + lane;
-                    if (cc < p.n_ctas && unset(v[b])) v[b] = poll_value(row + cc, p.status, aborted);
-                    sum += v[b];
+                if (lane == 0) {
+                    st_flag(part + (long long)o0 * p.n_ctas, a0);
+                    if (o0 + PP_CONTRIB_WARPS < O) st_flag(part + (long long)(o0 + PP_CONTRIB_WARPS) * p.n_ctas, a1);
+                    if (o0 + 2 * PP_CONTRIB_WARPS < O) st_flag(part + (long long)(o0 + 2 * PP_CONTRIB_WARPS) * p.n_ctas, a2);
+                    if (o0 + 3 * PP_CONTRIB_WARPS < O) st_flag(part + (long long)(o0 + 3 * PP_CONTRIB_WARPS) * p.n_ctas, a3);
                 }
-            }
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-            if (lane == 0) {
-                st_flag(p.v_ring + (long long)(n - 1) * O + red_o, sum);
-                add_hint(p.hint);
-                p.pred[red_cell * p.ldp + p.col0 + n] = sum;
             }
         }
     }
 #ifdef XESN_RECUR_TRACE
     if (tid == 0 && c < 64)
-        for (int i = 0; i < 8; ++i) g_recur_trace[c * 8 + i] = tr_sum[i];
+        for (int i = 0; i < 5; ++i) g_recur_trace[c * 8 + i] = tr_sum[i];
+    if (tid == PP_CONTRIB_WARP0 * 32 && c < 64)
+        for (int i = 5; i < 8; ++i) g_recur_trace[c * 8 + i] = tr_sum[i];
 #endif
     if (owner) p.r[unit] = r_cur;
-    if (c == 0)
-        for (int e = tid; e < p.n_cells; e += PP_THREADS) p.field[e] = s_field[e];
 }
 
 }  // namespace
 
 size_t predict_pull_smem(int I, int O, int upc, long long n_cells, int n_ctas) {
     const int ldw = I + 1 + (I & 1);
-    (void)n_ctas;
-    return sizeof(double) * ((size_t)upc * ldw + (size_t)O * upc + (size_t)n_cells + I + upc);
+    (void)n_ctas, (void)n_cells;
+    return sizeof(double) * ((size_t)upc * ldw + (size_t)O * upc + 2 * (size_t)I + upc) + sizeof(int) * (size_t)(I + 1);
 }
 
 // geometry of the pull forecast; returns false when the configuration does not fit (caller falls back)
@@ -285,7 +323,7 @@ bool predict_pull_geometry(int N, int I, int O, long long n_cells, int num_sms, 
     const int upc = ((N + num_sms - 1) / num_sms + 7) & ~7;
     if (upc > PP_UNITS) return false;
     const int n_ctas = (N + upc - 1) / upc;
-    if (O > (PP_WARPS - PP_UNITS / 32) * n_ctas) return false;  // one reducer warp per output
+    if (O > PP_RED_WARPS * n_ctas || n_ctas > 160) return false;  // one reducer warp per output, five contributions per lane
     if (predict_pull_smem(I, O, upc, n_cells, n_ctas) > 200 * 1024) return false;
     *upc_out = upc, *n_ctas_out = n_ctas;
     return true;

@@ -11,10 +11,15 @@ namespace recur {
 #ifdef XESN_RECUR_TRACE
 // debug builds only: per-CTA cycle sums of the four phases of a step (thread 0's view)
 static __device__ long long g_recur_trace[64 * 8];
+__device__ __forceinline__ long long trace_clock() {
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;\n" : "=l"(t)::"memory");  // ordered against the other volatile asm (barriers, polls)
+    return t;
+}
 #define XESN_TRACE_MARK(i)                         \
     do {                                           \
         if (tid == 0) {                            \
-            const long long now_ = clock64();      \
+            const long long now_ = trace_clock();  \
             tr_sum[i] += now_ - tr_last;           \
             tr_last = now_;                        \
         }                                          \
