@@ -53,11 +53,19 @@ WORKLOADS = {
     # BASELINE.json configs[2] per GPU: 16 groups of 16 variables, overlap 1, N=2000 (weak scaling)
     "lazy": dict(kind="lazy", groups_per_gpu=16, chunk=16, overlap=1, n_reservoir=2000, n_train=20000,
                  n_spinup_train=0, pred_spinup=500, pred_steps=1000, leak=0.5, beta=1e-6),
+    # BASELINE.json configs[3] per GPU at 8 GPUs: 2 x 16 groups of 32 x 32 cells, overlap 2 (I=1296, O=1024), N=6000;
+    # the domain is (64 x world) x 512, doubly periodic, sharded by group rows (weak scaling)
+    "lazy2d": dict(kind="lazy2d", groups_per_gpu=32, group_rows_per_gpu=2, group_cols=16, chunk=32, overlap=2,
+                   n_reservoir=6000, n_train=4096, n_spinup_train=0, pred_spinup=64, pred_steps=256, leak=0.5, beta=1e-6),
+    # BASELINE.json configs[4] per GPU: 8 of the 64 hyper-parameter candidates (N=4000, Lorenz-96 with 40 variables), each
+    # trained on 20 000 steps and scored on 5 forecasts of 100 spin-up + 500 steps (docs/config.yaml:70-74)
+    "macro": dict(kind="macro", groups_per_gpu=8, n_vars=40, n_reservoir=4000, n_train=20000, n_spinup_train=0,
+                  n_forecasts=5, pred_spinup=100, pred_steps=500),
 }
 
 
 def unit_steps(w, n_groups):
-    return n_groups * w["n_reservoir"] * (w["n_train"] + w["pred_spinup"] + w["pred_steps"])
+    return n_groups * w["n_reservoir"] * (w["n_train"] + w.get("n_forecasts", 1) * (w["pred_spinup"] + w["pred_steps"]))
 
 
 # --------------------------------------------------------------------------- clocks
@@ -206,7 +214,8 @@ def workload_config(name, w, world):
     cfg.update({k: v for k, v in w.items() if k != "kind"})
     cfg["parallelism"] = "single GPU" if world == 1 else (
         f"{world} independent replicas (eager ESN does not shard)" if w["kind"] == "eager"
-        else f"LazyESN groups sharded over {world} ranks, halo all-gather per forecast step")
+        else f"{w['groups_per_gpu']} independent candidates per rank, no communication" if w["kind"] == "macro"
+        else f"LazyESN groups sharded over {world} ranks, halo exchange per forecast step")
     return cfg
 
 
@@ -267,8 +276,82 @@ def main():
         torch.cuda.synchronize()
 
     # ------------------------------------------------------------------ build the workload
-    t_total = w["n_train"] + w["pred_spinup"] + w["pred_steps"] + 1
-    if w["kind"] == "eager":
+    t_total = w["n_train"] + w.get("n_forecasts", 1) * (w["pred_spinup"] + w["pred_steps"] + 1)
+    if w["kind"] == "macro":
+        # candidates drawn like the reference's macro-training search space; every candidate
+        # is an ESN rebuilt from the same seeds with its own factors, leak rate and Tikhonov parameter (cost.py:190-203)
+        from xesn_b200 import ESN
+        rs = np.random.RandomState(rank)
+        esns = []
+        for _ in range(w["groups_per_gpu"]):
+            f_in, f_adj, f_b = rs.uniform(0.01, 2.0, size=3)
+            leak, beta = rs.uniform(0.05, 1.0), 10.0 ** rs.uniform(-8, 0)
+            kw = {k: dict(v) for k, v in ESN_KW.items()}
+            kw["input_kwargs"]["factor"], kw["adjacency_kwargs"]["factor"], kw["bias_kwargs"]["factor"] = f_in, f_adj, f_b
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                e = ESN(w["n_vars"], w["n_vars"], w["n_reservoir"], leak, beta, **kw)
+                e.build()
+            e._device_reservoir()
+            esns.append(e)
+        esn = esns[0]
+        data = lorenz96(w["n_vars"], t_total)
+        n_groups_total = w["groups_per_gpu"] * world
+        seg = w["pred_spinup"] + w["pred_steps"] + 1
+        train_host = torch.from_numpy(np.ascontiguousarray(data[:, :w["n_train"]])).pin_memory()
+        tests_host = [torch.from_numpy(np.ascontiguousarray(data[:, w["n_train"] + k * seg: w["n_train"] + (k + 1) * seg])).pin_memory()
+                      for k in range(w["n_forecasts"])]
+        train_dev, tests_dev = train_host.to(dev), [t.to(dev) for t in tests_host]
+
+        def step_device():
+            out = None
+            for e in esns:
+                e._wout_dev = e._train_device(train_dev, train_dev, 1, w["n_train"], w["n_spinup_train"], None)
+                e._wout_host = None
+                for t in tests_dev:
+                    out = e._predict_device(t, w["pred_steps"], w["pred_spinup"])
+            return out
+
+        def step_e2e():
+            # per candidate: the normalised RMSE of every forecast comes back to the host (cost.py:94-122 needs no more)
+            costs = []
+            for e in esns:
+                e.train(train_host, n_spinup=w["n_spinup_train"])
+                for t in tests_host:
+                    pred = e.predict(t, n_steps=w["pred_steps"], n_spinup=w["pred_spinup"])
+                    truth = t.numpy()[:, w["pred_spinup"]:]
+                    costs.append(float(np.sqrt(np.mean((pred - truth) ** 2 / truth.std(axis=1, keepdims=True) ** 2))))
+            return costs
+
+        h2d = (train_host.numel() + sum(t.numel() for t in tests_host)) * 8 * w["groups_per_gpu"]
+        d2h = w["groups_per_gpu"] * w["n_forecasts"] * w["n_vars"] * (w["pred_steps"] + 1) * 8
+    elif w["kind"] == "lazy2d":
+        from xesn_b200 import LazyESN
+        from xesn_b200.synthetic import wave_field_2d
+        nx, ny = w["group_rows_per_gpu"] * w["chunk"] * world, w["group_cols"] * w["chunk"]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            esn = LazyESN({"x": w["chunk"], "y": w["chunk"]}, {"x": w["overlap"], "y": w["overlap"]}, "periodic",
+                          w["n_reservoir"], w["leak"], w["beta"], **{k: dict(v) for k, v in ESN_KW.items()})
+            esn.build()
+        data = wave_field_2d(nx, ny, t_total)
+        n_groups_total = w["groups_per_gpu"] * world
+        train_host = torch.from_numpy(np.ascontiguousarray(data[..., :w["n_train"]])).pin_memory()
+        test_host = torch.from_numpy(np.ascontiguousarray(data[..., w["n_train"]:])).pin_memory()
+        train_dev, test_dev = train_host.to(dev), test_host.to(dev)
+        esn._device_reservoir()
+
+        def step_device():
+            esn.train(train_dev, n_spinup=w["n_spinup_train"])
+            return esn._predict_core(test_dev, w["pred_steps"], w["pred_spinup"])
+
+        def step_e2e():
+            esn.train(train_host, n_spinup=w["n_spinup_train"])
+            return esn.predict(test_host, n_steps=w["pred_steps"], n_spinup=w["pred_spinup"])
+
+        h2d = (train_host.numel() + test_host.numel()) * 8 // world
+        d2h = nx * ny * (w["pred_steps"] + 1) * 8
+    elif w["kind"] == "eager":
         esn = build_eager_matrices(w)
         data = lorenz96(w["n_vars"], t_total)
         n_groups_total = world  # replicas
@@ -364,7 +447,8 @@ def main():
     # CUDA events recorded by the library on the launching stream.
     fused = prof.get("fused_chunk", (0, 0.0))[0] > 0
     n_gram, ms_gram = prof["fused_chunk"] if fused else prof["gram_syrk"]
-    n_gram_launches = max(n_gram - args.steps, 1) if fused else n_gram  # first fused launch of a train() has no Gram role
+    n_trains = args.steps * (w["groups_per_gpu"] if w["kind"] == "macro" else 1)
+    n_gram_launches = max(n_gram - n_trains, 1) if fused else n_gram  # first fused launch of a train() has no Gram role
     peak_tf = dgemm_peak(torch)
     # algorithmic FP64 flops of the Gram accumulation: N(N+1) per reservoir per time step (one triangle)
     gram_flops = float(G_local) * N * (N + 1) * w["n_train"] * args.steps

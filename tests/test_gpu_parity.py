@@ -389,3 +389,78 @@ def test_dense_adjacency_falls_back_to_global_w(torch, lib):
     esn.train(data, n_spinup=7, batch_size=200)
     refw = oc.ridge_train(data, data, 7, 200, esn.W, esn.Win, esn.bias_vector, 0.5, 1e-4)
     assert oc.max_normalised_err(esn.Wout, refw) < WOUT_TOL
+
+
+# --------------------------------------------------------------------------- BASELINE.json configuration shapes, reduced sizes
+def test_baseline_cfg3_shape_lazy_l96(torch):
+    """cfg 3: LazyESN on Lorenz-96 with 256 variables, chunks of 16, overlap 1 (I=18, O=16, 16 groups); N reduced."""
+    from xesn_b200 import LazyESN
+    from xesn_b200.synthetic import lorenz96
+    data = lorenz96(256, 700)
+    kw = {k: dict(v) for k, v in ESN_KW.items()}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        esn = LazyESN({"x": 16}, {"x": 1}, "periodic", 300, 0.5, 1e-6, **kw)
+    esn.build()
+    esn.train(data[:, :500], n_spinup=0, batch_size=200)
+    W = sp.csr_matrix(esn.W)
+    depth = {0: 1, 1: 0}
+    ref = oc.lazy_train(data[:, :500], (16,), depth, "periodic", 0, 200, W, esn.Win, esn.bias_vector, 0.5, 1e-6)
+    assert esn.Wout_groups.shape[0] == 16
+    assert oc.max_normalised_err(esn.Wout_groups, ref.reshape(esn.Wout_groups.shape)) < 1e-5
+    pred = esn.predict(data[:, 500:], n_steps=40, n_spinup=100)
+    refp = oc.lazy_predict(data[:, 500:], (16,), depth, "periodic", 40, 100, W, esn.Win, esn.bias_vector, 0.5,
+                           esn.Wout_groups.reshape(ref.shape))
+    np.testing.assert_allclose(pred, refp, rtol=0, atol=1e-7)
+
+
+def test_baseline_cfg4_shape_lazy_2d(torch):
+    """cfg 4: 2-D doubly periodic field, 32x32 chunks with overlap 2 (I=1296, O=1024); 64x64 domain (4 groups), N reduced."""
+    from xesn_b200 import LazyESN
+    from xesn_b200.synthetic import wave_field_2d
+    field = wave_field_2d(64, 64, 260)
+    kw = {k: dict(v) for k, v in ESN_KW.items()}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        esn = LazyESN({"x": 32, "y": 32}, {"x": 2, "y": 2}, "periodic", 400, 0.5, 1e-4, **kw)
+    esn.build()
+    assert esn.Win.shape == (400, 1296)
+    esn.train(field[..., :200], n_spinup=8)
+    W = sp.csr_matrix(esn.W)
+    depth = {0: 2, 1: 2, 2: 0}
+    ref = oc.lazy_train(field[..., :200], (32, 32), depth, "periodic", 8, None, W, esn.Win, esn.bias_vector, 0.5, 1e-4)
+    got = esn.Wout_groups.reshape(ref.shape)
+    assert got.shape == (2, 2, 1024, 400)
+    assert oc.max_normalised_err(got, ref) < 1e-5
+    pred = esn.predict(field[..., 200:], n_steps=10, n_spinup=30)
+    refp = oc.lazy_predict(field[..., 200:], (32, 32), depth, "periodic", 10, 30, W, esn.Win, esn.bias_vector, 0.5, got)
+    assert pred.shape == (64, 64, 11)
+    np.testing.assert_allclose(pred, refp, rtol=0, atol=1e-7)
+
+
+def test_baseline_cfg5_shape_macro_candidates(torch):
+    """cfg 5: candidates of a hyper-parameter search (cost.py:190-203 rebuilds an ESN per candidate from the same
+    seeds with its own factors, leak rate and Tikhonov parameter); each trained and forecast against the oracle."""
+    from xesn_b200.synthetic import lorenz96
+    data = lorenz96(40, 1100)
+    rs = np.random.RandomState(0)
+    for _ in range(4):
+        f_in, f_adj, f_b = rs.uniform(0.01, 2.0, size=3)
+        leak = rs.uniform(0.05, 1.0)
+        beta = 10.0 ** rs.uniform(-8, 0)
+        kw = {k: dict(v) for k, v in ESN_KW.items()}
+        kw["input_kwargs"]["factor"], kw["adjacency_kwargs"]["factor"], kw["bias_kwargs"]["factor"] = f_in, f_adj, f_b
+        from xesn_b200 import ESN
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            esn = ESN(40, 40, 500, leak, beta, **kw)
+        esn.build()
+        esn.train(data[:, :800], n_spinup=20)
+        W = sp.csr_matrix(esn.W)
+        ref = oc.ridge_train(data[:, :800], data[:, :800], 20, None, W, esn.Win, esn.bias_vector, leak, beta)
+        # north-star bound for the readout (1e-4); the candidates reach down to beta = 1e-8 (ill-conditioned systems)
+        err = oc.max_normalised_err(esn.Wout, ref)
+        assert err < 1e-4, (err, f_in, f_adj, f_b, leak, beta)
+        pred = esn.predict(data[:, 800:], n_steps=50, n_spinup=100)
+        refp = oc.closed_loop(data[:, 800:], 50, 100, W, esn.Win, esn.bias_vector, leak, esn.Wout)
+        np.testing.assert_allclose(pred, refp, rtol=0, atol=1e-6)
