@@ -292,8 +292,10 @@ def main():
                 warnings.simplefilter("ignore")
                 e = ESN(w["n_vars"], w["n_vars"], w["n_reservoir"], leak, beta, **kw)
                 e.build()
-            e._device_reservoir()
             esns.append(e)
+        from xesn_b200 import ESNEnsemble
+        ens = ESNEnsemble(esns)
+        ens.build()
         esn = esns[0]
         data = lorenz96(w["n_vars"], t_total)
         n_groups_total = w["groups_per_gpu"] * world
@@ -303,27 +305,26 @@ def main():
                       for k in range(w["n_forecasts"])]
         train_dev, tests_dev = train_host.to(dev), [t.to(dev) for t in tests_host]
 
+        # all candidates of the rank as ONE batch (ESNEnsemble: per-group parameters on a shared sparsity pattern)
         def step_device():
+            ens.train(train_dev, n_spinup=w["n_spinup_train"])
             out = None
-            for e in esns:
-                e._wout_dev = e._train_device(train_dev, train_dev, 1, w["n_train"], w["n_spinup_train"], None)
-                e._wout_host = None
-                for t in tests_dev:
-                    out = e._predict_device(t, w["pred_steps"], w["pred_spinup"])
+            for t in tests_dev:
+                out = ens._predict_device(t, w["pred_steps"], w["pred_spinup"])
             return out
 
         def step_e2e():
-            # per candidate: the normalised RMSE of every forecast comes back to the host (cost.py:94-122 needs no more)
+            # per candidate and forecast the normalised RMSE (cost.py:94-122) is formed from the forecasts on the host
+            ens.train(train_host, n_spinup=w["n_spinup_train"])
             costs = []
-            for e in esns:
-                e.train(train_host, n_spinup=w["n_spinup_train"])
-                for t in tests_host:
-                    pred = e.predict(t, n_steps=w["pred_steps"], n_spinup=w["pred_spinup"])
-                    truth = t.numpy()[:, w["pred_spinup"]:]
-                    costs.append(float(np.sqrt(np.mean((pred - truth) ** 2 / truth.std(axis=1, keepdims=True) ** 2))))
+            for t in tests_host:
+                preds = ens.predict(t, n_steps=w["pred_steps"], n_spinup=w["pred_spinup"])
+                truth = t.numpy()[:, w["pred_spinup"]:]
+                costs.append(np.sqrt(np.mean((preds - truth[None]) ** 2 / truth.std(axis=1, keepdims=True)[None] ** 2,
+                                             axis=(1, 2))))
             return costs
 
-        h2d = (train_host.numel() + sum(t.numel() for t in tests_host)) * 8 * w["groups_per_gpu"]
+        h2d = (train_host.numel() + sum(t.numel() for t in tests_host)) * 8  # one upload serves every candidate
         d2h = w["groups_per_gpu"] * w["n_forecasts"] * w["n_vars"] * (w["pred_steps"] + 1) * 8
     elif w["kind"] == "lazy2d":
         from xesn_b200 import LazyESN

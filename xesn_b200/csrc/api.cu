@@ -89,6 +89,10 @@ struct xesn_reservoir {
     double* d_values = nullptr;
     double* d_win = nullptr;
     double* d_bias = nullptr;
+    // per-group parameters (xesn_reservoir_set_group_params): d_values / d_win / d_bias then hold n_param_groups copies
+    int n_param_groups = 0;
+    long long values_gs = 0, win_gs = 0, bias_gs = 0;
+    double* d_alpha_g = nullptr;
     int* d_status = nullptr;
     unsigned* d_bar = nullptr;  // [0..1] grid barrier words of the persistent forecast kernel, [2] hint counter of the pull recurrence
     int persistent_predict = 1;
@@ -225,6 +229,7 @@ int xesn_reservoir_destroy(xesn_reservoir* h) {
     cudaFree(h->d_values);
     cudaFree(h->d_win);
     cudaFree(h->d_bias);
+    cudaFree(h->d_alpha_g);
     cudaFree(h->d_status);
     cudaFree(h->d_bar);
     cudaFree(h->d_tiles);
@@ -235,6 +240,33 @@ int xesn_reservoir_destroy(xesn_reservoir* h) {
     return 0;
 }
 
+// Per-group parameters: G independent reservoirs that share the sparsity pattern of W but have their own values of W,
+// Win, bias and leak rate (candidates of a hyper-parameter search, reference cost.py:190-203: the same seeds, other
+// scaling factors).  Host arrays values[G][nnz], win[G][N*I], bias[G][N], leak[G]; G = 0 restores shared parameters
+// (the arrays given to xesn_reservoir_create are then needed again: pass them as group 0 with G = 1 first if wanted).
+int xesn_reservoir_set_group_params(xesn_reservoir* h, int32_t G, const double* values, const double* win,
+                                    const double* bias, const double* leak) {
+    XESN_REQUIRE(h && G >= 1 && values && win && bias && leak, "bad arguments");
+    XESN_CUDA_OK(cudaSetDevice(h->device));
+    const size_t nnz = (size_t)(h->nnz > 0 ? h->nnz : 1), nw = (size_t)h->N * h->I, nb = (size_t)h->N;
+    cudaFree(h->d_values), cudaFree(h->d_win), cudaFree(h->d_bias), cudaFree(h->d_alpha_g);
+    h->d_values = h->d_win = h->d_bias = h->d_alpha_g = nullptr;
+    XESN_CUDA_OK(cudaMalloc(&h->d_values, sizeof(double) * nnz * G));
+    XESN_CUDA_OK(cudaMalloc(&h->d_win, sizeof(double) * nw * G));
+    XESN_CUDA_OK(cudaMalloc(&h->d_bias, sizeof(double) * nb * G));
+    XESN_CUDA_OK(cudaMalloc(&h->d_alpha_g, sizeof(double) * G));
+    if (h->nnz > 0) XESN_CUDA_OK(cudaMemcpy(h->d_values, values, sizeof(double) * (size_t)h->nnz * G, cudaMemcpyHostToDevice));
+    XESN_CUDA_OK(cudaMemcpy(h->d_win, win, sizeof(double) * nw * G, cudaMemcpyHostToDevice));
+    XESN_CUDA_OK(cudaMemcpy(h->d_bias, bias, sizeof(double) * nb * G, cudaMemcpyHostToDevice));
+    XESN_CUDA_OK(cudaMemcpy(h->d_alpha_g, leak, sizeof(double) * G, cudaMemcpyHostToDevice));
+    h->n_param_groups = G;
+    h->values_gs = (long long)h->nnz, h->win_gs = (long long)nw, h->bias_gs = (long long)nb;
+    h->alpha = leak[0];
+    return 0;
+}
+#define XESN_REQUIRE_GROUPS(h, G) \
+    XESN_REQUIRE((h)->n_param_groups == 0 || (G) == (h)->n_param_groups, "n_groups must equal the number of parameter groups")
+
 int xesn_reservoir_status(xesn_reservoir* h, int32_t* status_host) {
     XESN_REQUIRE(h && status_host, "null pointer");
     XESN_CUDA_OK(cudaMemcpy(status_host, h->d_status, sizeof(int), cudaMemcpyDeviceToHost));
@@ -244,9 +276,11 @@ int xesn_reservoir_status(xesn_reservoir* h, int32_t* status_host) {
 int xesn_update(xesn_reservoir* h, const double* r_in, const double* u, double* r_out, int32_t G, void* stream) {
     XESN_REQUIRE(h && r_in && u && r_out && G > 0, "bad arguments");
     XESN_REQUIRE(r_in != r_out, "r_in and r_out must not alias");
+    XESN_REQUIRE_GROUPS(h, G);
     StepArgs a = {};
     a.indptr = h->d_indptr, a.indices = h->d_indices, a.values = h->d_values;
     a.Win = h->d_win, a.bias = h->d_bias, a.u = u, a.drive = nullptr;
+    a.values_gs = h->values_gs, a.win_gs = h->win_gs, a.bias_gs = h->bias_gs, a.alpha_g = h->d_alpha_g;
     a.r_in = r_in, a.r_out = r_out, a.N = h->N, a.I = h->I, a.alpha = h->alpha;
     return launch_step_update(a, G, (cudaStream_t)stream);
 }
@@ -274,9 +308,9 @@ static int drive_gemm(xesn_reservoir* h, const double* ubase, long long ldu, lon
     ProfScope prof(PROF_DRIVE, st);
     GemmArgs g = {};
     g.A = ubase, g.lda = ldu, g.strideA = ugstride;           // A(t,i) = U[i*ld + t]   (MN-contiguous)
-    g.B = h->d_win, g.ldb = h->I, g.strideB = 0;              // B(i,n) = Win[n*I + i]  (K-contiguous)
+    g.B = h->d_win, g.ldb = h->I, g.strideB = h->win_gs;      // B(i,n) = Win[n*I + i]  (K-contiguous)
     g.C = D, g.ldc = h->N, g.strideC = (long long)m * h->N;
-    g.bias = h->d_bias;
+    g.bias = h->d_bias, g.strideBias = h->bias_gs;
     g.M = m, g.N = h->N, g.K = h->I, g.batch = G;
     g.alpha = 1.0, g.beta = 0.0, g.flags = GEMM_B_KMAJOR;
     return launch_gemm_f64(g, st);
@@ -292,6 +326,7 @@ static int forced_launch(xesn_reservoir* h, const RecurArgs& r, int G, cudaStrea
 static RecurArgs recur_args(xesn_reservoir* h) {
     RecurArgs r = {};
     r.indptr = h->d_indptr, r.indices = h->d_indices, r.values = h->d_values;
+    r.values_gs = h->values_gs, r.alpha_g = h->d_alpha_g;
     r.N = h->N, r.alpha = h->alpha, r.smem_nnz = h->max_slice_nnz, r.status = h->d_status;
     r.debug_no_exchange = getenv("XESN_B200_DEBUG_NO_EXCHANGE") != nullptr;
     r.hint = getenv("XESN_B200_NO_HINT") ? nullptr : h->d_bar + 2;
@@ -313,6 +348,7 @@ int64_t xesn_forced_scratch_bytes(xesn_reservoir* h, int32_t G, int32_t n_steps,
 int xesn_forced_run(xesn_reservoir* h, const xesn_series* u, int64_t t0, int32_t n_steps, int32_t G, double* carry,
                     double* states, void* scratch, int64_t scratch_bytes, void* stream) {
     XESN_REQUIRE(h && u && carry && G > 0 && n_steps >= 0, "bad arguments");
+    XESN_REQUIRE_GROUPS(h, G);
     const int gathered = (u->map_dev || u->zero_row_dev) ? 1 : 0;
     XESN_REQUIRE(scratch && scratch_bytes >= xesn_forced_scratch_bytes(h, G, n_steps, gathered), "scratch too small");
     cudaStream_t st = (cudaStream_t)stream;
@@ -390,6 +426,7 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
                           int64_t scratch_bytes, void* stream) {
     XESN_REQUIRE(h && u && y && gram && wout && scratch, "null pointer");
     XESN_REQUIRE(O > 0 && G > 0 && chunk > 0 && T >= 0 && n_spinup >= 0 && n_spinup <= T, "bad sizes");
+    XESN_REQUIRE_GROUPS(h, G);
     const int gu = (u->map_dev || u->zero_row_dev) ? 1 : 0, gy = (y->map_dev || y->zero_row_dev) ? 1 : 0;
     XESN_REQUIRE(scratch_bytes >= xesn_train_scratch_bytes(h, O, G, chunk, gu, gy), "scratch too small");
     XESN_REQUIRE(chunk <= gi8::MAX_K, "chunk: at most 16384 time steps per chunk (int32 accumulators of the int8 Gram)");
@@ -619,14 +656,15 @@ static int closed_loop_step(xesn_reservoir* h, const double* wout, int O, int G,
     StepArgs a = {};
     a.indptr = h->d_indptr, a.indices = h->d_indices, a.values = h->d_values;
     a.Win = h->d_win, a.bias = h->d_bias, a.N = N, a.I = I, a.alpha = h->alpha;
+    a.values_gs = h->values_gs, a.win_gs = h->win_gs, a.bias_gs = h->bias_gs, a.alpha_g = h->d_alpha_g;
     a.r_in = r_in, a.r_out = r_out;
     if (G > INLINE_PROJECTION_MAX_GROUPS) {
         if ((rc = launch_gather_vec(field_in, 1, in_map, fill, Ug, (long long)G * I, 1, st))) return rc;
         GemmArgs g = {};
         g.A = Ug, g.lda = I, g.strideA = 0;
-        g.B = h->d_win, g.ldb = I, g.strideB = 0;
+        g.B = h->d_win, g.ldb = I, g.strideB = h->win_gs;
         g.C = drive, g.ldc = N, g.strideC = 0;
-        g.bias = h->d_bias;
+        g.bias = h->d_bias, g.strideBias = h->bias_gs;
         g.M = G, g.N = N, g.K = I, g.batch = 1, g.alpha = 1.0, g.beta = 0.0;
         g.flags = GEMM_A_KMAJOR | GEMM_B_KMAJOR;
         if ((rc = launch_gemm_f64(g, st))) return rc;
@@ -655,6 +693,7 @@ static PredictLoopArgs predict_loop_args(xesn_reservoir* h, const double* wout, 
     PredictLoopArgs a = {};
     a.indptr = h->d_indptr, a.indices = h->d_indices, a.values = h->d_values;
     a.Win = h->d_win, a.bias = h->d_bias, a.Wout = wout;
+    a.values_gs = h->values_gs, a.win_gs = h->win_gs, a.bias_gs = h->bias_gs, a.alpha_g = h->d_alpha_g;
     a.in_map = in_map, a.fill = fill, a.out_map = out_map;
     a.field[0] = fbuf[0], a.field[1] = fbuf[1], a.r[0] = rbuf[0], a.r[1] = rbuf[1];
     a.pred = pred, a.ldp = ldp;
@@ -678,7 +717,7 @@ static PredictLoopArgs predict_loop_args(xesn_reservoir* h, const double* wout, 
 constexpr int PULL_PREDICT_CHUNK = 256;
 
 static bool predict_pull_eligible(xesn_reservoir* h, int O, int G, long long n_cells, int* upc, int* n_ctas) {
-    return h->persistent_predict == 1 && G == 1 && n_cells > 0 &&
+    return h->persistent_predict == 1 && G == 1 && h->n_param_groups == 0 && n_cells > 0 &&
            predict_pull_geometry(h->N, h->I, O, n_cells, h->num_sms, upc, n_ctas);
 }
 
@@ -715,6 +754,7 @@ int xesn_predict(xesn_reservoir* h, const double* wout, int32_t O, int32_t G, in
                  void* scratch, int64_t scratch_bytes, void* stream) {
     XESN_REQUIRE(h && wout && in_map && field && r && pred && scratch, "null pointer");
     XESN_REQUIRE(n_steps >= 0 && n_cells > 0, "bad sizes");
+    XESN_REQUIRE_GROUPS(h, G);
     XESN_REQUIRE(scratch_bytes >= xesn_predict_scratch_bytes(h, O, G, n_cells), "scratch too small");
     cudaStream_t st = (cudaStream_t)stream;
     const int N = h->N, I = h->I;

@@ -52,6 +52,7 @@ struct GemmArgs {
     const double* B;
     double* C;
     const double* bias;  // optional, length N, added to every row of C
+    long long strideBias;  // per batch entry (0 = shared)
     int M, N, K;
     long long lda, ldb, ldc;
     long long strideA, strideB, strideC;  // per batch entry (0 = shared)

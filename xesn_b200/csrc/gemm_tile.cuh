@@ -105,6 +105,7 @@ __device__ __forceinline__ void gemm_tile(const GemmArgs& p, int ti, int tj, int
 
     const int m0 = ti * BM, n0 = tj * BN;
     double* C = p.C + (long long)bz * p.strideC;
+    const double* bias = p.bias ? p.bias + (long long)bz * p.strideBias : nullptr;
     __syncthreads();  // persistent callers: every warp has left the previous tile's shared-memory stages
 
     TileLoader<A_K, VEC> la;
@@ -226,9 +227,9 @@ __device__ __forceinline__ void gemm_tile(const GemmArgs& p, int ti, int tj, int
                     v.x += beta * cold[ii][j].x;
                     v.y += beta * cold[ii][j].y;
                 }
-                if (p.bias) {
-                    if (n < p.N) v.x += p.bias[n];
-                    if (n + 1 < p.N) v.y += p.bias[n + 1];
+                if (bias) {
+                    if (n < p.N) v.x += bias[n];
+                    if (n + 1 < p.N) v.y += bias[n + 1];
                 }
                 double* cp = C + (long long)m * p.ldc + n;
                 if (cvec && n + 1 < p.N) {

@@ -8,6 +8,8 @@ struct RecurArgs {
     const int* indptr;       // CSR of W, shared by every group
     const int* indices;
     const double* values;
+    long long values_gs;     // stride between the groups' value arrays (0: all groups share W)
+    const double* alpha_g;   // optional per-group leak rates (else `alpha`)
     const double* drive;     // [G][steps][N] : Win u_t + b for every step of the chunk
     long long drive_group_stride;
     double* states;          // [G][steps+1][N] ring: row 0 <- carry, rows 1..steps written (pre-filled "unset")
@@ -34,6 +36,8 @@ struct StepArgs {
     const int* indptr;
     const int* indices;
     const double* values;
+    long long values_gs, win_gs, bias_gs;  // strides between groups (0: shared parameters)
+    const double* alpha_g;                 // optional per-group leak rates
     const double* Win;    // [N][I] (inline projection) -- used when drive == nullptr
     const double* bias;   // [N]
     const double* u;      // [G][I] dense inputs, or (when in_map != nullptr) gathered from `field`:
@@ -99,6 +103,8 @@ struct PredictLoopArgs {
     const double* values;
     const double* Win;
     const double* bias;
+    long long values_gs, win_gs, bias_gs;  // strides between groups (0: shared parameters)
+    const double* alpha_g;                 // optional per-group leak rates
     const double* Wout;     // [G][O][N]
     const int* in_map;      // [G][I] cell index or -1-k -> fill[k]
     const double* fill;

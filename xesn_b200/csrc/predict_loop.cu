@@ -93,7 +93,6 @@ __global__ void __launch_bounds__(PL_THREADS, 1) predict_loop_kernel(PredictLoop
     const int row_blocks = (p.O + PL_WARPS - 1) / PL_WARPS;
     const long long items_u = (long long)p.G * nblk;
     const long long items_r = (long long)p.G * row_blocks * p.n_slices;
-    const double oma = 1.0 - p.alpha;
     unsigned gen = 0;
     if (tid == 0) gen = ld_acquire_u32(&p.bar[1]);
 
@@ -117,8 +116,8 @@ __global__ void __launch_bounds__(PL_THREADS, 1) predict_loop_kernel(PredictLoop
             if (i < p.N) {
                 const double* rg = r_cur + (long long)g * p.N;
                 const int lo = __ldg(p.indptr + i), len = __ldg(p.indptr + i + 1) - lo;
-                const double wr = sparse_row_dot(p.indices + lo, p.values + lo, len, rg);
-                const double* wrow = p.Win + (long long)i * p.I;
+                const double wr = sparse_row_dot(p.indices + lo, p.values + (long long)g * p.values_gs + lo, len, rg);
+                const double* wrow = p.Win + (long long)g * p.win_gs + (long long)i * p.I;
                 double acc = 0.0;
                 if ((p.I & 1) == 0 && ((reinterpret_cast<uintptr_t>(p.Win) & 15) == 0)) {
                     const double2* w2 = reinterpret_cast<const double2*>(wrow);
@@ -136,8 +135,9 @@ __global__ void __launch_bounds__(PL_THREADS, 1) predict_loop_kernel(PredictLoop
 #pragma unroll 4
                     for (int k = 0; k < p.I; ++k) acc = fma(__ldg(wrow + k), s_u[k], acc);
                 }
-                const double pre = __dadd_rn(__dadd_rn(wr, acc), __ldg(p.bias + i));
-                r_nxt[(long long)g * p.N + i] = leaky(pre, ld_cg(rg + i), p.alpha, oma);
+                const double pre = __dadd_rn(__dadd_rn(wr, acc), __ldg(p.bias + (long long)g * p.bias_gs + i));
+                const double alpha = p.alpha_g ? p.alpha_g[g] : p.alpha;
+                r_nxt[(long long)g * p.N + i] = leaky(pre, ld_cg(rg + i), alpha, 1.0 - alpha);
             }
         }
         grid_barrier(p, gen, false, 0);

@@ -101,6 +101,7 @@ __device__ __forceinline__ void pull_body(const RecurArgs& p, const int G, const
     const double* drive = p.drive + (long long)g * p.drive_group_stride;
     double* carry = p.carry + (long long)g * N;
     signed char* digits = p.planes ? p.planes + (long long)g * p.plane_group_stride : nullptr;
+    const double* const w_values = p.values + (long long)g * p.values_gs;
 
     constexpr int KREG = PullRegs<UPT>::K;
     constexpr int KTAIL = 4;
@@ -121,7 +122,7 @@ __device__ __forceinline__ void pull_body(const RecurArgs& p, const int G, const
 #pragma unroll
         for (int k = 0; k < KREG; ++k) {
             const bool in = k < row_len[j];
-            hv[j][k] = in ? p.values[row_lo[j] + k] : 0.0;
+            hv[j][k] = in ? w_values[row_lo[j] + k] : 0.0;
             hi[j][k] = in ? p.indices[row_lo[j] + k] : 0;
             if (in) head_mask |= 1u << (j * KREG + k);
         }
@@ -129,7 +130,7 @@ __device__ __forceinline__ void pull_body(const RecurArgs& p, const int G, const
     put_states<UPT>(states + i0, r_cur, UPT);  // row 0 = state entering the chunk
     if (digits && p.steps > 0) put_digits<UPT>(digits, p, 0, i0, r_cur, UPT);
     if (p.hint) hint_arrive(p, s_sync, lane, wmask, active_warps, 0);
-    const double alpha = p.alpha, oma = 1.0 - p.alpha;
+    const double alpha = p.alpha_g ? p.alpha_g[g] : p.alpha, oma = 1.0 - alpha;
     bool aborted = false;
 #ifdef XESN_RECUR_TRACE
     const int tid = rtid;  // XESN_TRACE_MARK records thread 0 of the CTA
@@ -154,7 +155,7 @@ __device__ __forceinline__ void pull_body(const RecurArgs& p, const int G, const
                     const bool in = KREG + k < row_len[j];
                     const int e = row_lo[j] + KREG + k;
                     ti[j][k] = in ? __ldg(p.indices + e) : 0;
-                    tv[j][k] = in ? __ldg(p.values + e) : 0.0;
+                    tv[j][k] = in ? __ldg(w_values + e) : 0.0;
                     tg[j][k] = 0.0;
                     if (in) tpend |= 1u << (j * KTAIL + k);
                 }
@@ -234,7 +235,7 @@ __device__ __forceinline__ void pull_body(const RecurArgs& p, const int G, const
                     const bool in = kb + k < row_len[j];
                     const int e = row_lo[j] + kb + k;
                     ti[j][k] = in ? __ldg(p.indices + e) : 0;
-                    tv[j][k] = in ? __ldg(p.values + e) : 0.0;
+                    tv[j][k] = in ? __ldg(w_values + e) : 0.0;
                     tg[j][k] = 0.0;
                     if (in) pend |= 1u << (j * KTAIL + k);
                 }

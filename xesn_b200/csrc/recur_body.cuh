@@ -188,6 +188,7 @@ __device__ __forceinline__ void recur_body(const RecurArgs& p, const unsigned c,
 
     double* s_r = reinterpret_cast<double*>(smem_raw);  // [n_pad] copy of r_t
     // ---- stage this CTA's CSR slice of W in shared memory (or fall back to global) ----
+    const double* const w_values = p.values + (long long)g * p.values_gs;
     const int slice_lo = p.indptr[u0], slice_hi = p.indptr[u1];
     // WS: the slice lives in shared memory with the column indices pre-multiplied to byte offsets
     // into the state copy; else it is read from global memory (huge or dense W)
@@ -195,7 +196,7 @@ __device__ __forceinline__ void recur_body(const RecurArgs& p, const unsigned c,
     int* s_off = reinterpret_cast<int*>(s_val + p.smem_nnz);
     if (WS) {
         for (int k = slice_lo + tid; k < slice_hi; k += RC_THREADS) {
-            s_val[k - slice_lo] = p.values[k];
+            s_val[k - slice_lo] = w_values[k];
             s_off[k - slice_lo] = p.indices[k] * (int)sizeof(double);
         }
     }
@@ -232,7 +233,7 @@ __device__ __forceinline__ void recur_body(const RecurArgs& p, const unsigned c,
 #pragma unroll
         for (int k = 0; k < KREG; ++k) {
             const bool in = k < row_len[j];
-            hv[j][k] = in ? p.values[row_lo[j] + k] : 0.0;
+            hv[j][k] = in ? w_values[row_lo[j] + k] : 0.0;
             ho[j][k] = in ? p.indices[row_lo[j] + k] * (int)sizeof(double) : 0;
         }
     // pieces of the state copy this thread refreshes per polling round (own slice excluded); constant over
@@ -250,7 +251,7 @@ __device__ __forceinline__ void recur_body(const RecurArgs& p, const unsigned c,
             }
     put_states<UPT>(states + ubase, r_cur, nvalid);  // row 0 = state entering the chunk (read by the Gram kernel)
     if (digits && p.steps > 0) put_digits<UPT>(digits, p, 0, ubase, r_cur, nvalid);
-    const double alpha = p.alpha, oma = 1.0 - p.alpha;
+    const double alpha = p.alpha_g ? p.alpha_g[g] : p.alpha, oma = 1.0 - alpha;
     const bool vec2 = (N % 2 == 0) && ((reinterpret_cast<uintptr_t>(states) & 15) == 0);
     bool aborted = false;
     __syncthreads();
@@ -301,7 +302,7 @@ __device__ __forceinline__ void recur_body(const RecurArgs& p, const unsigned c,
                         tv[j][k] = in ? s_val[e - slice_lo] : 0.0;
                     } else {
                         to[j][k] = in ? __ldg(p.indices + e) * (int)sizeof(double) : 0;
-                        tv[j][k] = in ? __ldg(p.values + e) : 0.0;
+                        tv[j][k] = in ? __ldg(w_values + e) : 0.0;
                     }
                 }
 #pragma unroll
@@ -326,7 +327,7 @@ __device__ __forceinline__ void recur_body(const RecurArgs& p, const unsigned c,
                                                                       reinterpret_cast<const char*>(s_r) + of[k])));
                     } else {
                         const int* ix = p.indices + row_lo[j];
-                        const double* vl = p.values + row_lo[j];
+                        const double* vl = w_values + row_lo[j];
                         for (int k = KREG + KTAIL; k < row_len[j]; ++k)
                             acc = __dadd_rn(acc, __dmul_rn(__ldg(vl + k), s_r[__ldg(ix + k)]));
                     }

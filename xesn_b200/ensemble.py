@@ -1,0 +1,188 @@
+"""ESNEnsemble -- G eager ESNs that differ only in their hyper-parameters, trained and forecast as ONE batch.
+
+The reference's macro training (`xesn/cost.py:190-203`, `xesn/optim.py:97-137`) evaluates every candidate
+of the search by building a fresh `ESN(**params)` from the SAME seeds with its own `input_factor`,
+`adjacency_factor`, `bias_factor`, `leak_rate` and `tikhonov_parameter`, training it and forecasting a few
+test windows -- one candidate after the other.  A reservoir of a few thousand units is latency-bound on a
+B200 (one step is a serial dependency), so the candidates are independent work that belongs side by side:
+they share the sparsity pattern of W (same seed), so one device reservoir holds G value sets
+(`xesn_reservoir_set_group_params`, include/xesn_b200.h) and every kernel of the hot path runs the G
+reservoirs as groups -- the recurrence of all of them in one persistent kernel, their Gram matrices on the
+tensor cores back to back, their ridge systems as one batched Cholesky, their forecasts in one loop.
+
+    esns = [ESN(40, 40, 4000, leak, beta, input_kwargs=..., ...) for leak, beta, ... in candidates]
+    ens = ESNEnsemble(esns); ens.build()
+    ens.train(u, n_spinup=0)                 # every member's Wout, as ESN.train would have produced it
+    preds = ens.predict(y, n_steps, n_spinup)  # (G, n_output, n_steps+1)
+
+Each member remains a normal `ESN` (its `Wout` is filled in), so the results can be checked member by member
+against the single-reservoir path and against the reference.
+"""
+import ctypes
+
+import numpy as np
+import scipy.sparse
+
+from . import _lib
+from .esn import ESN, DeviceReservoir, _ptr, _time_last, _torch, auto_chunk
+
+
+class ESNEnsemble:
+    def __init__(self, members, device=None):
+        members = list(members)
+        assert members, "ESNEnsemble: at least one member"
+        m0 = members[0]
+        for m in members:
+            assert isinstance(m, ESN)
+            assert (m.n_input, m.n_output, m.n_reservoir) == (m0.n_input, m0.n_output, m0.n_reservoir), \
+                "ESNEnsemble: members must have the same sizes"
+        self.members = members
+        self.n_input, self.n_output, self.n_reservoir = m0.n_input, m0.n_output, m0.n_reservoir
+        self.device = device
+        self._reservoir = None
+        self._wout_dev = None
+        self.last_info = None
+
+    def __len__(self):
+        return len(self.members)
+
+    # ------------------------------------------------------------------ build
+    def build(self):
+        """Build every member on the host exactly as `ESN.build` does (reference esn.py:147-187; same seeds,
+        own factors) and upload them as the parameter groups of one device reservoir."""
+        for m in self.members:
+            if m.W is None:
+                m.build()
+        self._upload()
+
+    def _upload(self):
+        csrs = []
+        for m in self.members:
+            c = scipy.sparse.csr_matrix(m.W) if not scipy.sparse.issparse(m.W) else m.W.tocsr()
+            c.sum_duplicates()
+            c.sort_indices()
+            csrs.append(c)
+        c0 = csrs[0]
+        for c in csrs[1:]:
+            if not (np.array_equal(c.indptr, c0.indptr) and np.array_equal(c.indices, c0.indices)):
+                raise _lib.XesnError("ESNEnsemble: the members' adjacency matrices must share one sparsity pattern "
+                                     "(same adjacency seed, density and size)")
+        m0 = self.members[0]
+        self._reservoir = DeviceReservoir(c0, m0.Win, m0.bias_vector, m0.leak_rate, self.device)
+        values = np.ascontiguousarray(np.stack([c.data for c in csrs]), dtype=np.float64)
+        win = np.ascontiguousarray(np.stack([np.asarray(m.Win, dtype=np.float64) for m in self.members]))
+        bias = np.ascontiguousarray(np.stack([np.asarray(m.bias_vector, dtype=np.float64).reshape(-1)
+                                              for m in self.members]))
+        leak = np.ascontiguousarray([float(m.leak_rate) for m in self.members], dtype=np.float64)
+        res = self._reservoir
+        _lib.check(res._lib.xesn_reservoir_set_group_params(
+            res.handle, len(self.members), values.ctypes.data, win.ctypes.data, bias.ctypes.data, leak.ctypes.data))
+
+    def _device_reservoir(self):
+        if self._reservoir is None:
+            raise _lib.XesnError("ESNEnsemble: call build() first")
+        return self._reservoir
+
+    def _to_device(self, x):
+        torch = _torch()
+        res = self._device_reservoir()
+        if isinstance(x, torch.Tensor):
+            return x.to(device=res.device, dtype=torch.float64).contiguous()
+        data = getattr(x, "data", x) if getattr(x, "dims", None) is not None else x
+        host = torch.from_numpy(np.ascontiguousarray(np.asarray(data, dtype=np.float64)))
+        try:
+            host = host.pin_memory()
+        except Exception:  # pragma: no cover
+            pass
+        return host.to(res.device, non_blocking=True)
+
+    def _shared_series(self, x_dev, rows):
+        """All G groups read the same `rows` rows of x_dev: an index map instead of G copies."""
+        torch = _torch()
+        G = len(self.members)
+        idx = torch.arange(rows, dtype=torch.int32, device=x_dev.device).repeat(G)
+        return _lib.Series(_ptr(x_dev), x_dev.stride(0), _ptr(idx), None, None), idx
+
+    # ------------------------------------------------------------------ train
+    def train(self, u, y=None, n_spinup=0, batch_size=None):
+        """`ESN.train(u, y, n_spinup, batch_size)` of every member (reference esn.py:190-220 -> `_train_1d`)."""
+        _time_last(u, "ESNEnsemble.train", "u")
+        torch = _torch()
+        res = self._device_reservoir()
+        lib = res._lib
+        G, N, O, I = len(self.members), self.n_reservoir, self.n_output, self.n_input
+        u_dev = self._to_device(u)
+        y_dev = u_dev if y is None else self._to_device(y)
+        n_time = y_dev.shape[1]
+        assert n_time >= n_spinup and u_dev.shape[0] == I and y_dev.shape[0] == O
+        chunk = auto_chunk(N, G, max(n_time - n_spinup, n_spinup, 1), batch_size)
+        u_series, ku = self._shared_series(u_dev, I)
+        y_series, ky = self._shared_series(y_dev, O)
+        with torch.cuda.device(res.device):
+            st = torch.cuda.current_stream().cuda_stream
+            nbytes = lib.xesn_train_scratch_bytes(res.handle, O, G, chunk, 1, 1)
+            scratch = torch.empty(nbytes, dtype=torch.uint8, device=res.device)
+            gram = torch.empty((G, N, N), dtype=torch.float64, device=res.device)
+            wout = torch.empty((G, O, N), dtype=torch.float64, device=res.device)
+            info = torch.zeros(G, dtype=torch.int32, device=res.device)
+            beta = torch.tensor([float(m.tikhonov_parameter) for m in self.members], dtype=torch.float64,
+                                device=res.device)
+            _lib.check(lib.xesn_train_accumulate(
+                res.handle, ctypes.byref(u_series), ctypes.byref(y_series), O, G, n_time, n_spinup, chunk,
+                _ptr(gram), _ptr(wout), _ptr(scratch), nbytes, st))
+            _lib.check(lib.xesn_ridge_solve(res.handle, O, G, _ptr(beta), 0.0, _ptr(gram), _ptr(wout), _ptr(info),
+                                            _ptr(scratch), nbytes, st))
+            del gram, ku, ky
+        self._wout_dev = wout
+        self.last_info = info
+        bad = np.nonzero(info.cpu().numpy())[0]
+        if bad.size:
+            import warnings
+            warnings.warn(f"ESNEnsemble.train: the ridge system of member(s) {bad.tolist()} is not positive definite; "
+                          f"their readout is NaN", RuntimeWarning)
+            wout[torch.as_tensor(bad, device=wout.device, dtype=torch.long)] = float("nan")
+        for g, m in enumerate(self.members):
+            m._wout_dev = wout[g:g + 1]
+            m._wout_host = None
+        return self
+
+    @property
+    def Wout(self):
+        """(G, n_output, n_reservoir) on the host."""
+        return None if self._wout_dev is None else self._wout_dev.cpu().numpy()
+
+    # ------------------------------------------------------------------ predict
+    def predict(self, y, n_steps, n_spinup):
+        """`ESN.predict(y, n_steps, n_spinup)` of every member (reference esn.py:223-276): (G, n_output, n_steps+1)."""
+        _time_last(y, "ESNEnsemble.predict", "y")
+        assert self.n_input == self.n_output, "closed loop needs n_input == n_output"
+        y_dev = self._to_device(y)
+        assert y_dev.shape[1] >= n_spinup + 1
+        return self._predict_device(y_dev, n_steps, n_spinup).cpu().numpy()
+
+    def _predict_device(self, y_dev, n_steps, n_spinup):
+        torch = _torch()
+        res = self._device_reservoir()
+        lib = res._lib
+        if self._wout_dev is None:
+            raise _lib.XesnError("ESNEnsemble: no readout; call train() first")
+        G, N, O, I = len(self.members), self.n_reservoir, self.n_output, self.n_input
+        with torch.cuda.device(res.device):
+            st = torch.cuda.current_stream().cuda_stream
+            r = torch.zeros((G, N), dtype=torch.float64, device=res.device)
+            series, keep = self._shared_series(y_dev, I)
+            nb = lib.xesn_forced_scratch_bytes(res.handle, G, n_spinup, 1)
+            nb2 = lib.xesn_predict_scratch_bytes(res.handle, O, G, G * O)
+            scratch = torch.empty(max(nb, nb2), dtype=torch.uint8, device=res.device)
+            _lib.check(lib.xesn_forced_run(res.handle, ctypes.byref(series), 0, n_spinup, G, _ptr(r), None,
+                                           _ptr(scratch), scratch.numel(), st))
+            # every member forecasts its own copy of the field: cells [g*O, (g+1)*O)
+            cells = torch.arange(G * O, dtype=torch.int32, device=res.device)
+            fill = torch.zeros(1, dtype=torch.float64, device=res.device)
+            field = y_dev[:, n_spinup].contiguous().repeat(G)
+            pred = torch.empty((G * O, n_steps + 1), dtype=torch.float64, device=res.device)
+            _lib.check(lib.xesn_predict(res.handle, _ptr(self._wout_dev), O, G, G * O, _ptr(cells), _ptr(fill),
+                                        _ptr(cells), _ptr(field), _ptr(r), n_steps, _ptr(pred), _ptr(scratch),
+                                        scratch.numel(), st))
+            del keep
+        return pred.view(G, O, n_steps + 1)
