@@ -304,23 +304,21 @@ def main():
         tests_host = [torch.from_numpy(np.ascontiguousarray(data[:, w["n_train"] + k * seg: w["n_train"] + (k + 1) * seg])).pin_memory()
                       for k in range(w["n_forecasts"])]
         train_dev, tests_dev = train_host.to(dev), [t.to(dev) for t in tests_host]
+        tests_stacked = torch.cat(tests_dev, dim=0)
 
         # all candidates of the rank as ONE batch (ESNEnsemble: per-group parameters on a shared sparsity pattern)
         def step_device():
             ens.train(train_dev, n_spinup=w["n_spinup_train"])
-            out = None
-            for t in tests_dev:
-                out = ens._predict_device(t, w["pred_steps"], w["pred_spinup"])
-            return out
+            return ens._predict_device(tests_stacked, w["pred_steps"], w["pred_spinup"], w["n_forecasts"])
 
         def step_e2e():
             # per candidate and forecast the normalised RMSE (cost.py:94-122) is formed from the forecasts on the host
             ens.train(train_host, n_spinup=w["n_spinup_train"])
+            preds = ens.predict_windows(tests_host, n_steps=w["pred_steps"], n_spinup=w["pred_spinup"])  # (F, G, O, steps+1)
             costs = []
-            for t in tests_host:
-                preds = ens.predict(t, n_steps=w["pred_steps"], n_spinup=w["pred_spinup"])
+            for f, t in enumerate(tests_host):
                 truth = t.numpy()[:, w["pred_spinup"]:]
-                costs.append(np.sqrt(np.mean((preds - truth[None]) ** 2 / truth.std(axis=1, keepdims=True)[None] ** 2,
+                costs.append(np.sqrt(np.mean((preds[f] - truth[None]) ** 2 / truth.std(axis=1, keepdims=True)[None] ** 2,
                                              axis=(1, 2))))
             return costs
 

@@ -56,7 +56,8 @@ int xesn_reservoir_destroy(xesn_reservoir* h);
  * have their own values of W, Win, bias and leak rate -- the candidates of a hyper-parameter search, which the
  * reference rebuilds one by one from the same seeds with other scaling factors (xesn/cost.py:190-203).  Host arrays
  * values[n_groups][nnz], win[n_groups][N*I], bias[n_groups][N], leak[n_groups] are copied.  Afterwards every entry
- * point must be called with exactly this n_groups; the per-group Tikhonov parameters go to xesn_ridge_solve. */
+ * point must be called with a multiple of this n_groups: group g uses parameter set g % n_groups (several forecast
+ * windows of every candidate in one loop).  The per-group Tikhonov parameters go to xesn_ridge_solve. */
 int xesn_reservoir_set_group_params(xesn_reservoir* h, int32_t n_groups, const double* values, const double* win,
                                     const double* bias, const double* leak);
 /* Synchronous health check: *status_host = 0 if every persistent-kernel poll completed, 1 if one

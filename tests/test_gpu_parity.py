@@ -480,6 +480,12 @@ def test_ensemble_matches_members_and_oracle(torch, n_res, n_members):
     ens.train(data[:, :700], n_spinup=15, batch_size=300)
     preds = ens.predict(data[:, 700:], n_steps=40, n_spinup=80)
     assert preds.shape == (n_members, 40, 41)
+    # several forecast windows in one loop == window by window
+    wins = [data[:, 700:900], data[:, 760:960], data[:, 800:1000]]
+    many = ens.predict_windows(wins, n_steps=40, n_spinup=80)
+    assert many.shape == (3, n_members, 40, 41)
+    for f, wdw in enumerate(wins):
+        np.testing.assert_allclose(many[f], ens.predict(wdw, n_steps=40, n_spinup=80), rtol=0, atol=1e-9)
     for g, m in enumerate(members):
         W = sp.csr_matrix(m.W)
         ref, rr, yr = oc.ridge_train(data[:, :700], data[:, :700], 15, 300, W, m.Win, m.bias_vector, m.leak_rate,

@@ -265,7 +265,7 @@ int xesn_reservoir_set_group_params(xesn_reservoir* h, int32_t G, const double* 
     return 0;
 }
 #define XESN_REQUIRE_GROUPS(h, G) \
-    XESN_REQUIRE((h)->n_param_groups == 0 || (G) == (h)->n_param_groups, "n_groups must equal the number of parameter groups")
+    XESN_REQUIRE((h)->n_param_groups == 0 || (G) % (h)->n_param_groups == 0, "n_groups must be a multiple of the number of parameter sets")
 
 int xesn_reservoir_status(xesn_reservoir* h, int32_t* status_host) {
     XESN_REQUIRE(h && status_host, "null pointer");
@@ -281,6 +281,7 @@ int xesn_update(xesn_reservoir* h, const double* r_in, const double* u, double* 
     a.indptr = h->d_indptr, a.indices = h->d_indices, a.values = h->d_values;
     a.Win = h->d_win, a.bias = h->d_bias, a.u = u, a.drive = nullptr;
     a.values_gs = h->values_gs, a.win_gs = h->win_gs, a.bias_gs = h->bias_gs, a.alpha_g = h->d_alpha_g;
+    a.param_groups = h->n_param_groups;
     a.r_in = r_in, a.r_out = r_out, a.N = h->N, a.I = h->I, a.alpha = h->alpha;
     return launch_step_update(a, G, (cudaStream_t)stream);
 }
@@ -310,7 +311,7 @@ static int drive_gemm(xesn_reservoir* h, const double* ubase, long long ldu, lon
     g.A = ubase, g.lda = ldu, g.strideA = ugstride;           // A(t,i) = U[i*ld + t]   (MN-contiguous)
     g.B = h->d_win, g.ldb = h->I, g.strideB = h->win_gs;      // B(i,n) = Win[n*I + i]  (K-contiguous)
     g.C = D, g.ldc = h->N, g.strideC = (long long)m * h->N;
-    g.bias = h->d_bias, g.strideBias = h->bias_gs;
+    g.bias = h->d_bias, g.strideBias = h->bias_gs, g.modB = h->n_param_groups;
     g.M = m, g.N = h->N, g.K = h->I, g.batch = G;
     g.alpha = 1.0, g.beta = 0.0, g.flags = GEMM_B_KMAJOR;
     return launch_gemm_f64(g, st);
@@ -326,7 +327,7 @@ static int forced_launch(xesn_reservoir* h, const RecurArgs& r, int G, cudaStrea
 static RecurArgs recur_args(xesn_reservoir* h) {
     RecurArgs r = {};
     r.indptr = h->d_indptr, r.indices = h->d_indices, r.values = h->d_values;
-    r.values_gs = h->values_gs, r.alpha_g = h->d_alpha_g;
+    r.values_gs = h->values_gs, r.alpha_g = h->d_alpha_g, r.param_groups = h->n_param_groups;
     r.N = h->N, r.alpha = h->alpha, r.smem_nnz = h->max_slice_nnz, r.status = h->d_status;
     r.debug_no_exchange = getenv("XESN_B200_DEBUG_NO_EXCHANGE") != nullptr;
     r.hint = getenv("XESN_B200_NO_HINT") ? nullptr : h->d_bar + 2;
@@ -657,6 +658,7 @@ static int closed_loop_step(xesn_reservoir* h, const double* wout, int O, int G,
     a.indptr = h->d_indptr, a.indices = h->d_indices, a.values = h->d_values;
     a.Win = h->d_win, a.bias = h->d_bias, a.N = N, a.I = I, a.alpha = h->alpha;
     a.values_gs = h->values_gs, a.win_gs = h->win_gs, a.bias_gs = h->bias_gs, a.alpha_g = h->d_alpha_g;
+    a.param_groups = h->n_param_groups;
     a.r_in = r_in, a.r_out = r_out;
     if (G > INLINE_PROJECTION_MAX_GROUPS) {
         if ((rc = launch_gather_vec(field_in, 1, in_map, fill, Ug, (long long)G * I, 1, st))) return rc;
@@ -664,7 +666,7 @@ static int closed_loop_step(xesn_reservoir* h, const double* wout, int O, int G,
         g.A = Ug, g.lda = I, g.strideA = 0;
         g.B = h->d_win, g.ldb = I, g.strideB = h->win_gs;
         g.C = drive, g.ldc = N, g.strideC = 0;
-        g.bias = h->d_bias, g.strideBias = h->bias_gs;
+        g.bias = h->d_bias, g.strideBias = h->bias_gs, g.modB = h->n_param_groups;
         g.M = G, g.N = N, g.K = I, g.batch = 1, g.alpha = 1.0, g.beta = 0.0;
         g.flags = GEMM_A_KMAJOR | GEMM_B_KMAJOR;
         if ((rc = launch_gemm_f64(g, st))) return rc;
@@ -694,6 +696,7 @@ static PredictLoopArgs predict_loop_args(xesn_reservoir* h, const double* wout, 
     a.indptr = h->d_indptr, a.indices = h->d_indices, a.values = h->d_values;
     a.Win = h->d_win, a.bias = h->d_bias, a.Wout = wout;
     a.values_gs = h->values_gs, a.win_gs = h->win_gs, a.bias_gs = h->bias_gs, a.alpha_g = h->d_alpha_g;
+    a.param_groups = h->n_param_groups;
     a.in_map = in_map, a.fill = fill, a.out_map = out_map;
     a.field[0] = fbuf[0], a.field[1] = fbuf[1], a.r[0] = rbuf[0], a.r[1] = rbuf[1];
     a.pred = pred, a.ldp = ldp;

@@ -53,6 +53,7 @@ struct GemmArgs {
     double* C;
     const double* bias;  // optional, length N, added to every row of C
     long long strideBias;  // per batch entry (0 = shared)
+    int modB;              // > 0: B and bias of batch entry bz are those of entry bz % modB (parameter sets repeated)
     int M, N, K;
     long long lda, ldb, ldc;
     long long strideA, strideB, strideC;  // per batch entry (0 = shared)

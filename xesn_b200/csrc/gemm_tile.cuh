@@ -105,13 +105,14 @@ __device__ __forceinline__ void gemm_tile(const GemmArgs& p, int ti, int tj, int
 
     const int m0 = ti * BM, n0 = tj * BN;
     double* C = p.C + (long long)bz * p.strideC;
-    const double* bias = p.bias ? p.bias + (long long)bz * p.strideBias : nullptr;
+    const int bzB = p.modB > 0 ? bz % p.modB : bz;
+    const double* bias = p.bias ? p.bias + (long long)bzB * p.strideBias : nullptr;
     __syncthreads();  // persistent callers: every warp has left the previous tile's shared-memory stages
 
     TileLoader<A_K, VEC> la;
     TileLoader<B_K, VEC> lb;
     la.init(p.A + (long long)bz * p.strideA, p.lda, m0, p.M, tid);
-    lb.init(p.B + (long long)bz * p.strideB, p.ldb, n0, p.N, tid);
+    lb.init(p.B + (long long)bzB * p.strideB, p.ldb, n0, p.N, tid);
     const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem);
     constexpr unsigned STAGE_BYTES = STAGE_DOUBLES * sizeof(double);
     constexpr unsigned TILE_BYTES = TILE_DOUBLES * sizeof(double);

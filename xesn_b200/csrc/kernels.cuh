@@ -9,6 +9,7 @@ struct RecurArgs {
     const int* indices;
     const double* values;
     long long values_gs;     // stride between the groups' value arrays (0: all groups share W)
+    int param_groups;        // >= 1: group g uses parameter set g % param_groups
     const double* alpha_g;   // optional per-group leak rates (else `alpha`)
     const double* drive;     // [G][steps][N] : Win u_t + b for every step of the chunk
     long long drive_group_stride;
@@ -36,8 +37,9 @@ struct StepArgs {
     const int* indptr;
     const int* indices;
     const double* values;
-    long long values_gs, win_gs, bias_gs;  // strides between groups (0: shared parameters)
-    const double* alpha_g;                 // optional per-group leak rates
+    long long values_gs, win_gs, bias_gs;  // strides between parameter sets (0: shared parameters)
+    int param_groups;                      // >= 1: group g uses parameter set g % param_groups
+    const double* alpha_g;                 // optional per-set leak rates
     const double* Win;    // [N][I] (inline projection) -- used when drive == nullptr
     const double* bias;   // [N]
     const double* u;      // [G][I] dense inputs, or (when in_map != nullptr) gathered from `field`:
@@ -103,8 +105,9 @@ struct PredictLoopArgs {
     const double* values;
     const double* Win;
     const double* bias;
-    long long values_gs, win_gs, bias_gs;  // strides between groups (0: shared parameters)
-    const double* alpha_g;                 // optional per-group leak rates
+    long long values_gs, win_gs, bias_gs;  // strides between parameter sets (0: shared parameters)
+    int param_groups;                      // >= 1: group g uses parameter set g % param_groups
+    const double* alpha_g;                 // optional per-set leak rates
     const double* Wout;     // [G][O][N]
     const int* in_map;      // [G][I] cell index or -1-k -> fill[k]
     const double* fill;

@@ -116,8 +116,9 @@ __global__ void __launch_bounds__(PL_THREADS, 1) predict_loop_kernel(PredictLoop
             if (i < p.N) {
                 const double* rg = r_cur + (long long)g * p.N;
                 const int lo = __ldg(p.indptr + i), len = __ldg(p.indptr + i + 1) - lo;
-                const double wr = sparse_row_dot(p.indices + lo, p.values + (long long)g * p.values_gs + lo, len, rg);
-                const double* wrow = p.Win + (long long)g * p.win_gs + (long long)i * p.I;
+                const int pg = g % max(p.param_groups, 1);
+                const double wr = sparse_row_dot(p.indices + lo, p.values + (long long)pg * p.values_gs + lo, len, rg);
+                const double* wrow = p.Win + (long long)pg * p.win_gs + (long long)i * p.I;
                 double acc = 0.0;
                 if ((p.I & 1) == 0 && ((reinterpret_cast<uintptr_t>(p.Win) & 15) == 0)) {
                     const double2* w2 = reinterpret_cast<const double2*>(wrow);
@@ -135,8 +136,8 @@ __global__ void __launch_bounds__(PL_THREADS, 1) predict_loop_kernel(PredictLoop
 #pragma unroll 4
                     for (int k = 0; k < p.I; ++k) acc = fma(__ldg(wrow + k), s_u[k], acc);
                 }
-                const double pre = __dadd_rn(__dadd_rn(wr, acc), __ldg(p.bias + (long long)g * p.bias_gs + i));
-                const double alpha = p.alpha_g ? p.alpha_g[g] : p.alpha;
+                const double pre = __dadd_rn(__dadd_rn(wr, acc), __ldg(p.bias + (long long)pg * p.bias_gs + i));
+                const double alpha = p.alpha_g ? p.alpha_g[pg] : p.alpha;
                 r_nxt[(long long)g * p.N + i] = leaky(pre, ld_cg(rg + i), alpha, 1.0 - alpha);
             }
         }

@@ -101,7 +101,8 @@ __device__ __forceinline__ void pull_body(const RecurArgs& p, const int G, const
     const double* drive = p.drive + (long long)g * p.drive_group_stride;
     double* carry = p.carry + (long long)g * N;
     signed char* digits = p.planes ? p.planes + (long long)g * p.plane_group_stride : nullptr;
-    const double* const w_values = p.values + (long long)g * p.values_gs;
+    const int pg = g % max(p.param_groups, 1);
+    const double* const w_values = p.values + (long long)pg * p.values_gs;
 
     constexpr int KREG = PullRegs<UPT>::K;
     constexpr int KTAIL = 4;
@@ -130,7 +131,7 @@ __device__ __forceinline__ void pull_body(const RecurArgs& p, const int G, const
     put_states<UPT>(states + i0, r_cur, UPT);  // row 0 = state entering the chunk
     if (digits && p.steps > 0) put_digits<UPT>(digits, p, 0, i0, r_cur, UPT);
     if (p.hint) hint_arrive(p, s_sync, lane, wmask, active_warps, 0);
-    const double alpha = p.alpha_g ? p.alpha_g[g] : p.alpha, oma = 1.0 - alpha;
+    const double alpha = p.alpha_g ? p.alpha_g[pg] : p.alpha, oma = 1.0 - alpha;
     bool aborted = false;
 #ifdef XESN_RECUR_TRACE
     const int tid = rtid;  // XESN_TRACE_MARK records thread 0 of the CTA

@@ -188,7 +188,8 @@ __device__ __forceinline__ void recur_body(const RecurArgs& p, const unsigned c,
 
     double* s_r = reinterpret_cast<double*>(smem_raw);  // [n_pad] copy of r_t
     // ---- stage this CTA's CSR slice of W in shared memory (or fall back to global) ----
-    const double* const w_values = p.values + (long long)g * p.values_gs;
+    const int pg = g % max(p.param_groups, 1);
+    const double* const w_values = p.values + (long long)pg * p.values_gs;
     const int slice_lo = p.indptr[u0], slice_hi = p.indptr[u1];
     // WS: the slice lives in shared memory with the column indices pre-multiplied to byte offsets
     // into the state copy; else it is read from global memory (huge or dense W)
@@ -251,7 +252,7 @@ __device__ __forceinline__ void recur_body(const RecurArgs& p, const unsigned c,
             }
     put_states<UPT>(states + ubase, r_cur, nvalid);  // row 0 = state entering the chunk (read by the Gram kernel)
     if (digits && p.steps > 0) put_digits<UPT>(digits, p, 0, ubase, r_cur, nvalid);
-    const double alpha = p.alpha_g ? p.alpha_g[g] : p.alpha, oma = 1.0 - alpha;
+    const double alpha = p.alpha_g ? p.alpha_g[pg] : p.alpha, oma = 1.0 - alpha;
     const bool vec2 = (N % 2 == 0) && ((reinterpret_cast<uintptr_t>(states) & 15) == 0);
     bool aborted = false;
     __syncthreads();

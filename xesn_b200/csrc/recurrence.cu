@@ -75,12 +75,13 @@ __global__ void __launch_bounds__(SU_THREADS) step_update_kernel(StepArgs p) {
     }
     if (i >= p.N) return;
     const int lo = p.indptr[i], len = p.indptr[i + 1] - lo;
-    double wr = sparse_row_dot(p.indices + lo, p.values + (long long)g * p.values_gs + lo, len, r_in);
+    const int pg = g % max(p.param_groups, 1);
+    double wr = sparse_row_dot(p.indices + lo, p.values + (long long)pg * p.values_gs + lo, len, r_in);
     double pre;
     if (p.drive) {
         pre = __dadd_rn(wr, p.drive[(long long)g * p.N + i]);
     } else {
-        const double* wrow = p.Win + (long long)g * p.win_gs + (long long)i * p.I;
+        const double* wrow = p.Win + (long long)pg * p.win_gs + (long long)i * p.I;
         double acc = 0.0;
         if ((p.I & 1) == 0 && ((reinterpret_cast<uintptr_t>(p.Win) & 15) == 0)) {
             const double2* w2 = reinterpret_cast<const double2*>(wrow);
@@ -98,10 +99,10 @@ __global__ void __launch_bounds__(SU_THREADS) step_update_kernel(StepArgs p) {
 #pragma unroll 4
             for (int k = 0; k < p.I; ++k) acc = fma(__ldg(wrow + k), s_u[k], acc);
         }
-        pre = __dadd_rn(__dadd_rn(wr, acc), p.bias[(long long)g * p.bias_gs + i]);
+        pre = __dadd_rn(__dadd_rn(wr, acc), p.bias[(long long)pg * p.bias_gs + i]);
     }
     double r_old = ld_cg(r_in + i);
-    const double alpha = p.alpha_g ? p.alpha_g[g] : p.alpha;
+    const double alpha = p.alpha_g ? p.alpha_g[pg] : p.alpha;
     p.r_out[(long long)g * p.N + i] = leaky(pre, r_old, alpha, 1.0 - alpha);
 }
 

@@ -160,17 +160,38 @@ class ESNEnsemble:
         assert y_dev.shape[1] >= n_spinup + 1
         return self._predict_device(y_dev, n_steps, n_spinup).cpu().numpy()
 
-    def _predict_device(self, y_dev, n_steps, n_spinup):
+    def predict_windows(self, windows, n_steps, n_spinup):
+        """Several test windows at once (the reference scores a candidate on `n_samples` forecasts, cost.py:196-203):
+        windows is a sequence of F arrays (n_output, T >= n_spinup+1) of equal length, or one array (F, n_output, T).
+        Returns (F, G, n_output, n_steps+1); equals [predict(w, ...) for w in windows] with F x G reservoirs in one loop."""
         torch = _torch()
         res = self._device_reservoir()
+        ws = [self._to_device(w) for w in windows]
+        F, O = len(ws), self.n_output
+        assert F >= 1 and all(w.shape == ws[0].shape for w in ws) and ws[0].shape[0] == O
+        assert ws[0].shape[1] >= n_spinup + 1
+        stacked = torch.cat(ws, dim=0) if F > 1 else ws[0]          # rows f*O + o
+        return self._predict_device(stacked, n_steps, n_spinup, F).cpu().numpy()
+
+    def _predict_device(self, y_dev, n_steps, n_spinup, n_windows=1):
+        """y_dev: (n_windows * n_output, T) rows on the device -> (n_windows, G, O, n_steps+1), or (G, O, n_steps+1)
+        for a single window."""
+        torch = _torch()
+        F = int(n_windows)
+        res = self._device_reservoir()  # group f*G + g uses parameter set g (xesn_reservoir_set_group_params)
         lib = res._lib
         if self._wout_dev is None:
             raise _lib.XesnError("ESNEnsemble: no readout; call train() first")
-        G, N, O, I = len(self.members), self.n_reservoir, self.n_output, self.n_input
+        Gm, N, O, I = len(self.members), self.n_reservoir, self.n_output, self.n_input
+        G = F * Gm
+        wout = self._wout_dev if F == 1 else self._wout_dev.repeat(F, 1, 1)
         with torch.cuda.device(res.device):
             st = torch.cuda.current_stream().cuda_stream
             r = torch.zeros((G, N), dtype=torch.float64, device=res.device)
-            series, keep = self._shared_series(y_dev, I)
+            # group f*Gm + g reads the rows of window f
+            rows = (torch.arange(F, dtype=torch.int32, device=res.device).repeat_interleave(Gm * I) * I
+                    + torch.arange(I, dtype=torch.int32, device=res.device).repeat(G))
+            series, keep = _lib.Series(_ptr(y_dev), y_dev.stride(0), _ptr(rows), None, None), rows
             nb = lib.xesn_forced_scratch_bytes(res.handle, G, n_spinup, 1)
             nb2 = lib.xesn_predict_scratch_bytes(res.handle, O, G, G * O)
             scratch = torch.empty(max(nb, nb2), dtype=torch.uint8, device=res.device)
@@ -179,10 +200,10 @@ class ESNEnsemble:
             # every member forecasts its own copy of the field: cells [g*O, (g+1)*O)
             cells = torch.arange(G * O, dtype=torch.int32, device=res.device)
             fill = torch.zeros(1, dtype=torch.float64, device=res.device)
-            field = y_dev[:, n_spinup].contiguous().repeat(G)
+            field = y_dev[:, n_spinup].contiguous().view(F, 1, O).expand(F, Gm, O).contiguous().view(-1)
             pred = torch.empty((G * O, n_steps + 1), dtype=torch.float64, device=res.device)
-            _lib.check(lib.xesn_predict(res.handle, _ptr(self._wout_dev), O, G, G * O, _ptr(cells), _ptr(fill),
+            _lib.check(lib.xesn_predict(res.handle, _ptr(wout), O, G, G * O, _ptr(cells), _ptr(fill),
                                         _ptr(cells), _ptr(field), _ptr(r), n_steps, _ptr(pred), _ptr(scratch),
                                         scratch.numel(), st))
             del keep
-        return pred.view(G, O, n_steps + 1)
+        return pred.view(Gm, O, n_steps + 1) if F == 1 else pred.view(F, Gm, O, n_steps + 1)
