@@ -111,7 +111,12 @@ int xesn_ridge_solve(xesn_reservoir* h, int32_t n_output, int32_t n_groups, cons
  *        field_dev  : [n_cells] initial condition (truth at n_spinup); overwritten with the last step
  *        r_dev      : [G][N] reservoir states after spin-up; updated in place
  *        pred_dev   : [n_cells][n_steps+1] (time last); column 0 is written with the initial field
- *      scratch: xesn_predict_scratch_bytes(). */
+ *      scratch: xesn_predict_scratch_bytes().
+ *      Engines (same results to rounding of the readout sums): one reservoir (n_groups == 1, shared parameters)
+ *      runs the barrier-free kernel of predict_pull.cu (every CTA publishes its slice of r and its contribution
+ *      to each output, one reducer warp per output); several reservoirs run the persistent kernel with software
+ *      grid barriers (predict_loop.cu); configurations whose input projection is too large to inline fall back
+ *      to one update + one readout launch per step.  XESN_B200_PREDICT=barrier|steps forces the latter two. */
 int64_t xesn_predict_scratch_bytes(xesn_reservoir* h, int32_t n_output, int32_t n_groups, int64_t n_cells);
 int xesn_predict(xesn_reservoir* h, const double* wout_dev, int32_t n_output, int32_t n_groups,
                  int64_t n_cells, const int32_t* in_map_dev, const double* fill_dev,

@@ -206,3 +206,41 @@ def test_wout_block_layout_roundtrip(grid):
     blocks = halo.wout_to_blocks(w, grid)
     np.testing.assert_array_equal(blocks, oc.wout_block_layout(w.reshape(grid + (O, N))))
     np.testing.assert_array_equal(halo.blocks_to_wout(blocks, grid, O, N), w)
+
+
+# --------------------------------------------------------------------------- ESNEnsemble host logic (no GPU needed)
+def _member(seed_adj=1, n_res=80, n_in=3):
+    from xesn_b200 import ESN
+    kw = {k: dict(v) for k, v in ESN_KW.items()}
+    kw["adjacency_kwargs"]["random_seed"] = seed_adj
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return ESN(n_in, n_in, n_res, 0.5, 1e-4, **kw)
+
+
+def test_ensemble_rejects_mismatched_members():
+    """Members must have the same sizes (constructor) and the same sparsity pattern of W (build, checked on the
+    host before any device call): the batch shares one CSR structure, xesn_reservoir_set_group_params."""
+    from xesn_b200 import ESNEnsemble, XesnError
+    with pytest.raises(AssertionError):
+        ESNEnsemble([_member(n_res=80), _member(n_res=90)])
+    with pytest.raises(AssertionError):
+        ESNEnsemble([])
+    ens = ESNEnsemble([_member(seed_adj=1), _member(seed_adj=7)])
+    with pytest.raises(XesnError, match="sparsity pattern"):
+        ens.build()
+    with pytest.raises(XesnError, match="build"):
+        ESNEnsemble([_member()]).train(np.zeros((3, 10)))
+
+
+def test_bench_workloads_are_the_baseline_configs():
+    """bench.py names one workload per BASELINE.json configuration; unit-steps follow SURVEY.md section 8(d)."""
+    import bench
+    w = bench.WORKLOADS
+    assert w["eager16k"]["n_reservoir"] == 16000 and w["eager1k"]["n_reservoir"] == 1000
+    assert (w["lazy"]["chunk"], w["lazy"]["overlap"], w["lazy"]["n_reservoir"]) == (16, 1, 2000)
+    assert (w["lazy2d"]["chunk"], w["lazy2d"]["overlap"], w["lazy2d"]["n_reservoir"]) == (32, 2, 6000)
+    assert w["lazy2d"]["groups_per_gpu"] == w["lazy2d"]["group_rows_per_gpu"] * w["lazy2d"]["group_cols"]
+    assert w["macro"]["groups_per_gpu"] * 8 == 64 and w["macro"]["n_reservoir"] == 4000
+    assert bench.unit_steps(w["eager16k"], 1) == 16000 * (20000 + 1500)
+    assert bench.unit_steps(w["macro"], 8) == 8 * 4000 * (20000 + 5 * 600)
