@@ -242,8 +242,8 @@ int xesn_reservoir_destroy(xesn_reservoir* h) {
 
 // Per-group parameters: G independent reservoirs that share the sparsity pattern of W but have their own values of W,
 // Win, bias and leak rate (candidates of a hyper-parameter search, reference cost.py:190-203: the same seeds, other
-// scaling factors).  Host arrays values[G][nnz], win[G][N*I], bias[G][N], leak[G]; G = 0 restores shared parameters
-// (the arrays given to xesn_reservoir_create are then needed again: pass them as group 0 with G = 1 first if wanted).
+// scaling factors).  Host arrays values[G][nnz], win[G][N*I], bias[G][N], leak[G], G >= 1; they replace the arrays given
+// to xesn_reservoir_create.  Afterwards n_groups of every entry point must be a multiple of G: group g uses set g % G.
 int xesn_reservoir_set_group_params(xesn_reservoir* h, int32_t G, const double* values, const double* win,
                                     const double* bias, const double* leak) {
     XESN_REQUIRE(h && G >= 1 && values && win && bias && leak, "bad arguments");
