@@ -154,6 +154,10 @@ int fused_recur_geometry(int N, int n_groups, int threads, int* team_out, int* u
     // fused kernels per 20000 steps against 71.5 with 32 CTAs and 66.8 with 48)
     int want_team = 0;
     if (n_groups == 1 && best_upt == 1 && !force_upt) want_team = std::min(cap, (N + 399) / 400);
+    // one small reservoir is latency-bound and its Gram role needs few SMs: ~64 units per CTA (two warps) keeps the
+    // arithmetic of a step short (measured at N=1000, ms of fused kernels per 20000 steps: 2 CTAs 36.5, 8: 32.3,
+    // 16: 32.0, 32: 31.7)
+    if (n_groups == 1 && !force_upt && N <= 4096) want_team = std::max(want_team, std::min(32, N / 64));
     if (const char* e = getenv("XESN_B200_REC_TEAM")) want_team = atoi(e);  // experiments: any team size
     if (want_team > best_team && (long long)want_team * n_groups <= 96) {
         const int upc = recur_units_per_cta(N, want_team);
