@@ -166,6 +166,15 @@ int xesn_gram_i8(const double* states_dev, int64_t lds, int32_t n_rows, int32_t 
 /* readout v[g][o] = Wout[g][o][:] . r[g][:]   (xesn/esn.py:268, xesn/lazyesn.py:325-327) */
 int xesn_readout(const double* wout_dev, const double* r_dev, double* v_dev, int32_t n_reservoir,
                  int32_t n_output, int32_t n_groups, void* stream);
+/* ---- cost of a batch of forecasts: the NRMSE term of xesn/cost.py:227-254 and the
+ *      per-candidate average + clamp of xesn/cost.py:201-225.
+ *        pred_dev  : [n_windows][n_groups][n_output][n_times] forecasts (xesn_predict with n_windows * n_groups groups)
+ *        truth_dev : row (f, o) = truth_dev[(f*n_output + o) * truth_ld + t0 + s], s < n_times
+ *        nrmse_fg_dev : [n_windows][n_groups] out;  cost_dev : [n_groups] out = mean over the windows, with NaN, inf and
+ *                       values above upper_bound replaced by upper_bound */
+int xesn_cost_nrmse(const double* pred_dev, const double* truth_dev, int64_t truth_ld, int64_t t0, int32_t n_windows,
+                    int32_t n_groups, int32_t n_output, int32_t n_times, double upper_bound, double* nrmse_fg_dev,
+                    double* cost_dev, void* stream);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 int64_t xesn_launch_count(void);
 /* per-phase device timers (CUDA events on the launching stream).  enable(1) clears and starts

@@ -295,3 +295,21 @@ def agreement_horizon(a, ref, atol):
     bad = np.abs(a - ref).reshape(-1, a.shape[-1]).max(axis=0) > atol
     idx = np.nonzero(bad)[0]
     return int(idx[0]) if idx.size else a.shape[-1]
+
+
+# --------------------------------------------------------------------------- cost of forecasts
+def nrmse_cost(preds, truths, upper_bound=1e9):
+    """NRMSE cost of G candidates over F forecast windows.  Restates xesn/cost.py:227-254 (`nrmse`, drop_time=True:
+    error normalised by the temporal standard deviation of the truth per variable, ddof 0, mean over variables and
+    time, square root) and xesn/cost.py:201-225 (mean over the windows, NaN/inf/too-large -> cost_upper_bound).
+    PARITY UNPINNED: the reference's version is written with xarray, which is not installed here, so this
+    restatement could not be run against it.
+
+    preds: (F, G, O, S), truths: (F, O, S).  Returns (cost (G,), nrmse (F, G))."""
+    preds, truths = np.asarray(preds, dtype=np.float64), np.asarray(truths, dtype=np.float64)
+    w = 1.0 / truths.std(axis=-1, keepdims=True)                      # (F, O, 1)
+    err = (preds - truths[:, None]) * w[:, None]                       # (F, G, O, S)
+    fg = np.sqrt((err ** 2).mean(axis=(2, 3)))
+    cost = fg.mean(axis=0)
+    bad = np.isnan(cost) | np.isinf(cost) | (cost > upper_bound)
+    return np.where(bad, upper_bound, cost), fg

@@ -486,6 +486,13 @@ def test_ensemble_matches_members_and_oracle(torch, n_res, n_members):
     assert many.shape == (3, n_members, 40, 41)
     for f, wdw in enumerate(wins):
         np.testing.assert_allclose(many[f], ens.predict(wdw, n_steps=40, n_spinup=80), rtol=0, atol=1e-9)
+    # device-side NRMSE cost of the same forecasts (cost.py:201-254) against the oracle's restatement
+    cost, fg = ens.cost(wins, n_steps=40, n_spinup=80, cost_upper_bound=50.0)
+    truths = np.stack([wdw[:, 80:121] for wdw in wins])
+    ref_cost, ref_fg = oc.nrmse_cost(many, truths, upper_bound=50.0)
+    np.testing.assert_allclose(fg, ref_fg, rtol=1e-10)
+    np.testing.assert_allclose(cost, ref_cost, rtol=1e-10)
+    assert np.all(cost <= 50.0)
     for g, m in enumerate(members):
         W = sp.csr_matrix(m.W)
         ref, rr, yr = oc.ridge_train(data[:, :700], data[:, :700], 15, 300, W, m.Win, m.bias_vector, m.leak_rate,

@@ -1,0 +1,85 @@
+// Device-side cost of a batch of forecasts: the NRMSE term of the reference's macro-training cost
+// (xesn/cost.py:227-254 `nrmse`, :201-225 the per-candidate average and the clamp).
+//
+//   nrmse(f, g) = sqrt( mean_{o, s} ( (pred[f][g][o][s] - truth[f][o][s]) / std_s(truth[f][o][:]) )^2 )
+//   cost(g)     = mean_f nrmse(f, g);   NaN, inf or > upper_bound  ->  upper_bound
+//
+// with the standard deviation over the forecast times of one variable (ddof 0, numpy's default, which
+// xarray's `.std("ftime")` uses).  The forecasts of an ESNEnsemble never leave the device: only the G costs do.
+// HBM-bound streaming of the forecasts (8 bytes per value, read once); one CTA per (window, candidate).
+#include "common.cuh"
+
+namespace xesn {
+namespace {
+
+constexpr int CT = 256;
+
+__device__ __forceinline__ double block_sum(double v, double* s_red) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) s_red[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < CT / 32; ++w) t += s_red[w];  // same order in every thread: deterministic
+    return t;
+}
+
+// pred: [F][G][O][S] contiguous; truth row (f, o) = truth[(f*O + o) * ld + t0 + s]
+__global__ void __launch_bounds__(CT) nrmse_kernel(const double* __restrict__ pred, const double* __restrict__ truth,
+                                                   long long ld, long long t0, int G, int O, int S,
+                                                   double* __restrict__ out_fg) {
+    __shared__ double s_red[CT / 32];
+    const int f = blockIdx.x / G, g = blockIdx.x % G;
+    double total = 0.0;
+    for (int o = 0; o < O; ++o) {
+        const double* tr = truth + ((long long)f * O + o) * ld + t0;
+        const double* pr = pred + (((long long)f * G + g) * O + o) * S;
+        double a = 0.0;
+        for (int s = threadIdx.x; s < S; s += CT) a += tr[s];
+        const double mean = block_sum(a, s_red) / S;
+        double v = 0.0, e = 0.0;
+        for (int s = threadIdx.x; s < S; s += CT) {
+            const double d = tr[s] - mean, q = pr[s] - tr[s];
+            v += d * d;
+            e += q * q;
+        }
+        const double var = block_sum(v, s_red) / S;
+        const double err = block_sum(e, s_red);
+        total += err / var;  // sum_s ((pred - truth) / std)^2
+    }
+    if (threadIdx.x == 0) out_fg[blockIdx.x] = sqrt(total / ((double)O * S));
+}
+
+__global__ void cost_mean_kernel(const double* __restrict__ fg, int F, int G, double upper, double* __restrict__ cost) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    double a = 0.0;
+    for (int f = 0; f < F; ++f) a += fg[(long long)f * G + g];
+    a /= F;
+    if (!(a <= upper) || isinf(a)) a = upper;  // NaN fails the comparison
+    cost[g] = a;
+}
+
+}  // namespace
+}  // namespace xesn
+
+using namespace xesn;
+
+extern "C" int xesn_cost_nrmse(const double* pred_dev, const double* truth_dev, int64_t truth_ld, int64_t t0,
+                               int32_t n_windows, int32_t n_groups, int32_t n_output, int32_t n_times,
+                               double upper_bound, double* nrmse_fg_dev, double* cost_dev, void* stream) {
+    XESN_REQUIRE(pred_dev && truth_dev && nrmse_fg_dev && cost_dev, "null pointer");
+    XESN_REQUIRE(n_windows > 0 && n_groups > 0 && n_output > 0 && n_times > 0 && truth_ld >= t0 + n_times, "bad sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    nrmse_kernel<<<(unsigned)(n_windows * n_groups), CT, 0, st>>>(pred_dev, truth_dev, truth_ld, t0, n_groups, n_output,
+                                                                n_times, nrmse_fg_dev);
+    XESN_CUDA_OK(cudaGetLastError());
+    count_launch();
+    cost_mean_kernel<<<(unsigned)((n_groups + 127) / 128), 128, 0, st>>>(nrmse_fg_dev, n_windows, n_groups, upper_bound,
+                                                                       cost_dev);
+    XESN_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return 0;
+}

@@ -173,6 +173,26 @@ class ESNEnsemble:
         stacked = torch.cat(ws, dim=0) if F > 1 else ws[0]          # rows f*O + o
         return self._predict_device(stacked, n_steps, n_spinup, F).cpu().numpy()
 
+    def cost(self, windows, n_steps, n_spinup, cost_upper_bound=1e9):
+        """The reference's default macro-training cost of every member (`cost._cost`, xesn/cost.py:195-225 with
+        `cost_terms = {"nrmse": 1}`): forecast the F windows, NRMSE of each (cost.py:227-254), average, clamp.
+        Forecasts and errors stay on the device; returns (costs (G,), nrmse (F, G)) as numpy arrays."""
+        torch = _torch()
+        res = self._device_reservoir()
+        ws = [self._to_device(w) for w in windows]
+        F, O, G = len(ws), self.n_output, len(self.members)
+        assert F >= 1 and all(w.shape == ws[0].shape for w in ws) and ws[0].shape[0] == O
+        assert ws[0].shape[1] >= n_spinup + n_steps + 1, "the truth must cover the forecast"
+        stacked = torch.cat(ws, dim=0).contiguous() if F > 1 else ws[0]
+        pred = self._predict_device(stacked, n_steps, n_spinup, F).contiguous()
+        with torch.cuda.device(res.device):
+            fg = torch.empty((F, G), dtype=torch.float64, device=res.device)
+            cost = torch.empty(G, dtype=torch.float64, device=res.device)
+            _lib.check(res._lib.xesn_cost_nrmse(_ptr(pred), _ptr(stacked), stacked.stride(0), n_spinup, F, G, O,
+                                                n_steps + 1, float(cost_upper_bound), _ptr(fg), _ptr(cost),
+                                                torch.cuda.current_stream().cuda_stream))
+        return cost.cpu().numpy(), fg.cpu().numpy()
+
     def _predict_device(self, y_dev, n_steps, n_spinup, n_windows=1):
         """y_dev: (n_windows * n_output, T) rows on the device -> (n_windows, G, O, n_steps+1), or (G, O, n_steps+1)
         for a single window."""
