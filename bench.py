@@ -393,18 +393,14 @@ def main():
             return ens._predict_device(tests_stacked, w["pred_steps"], w["pred_spinup"], w["n_forecasts"])
 
         def step_e2e():
-            # per candidate and forecast the normalised RMSE (cost.py:94-122) is formed from the forecasts on the host
+            # what cost._cost returns per candidate (cost.py:195-225): the NRMSE of the forecasts, averaged over the
+            # windows and clamped -- evaluated on the device, only the costs come back
             ens.train(train_host, n_spinup=w["n_spinup_train"])
-            preds = ens.predict_windows(tests_host, n_steps=w["pred_steps"], n_spinup=w["pred_spinup"])  # (F, G, O, steps+1)
-            costs = []
-            for f, t in enumerate(tests_host):
-                truth = t.numpy()[:, w["pred_spinup"]:]
-                costs.append(np.sqrt(np.mean((preds[f] - truth[None]) ** 2 / truth.std(axis=1, keepdims=True)[None] ** 2,
-                                             axis=(1, 2))))
+            costs, _ = ens.cost(tests_host, n_steps=w["pred_steps"], n_spinup=w["pred_spinup"])
             return costs
 
         h2d = (train_host.numel() + sum(t.numel() for t in tests_host)) * 8  # one upload serves every candidate
-        d2h = w["groups_per_gpu"] * w["n_forecasts"] * w["n_vars"] * (w["pred_steps"] + 1) * 8
+        d2h = w["groups_per_gpu"] * (1 + w["n_forecasts"]) * 8  # costs and per-window NRMSE
     elif w["kind"] == "lazy2d":
         from xesn_b200 import LazyESN
         from xesn_b200.synthetic import wave_field_2d
