@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Benchmark of the ESN hot path: reservoir unit-steps/s (train + predict).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload eager16k|lazy]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload eager16k|eager1k|lazy|lazy2d|macro]
 
 A "step" is one full pass of the hot path over one synthetic series:
 `train` (recurrence + Gram accumulation + ridge solve) followed by `predict` (spin-up + closed
@@ -18,6 +19,10 @@ the upload of the reservoir matrices are outside the timed region.
           groups over the ranks instead (weak scaling, halo exchange per forecast step).
   --impl reference : the reference's numpy algorithm (oracle port of xesn/esn.py) on the host cores,
           timed on a bounded sample of the same workload and extrapolated linearly in T.
+  --workload : eager16k = BASELINE configs[1] (default, the configuration the metric is quoted on);
+          eager1k = configs[0]; lazy = configs[2] (16 groups per GPU); lazy2d = the share of configs[3] one of
+          8 GPUs holds (32 groups of N=6000, I=1296, O=1024); macro = the share of configs[4] one of 8 GPUs
+          holds (8 candidates of N=4000 as one ESNEnsemble batch, 5 forecast windows, device-side NRMSE cost).
 """
 import argparse
 import json
