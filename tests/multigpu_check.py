@@ -2,7 +2,7 @@
 """Multi-GPU LazyESN parity check (run on a GPU box):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
-        --master-port 29511 tools/multigpu_check.py
+        --master-port 29511 tests/multigpu_check.py
 
 Every rank trains/forecasts its slab of groups on its own GPU; the result is compared with the
 CPU oracle (test infrastructure) on rank 0."""
