@@ -244,3 +244,24 @@ def test_bench_workloads_are_the_baseline_configs():
     assert w["macro"]["groups_per_gpu"] * 8 == 64 and w["macro"]["n_reservoir"] == 4000
     assert bench.unit_steps(w["eager16k"], 1) == 16000 * (20000 + 1500)
     assert bench.unit_steps(w["macro"], 8) == 8 * 4000 * (20000 + 5 * 600)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the oracle port on the host cores) prints ONE JSON line with the keys the driver
+    reads; run here on the reference's own CPU-sized configuration (BASELINE configs[0]) and on a multi-reservoir one."""
+    import json
+    import subprocess
+    import sys
+    for workload in ("eager1k", "lazy"):
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", workload,
+                              "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+        assert out.returncode == 0, out.stderr[-2000:]
+        lines = [l for l in out.stdout.strip().splitlines() if l.startswith("{")]
+        assert len(lines) == 1
+        d = json.loads(lines[0])
+        assert d["impl"] == "reference" and d["unit"] == "unit-steps/s" and d["higher_is_better"] is True
+        assert d["metric"].startswith("reservoir unit-steps/sec") and d["value"] > 0 and d["vs_baseline"] is None
+        assert d["config"]["workload"] == workload and d["dtype"] == "f64" and d["data"] == "synthetic"
+        cb = d["cpu_baseline"]
+        assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "oracle port" in cb["sample"]
+        assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
