@@ -13,8 +13,9 @@
  *     asynchronous with respect to the host unless stated otherwise;
  *   - all floating-point data is IEEE binary64, row-major; "series" arrays are time-LAST like the
  *     reference's `(n_vars, n_time)` DataArrays;
- *   - G = number of independent reservoirs ("groups": LazyESN chunks, or 1 for the eager ESN);
- *     all groups share one (W, Win, b) as in xesn/lazyesn.py:175-177;
+ *   - G = number of independent reservoirs ("groups": LazyESN chunks, the candidates of an ESNEnsemble, or 1 for
+ *     the eager ESN); all groups share one (W, Win, b) as in xesn/lazyesn.py:175-177 unless
+ *     xesn_reservoir_set_group_params installed per-group parameter sets;
  *   - handles are not thread safe; one handle lives on one device.
  */
 #ifndef XESN_B200_H
