@@ -176,6 +176,11 @@ int xesn_readout(const double* wout_dev, const double* r_dev, double* v_dev, int
 int xesn_cost_nrmse(const double* pred_dev, const double* truth_dev, int64_t truth_ld, int64_t t0, int32_t n_windows,
                     int32_t n_groups, int32_t n_output, int32_t n_times, double upper_bound, double* nrmse_fg_dev,
                     double* cost_dev, void* stream);
+/* the PSD term of the cost for fields with ONE spatial axis (xesn/cost.py:257-272 over xesn/psd.py:12-65): NRMSE of the
+ * 1-D power spectral density, per window and candidate; same array conventions as xesn_cost_nrmse.  The caller combines
+ * the terms (cost.py:204-210: factor-weighted sum per window), averages over the windows and clamps. */
+int xesn_cost_psd_nrmse(const double* pred_dev, const double* truth_dev, int64_t truth_ld, int64_t t0, int32_t n_windows,
+                        int32_t n_groups, int32_t n_output, int32_t n_times, double* psd_nrmse_fg_dev, void* stream);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 int64_t xesn_launch_count(void);
 /* per-phase device timers (CUDA events on the launching stream).  enable(1) clears and starts

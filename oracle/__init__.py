@@ -5,8 +5,8 @@ legitimate users are `tests/`, `__graft_entry__.smoke()` and the `cpu_baseline`
 / `--impl reference` legs of `bench.py`, and there only as the checker or as
 the timed CPU baseline, never as the thing shipped.
 
-Parity status: PINNED for the hot path (a1-a6); `nrmse_cost` (the SURVEY section 8f cost term) is UNPINNED: the
-reference's version needs xarray, which this image lacks.
+Parity status: PINNED for the hot path (a1-a6); `nrmse_cost`, `psd_1d`, `psd_nrmse_fg` (the SURVEY section 8f cost terms) are UNPINNED: the
+reference's versions need xarray, which this image lacks.
 
 Hot path:  `oracle/make_golden.py` imports the reference's own
 source files (through a stub shim for the missing xarray/dask packages) in the

@@ -313,3 +313,41 @@ def nrmse_cost(preds, truths, upper_bound=1e9):
     cost = fg.mean(axis=0)
     bad = np.isnan(cost) | np.isinf(cost) | (cost > upper_bound)
     return np.where(bad, upper_bound, cost), fg
+
+
+def psd_1d(x):
+    """1-D power spectral density of a field with one spatial axis.  Restates xesn/psd.py:12-65 (`psd`) for
+    2-D input (n_x, n_time), with the same scipy calls (fft along space, `binned_statistic` mean over unit-width
+    wavenumber bins, annulus factor).  Returns (n_x // 2, n_time); for even n_x the last bin is empty (NaN), as in
+    the reference.  PARITY UNPINNED (the reference wraps this in xarray, absent here)."""
+    from scipy.fft import fft, fftfreq
+    from scipy.stats import binned_statistic
+    x = np.asarray(x, dtype=np.float64)
+    n_x, n_time = x.shape
+    psi = np.abs(fft(x.T)) ** 2                       # (n_time, n_x)
+    n_k = n_x // 2 + 1
+    k = n_x * fftfreq(n_x)
+    k_bins = np.arange(.5, n_k, 1.)
+    out = np.zeros((n_x // 2, n_time))
+    for n in range(n_time):
+        tmp1d, *_ = binned_statistic(k.flatten(), psi[n].flatten(), statistic="mean", bins=k_bins)
+        out[:, n] = tmp1d * np.pi * (k_bins[1:] ** 2 - k_bins[:-1] ** 2)
+    return out
+
+
+def psd_nrmse_fg(preds, truths):
+    """NRMSE of the PSD per window and candidate.  Restates xesn/cost.py:257-272 (`psd_nrmse` = `nrmse` of the two
+    spectra, cost.py:227-254) with xarray's skip-NaN reductions.  preds: (F, G, O, S), truths: (F, O, S) -> (F, G)."""
+    preds, truths = np.asarray(preds, dtype=np.float64), np.asarray(truths, dtype=np.float64)
+    F, G = preds.shape[:2]
+    out = np.zeros((F, G))
+    import warnings
+    with np.errstate(all="ignore"), warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)   # the empty last bin of an even n_x is all-NaN by design
+        for f in range(F):
+            pt = psd_1d(truths[f])
+            w = 1.0 / np.nanstd(pt, axis=-1, keepdims=True)
+            for g in range(G):
+                err = (psd_1d(preds[f, g]) - pt) * w
+                out[f, g] = np.sqrt(np.nanmean(err ** 2))
+    return out

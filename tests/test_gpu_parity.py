@@ -493,6 +493,15 @@ def test_ensemble_matches_members_and_oracle(torch, n_res, n_members):
     np.testing.assert_allclose(fg, ref_fg, rtol=1e-10)
     np.testing.assert_allclose(cost, ref_cost, rtol=1e-10)
     assert np.all(cost <= 50.0)
+    # both cost terms of the reference (cost.py:204-210): nrmse + 0.5 * psd_nrmse per window
+    cost2, fg2 = ens.cost(wins, n_steps=40, n_spinup=80, cost_upper_bound=50.0, cost_terms={"nrmse": 1.0, "psd_nrmse": 0.5})
+    ref_fg2 = ref_fg + 0.5 * oc.psd_nrmse_fg(many, truths)
+    np.testing.assert_allclose(fg2, ref_fg2, rtol=1e-9)
+    ref_cost2 = ref_fg2.mean(axis=0)
+    ref_cost2 = np.where(np.isnan(ref_cost2) | np.isinf(ref_cost2) | (ref_cost2 > 50.0), 50.0, ref_cost2)
+    np.testing.assert_allclose(cost2, ref_cost2, rtol=1e-9)
+    with pytest.raises(NotImplementedError):
+        ens.cost(wins, n_steps=40, n_spinup=80, cost_terms={"mae": 1.0})
     for g, m in enumerate(members):
         W = sp.csr_matrix(m.W)
         ref, rr, yr = oc.ridge_train(data[:, :700], data[:, :700], 15, 300, W, m.Win, m.bias_vector, m.leak_rate,

@@ -62,6 +62,8 @@ SIGNATURES = {
     "xesn_gemm_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
                                 C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_void_p]),
     "xesn_set_fused": (C.c_int, [C.c_void_p, C.c_int32]),
+    "xesn_cost_psd_nrmse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                      C.c_void_p, C.c_void_p]),
     "xesn_cost_nrmse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     "xesn_reservoir_set_group_params": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -52,6 +52,60 @@ __global__ void __launch_bounds__(CT) nrmse_kernel(const double* __restrict__ pr
     if (threadIdx.x == 0) out_fg[blockIdx.x] = sqrt(total / ((double)O * S));
 }
 
+// NRMSE of the 1-D power spectral density (xesn/cost.py:257-272 `psd_nrmse` over xesn/psd.py:12-65 `psd` for a field
+// with ONE spatial axis, e.g. Lorenz-96): for every time, |FFT over the O variables|^2 at the integer wavenumbers
+// k = 1 .. O/2 times the annulus factor pi((k+.5)^2 - (k-.5)^2); then the NRMSE over (k, time) with the temporal
+// standard deviation of the truth's spectrum per wavenumber.  For even O the reference's last bin (k = O/2) is empty
+// (scipy's fftfreq files that wavenumber as -O/2, outside the bins) and xarray's skipna mean ignores it: skipped here.
+// One CTA per (window, candidate); the O-point transform is a direct sum with an exact-argument twiddle table.
+__global__ void __launch_bounds__(CT) psd_nrmse_kernel(const double* __restrict__ pred, const double* __restrict__ truth,
+                                                       long long ld, long long t0, int G, int O, int S,
+                                                       double* __restrict__ out_fg) {
+    extern __shared__ double s_dyn[];  // [O] cos, [O] sin, [S] truth spectrum, [S] forecast spectrum
+    __shared__ double s_red[CT / 32];
+    double* s_cos = s_dyn;
+    double* s_sin = s_cos + O;
+    double* s_pt = s_sin + O;
+    double* s_pp = s_pt + S;
+    const int f = blockIdx.x / G, g = blockIdx.x % G;
+    for (int m = threadIdx.x; m < O; m += CT) sincospi(2.0 * m / O, &s_sin[m], &s_cos[m]);
+    __syncthreads();
+    const int kmax = (O % 2 == 0) ? O / 2 - 1 : O / 2;  // wavenumbers that own a non-empty bin
+    double total = 0.0;
+    for (int k = 1; k <= kmax; ++k) {
+        const double annulus = 3.14159265358979323846 * ((k + 0.5) * (k + 0.5) - (k - 0.5) * (k - 0.5));
+        for (int s = threadIdx.x; s < S; s += CT) {
+            double tre = 0.0, tim = 0.0, pre = 0.0, pim = 0.0;
+            int m = 0;  // (k * o) mod O
+            for (int o = 0; o < O; ++o) {
+                const double xt = truth[((long long)f * O + o) * ld + t0 + s];
+                const double xp = pred[(((long long)f * G + g) * O + o) * S + s];
+                tre = fma(xt, s_cos[m], tre), tim = fma(-xt, s_sin[m], tim);
+                pre = fma(xp, s_cos[m], pre), pim = fma(-xp, s_sin[m], pim);
+                m += k;
+                if (m >= O) m -= O;
+            }
+            s_pt[s] = (tre * tre + tim * tim) * annulus;
+            s_pp[s] = (pre * pre + pim * pim) * annulus;
+        }
+        __syncthreads();
+        double a = 0.0;
+        for (int s = threadIdx.x; s < S; s += CT) a += s_pt[s];
+        const double mean = block_sum(a, s_red) / S;
+        double v = 0.0, e = 0.0;
+        for (int s = threadIdx.x; s < S; s += CT) {
+            const double d = s_pt[s] - mean, q = s_pp[s] - s_pt[s];
+            v += d * d;
+            e += q * q;
+        }
+        const double var = block_sum(v, s_red) / S;
+        const double err = block_sum(e, s_red);
+        total += err / var;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out_fg[blockIdx.x] = kmax > 0 ? sqrt(total / ((double)kmax * S)) : 0.0;
+}
+
 __global__ void cost_mean_kernel(const double* __restrict__ fg, int F, int G, double upper, double* __restrict__ cost) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= G) return;
@@ -79,6 +133,21 @@ extern "C" int xesn_cost_nrmse(const double* pred_dev, const double* truth_dev, 
     count_launch();
     cost_mean_kernel<<<(unsigned)((n_groups + 127) / 128), 128, 0, st>>>(nrmse_fg_dev, n_windows, n_groups, upper_bound,
                                                                        cost_dev);
+    XESN_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+extern "C" int xesn_cost_psd_nrmse(const double* pred_dev, const double* truth_dev, int64_t truth_ld, int64_t t0,
+                                   int32_t n_windows, int32_t n_groups, int32_t n_output, int32_t n_times,
+                                   double* psd_nrmse_fg_dev, void* stream) {
+    XESN_REQUIRE(pred_dev && truth_dev && psd_nrmse_fg_dev, "null pointer");
+    XESN_REQUIRE(n_windows > 0 && n_groups > 0 && n_output > 1 && n_times > 0 && truth_ld >= t0 + n_times, "bad sizes");
+    const size_t smem = sizeof(double) * (2 * (size_t)n_output + 2 * (size_t)n_times);
+    XESN_REQUIRE(smem <= 200 * 1024, "forecast too long for the spectrum buffers (n_times <= ~12000)");
+    XESN_CUDA_OK(cudaFuncSetAttribute(psd_nrmse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    psd_nrmse_kernel<<<(unsigned)(n_windows * n_groups), CT, smem, (cudaStream_t)stream>>>(
+        pred_dev, truth_dev, truth_ld, t0, n_groups, n_output, n_times, psd_nrmse_fg_dev);
     XESN_CUDA_OK(cudaGetLastError());
     count_launch();
     return 0;

@@ -173,12 +173,19 @@ class ESNEnsemble:
         stacked = torch.cat(ws, dim=0) if F > 1 else ws[0]          # rows f*O + o
         return self._predict_device(stacked, n_steps, n_spinup, F).cpu().numpy()
 
-    def cost(self, windows, n_steps, n_spinup, cost_upper_bound=1e9):
-        """The reference's default macro-training cost of every member (`cost._cost`, xesn/cost.py:195-225 with
-        `cost_terms = {"nrmse": 1}`): forecast the F windows, NRMSE of each (cost.py:227-254), average, clamp.
-        Forecasts and errors stay on the device; returns (costs (G,), nrmse (F, G)) as numpy arrays."""
+    def cost(self, windows, n_steps, n_spinup, cost_upper_bound=1e9, cost_terms=None):
+        """The reference's macro-training cost of every member (`cost._cost`, xesn/cost.py:195-225): forecast the F
+        windows, per window the factor-weighted sum of the cost terms -- "nrmse" (cost.py:227-254) and, for fields with
+        one spatial axis, "psd_nrmse" (cost.py:257-272 over psd.py:12-65); default {"nrmse": 1} like the reference --
+        then the average over the windows and the clamp to `cost_upper_bound`.  Forecasts, spectra and errors stay on
+        the device; returns (costs (G,), per-window totals (F, G)) as numpy arrays."""
         torch = _torch()
         res = self._device_reservoir()
+        terms = {"nrmse": 1.0} if cost_terms is None else dict(cost_terms)
+        for key in terms:
+            if key not in ("nrmse", "psd_nrmse"):
+                raise NotImplementedError(f"ESNEnsemble.cost: found '{key}' in cost_terms, only 'nrmse' and 'psd_nrmse' "
+                                          f"are implemented")
         ws = [self._to_device(w) for w in windows]
         F, O, G = len(ws), self.n_output, len(self.members)
         assert F >= 1 and all(w.shape == ws[0].shape for w in ws) and ws[0].shape[0] == O
@@ -186,11 +193,22 @@ class ESNEnsemble:
         stacked = torch.cat(ws, dim=0).contiguous() if F > 1 else ws[0]
         pred = self._predict_device(stacked, n_steps, n_spinup, F).contiguous()
         with torch.cuda.device(res.device):
+            st = torch.cuda.current_stream().cuda_stream
             fg = torch.empty((F, G), dtype=torch.float64, device=res.device)
             cost = torch.empty(G, dtype=torch.float64, device=res.device)
             _lib.check(res._lib.xesn_cost_nrmse(_ptr(pred), _ptr(stacked), stacked.stride(0), n_spinup, F, G, O,
-                                                n_steps + 1, float(cost_upper_bound), _ptr(fg), _ptr(cost),
-                                                torch.cuda.current_stream().cuda_stream))
+                                                n_steps + 1, float(cost_upper_bound), _ptr(fg), _ptr(cost), st))
+            if terms != {"nrmse": 1.0}:
+                total = float(terms.get("nrmse", 0.0)) * fg if "nrmse" in terms else torch.zeros_like(fg)
+                if "psd_nrmse" in terms:
+                    pfg = torch.empty((F, G), dtype=torch.float64, device=res.device)
+                    _lib.check(res._lib.xesn_cost_psd_nrmse(_ptr(pred), _ptr(stacked), stacked.stride(0), n_spinup, F, G,
+                                                            O, n_steps + 1, _ptr(pfg), st))
+                    total = total + float(terms["psd_nrmse"]) * pfg
+                fg = total
+                cost = fg.mean(dim=0)
+                ub = torch.full_like(cost, float(cost_upper_bound))
+                cost = torch.where(torch.isnan(cost) | torch.isinf(cost) | (cost > ub), ub, cost)
         return cost.cpu().numpy(), fg.cpu().numpy()
 
     def _predict_device(self, y_dev, n_steps, n_spinup, n_windows=1):
