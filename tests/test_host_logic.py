@@ -265,3 +265,33 @@ def test_bench_reference_arm_contract():
         cb = d["cpu_baseline"]
         assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "oracle port" in cb["sample"]
         assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_ensemble_host_build_reuses_unscaled_matrices():
+    """ESNEnsemble.build_host draws every random matrix once per seed and applies each member's factor with the
+    reference's expression (matrix.py:183-193, :296-316): same W, Win, bias as building the members one by one."""
+    from xesn_b200 import ESNEnsemble
+    rs = np.random.RandomState(5)
+
+    def members():
+        out = []
+        for f_in, f_adj, f_b in rs.uniform(0.01, 2.0, size=(4, 3)):
+            kw = {k: dict(v) for k, v in ESN_KW.items()}
+            kw["input_kwargs"]["factor"], kw["adjacency_kwargs"]["factor"], kw["bias_kwargs"]["factor"] = f_in, f_adj, f_b
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                out.append(ESN(7, 7, 300, 0.3, 1e-5, **kw))
+        return out
+
+    state = rs.get_state()
+    fast = members()
+    rs.set_state(state)
+    slow = members()
+    ESNEnsemble(fast).build_host()
+    for a, b in zip(fast, slow):
+        b.build()
+        assert (a.W != b.W).nnz == 0 or np.allclose(a.W.toarray(), b.W.toarray(), rtol=1e-13, atol=0)
+        assert np.array_equal(a.W.tocsr().indices, b.W.tocsr().indices)
+        np.testing.assert_allclose(a.W.toarray(), b.W.toarray(), rtol=1e-13, atol=0)   # ARPACK jitter in sigma_max only
+        np.testing.assert_allclose(a.Win, b.Win, rtol=1e-15, atol=0)
+        np.testing.assert_array_equal(a.bias_vector, b.bias_vector)

@@ -25,6 +25,7 @@ import scipy.sparse
 
 from . import _lib
 from .esn import ESN, DeviceReservoir, _ptr, _time_last, _torch, auto_chunk
+from .matrix import RandomMatrix, SparseRandomMatrix, _dense_scale, _sparse_scale
 
 
 class ESNEnsemble:
@@ -50,10 +51,47 @@ class ESNEnsemble:
     def build(self):
         """Build every member on the host exactly as `ESN.build` does (reference esn.py:147-187; same seeds,
         own factors) and upload them as the parameter groups of one device reservoir."""
-        for m in self.members:
-            if m.W is None:
-                m.build()
+        self.build_host()
         self._upload()
+
+    def build_host(self):
+        """Host part of build().  The members of a search generation are built from the SAME seeds and differ only
+        in their factors (cost.py:190-193), so the unscaled random matrix and its normalisation constant (the
+        25 s of `scipy.sparse.random` + ARPACK `svds` at N=16000) are computed once per
+        distinct (shape, distribution, normalization, density, format, seed) and every member then applies its own
+        `factor / scale * A` -- the reference's expression (matrix.py:183-193, :296-316), hence the same matrices
+        up to ARPACK's ~1e-15 run-to-run jitter in `scale`, which the cache removes."""
+        cache = {}
+
+        def make(kwargs, n_rows, n_cols):
+            kw = dict(kwargs)
+            sparse = kw.pop("is_sparse", False)
+            factor = kw.pop("factor")
+            key = (sparse, n_rows, n_cols, tuple(sorted((k, repr(v)) for k, v in kw.items())))
+            if key not in cache:
+                maker = (SparseRandomMatrix if sparse else RandomMatrix)(n_rows=n_rows, n_cols=n_cols, factor=1.0, **kw)
+                A = maker.create_matrix()
+                scale = (_sparse_scale if sparse else _dense_scale)(A, maker.normalization)
+                cache[key] = (maker, A, scale)
+            maker, A, scale = cache[key]
+            if sparse:
+                B = A.copy()
+                B.data = factor / scale * A.data
+                return maker, B
+            return maker, factor / scale * A
+
+        for m in self.members:
+            if m.W is not None:
+                continue
+            maker, m.W = make(m.adjacency_kwargs, m.n_reservoir, m.n_reservoir)
+            if isinstance(maker, SparseRandomMatrix) and maker.density > 0.2:
+                import warnings
+                warnings.warn("ESN.__init__: adjacency matrix density is >20% but adjacency_kwargs['is_sparse'] = True. "
+                              "Performance could suffer from dense matrix operations with scipy.sparse.", RuntimeWarning)
+            _, m.Win = make(m.input_kwargs, m.n_reservoir, m.n_input)
+            _, b = make(dict(m.bias_kwargs), 1, m.n_reservoir)
+            m.bias_vector = b.squeeze()
+            m._drop_device_state()
 
     def _upload(self):
         csrs = []
