@@ -106,3 +106,33 @@ def test_wout_block_layout_shapes():
     g = np.arange(2 * 3 * 4 * 5, dtype=float).reshape(2, 3, 4, 5)
     lay = oc.wout_block_layout(g)
     assert np.array_equal(lay[4:8, 10:15], g[1, 2])
+
+
+# --------------------------------------------------------------------------- cost terms (unpinned restatements): known answers
+def test_cost_oracle_known_answers():
+    """`nrmse_cost`, `psd_1d`, `psd_nrmse_fg` restate xesn/cost.py:201-272 and xesn/psd.py:12-65, which cannot run here
+    (xarray); these are closed-form checks of the restatements themselves."""
+    from oracle import esn_oracle as oc
+    rs = np.random.RandomState(1)
+    truth = rs.normal(size=(2, 6, 50))                                  # (F, O, S)
+    # a forecast that is off by exactly one temporal standard deviation everywhere has NRMSE 1; a perfect one 0
+    off = truth + truth.std(axis=-1, keepdims=True)
+    preds = np.stack([truth, off], axis=1)                              # (F, G=2, O, S)
+    cost, fg = oc.nrmse_cost(preds, truth, upper_bound=10.0)
+    np.testing.assert_allclose(fg, [[0.0, 1.0], [0.0, 1.0]], atol=1e-12)
+    np.testing.assert_allclose(cost, [0.0, 1.0], atol=1e-12)
+    # NaN and too-large costs are clamped (cost.py:218-223)
+    bad = preds.copy()
+    bad[0, 0, 0, 0] = np.nan
+    bad[:, 1] *= 1e6
+    cost, _ = oc.nrmse_cost(bad, truth, upper_bound=10.0)
+    np.testing.assert_array_equal(cost, [10.0, 10.0])
+    # a pure cosine of wavenumber 3 on 16 points: all power in bin k=3, |X_3|^2 = (16/2)^2, annulus factor 2 pi k
+    x = np.cos(2 * np.pi * 3 * np.arange(16) / 16)[:, None] * np.ones((1, 4))
+    p = oc.psd_1d(x)
+    assert p.shape == (8, 4) and np.isnan(p[7]).all()                   # even n_x: the reference's last bin is empty
+    np.testing.assert_allclose(p[2], 64.0 * 2 * np.pi * 3, rtol=1e-12)
+    assert np.abs(np.delete(p[:7], 2, axis=0)).max() < 1e-20 * 1e3 + 1e-9
+    # the PSD error of a perfect forecast is 0
+    tr = rs.normal(size=(1, 16, 30))
+    np.testing.assert_allclose(oc.psd_nrmse_fg(tr[:, None], tr), [[0.0]], atol=1e-12)
