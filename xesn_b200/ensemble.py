@@ -182,6 +182,7 @@ class ESNEnsemble:
         for g, m in enumerate(self.members):
             m._wout_dev = wout[g:g + 1]
             m._wout_host = None
+            m.last_info = info[g:g + 1]
         return self
 
     @property
