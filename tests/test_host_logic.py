@@ -295,3 +295,117 @@ def test_ensemble_host_build_reuses_unscaled_matrices():
         np.testing.assert_allclose(a.W.toarray(), b.W.toarray(), rtol=1e-13, atol=0)   # ARPACK jitter in sigma_max only
         np.testing.assert_allclose(a.Win, b.Win, rtol=1e-15, atol=0)
         np.testing.assert_array_equal(a.bias_vector, b.bias_vector)
+
+
+# --------------------------------------------------------------------------- CostFunction host logic
+MACRO_CONFIG = {
+    "esn": dict(n_input=3, n_output=3, n_reservoir=60, leak_rate=0.5, tikhonov_parameter=1e-6,
+                **{k: dict(v) for k, v in ESN_KW.items()}),
+    "training": {"n_spinup": 5, "batch_size": 50},
+    "macro_training": {
+        "parameters": {"input_factor": [0.0, 2.0], "adjacency_factor": [0.0, 2.0], "leak_rate": [0.0, 1.0],
+                       "tikhonov_parameter": [1e-12, 1.0]},
+        "transformations": {"tikhonov_parameter": "log10"},
+        "forecast": {"n_spinup": 10, "n_samples": 2, "n_steps": 20},
+        "cost_upper_bound": 1e9,
+        "cost_terms": {"nrmse": 1.0, "psd_nrmse": 1.0},
+    },
+}
+
+
+def test_transform_known_answers():
+    """The docstring examples of the reference (xesn/optim.py:64-70 and :116-123)."""
+    from xesn_b200.cost import inverse_transform, transform
+    t = {"input_factor": "log", "adjacency_factor": "log10"}
+    assert transform({"input_factor": 0.5, "adjacency_factor": 0.5, "bias_factor": 0.5}, t) == {
+        "input_factor": -0.6931471805599453, "adjacency_factor": -0.3010299956639812, "bias_factor": 0.5}
+    got = inverse_transform({"input_factor": -0.69, "adjacency_factor": -0.3, "bias_factor": 0.5}, t)
+    assert got == {"input_factor": 0.5015760690660556, "adjacency_factor": 0.5011872336272722, "bias_factor": 0.5}
+    assert inverse_transform({"a": [0.0, 1.0]}, {"a": "log10"}) == {"a": [1.0, 10.0]}
+    with pytest.raises(KeyError):
+        inverse_transform({"a": 1.0}, {"b": "log"})
+    with pytest.raises(NotImplementedError):
+        transform({"a": 1.0}, {"a": "sqrt"})
+
+
+def test_update_esn_kwargs_and_candidates():
+    """Reference xesn/utils.py:65-100 and cost.py:177-190: factors go into the *_kwargs dicts, the rest to the top level."""
+    from xesn_b200.cost import CostFunction, update_esn_kwargs
+    orig = {"leak_rate": 0.5, "input_kwargs": {"factor": 1.0, "random_seed": 0}}
+    new = update_esn_kwargs({"input_factor": 0.25, "bias_factor": 0.1, "leak_rate": 0.9, "n_reservoir": 10}, orig)
+    assert new == {"leak_rate": 0.9, "input_kwargs": {"factor": 0.25, "random_seed": 0}, "bias_kwargs": {"factor": 0.1},
+                   "n_reservoir": 10}
+    assert orig["input_kwargs"]["factor"] == 1.0                      # the original is not modified
+    cf = CostFunction(ESN, None, None, MACRO_CONFIG)
+    kws = cf.candidate_kwargs([[0.3, 0.8, 0.4, -3.0], [1.5, 0.2, 0.9, -8.0]])
+    assert [k["input_kwargs"]["factor"] for k in kws] == [0.3, 1.5]
+    assert [k["adjacency_kwargs"]["factor"] for k in kws] == [0.8, 0.2]
+    assert [k["leak_rate"] for k in kws] == [0.4, 0.9]
+    np.testing.assert_allclose([k["tikhonov_parameter"] for k in kws], [1e-3, 1e-8], rtol=1e-14)
+    assert cf.candidate_kwargs([0.3, 0.8, 0.4, 1e-3], is_transformed=False)[0]["tikhonov_parameter"] == 1e-3
+    assert kws[0]["bias_kwargs"] == MACRO_CONFIG["esn"]["bias_kwargs"]
+    assert cf.batch_size(4000, 64) >= 8 and cf.batch_size(16000, 64) >= 1
+    with pytest.raises(NotImplementedError):
+        CostFunction(ESN, None, None, {"macro_training": {"cost_terms": {"mae": 1.0}}})
+    with pytest.raises(NotImplementedError):
+        CostFunction(LazyESN, None, None, MACRO_CONFIG)
+
+
+def test_cost_function_batches_and_orders_the_sets():
+    """__call__ builds one member per set, evaluates them in batches of `max_batch` and returns (n_sets, 1) in the
+    order of the sets (cost.py:94-122); the per-batch device evaluation is stubbed here (it is covered by the GPU
+    test of ESNEnsemble.cost)."""
+    from xesn_b200.cost import CostFunction, shard
+
+    class Stub(CostFunction):
+        __slots__ = ("batches",)
+
+        def _evaluate_members(self, members):
+            self.batches.append(len(members))
+            return np.array([m.leak_rate + 10.0 * m.input_kwargs["factor"] for m in members])
+
+    cf = Stub(ESN, None, None, MACRO_CONFIG, max_batch=3)
+    cf.batches = []
+    sets = np.array([[0.1 * i, 0.5, 0.01 * i, -3.0] for i in range(1, 8)])
+    out = cf(sets)
+    assert out.shape == (7, 1) and cf.batches == [3, 3, 1]
+    np.testing.assert_allclose(out[:, 0], [0.01 * i + 1.0 * i for i in range(1, 8)], rtol=1e-12)
+    assert shard(7, 0, 2) == [0, 2, 4, 6] and shard(7, 1, 2) == [1, 3, 5] and shard(2, 3, 4) == []
+
+
+def test_cost_function_device_glue_calls_match_the_ensemble_api(monkeypatch):
+    """`CostFunction._evaluate_members` is a thin sequence of ESNEnsemble calls (each covered by the GPU tests); here
+    the calls are bound against the real signatures with a recording stand-in, so that a keyword mismatch cannot hide
+    behind the missing GPU."""
+    import inspect
+    from xesn_b200 import cost as cost_mod
+    from xesn_b200.ensemble import ESNEnsemble
+    calls = []
+
+    class Fake:
+        def __init__(self, members):
+            inspect.signature(ESNEnsemble.__init__).bind(self, members)
+            self.members = list(members)
+
+        def build(self):
+            calls.append("build")
+
+        def train(self, *a, **k):
+            inspect.signature(ESNEnsemble.train).bind(self, *a, **k)
+            calls.append(("train", k))
+            return self
+
+        def cost(self, *a, **k):
+            bound = inspect.signature(ESNEnsemble.cost).bind(self, *a, **k)
+            calls.append(("cost", dict(bound.arguments)))
+            return np.arange(len(self.members), dtype=np.float64), None
+
+    monkeypatch.setattr(cost_mod, "ESNEnsemble", Fake)
+    train, windows = np.zeros((3, 100)), [np.zeros((3, 31)), np.zeros((3, 31))]
+    cf = cost_mod.CostFunction(ESN, train, windows, MACRO_CONFIG)
+    out = cf([[0.3, 0.8, 0.4, -3.0], [1.5, 0.2, 0.9, -8.0], [1.0, 1.0, 0.5, -6.0]])
+    np.testing.assert_array_equal(out[:, 0], [0.0, 1.0, 2.0])
+    assert calls[0] == "build" and calls[1] == ("train", {"n_spinup": 5, "batch_size": 50})
+    args = calls[2][1]
+    assert args["n_steps"] == 20 and args["n_spinup"] == 10 and args["cost_upper_bound"] == 1e9
+    assert args["cost_terms"] == {"nrmse": 1.0, "psd_nrmse": 1.0} and args["windows"] is windows

@@ -105,3 +105,42 @@ def test_partition_rules():
     assert [partition_groups(16, r, 4) for r in range(4)] == [(0, 4), (4, 8), (8, 12), (12, 16)]
     with pytest.raises(ValueError):
         partition_groups(6, 0, 4)
+
+
+# --------------------------------------------------------------------------- CostFunction: sets dealt to the ranks, costs gathered
+def _cost_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    from tests.test_host_logic import MACRO_CONFIG
+    from xesn_b200 import ESN
+    from xesn_b200.cost import CostFunction
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        class Stub(CostFunction):
+            __slots__ = ("seen",)
+
+            def _evaluate_members(self, members):      # the device evaluation of a batch (GPU tests cover it)
+                self.seen.extend(m.input_kwargs["factor"] for m in members)
+                return np.array([100.0 * m.input_kwargs["factor"] + m.leak_rate for m in members])
+
+        cf = Stub(ESN, None, None, MACRO_CONFIG, max_batch=2)
+        cf.seen = []
+        sets = np.array([[0.1 * i, 0.5, 0.01 * i, -3.0] for i in range(1, 8)])
+        out = cf(sets)
+        np.save(os.path.join(out_dir, f"cost_{rank}.npy"), out)
+        np.save(os.path.join(out_dir, f"seen_{rank}.npy"), np.array(cf.seen))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_cost_function(tmp_path):
+    """BASELINE configs[4] plumbing: every rank evaluates its share of the parameter sets and every rank ends up with
+    all costs, in the order of the sets."""
+    world = 2
+    mp.spawn(_cost_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    want = np.array([100.0 * 0.1 * i + 0.01 * i for i in range(1, 8)]).reshape(-1, 1)
+    for rank in range(world):
+        np.testing.assert_allclose(np.load(tmp_path / f"cost_{rank}.npy"), want, rtol=1e-12)
+    np.testing.assert_allclose(np.load(tmp_path / "seen_0.npy"), [0.1, 0.3, 0.5, 0.7], rtol=1e-12)
+    np.testing.assert_allclose(np.load(tmp_path / "seen_1.npy"), [0.2, 0.4, 0.6], rtol=1e-12)

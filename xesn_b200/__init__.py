@@ -10,7 +10,8 @@ from .matrix import RandomMatrix, SparseRandomMatrix
 from .esn import ESN
 from .lazyesn import LazyESN
 from .ensemble import ESNEnsemble
+from .cost import CostFunction
 from ._lib import XesnError, LIB_PATH, launch_count
 
-__all__ = ["ESN", "LazyESN", "ESNEnsemble", "RandomMatrix", "SparseRandomMatrix", "XesnError", "LIB_PATH", "launch_count"]
+__all__ = ["ESN", "LazyESN", "ESNEnsemble", "CostFunction", "RandomMatrix", "SparseRandomMatrix", "XesnError", "LIB_PATH", "launch_count"]
 __version__ = "0.1.0"
