@@ -587,7 +587,8 @@ def main():
     phases = {k: {"regions": v[0], "ms_per_step": v[1] / args.steps} for k, v in prof.items() if v[0]}
 
     cpu = None
-    if not args.no_cpu_baseline and w["kind"] == "eager":
+    # the CPU baseline is a single-process measurement: rank 0 at N=1 only (torchrun also pins OMP_NUM_THREADS to 1)
+    if not args.no_cpu_baseline and world == 1 and w["kind"] == "eager":
         import scipy.sparse as sp
         big = N > 4000
         st, sp_ = (200, 60) if big else (2000, 500)
@@ -601,7 +602,7 @@ def main():
                           f"({parts['per_predict_step_s'] * 1e3:.2f} ms/step); extrapolated linearly to the full "
                           f"workload ({total:.1f} s)")}
 
-    if not args.no_cpu_baseline and w["kind"] != "eager":
+    if not args.no_cpu_baseline and world == 1 and w["kind"] != "eager":
         import scipy.sparse as sp
         if w["kind"] == "macro":
             n_in = n_out = w["n_vars"]
