@@ -204,9 +204,19 @@ def build_eager_matrices(w):
     return esn
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is one process that should use the box's cores."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+
+
 def run_reference(args, w, rank):
     if rank != 0:
         return
+    use_all_host_threads()
     if w["kind"] != "eager":
         run_reference_grouped(args, w)
         return
