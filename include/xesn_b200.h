@@ -61,12 +61,21 @@ int xesn_reservoir_destroy(xesn_reservoir* h);
  * windows of every candidate in one loop).  The per-group Tikhonov parameters go to xesn_ridge_solve. */
 int xesn_reservoir_set_group_params(xesn_reservoir* h, int32_t n_groups, const double* values, const double* win,
                                     const double* bias, const double* leak);
-/* Synchronous health check: *status_host = 0 if every persistent-kernel poll completed, 1 if one
- * timed out (the CTAs of a cluster lost co-residency; results of that run are invalid). */
+/* Synchronous health check, read-and-clear: *status_host = 0 if every persistent-kernel poll completed since the
+ * last call, 1 if one timed out (the CTAs of a team lost co-residency or a peer rank died; results of that run
+ * are invalid).  Reporting clears the flag, so the next run on the handle starts clean. */
 int xesn_reservoir_status(xesn_reservoir* h, int32_t* status_host);
+/* Upper bound of any single in-kernel wait, by wall clock (%globaltimer), default 2000 ms
+ * (XESN_B200_POLL_TIMEOUT_MS at creation).  Raise it under time-slicing, MPS or a profiler. */
+int xesn_set_poll_timeout_ms(xesn_reservoir* h, int32_t milliseconds);
+/* Closed-loop / xesn_update input handling: on = NaN inputs read as 0, the LazyESN rule
+ * (xesn/lazyesn.py:357-365 _prepare_1d_inputs); off (default) = NaN propagates like the eager
+ * ESN.predict / _update of the reference (xesn/esn.py:251-268, :458-460). */
+int xesn_set_nan_input_mask(xesn_reservoir* h, int32_t on);
 
 /* ---- a1: one update, r' = (1-a) r + a tanh(W r + Win u + b)      xesn/esn.py:458-460 (_update),
- *      xesn/lazyesn.py:319-322 (_update_nd).  r_in/r_out: [G][N]; u: [G][I]; NaN inputs count as 0. */
+ *      xesn/lazyesn.py:319-322 (_update_nd).  r_in/r_out: [G][N]; u: [G][I]; NaN inputs propagate unless
+ *      xesn_set_nan_input_mask(h, 1). */
 int xesn_update(xesn_reservoir* h, const double* r_in_dev, const double* u_dev, double* r_out_dev,
                 int32_t n_groups, void* stream);
 
@@ -107,7 +116,7 @@ int xesn_ridge_solve(xesn_reservoir* h, int32_t n_output, int32_t n_groups, cons
 /* ---- a3/a6: closed-loop forecast                            xesn/esn.py:264-268 (ESN.predict),
  *      xesn/lazyesn.py:226-236 (+ _update_nd, _readout, overlap per step).
  *      The domain is a flat vector of `n_cells` values.  in_map [G][I] gathers every group's
- *      (halo'd) input from it (negative -> fill constant, NaN -> 0); out_map [G][O] scatters the
+ *      (halo'd) input from it (negative -> fill constant; NaN -> 0 with xesn_set_nan_input_mask); out_map [G][O] scatters the
  *      readout back.  Eager ESN: G=1, identity maps.
  *        field_dev  : [n_cells] initial condition (truth at n_spinup); overwritten with the last step
  *        r_dev      : [G][N] reservoir states after spin-up; updated in place
@@ -196,9 +205,12 @@ int xesn_set_fused(xesn_reservoir* h, int32_t on);
  * forced runs and spin-up, team model inside the fused training kernel, 2 = pull model there too (run by the
  * idle warps of the Gram CTAs).  Same arithmetic, bitwise the same results. */
 int xesn_set_recur_mode(xesn_reservoir* h, int32_t mode);
-/* Gram accumulation engine of the fused pipeline: 1 (default) = error-free int8 digit planes on the
- * tcgen05 tensor cores, 0 = FP64 DMMA. */
+/* Gram accumulation engine of the fused pipeline: 1 (default) = fixed-point int8 digit planes on the
+ * tcgen05 tensor cores (needs |r| <= 1), 0 = FP64 DMMA.  xesn_get_gram_mode returns the engine that will
+ * actually run: a leak rate outside [0, 1] (accepted by the reference) lets |r| exceed 1, so such
+ * reservoirs always use the FP64 engine. */
 int xesn_set_gram_mode(xesn_reservoir* h, int32_t mode);
+int xesn_get_gram_mode(xesn_reservoir* h, int32_t* mode_out);
 int xesn_profile_enable(int32_t on);
 int xesn_profile_read(int32_t cls, int64_t* n_regions, double* total_ms);
 

@@ -90,16 +90,31 @@ def test_update_matches_oracle(torch, lib, N, n_in):
     G = 3
     r = rs.uniform(-1, 1, size=(G, N))
     u = rs.normal(size=(G, n_in))
-    u[1, 0] = np.nan  # masked input counts as zero
+    u[1, 0] = np.nan
     W = sp.csr_matrix(esn.W)
     r_in = torch.from_numpy(r).cuda()
     u_dev = torch.from_numpy(u).cuda()
     r_out = torch.empty_like(r_in)
+    # default = the eager reference (_update, esn.py:458-460): a NaN input poisons every unit it feeds
+    _lib.check(lib.xesn_update(res.handle, r_in.data_ptr(), u_dev.data_ptr(), r_out.data_ptr(), G, None))
+    got = r_out.cpu().numpy()
+    for g in range(G):
+        ref = oc.leaky_step(r[g], u[g], W, esn.Win, esn.bias_vector, 0.5)
+        assert np.array_equal(np.isnan(got[g]), np.isnan(ref))
+        np.testing.assert_allclose(got[g], ref, rtol=0, atol=STATE_ATOL)
+    assert np.isnan(got[1]).all() and not np.isnan(got[0]).any()
+    # LazyESN rule (_prepare_1d_inputs, lazyesn.py:357-365): masked input counts as zero
+    _lib.check(lib.xesn_set_nan_input_mask(res.handle, 1))
     _lib.check(lib.xesn_update(res.handle, r_in.data_ptr(), u_dev.data_ptr(), r_out.data_ptr(), G, None))
     got = r_out.cpu().numpy()
     for g in range(G):
         ref = oc.leaky_step(r[g], np.nan_to_num(u[g], nan=0.0), W, esn.Win, esn.bias_vector, 0.5)
         np.testing.assert_allclose(got[g], ref, rtol=0, atol=STATE_ATOL)
+    _lib.check(lib.xesn_set_nan_input_mask(res.handle, 0))
+    st = ctypes.c_int32(7)
+    _lib.check(lib.xesn_set_poll_timeout_ms(res.handle, 5000))
+    _lib.check(lib.xesn_reservoir_status(res.handle, ctypes.byref(st)))
+    assert st.value == 0
 
 
 # --------------------------------------------------------------------------- forced states
@@ -541,3 +556,139 @@ def test_baseline_cfg5_shape_macro_candidates(torch):
         pred = esn.predict(data[:, 800:], n_steps=50, n_spinup=100)
         refp = oc.closed_loop(data[:, 800:], 50, 100, W, esn.Win, esn.bias_vector, leak, esn.Wout)
         np.testing.assert_allclose(pred, refp, rtol=0, atol=1e-6)
+
+
+# --------------------------------------------------------------------------- semantics at the edges
+def test_leak_rate_outside_unit_range_uses_f64_gram(torch, lib):
+    """leak_rate > 1 is accepted by the reference; |r| may then exceed 1, which the fixed-point digit planes of the
+    int8 Gram cannot represent -> the library must switch such reservoirs to the FP64 engine and still match."""
+    from xesn_b200 import _lib
+    from xesn_b200.synthetic import lorenz96
+    data = lorenz96(10, 1500)
+    esn = make_esn(10, 10, 700, leak=1.2, beta=1e-5)
+    res = esn._device_reservoir()
+    mode = ctypes.c_int32(-1)
+    _lib.check(lib.xesn_get_gram_mode(res.handle, ctypes.byref(mode)))
+    assert mode.value == 0
+    states, _ = forced_states_gpu(torch, lib, esn, data, 300)
+    assert np.abs(states).max() > 1.0            # the case really leaves the unit interval
+    esn.train(data, n_spinup=40, batch_size=333)
+    ref = oc.ridge_train(data, data, 40, 333, sp.csr_matrix(esn.W), esn.Win, esn.bias_vector, 1.2, 1e-5)
+    assert oc.max_normalised_err(esn.Wout, ref) < WOUT_TOL
+    ok = make_esn(10, 10, 700, leak=1.0, beta=1e-5)._device_reservoir()
+    _lib.check(lib.xesn_get_gram_mode(ok.handle, ctypes.byref(mode)))
+    assert mode.value == 1
+
+
+def test_eager_predict_propagates_nan_lazy_masks_it(torch):
+    """A NaN in the initial condition: the eager reference loop (esn.py:264-268) returns NaN from step 1 on;
+    LazyESN (lazyesn.py:357-365) treats the cell as masked input."""
+    from xesn_b200.synthetic import lorenz96
+    data = lorenz96(6, 400)
+    esn = make_esn(6, 6, 300, beta=1e-4)
+    esn.train(data[:, :300])
+    y = data[:, 300:].copy()
+    y[2, 20] = np.nan
+    pred = esn.predict(y, n_steps=5, n_spinup=20)
+    ref = oc.closed_loop(y, 5, 20, sp.csr_matrix(esn.W), esn.Win, esn.bias_vector, 0.5, esn.Wout)
+    assert np.array_equal(np.isnan(pred), np.isnan(ref))
+    assert np.isnan(pred[:, 1:]).all()
+
+
+# --------------------------------------------------------------------------- BASELINE.json shapes at full size
+def _horizon_report(pred, ref, atol):
+    h = oc.agreement_horizon(pred, ref, atol=atol)
+    return h
+
+
+def test_baseline_cfg1_full(torch):
+    """cfg 1 in full: eager ESN, L96-40, N=1000, 20 000 training steps, forecast 500 spin-up + 1000 steps."""
+    from xesn_b200.synthetic import lorenz96
+    data = lorenz96(40, 20000 + 1501)
+    esn = make_esn(40, 40, 1000)
+    W = sp.csr_matrix(esn.W)
+    esn.train(data[:, :20000])
+    ref, rr, yr = oc.ridge_train(data[:, :20000], data[:, :20000], 0, None, W, esn.Win, esn.bias_vector, 0.5, 1e-6,
+                                 return_gram=True)
+    _assert_readout(np.array(esn.Wout), ref, rr, yr, 1e-6, "cfg1")
+    pred = esn.predict(data[:, 20000:], n_steps=1000, n_spinup=500)
+    refp = oc.closed_loop(data[:, 20000:], 1000, 500, W, esn.Win, esn.bias_vector, 0.5, np.array(esn.Wout))
+    assert pred.shape == (40, 1001)
+    # same readout on both sides: only rounding differences, amplified by the chaotic closed loop
+    assert _horizon_report(pred, refp, 1e-6) >= 300, _horizon_report(pred, refp, 1e-6)
+    # against the oracle's own readout: stated pre-divergence horizon (north star)
+    refp2 = oc.closed_loop(data[:, 20000:], 1000, 500, W, esn.Win, esn.bias_vector, 0.5, ref)
+    assert _horizon_report(pred, refp2, 1e-3) >= 25
+
+
+def test_baseline_cfg3_one_gpu_full_n(torch):
+    """cfg 3 on one GPU at the real reservoir size: 16 groups x N=2000 (I=18, O=16), T=2200 (two internal chunks)."""
+    from xesn_b200 import LazyESN
+    from xesn_b200.synthetic import lorenz96
+    data = lorenz96(256, 2200 + 400)
+    kw = {k: dict(v) for k, v in ESN_KW.items()}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        esn = LazyESN({"x": 16}, {"x": 1}, "periodic", 2000, 0.5, 1e-6, **kw)
+    esn.build()
+    esn.train(data[:, :2200])
+    W = sp.csr_matrix(esn.W)
+    depth = {0: 1, 1: 0}
+    ref = oc.lazy_train(data[:, :2200], (16,), depth, "periodic", 0, None, W, esn.Win, esn.bias_vector, 0.5, 1e-6)
+    got = esn.Wout_groups.reshape(ref.shape)
+    assert oc.max_normalised_err(got, ref) < 1e-4, oc.max_normalised_err(got, ref)
+    pred = esn.predict(data[:, 2200:], n_steps=299, n_spinup=100)
+    refp = oc.lazy_predict(data[:, 2200:], (16,), depth, "periodic", 299, 100, W, esn.Win, esn.bias_vector, 0.5, got)
+    assert _horizon_report(pred, refp, 1e-6) >= 150, _horizon_report(pred, refp, 1e-6)
+
+
+def test_baseline_cfg2_benchmarked_shape(torch):
+    """cfg 2, the benchmarked eager shape: N=16000, L96-40.  T=2100 crosses an internal 2048-step chunk; the oracle
+    (numpy `_train_1d` restatement incl. scipy's LDL^T solve) takes about a minute.  Then a 700-step forecast given
+    that readout: 143 CTAs x 112 units, three 256-step launches of the barrier-free forecast kernel."""
+    from xesn_b200.synthetic import lorenz96
+    data = lorenz96(40, 2100 + 901)
+    esn = make_esn(40, 40, 16000)
+    W = sp.csr_matrix(esn.W)
+    esn.train(data[:, :2100])
+    ref, rr, yr = oc.ridge_train(data[:, :2100], data[:, :2100], 0, None, W, esn.Win, esn.bias_vector, 0.5, 1e-6,
+                                 return_gram=True)
+    _assert_readout(np.array(esn.Wout), ref, rr, yr, 1e-6, "cfg2")
+    del rr
+    wout = np.array(esn.Wout)
+    pred = esn.predict(data[:, 2100:], n_steps=700, n_spinup=200)
+    refp = oc.closed_loop(data[:, 2100:], 700, 200, W, esn.Win, esn.bias_vector, 0.5, wout)
+    assert pred.shape == (40, 701)
+    h = _horizon_report(pred, refp, 1e-6)
+    assert h >= 300, h
+
+
+@pytest.mark.parametrize("case", ["k16384", "tiny", "pm1"])
+def test_gram_i8_bounds(torch, lib, case):
+    """What the int8 Gram guarantees: an ABSOLUTE error bound per entry, K * 2^-50 (fixed-point image 2^-55 per
+    state, digit pairs below 2^-51 per product dropped), whatever the magnitude of the states -- i.e. FP64-DGEMM
+    accuracy for |r| ~ 1 and a relative accuracy that degrades for states near 0; exact on +-1 and 0."""
+    from xesn_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(11)
+    if case == "k16384":
+        K, N = 16384, 384                       # the int32-accumulator limit of one launch (gi8::MAX_K)
+        S = torch.rand((K, N), dtype=torch.float64, device="cuda", generator=g) * 2 - 1
+        S[:, 0] = 1.0                            # a column of ones: 16384 x the largest digit product
+        S[:, 1] = -1.0
+    elif case == "tiny":
+        K, N = 512, 256
+        S = (torch.rand((K, N), dtype=torch.float64, device="cuda", generator=g) * 2 - 1) * 1e-9
+    else:
+        K, N = 256, 256
+        S = torch.randint(-1, 2, (K, N), device="cuda", generator=g).to(torch.float64)
+    low = torch.tril(torch.ones((N, N), device="cuda")).bool()
+    G = torch.zeros((N, N), dtype=torch.float64, device="cuda")
+    _lib.check(lib.xesn_gram_i8(S.data_ptr(), N, K, N, G.data_ptr(), N, None))
+    ref = S.T @ S
+    err = float((G - ref)[low].abs().max())
+    if case == "pm1":
+        assert err == 0.0
+    else:
+        assert err <= K * 2.0 ** -50, (err, K * 2.0 ** -50)
+    if case == "k16384":
+        assert float(G[0, 0]) == K and float(G[1, 0]) == -K and float(G[1, 1]) == K

@@ -69,6 +69,9 @@ SIGNATURES = {
     "xesn_reservoir_set_group_params": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "xesn_set_recur_mode": (C.c_int, [C.c_void_p, C.c_int32]),
     "xesn_set_gram_mode": (C.c_int, [C.c_void_p, C.c_int32]),
+    "xesn_get_gram_mode": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
+    "xesn_set_poll_timeout_ms": (C.c_int, [C.c_void_p, C.c_int32]),
+    "xesn_set_nan_input_mask": (C.c_int, [C.c_void_p, C.c_int32]),
     "xesn_profile_enable": (C.c_int, [C.c_int32]),
     "xesn_profile_read": (C.c_int, [C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "xesn_gram_i8": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),

@@ -73,6 +73,18 @@ __global__ void strided_copy_kernel(const double* __restrict__ src, double* __re
     if (k < n) dst[k * dst_stride] = src[k];
 }
 inline long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
+// makes `device` current for the scope and restores the caller's device afterwards
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != device) cudaSetDevice(device);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
 }  // namespace
 
 }  // namespace xesn
@@ -112,7 +124,14 @@ struct xesn_reservoir {
     // recurrence engine: 0 = team model everywhere (recur_body.cuh), 1 = pull model (pull_body.cuh) for forced runs and
     // spin-up, team model inside the fused training kernel (default: measured fastest), 2 = pull model everywhere
     int recur_pull = 1;
+    // leak rates all inside [0, 1]: the recurrence is then a convex combination and |r| <= 1 holds, which the
+    // fixed-point digit planes of the int8 Gram role rely on; otherwise the FP64 DMMA Gram is used
+    bool leak_unit_range = true;
+    // closed loop: NaN inputs read as 0 (LazyESN, xesn/lazyesn.py:362-364) instead of propagating (eager ESN)
+    int mask_nan_inputs = 0;
+    SolveCtx solve;  // side stream + events of the look-ahead Cholesky, per handle (= per device)
 };
+static inline int gram_mode_effective(const xesn_reservoir* h) { return (h->gram_mode == 1 && h->leak_unit_range) ? 1 : 0; }
 
 extern "C" {
 
@@ -166,13 +185,19 @@ int xesn_reservoir_create(xesn_reservoir** out, int device, int32_t N, int32_t I
 
     auto* h = new xesn_reservoir();
     h->device = device, h->N = N, h->I = I, h->nnz = nnz, h->alpha = leak_rate;
+    h->leak_unit_range = leak_rate >= 0.0 && leak_rate <= 1.0;
     XESN_CUDA_OK(cudaMalloc(&h->d_indptr, sizeof(int) * (N + 1)));
     XESN_CUDA_OK(cudaMalloc(&h->d_indices, sizeof(int) * (nnz > 0 ? nnz : 1)));
     XESN_CUDA_OK(cudaMalloc(&h->d_values, sizeof(double) * (nnz > 0 ? nnz : 1)));
     XESN_CUDA_OK(cudaMalloc(&h->d_win, sizeof(double) * (size_t)N * I));
     XESN_CUDA_OK(cudaMalloc(&h->d_bias, sizeof(double) * N));
-    XESN_CUDA_OK(cudaMalloc(&h->d_status, sizeof(int)));
-    XESN_CUDA_OK(cudaMemset(h->d_status, 0, sizeof(int)));
+    // d_status[0] = flag (0 ok, 1 poll timed out, 2 grid/peer barrier timed out), d_status[1] = poll limit in microseconds
+    XESN_CUDA_OK(cudaMalloc(&h->d_status, 2 * sizeof(int)));
+    {
+        int init[2] = {0, 2000000};
+        if (const char* e = getenv("XESN_B200_POLL_TIMEOUT_MS")) init[1] = std::max(1, atoi(e)) * 1000;
+        XESN_CUDA_OK(cudaMemcpy(h->d_status, init, sizeof(init), cudaMemcpyHostToDevice));
+    }
     XESN_CUDA_OK(cudaMalloc(&h->d_bar, 4 * sizeof(unsigned)));
     XESN_CUDA_OK(cudaMemset(h->d_bar, 0, 4 * sizeof(unsigned)));
     // forecast engine: 1 = barrier-free pull kernel for a single reservoir (else the barrier kernel), 2 = always the
@@ -236,6 +261,7 @@ int xesn_reservoir_destroy(xesn_reservoir* h) {
     cudaFree(h->d_tiles_i8);
     cudaFree(h->d_ro_partial);
     cudaFree(h->d_ro_counters);
+    solve_ctx_destroy(h->solve);
     delete h;
     return 0;
 }
@@ -262,6 +288,8 @@ int xesn_reservoir_set_group_params(xesn_reservoir* h, int32_t G, const double* 
     h->n_param_groups = G;
     h->values_gs = (long long)h->nnz, h->win_gs = (long long)nw, h->bias_gs = (long long)nb;
     h->alpha = leak[0];
+    h->leak_unit_range = true;
+    for (int g = 0; g < G; ++g) h->leak_unit_range = h->leak_unit_range && leak[g] >= 0.0 && leak[g] <= 1.0;
     return 0;
 }
 #define XESN_REQUIRE_GROUPS(h, G) \
@@ -269,7 +297,30 @@ int xesn_reservoir_set_group_params(xesn_reservoir* h, int32_t G, const double* 
 
 int xesn_reservoir_status(xesn_reservoir* h, int32_t* status_host) {
     XESN_REQUIRE(h && status_host, "null pointer");
+    DeviceGuard guard(h->device);
     XESN_CUDA_OK(cudaMemcpy(status_host, h->d_status, sizeof(int), cudaMemcpyDeviceToHost));
+    // read-and-clear: a timed-out run is reported once; later runs on this handle start clean
+    if (*status_host) XESN_CUDA_OK(cudaMemset(h->d_status, 0, sizeof(int)));
+    return 0;
+}
+
+int xesn_set_poll_timeout_ms(xesn_reservoir* h, int32_t ms) {
+    XESN_REQUIRE(h && ms > 0, "bad arguments");
+    DeviceGuard guard(h->device);
+    const int us = ms > 2000000 ? 2000000000 : ms * 1000;
+    XESN_CUDA_OK(cudaMemcpy(h->d_status + 1, &us, sizeof(int), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int xesn_set_nan_input_mask(xesn_reservoir* h, int32_t on) {
+    XESN_REQUIRE(h, "null pointer");
+    h->mask_nan_inputs = on != 0;
+    return 0;
+}
+
+int xesn_get_gram_mode(xesn_reservoir* h, int32_t* mode_out) {
+    XESN_REQUIRE(h && mode_out, "null pointer");
+    *mode_out = gram_mode_effective(h);
     return 0;
 }
 
@@ -283,6 +334,7 @@ int xesn_update(xesn_reservoir* h, const double* r_in, const double* u, double* 
     a.values_gs = h->values_gs, a.win_gs = h->win_gs, a.bias_gs = h->bias_gs, a.alpha_g = h->d_alpha_g;
     a.param_groups = h->n_param_groups;
     a.r_in = r_in, a.r_out = r_out, a.N = h->N, a.I = h->I, a.alpha = h->alpha;
+    a.mask_nan = h->mask_nan_inputs;
     return launch_step_update(a, G, (cudaStream_t)stream);
 }
 
@@ -457,9 +509,9 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
     // accumulate: xesn/esn.py:502-513
     int team = 0, upt = 0;
     int pull_upc = 0, pull_upt = 0;
-    const bool pull = h->recur_pull == 2 && h->gram_mode == 1 && pull_geometry(N, G, h->num_sms, &pull_upc, &pull_upt) == 0;
+    const bool pull = h->recur_pull == 2 && gram_mode_effective(h) == 1 && pull_geometry(N, G, h->num_sms, &pull_upc, &pull_upt) == 0;
     const bool fuse = h->fused_enabled && (N % 2 == 0) && T > n_spinup &&
-                      (pull || (fused_recur_geometry(N, G, fused_threads(h->gram_mode == 1), &team, &upt) == 0 &&
+                      (pull || (fused_recur_geometry(N, G, fused_threads(gram_mode_effective(h) == 1), &team, &upt) == 0 &&
                                 (long long)team * G < h->num_sms));
     if (fuse) {
         // software pipeline over chunks: launch c runs recurrence(c) || Gram(c-1) in one cooperative kernel
@@ -471,7 +523,7 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
         }
         double* Dbuf[2] = {D, base + L.D2};
         double* Rbuf[2] = {R, base + L.R2};
-        const bool i8 = h->gram_mode == 1;
+        const bool i8 = gram_mode_effective(h) == 1;
         signed char* Pbuf[2] = {reinterpret_cast<signed char*>(base + L.P1), reinterpret_cast<signed char*>(base + L.P2)};
         const long long plane_group = (long long)gi8::NDIG * L.plane_stride;
         if (i8 && L.ldp > N) {  // padding columns must read as zero digits
@@ -618,8 +670,8 @@ int xesn_ridge_solve(xesn_reservoir* h, int32_t O, int32_t G, const double* beta
     ProfScope prof(PROF_SOLVE, st);
     int rc = launch_add_diag(gram, N, (long long)N * N, N, G, beta_dev, beta_scalar, st);
     if (rc) return rc;
-    return launch_cholesky_solve_ws(gram, N, (long long)N * N, wout, N, (long long)O * N, N, O, G, info, (double*)scratch,
-                                    st);
+    return launch_cholesky_solve_ws(h->solve, gram, N, (long long)N * N, wout, N, (long long)O * N, N, O, G, info,
+                                    (double*)scratch, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -659,9 +711,9 @@ static int closed_loop_step(xesn_reservoir* h, const double* wout, int O, int G,
     a.Win = h->d_win, a.bias = h->d_bias, a.N = N, a.I = I, a.alpha = h->alpha;
     a.values_gs = h->values_gs, a.win_gs = h->win_gs, a.bias_gs = h->bias_gs, a.alpha_g = h->d_alpha_g;
     a.param_groups = h->n_param_groups;
-    a.r_in = r_in, a.r_out = r_out;
+    a.r_in = r_in, a.r_out = r_out, a.mask_nan = h->mask_nan_inputs;
     if (G > INLINE_PROJECTION_MAX_GROUPS) {
-        if ((rc = launch_gather_vec(field_in, 1, in_map, fill, Ug, (long long)G * I, 1, st))) return rc;
+        if ((rc = launch_gather_vec(field_in, 1, in_map, fill, Ug, (long long)G * I, h->mask_nan_inputs, st))) return rc;
         GemmArgs g = {};
         g.A = Ug, g.lda = I, g.strideA = 0;
         g.B = h->d_win, g.ldb = I, g.strideB = h->win_gs;
@@ -711,7 +763,7 @@ static PredictLoopArgs predict_loop_args(xesn_reservoir* h, const double* wout, 
     a.slice = (h->N + n_slices - 1) / n_slices;
     a.slice += a.slice & 1;
     a.partial = h->d_ro_partial, a.counters = h->d_ro_counters;
-    a.bar = h->d_bar, a.status = h->d_status;
+    a.bar = h->d_bar, a.status = h->d_status, a.mask_nan = h->mask_nan_inputs;
     a.world = 1, a.rank = 0, a.step_base = 0;
     return a;
 }
@@ -791,7 +843,7 @@ int xesn_predict(xesn_reservoir* h, const double* wout, int32_t O, int32_t G, in
         a.v_ring = a.part_ring + (long long)PULL_PREDICT_CHUNK * pp_ctas * O;
         a.pred = pred, a.ldp = ldp, a.n_cells = n_cells;
         a.N = N, a.I = I, a.O = O, a.alpha = h->alpha, a.upc = pp_upc, a.n_ctas = pp_ctas;
-        a.hint = h->d_bar + 2, a.status = h->d_status;
+        a.hint = h->d_bar + 2, a.status = h->d_status, a.mask_nan = h->mask_nan_inputs;
         for (int s0 = 0; s0 < n_steps; s0 += PULL_PREDICT_CHUNK) {
             a.col0 = s0, a.steps = std::min(PULL_PREDICT_CHUNK, n_steps - s0);
             if ((rc = launch_predict_pull(a, st))) return rc;

@@ -210,13 +210,56 @@ long long cholesky_workspace_doubles(int n, int nrhs, int batch) {
     return d;
 }
 
-int launch_cholesky_solve_ws(double* A, long long lda, long long strideA, double* B, long long ldb, long long strideB,
-                             int n, int nrhs, int batch, int* info, double* work, cudaStream_t stream) {
-    static bool attr = false;
-    if (!attr) {
-        XESN_CUDA_OK(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PD_SMEM));
-        attr = true;
+void solve_ctx_destroy(SolveCtx& c) {
+    if (c.side) cudaStreamDestroy(c.side);
+    for (int k = 0; k < 2; ++k) {
+        if (c.ev_panel[k]) cudaEventDestroy(c.ev_panel[k]);
+        if (c.ev_trail[k]) cudaEventDestroy(c.ev_trail[k]);
     }
+    if (c.ev_fork) cudaEventDestroy(c.ev_fork);
+    if (c.ev_join) cudaEventDestroy(c.ev_join);
+    c = SolveCtx();
+}
+
+static int solve_ctx_init(SolveCtx& c) {
+    if (c.side) return 0;
+    int lo = 0, hi = 0, dev = 0;
+    XESN_CUDA_OK(cudaGetDevice(&dev));
+    XESN_CUDA_OK(cudaDeviceGetAttribute(&c.num_sms, cudaDevAttrMultiProcessorCount, dev));
+    XESN_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    XESN_CUDA_OK(cudaStreamCreateWithPriority(&c.side, cudaStreamNonBlocking, hi));
+    for (int k = 0; k < 2; ++k) {
+        XESN_CUDA_OK(cudaEventCreateWithFlags(&c.ev_panel[k], cudaEventDisableTiming));
+        XESN_CUDA_OK(cudaEventCreateWithFlags(&c.ev_trail[k], cudaEventDisableTiming));
+    }
+    XESN_CUDA_OK(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
+    XESN_CUDA_OK(cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming));
+    return 0;
+}
+
+static int cholesky_solve_body(SolveCtx& ctx, double* A, long long lda, long long strideA, double* B, long long ldb,
+                               long long strideB, int n, int nrhs, int batch, int* info, double* work,
+                               cudaStream_t stream);
+
+int launch_cholesky_solve_ws(SolveCtx& ctx, double* A, long long lda, long long strideA, double* B, long long ldb,
+                             long long strideB, int n, int nrhs, int batch, int* info, double* work,
+                             cudaStream_t stream) {
+    if (int rc = solve_ctx_init(ctx)) return rc;
+    // the attribute is per device: set it on every call (cheap) rather than once per process
+    XESN_CUDA_OK(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PD_SMEM));
+    XESN_CUDA_OK(cudaEventRecord(ctx.ev_fork, stream));
+    XESN_CUDA_OK(cudaStreamWaitEvent(ctx.side, ctx.ev_fork, 0));
+    const int rc = cholesky_solve_body(ctx, A, lda, strideA, B, ldb, strideB, n, nrhs, batch, info, work, stream);
+    // join the side stream on every path, errors included: nothing of this solve may still be running on it when
+    // the caller's stream moves on (or the caller frees the buffers)
+    cudaEventRecord(ctx.ev_join, ctx.side);
+    cudaStreamWaitEvent(stream, ctx.ev_join, 0);
+    return rc;
+}
+
+static int cholesky_solve_body(SolveCtx& ctx, double* A, long long lda, long long strideA, double* B, long long ldb,
+                               long long strideB, int n, int nrhs, int batch, int* info, double* work,
+                               cudaStream_t stream) {
     const int nblk = (n + NB - 1) / NB;
     const long long strideLinv = (long long)nblk * NB * NB;
     XESN_CUDA_OK(cudaMemsetAsync(info, 0, sizeof(int) * batch, stream));
@@ -234,20 +277,9 @@ int launch_cholesky_solve_ws(double* A, long long lda, long long strideA, double
     // the forward sweep (125 dependent pairs of small launches at n = 16000) disappears.
     const bool fold = batch == 1 && nrhs <= FOLD_MAX_RHS && ldb == lda && B == A + (long long)n * lda;
     const int xr = fold ? nrhs : 0;
-    static cudaStream_t side = nullptr;
-    static cudaEvent_t ev_panel[2] = {nullptr, nullptr}, ev_trail[2] = {nullptr, nullptr}, ev_fork = nullptr;
-    if (!side) {
-        int lo = 0, hi = 0;
-        XESN_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        XESN_CUDA_OK(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, hi));
-        for (int k = 0; k < 2; ++k) {
-            XESN_CUDA_OK(cudaEventCreateWithFlags(&ev_panel[k], cudaEventDisableTiming));
-            XESN_CUDA_OK(cudaEventCreateWithFlags(&ev_trail[k], cudaEventDisableTiming));
-        }
-        XESN_CUDA_OK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-    }
-    XESN_CUDA_OK(cudaEventRecord(ev_fork, stream));
-    XESN_CUDA_OK(cudaStreamWaitEvent(side, ev_fork, 0));
+    cudaStream_t side = ctx.side;
+    cudaEvent_t* ev_panel = ctx.ev_panel;
+    cudaEvent_t* ev_trail = ctx.ev_trail;
 
     auto factor_panel = [&](int J, int Jend, cudaStream_t s) -> int {
         for (int j0 = J; j0 < Jend; j0 += NB) {
@@ -313,12 +345,7 @@ int launch_cholesky_solve_ws(double* A, long long lda, long long strideA, double
         // T(J) on the caller's stream: everything right of the next panel (lower tiles)
         XESN_CUDA_OK(cudaStreamWaitEvent(stream, ev_panel[it & 1], 0));
         if (n - Jend2 >= I8_MIN_TRAIL && solve_uses_i8(n, batch) && (Jend - J) % 32 == 0) {
-            static int num_sms = 0;
-            if (!num_sms) {
-                int dev = 0;
-                XESN_CUDA_OK(cudaGetDevice(&dev));
-                XESN_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-            }
+            const int num_sms = ctx.num_sms;
             // the persistent SYRK kernel would otherwise hold every SM until it ends and starve the look-ahead
             // stream: leave some SMs to the panel factorisation (measured at N=16000, ms per solve: 0 free 42.8,
             // 8: 41.9, 16: 41.0, 32: 38.8, 48: 40.3, 64: 43.0)

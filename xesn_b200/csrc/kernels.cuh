@@ -51,6 +51,7 @@ struct StepArgs {
     double* r_out;        // [G][N]
     int N, I;
     double alpha;
+    int mask_nan;         // NaN inputs read as 0 (LazyESN: xesn/lazyesn.py:362-364); 0 = NaN propagates (eager ESN)
 };
 
 struct ReadoutArgs {
@@ -123,6 +124,7 @@ struct PredictLoopArgs {
     int* counters;          // [G][ceil(O/8)] zero-initialised, re-armed by the kernel
     unsigned* bar;          // [2] grid barrier: arrival counter, generation
     int* status;
+    int mask_nan;           // NaN inputs read as 0 (LazyESN) instead of propagating
     // multi-GPU exchange through peer-mapped memory (world == 1: unused)
     int world, rank;
     unsigned step_base;                      // flags count steps monotonically across launches
@@ -156,6 +158,7 @@ struct PredictPullArgs {
     int upc, n_ctas;        // units per CTA, CTAs
     unsigned* hint;
     int* status;
+    int mask_nan;           // NaN inputs read as 0 (LazyESN) instead of propagating
 };
 size_t predict_pull_smem(int I, int O, int upc, long long n_cells, int n_ctas);
 bool predict_pull_geometry(int N, int I, int O, long long n_cells, int num_sms, int* upc_out, int* n_ctas_out);
@@ -166,7 +169,15 @@ int launch_predict_pull(PredictPullArgs a, cudaStream_t stream);
 // leading dimension lda), then X = A^{-1} B for B[b] (n x nrhs, row-major, ldb) in place.
 // info[b] = 0 on success, k>0 if the leading minor of order k is not positive definite.
 long long cholesky_workspace_doubles(int n, int nrhs, int batch);
-int launch_cholesky_solve_ws(double* A, long long lda, long long strideA, double* B, long long ldb, long long strideB,
+// streams/events of the look-ahead factorisation: owned by a reservoir handle, created on first use on the
+// device that is current then (one handle lives on one device)
+struct SolveCtx {
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_panel[2] = {nullptr, nullptr}, ev_trail[2] = {nullptr, nullptr}, ev_fork = nullptr, ev_join = nullptr;
+    int num_sms = 0;
+};
+void solve_ctx_destroy(SolveCtx& c);
+int launch_cholesky_solve_ws(SolveCtx& ctx, double* A, long long lda, long long strideA, double* B, long long ldb, long long strideB,
                              int n, int nrhs, int batch, int* info, double* work, cudaStream_t stream);
 int launch_add_diag(double* A, long long lda, long long strideA, int n, int batch, const double* beta_dev,
                     double beta_scalar, cudaStream_t stream);

@@ -27,7 +27,6 @@ using namespace recur;
 
 constexpr int PL_THREADS = 256;
 constexpr int PL_WARPS = PL_THREADS / 32;
-constexpr int BAR_SPIN_LIMIT = 1 << 24;
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     unsigned v;
@@ -62,12 +61,8 @@ __device__ __forceinline__ void grid_barrier(const PredictLoopArgs& p, unsigned&
                 for (int k = 0; k < p.world; ++k) st_relaxed_sys_u32(p.peer_flags[k] + p.rank, step);
                 for (int k = 0; k < p.world; ++k) {
                     int spins = 0;
-                    while (ld_relaxed_sys_u32(p.peer_flags[p.rank] + k) < step) {
-                        if (++spins > BAR_SPIN_LIMIT) {
-                            atomicExch(p.status, 2);
-                            break;
-                        }
-                    }
+                    while (ld_relaxed_sys_u32(p.peer_flags[p.rank] + k) < step)
+                        if (poll_expired(spins, p.status)) break;
                 }
                 __threadfence_system();  // acquire side: the peers' field stores are visible before the local release
             }
@@ -76,12 +71,8 @@ __device__ __forceinline__ void grid_barrier(const PredictLoopArgs& p, unsigned&
             atomicExch(&p.bar[1], target);
         } else {
             int spins = 0;
-            while (ld_acquire_u32(&p.bar[1]) != target) {
-                if (++spins > BAR_SPIN_LIMIT) {
-                    atomicExch(p.status, 2);
-                    break;
-                }
-            }
+            while (ld_acquire_u32(&p.bar[1]) != target)
+                if (poll_expired(spins, p.status)) break;
         }
         gen = target;
     }
@@ -112,7 +103,7 @@ __global__ void __launch_bounds__(PL_THREADS, 1) predict_loop_kernel(PredictLoop
             for (int k = tid; k < p.I; k += PL_THREADS) {
                 const int m = p.in_map[(long long)g * p.I + k];
                 double x = (m >= 0) ? __ldcg(field_cur + m) : p.fill[-1 - m];
-                s_u[k] = (x != x) ? 0.0 : x;  // NaN inputs are masked out (lazyesn.py:362-364)
+                s_u[k] = (p.mask_nan && x != x) ? 0.0 : x;  // LazyESN masks NaN inputs (lazyesn.py:362-364)
             }
             __syncthreads();
             const int i = ib * PL_THREADS + tid;

@@ -77,7 +77,8 @@ __global__ void __launch_bounds__(PP_THREADS, 1) predict_pull_kernel(PredictPull
             for (int o = 0; o < O; ++o)
                 if ((p.out_map ? p.out_map[o] : o) == m) src = o;
         s_src[k] = src;
-        s_u0[k] = nan_to_zero(m >= 0 ? p.field[m] : p.fill[-1 - m]);
+        const double x0 = m >= 0 ? p.field[m] : p.fill[-1 - m];
+        s_u0[k] = p.mask_nan ? nan_to_zero(x0) : x0;
     }
 
     const double alpha = p.alpha, oma = 1.0 - p.alpha;
@@ -201,9 +202,12 @@ __global__ void __launch_bounds__(PP_THREADS, 1) predict_pull_kernel(PredictPull
 #endif
             for (int k = tid - PP_CONTRIB_WARP0 * 32; k < I; k += PP_CONTRIB_WARPS * 32) {
                 const int src = s_src[k];
-                s_u[k] = (n == 1 || src < 0)
-                             ? s_u0[k]
-                             : nan_to_zero(poll_value(p.v_ring + (long long)(n - 2) * O + src, p.status, aborted));
+                double x = s_u0[k];
+                if (n > 1 && src >= 0) {
+                    x = poll_value(p.v_ring + (long long)(n - 2) * O + src, p.status, aborted);
+                    if (p.mask_nan) x = nan_to_zero(x);
+                }
+                s_u[k] = x;
             }
 #ifdef XESN_RECUR_TRACE
             tr_sum[5] += trace_clock() - v0;

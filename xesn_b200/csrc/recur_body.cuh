@@ -79,7 +79,6 @@ __device__ __forceinline__ double leaky(double pre, double r_old, double alpha, 
 // value.  No fence and no cluster barrier sit on the per-step critical path (a release at cluster
 // scope compiles to MEMBAR.ALL.GPU per warp: 6.4 us per step in the first version).
 constexpr long long UNSET_BITS = -1LL;
-constexpr int SPIN_LIMIT = 1 << 22;  // ~1-2 s of polling, then the run is flagged as failed
 // 16-byte pieces in flight per thread while refreshing the copy (64 KB per CTA either way)
 template <int RC_THREADS, int UPT>
 struct PollCfg {
@@ -117,11 +116,26 @@ __device__ __forceinline__ void st_flag(double* p, double v) {
 __device__ __forceinline__ bool unset(double v) { return __double2hiint(v) == -1; }
 
 
-// bounded spin bookkeeping: returns true once the run has been flagged as failed
+// Bounded polling, by wall clock.  `spins` is the caller's per-wait scratch (0 before the first retry): the
+// first 32 retries (~10-20 us, far longer than any healthy wait) only count; after that it holds the
+// %globaltimer tick (~1 us units, top bit set) at which the slow path was entered, so a wait is bounded in
+// TIME (status[1] = limit in microseconds, default 2 s, xesn_set_poll_timeout_ms) however the SM is
+// time-sliced or profiled.  Returns true once the run has been flagged as failed (status[0] != 0).
+__device__ __forceinline__ unsigned poll_tick_us() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return (unsigned)(t >> 10) & 0x7FFFFFFFu;
+}
 __device__ __forceinline__ bool poll_expired(int& spins, int* status) {
-    if ((++spins & 255) != 0) return false;
-    if (spins >= SPIN_LIMIT) atomicExch(status, 1);
-    return *reinterpret_cast<volatile int*>(status) != 0;
+    if (spins >= 0) {
+        if (++spins < 32) return false;
+        spins = (int)(poll_tick_us() | 0x80000000u);
+        return false;
+    }
+    const unsigned waited = (poll_tick_us() - (unsigned)spins) & 0x7FFFFFFFu;
+    const volatile int* st = reinterpret_cast<const volatile int*>(status);
+    if (waited > (unsigned)st[1]) atomicExch(status, 1);
+    return st[0] != 0;
 }
 
 // publish UPT adjacent states (data-as-flag stores; every 8-byte element is single-copy atomic)

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(SU_THREADS) step_update_kernel(StepArgs p) {
             } else {
                 x = p.u[(long long)g * p.I + k];
             }
-            s_u[k] = (x != x) ? 0.0 : x;  // NaN inputs are masked out (lazyesn.py:362-364)
+            s_u[k] = (p.mask_nan && x != x) ? 0.0 : x;  // LazyESN masks NaN inputs (lazyesn.py:362-364); eager ESN propagates them
         }
         __syncthreads();
     }
@@ -297,11 +297,8 @@ int launch_step_update(const StepArgs& a, int n_groups, cudaStream_t stream) {
     dim3 grid((a.N + SU_THREADS - 1) / SU_THREADS, n_groups);
     size_t smem = a.drive ? 0 : (size_t)a.I * sizeof(double);
     if (smem > 48 * 1024) {
-        static bool done = false;
-        if (!done) {
-            XESN_CUDA_OK(cudaFuncSetAttribute(step_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            done = true;
-        }
+        // per device, so set on every such launch (not once per process)
+        XESN_CUDA_OK(cudaFuncSetAttribute(step_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         if (smem > 200 * 1024) {
             set_error("step_update: n_input too large for the inline projection");
             return -2;

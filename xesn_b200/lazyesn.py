@@ -26,8 +26,15 @@ def _prod(seq):
     return reduce(lambda a, b: a * b, seq)
 
 
+# set by measurement code that needs an unsharded run inside a distributed job (bench.py's multi-GPU parity
+# check runs the whole domain on rank 0 alone while the other ranks wait)
+_FORCE_SINGLE_RANK = False
+
+
 def _dist():
     """(rank, world) of the torch.distributed job, (0, 1) when not initialised."""
+    if _FORCE_SINGLE_RANK:
+        return 0, 1
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()
@@ -114,6 +121,25 @@ class LazyESN(ESN):
         return head + super().__str__().replace("ESN\n", "", 1)
 
     __repr__ = __str__
+
+    def _device_reservoir(self):
+        fresh = self._reservoir is None
+        res = super()._device_reservoir()
+        if fresh:
+            # LazyESN rule: NaN inputs of the closed loop read as 0 (`_prepare_1d_inputs`, lazyesn.py:357-365);
+            # the eager ESN lets them propagate, which is the library default
+            _lib.check(res._lib.xesn_set_nan_input_mask(res.handle, 1))
+        return res
+
+    def _drop_device_state(self):
+        self._p2p_release()
+        super()._drop_device_state()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self._p2p_release()
+        except Exception:
+            pass
 
     # ------------------------------------------------------------------ geometry
     def _space_dims(self, y):
@@ -370,6 +396,7 @@ class LazyESN(ESN):
         import torch.distributed as dist
         if self._p2p is not None and self._p2p["n_cells"] == n_cells and self._p2p["world"] == world:
             return self._p2p
+        self._p2p_release()  # other geometry: unmap the peers' buffers and free our own before allocating anew
         mine = {}
         handles = {}
         for name, nbytes in (("f0", 8 * n_cells), ("f1", 8 * n_cells), ("flags", 256)):
@@ -394,6 +421,20 @@ class LazyESN(ESN):
         dist.barrier()
         self._p2p = {"n_cells": n_cells, "world": world, "field": field, "flags": flags, "steps": 0, "own": mine}
         return self._p2p
+
+    def _p2p_release(self):
+        """Close the peer mappings and free this rank's peer-visible buffers (collective in effect: every rank
+        drops its buffers when its geometry changes or the model is rebuilt / destroyed)."""
+        p2p, self._p2p = getattr(self, "_p2p", None), None
+        if not p2p:
+            return
+        lib = _lib.load()
+        own = set(p2p["own"].values())
+        for ptr in set(p2p["field"][0]) | set(p2p["field"][1]) | set(p2p["flags"]):
+            if ptr and ptr not in own:
+                lib.xesn_p2p_close(ptr)
+        for ptr in own:
+            lib.xesn_p2p_free(ptr)
 
     def _predict_multi_nccl(self, lib, res, wout, G, g0, n_cells, t_in, t_fill, t_out, out_map, field, r, n_steps,
                        pred, scratch, nb, st):
