@@ -565,7 +565,10 @@ def test_leak_rate_outside_unit_range_uses_f64_gram(torch, lib):
     from xesn_b200 import _lib
     from xesn_b200.synthetic import lorenz96
     data = lorenz96(10, 1500)
-    esn = make_esn(10, 10, 700, leak=1.2, beta=1e-5)
+    # strong input and bias saturate tanh, so r' = 1.2 tanh(.) - 0.2 r overshoots +-1
+    over = dict(input_kwargs=dict(factor=4.0, distribution="uniform", normalization="svd", random_seed=0),
+                bias_kwargs=dict(factor=2.0, distribution="uniform", random_seed=2))
+    esn = make_esn(10, 10, 700, leak=1.2, beta=1e-5, **over)
     res = esn._device_reservoir()
     mode = ctypes.c_int32(-1)
     _lib.check(lib.xesn_get_gram_mode(res.handle, ctypes.byref(mode)))
@@ -575,7 +578,8 @@ def test_leak_rate_outside_unit_range_uses_f64_gram(torch, lib):
     esn.train(data, n_spinup=40, batch_size=333)
     ref = oc.ridge_train(data, data, 40, 333, sp.csr_matrix(esn.W), esn.Win, esn.bias_vector, 1.2, 1e-5)
     assert oc.max_normalised_err(esn.Wout, ref) < WOUT_TOL
-    ok = make_esn(10, 10, 700, leak=1.0, beta=1e-5)._device_reservoir()
+    keep = make_esn(10, 10, 700, leak=1.0, beta=1e-5)
+    ok = keep._device_reservoir()
     _lib.check(lib.xesn_get_gram_mode(ok.handle, ctypes.byref(mode)))
     assert mode.value == 1
 

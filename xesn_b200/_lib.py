@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libxesn_b200.so")
+# XESN_B200_LIB: another build of the same library (the -DXESN_RECUR_TRACE debug build used by tools/*trace*.py)
+LIB_PATH = os.environ.get("XESN_B200_LIB") or os.path.join(_HERE, "libxesn_b200.so")
 
 c_i32p = C.POINTER(C.c_int32)
 c_f64p = C.POINTER(C.c_double)
