@@ -124,9 +124,11 @@ int xesn_ridge_solve(xesn_reservoir* h, int32_t n_output, int32_t n_groups, cons
  *      scratch: xesn_predict_scratch_bytes().
  *      Engines (same results to rounding of the readout sums): one reservoir (n_groups == 1, shared parameters)
  *      runs the barrier-free kernel of predict_pull.cu (every CTA publishes its slice of r and its contribution
- *      to each output, one reducer warp per output); several reservoirs run the persistent kernel with software
- *      grid barriers (predict_loop.cu); configurations whose input projection is too large to inline fall back
- *      to one update + one readout launch per step.  XESN_B200_PREDICT=barrier|steps forces the latter two. */
+ *      to each output, one reducer warp per output); several reservoirs run the dataflow kernel of predict_flow.cu
+ *      (a team of CTAs per reservoir, consumers poll the values they read, no grid barrier) when a team's slices of
+ *      Win / Wout fit shared memory, else the persistent kernel with software grid barriers (predict_loop.cu);
+ *      configurations whose input projection is too large to inline fall back to one update + one readout launch
+ *      per step.  XESN_B200_PREDICT=barrier|steps forces the latter two. */
 int64_t xesn_predict_scratch_bytes(xesn_reservoir* h, int32_t n_output, int32_t n_groups, int64_t n_cells);
 int xesn_predict(xesn_reservoir* h, const double* wout_dev, int32_t n_output, int32_t n_groups,
                  int64_t n_cells, const int32_t* in_map_dev, const double* fill_dev,
@@ -161,6 +163,40 @@ int xesn_predict_p2p(xesn_reservoir* h, const double* wout_dev, int32_t n_output
                      int32_t n_steps, double* pred_dev, int32_t world, int32_t rank, uint32_t step_base,
                      const uint64_t* field_ptrs, const uint64_t* flag_ptrs, void* scratch_dev, int64_t scratch_bytes,
                      void* stream);
+
+/* ---- multi-GPU closed loop as a dataflow with neighbour-only exchange (predict_flow.cu) ----
+ * Replaces the per-step `overlap` of xesn/lazyesn.py:235 (and :226-236 around it) for several reservoirs per rank.
+ * A team of CTAs owns a group; per step every CTA publishes its slice of the state and its contribution to each
+ * output of the group into rings in global memory (the data is its own ready flag), and consumers poll exactly the
+ * values they read.  Cells that groups of OTHER ranks read are pushed into those ranks' rings with NVLink P2P
+ * stores -- only those cells, only to those ranks.  xesn_predict uses the same kernel for n_groups > 1 on one GPU.
+ *   ring slot s < G*O: local output (g, o) = (s / O, s % O); slot G*O + j: imported cell import_cell[j].
+ *   src[g][k]: slot feeding input k of local group g | -1-f: constant fill[f] | INT32_MIN: cell nobody produces.
+ *   exports of local slot s: entries exp_ptr[s] .. exp_ptr[s+1]-1 -> (exp_peer[e] = rank, exp_slot[e] = slot there).
+ *   ring_ptrs[parity*world + k]: rank k's partial ring of that parity as mapped in this process (k == rank: local;
+ *   ranks this one exports nothing to may be 0).  One ring = (G*O + n_import) * ring_steps * team doubles
+ *   (xesn_flow_geometry), allocated with xesn_p2p_alloc and filled with 0xFF bytes (xesn_memset_async) on every
+ *   rank BEFORE any rank's first call; the library re-arms a ring right after each launch that used it.
+ *   launches_done: zero at plan creation, advanced by the library; every rank makes the same calls. */
+typedef struct {
+    int32_t n_import;
+    const int32_t* src_dev;
+    const int32_t* import_cell_dev;
+    const int32_t* exp_ptr_dev;      /* may be NULL: nothing exported */
+    const int32_t* exp_peer_dev;
+    const int32_t* exp_slot_dev;
+    int32_t world, rank;
+    uint64_t ring_ptrs[16];
+    uint32_t launches_done;
+} xesn_flow_plan;
+/* 0 and (team, ring_steps) if n_groups reservoirs fit the dataflow kernel on this device, else -2 */
+int xesn_flow_geometry(xesn_reservoir* h, int32_t n_output, int32_t n_groups, int32_t* team_out, int32_t* ring_steps_out);
+/* arguments as xesn_predict (in_map/out_map index the GLOBAL cell vector; field_dev holds every cell this rank reads) */
+int xesn_predict_flow(xesn_reservoir* h, xesn_flow_plan* plan, const double* wout_dev, int32_t n_output, int32_t n_groups,
+                      int64_t n_cells, const int32_t* in_map_dev, const double* fill_dev, const int32_t* out_map_dev,
+                      double* field_dev, double* r_dev, int32_t n_steps, double* pred_dev, void* scratch_dev,
+                      int64_t scratch_bytes, void* stream);
+int xesn_memset_async(void* dst_dev, int32_t byte_value, int64_t bytes, void* stream);
 
 /* ---- building blocks exposed for parity tests and benchmarks ---- */
 /* C = alpha * op(A) op(B) + beta * C on the FP64 tensor pipe; flags: 1 = A is [M][K] (else [K][M]),

@@ -30,7 +30,8 @@ KW = dict(
 )
 
 
-def case(shape, chunks, overlap, boundary, N, rank):
+def case(shape, chunks, overlap, boundary, N, rank, engine):
+    os.environ["XESN_B200_EXCHANGE"] = engine
     names = ("x", "y")[:len(shape)]
     rs = np.random.RandomState(7)
     field = rs.normal(size=shape + (420,))
@@ -54,8 +55,8 @@ def case(shape, chunks, overlap, boundary, N, rank):
         ax = tuple(range(pred.ndim - 1))
         rel = np.abs(pred - refp).max(axis=ax) / np.maximum(np.abs(refp).max(axis=ax), 1.0)
         e2 = float(rel[:8].max())
-        print(f"case {shape} chunks {chunks}: Wout err {e1:.2e}, forecast rel err first 8 steps {e2:.2e}, "
-              f"all {float(rel.max()):.2e}")
+        print(f"case {shape} chunks {chunks} engine {engine}: Wout err {e1:.2e}, forecast rel err first 8 steps {e2:.2e}, "
+              f"all {float(rel.max()):.2e}", flush=True)
         assert e1 < 1e-6 and e2 < 1e-9, (e1, e2)
 
 
@@ -66,9 +67,13 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    case((64,), (4,), (1,), "periodic", 300, rank)
-    case((8, 12), (2, 3), (1, 1), "periodic", 200, rank)
-    case((16,), (2,), (2,), 0.0, 150, rank)
+    # engines: dataflow kernel with neighbour-only P2P stores (default), persistent kernel with every cell to every
+    # rank, per-step launches + NCCL
+    for engine in ("flow", "p2p", "nccl"):
+        case((64,), (4,), (1,), "periodic", 300, rank, engine)
+        case((8 * max(world // 2, 1), 12), (2, 3), (1, 1), "periodic", 200, rank, engine)
+        case((16,), (2,), (2,), 0.0, 150, rank, engine)
+        case((32, 6), (4, 3), (2, 1), {"x": "reflect", "y": "periodic"}, 150, rank, engine)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

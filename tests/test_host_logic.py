@@ -409,3 +409,57 @@ def test_cost_function_device_glue_calls_match_the_ensemble_api(monkeypatch):
     args = calls[2][1]
     assert args["n_steps"] == 20 and args["n_spinup"] == 10 and args["cost_upper_bound"] == 1e9
     assert args["cost_terms"] == {"nrmse": 1.0, "psd_nrmse": 1.0} and args["windows"] is windows
+
+
+# --------------------------------------------------------------------------- dataflow forecast tables (neighbour-only exchange)
+@pytest.mark.parametrize("shape,chunks,depth,boundary,world", [
+    ((64,), (4,), (1,), "periodic", 4),
+    ((64,), (4,), (2,), 0.0, 2),
+    ((16, 12), (2, 3), (1, 1), "periodic", 4),
+    ((16, 12), (4, 3), (2, 1), {"x": "reflect", "y": "periodic"}, 2),
+    ((32,), (4,), (1,), "periodic", 1),
+])
+def test_flow_tables_route_every_input(shape, chunks, depth, boundary, world):
+    """The tables of the dataflow forecast kernel: emulate one exchange step on the host -- every rank fills its local
+    ring slots, pushes its exports, and then must find, through `src`, exactly the values a whole-field gather
+    through in_map gives (what dask's overlap does in xesn/lazyesn.py:235); imports are neighbour-only."""
+    from xesn_b200 import halo
+    names = ("x", "y")[:len(shape)]
+    rules = halo.normalise_boundary(boundary, names, depth)
+    grid, in_map, out_map, fill = halo.build_maps(shape, chunks, depth, rules)
+    n_cells = int(np.prod(shape))
+    G_all, O = out_map.shape
+    per = G_all // world
+    value = np.random.RandomState(1).normal(size=n_cells)          # the freshly predicted field
+    tabs = [halo.flow_tables(in_map, out_map, n_cells, world, r) for r in range(world)]
+    rings = []
+    for r in range(world):
+        ring = np.full(per * O + int(tabs[r]["n_import_all"][r]), np.nan)
+        ring[:per * O] = value[out_map[r * per:(r + 1) * per].reshape(-1)]
+        rings.append(ring)
+    for r in range(world):
+        t = tabs[r]
+        assert len(t["import_cell"]) == t["n_import_all"][r]
+        for s in range(per * O):
+            for e in range(t["exp_ptr"][s], t["exp_ptr"][s + 1]):
+                peer, slot = int(t["exp_peer"][e]), int(t["exp_slot"][e])
+                assert peer != r and np.isnan(rings[peer][slot])       # exactly one producer per import slot
+                rings[peer][slot] = rings[r][s]
+    total_imports = 0
+    for r in range(world):
+        t = tabs[r]
+        assert not np.isnan(rings[r]).any()                            # every import slot was served
+        np.testing.assert_array_equal(rings[r][per * O:], value[t["import_cell"]])
+        src = t["src"].astype(np.int64)
+        m = in_map[r * per:(r + 1) * per].astype(np.int64)
+        direct = np.where(m >= 0, value[np.maximum(m, 0)], fill[np.maximum(-1 - m, 0)])
+        via = np.where(src >= 0, rings[r][np.maximum(src, 0)], fill[np.maximum(-1 - np.maximum(src, -len(fill)), 0)])
+        assert (src != halo.SRC_STATIC).all()                          # chunks tile the domain: nothing is static
+        np.testing.assert_array_equal(via, direct)
+        total_imports += len(t["import_cell"])
+        # neighbour-only: a slab imports from at most two other ranks along the split axis
+        assert len(set(t["import_owner"].tolist())) <= min(2, world - 1)
+    if world == 1:
+        assert total_imports == 0
+    else:
+        assert 0 < total_imports < n_cells                             # halo strips, not the whole field

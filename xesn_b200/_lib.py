@@ -26,6 +26,22 @@ class Series(C.Structure):
     ]
 
 
+class FlowPlan(C.Structure):
+    """`xesn_flow_plan` of include/xesn_b200.h."""
+    _fields_ = [
+        ("n_import", C.c_int32),
+        ("src_dev", C.c_void_p),
+        ("import_cell_dev", C.c_void_p),
+        ("exp_ptr_dev", C.c_void_p),
+        ("exp_peer_dev", C.c_void_p),
+        ("exp_slot_dev", C.c_void_p),
+        ("world", C.c_int32),
+        ("rank", C.c_int32),
+        ("ring_ptrs", C.c_uint64 * 16),
+        ("launches_done", C.c_uint32),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/xesn_b200.h declares
 SIGNATURES = {
     "xesn_last_error": (C.c_char_p, []),
@@ -60,6 +76,11 @@ SIGNATURES = {
     "xesn_predict_p2p": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_uint32,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "xesn_flow_geometry": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "xesn_predict_flow": (C.c_int, [C.c_void_p, C.POINTER(FlowPlan), C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                    C.c_int64, C.c_void_p]),
+    "xesn_memset_async": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]),
     "xesn_gemm_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
                                 C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_void_p]),
     "xesn_set_fused": (C.c_int, [C.c_void_p, C.c_int32]),

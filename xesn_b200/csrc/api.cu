@@ -776,13 +776,91 @@ static bool predict_pull_eligible(xesn_reservoir* h, int O, int G, long long n_c
            predict_pull_geometry(h->N, h->I, O, n_cells, h->num_sms, upc, n_ctas);
 }
 
+// dataflow forecast (predict_flow.cu): several reservoirs, no grid barrier
+static bool predict_flow_eligible(xesn_reservoir* h, int O, int G, int* team, int* upc) {
+    return h->persistent_predict == 1 && G > 1 && predict_flow_geometry(h->N, h->I, O, G, h->num_sms, team, upc);
+}
+struct FlowLayout {
+    long long r_ring, part_ring, src, owner, total;  // offsets in doubles from the start of the flow area
+};
+static FlowLayout flow_layout(xesn_reservoir* h, int O, int G, long long n_cells, int team, bool own_ring) {
+    FlowLayout L;
+    long long off = 0;
+    L.r_ring = off, off += round_up((long long)G * XESN_FLOW_CHUNK * h->N, 2);
+    L.part_ring = off, off += own_ring ? round_up((long long)G * O * XESN_FLOW_CHUNK * team, 2) : 0;
+    L.src = off, off += own_ring ? round_up(((long long)G * h->I + 1) / 2, 2) : 0;
+    L.owner = off, off += own_ring ? round_up((n_cells + 1) / 2, 2) : 0;
+    L.total = off;
+    return L;
+}
+
 int64_t xesn_predict_scratch_bytes(xesn_reservoir* h, int32_t O, int32_t G, int64_t n_cells) {
     if (!h) return -1;
     long long d = round_up((long long)G * h->I, 2) + 2 * round_up((long long)G * h->N, 2) + round_up(n_cells, 2);
-    int upc = 0, n_ctas = 0;
+    int upc = 0, n_ctas = 0, team = 0;
     if (predict_pull_eligible(h, O, G, n_cells, &upc, &n_ctas))
         d += (long long)(PULL_PREDICT_CHUNK + 1) * h->N + (long long)PULL_PREDICT_CHUNK * (n_ctas + 1) * O;
+    if (predict_flow_eligible(h, O, G, &team, &upc)) d += flow_layout(h, O, G, n_cells, team, true).total;
     return d * 8 + 256;
+}
+
+// one forecast through the dataflow kernel: launches of <= XESN_FLOW_CHUNK steps; the partial ring of parity p is
+// re-armed ("unset") right after the launch that used it, so a peer that runs ahead into its next-but-one launch
+// finds it clean (see INTEGRATION/DESIGN: only ranks that exchange cells with each other can drift, by one launch)
+struct FlowRun {
+    const double* wout;
+    int O, G;
+    long long n_cells;
+    const int32_t *in_map, *out_map, *src, *import_cell, *exp_ptr, *exp_peer, *exp_slot;
+    const double* fill;
+    int n_import, team, upc;
+    double *field, *field_alt, *r, *r_alt, *pred, *r_ring;
+    long long ldp;
+    int n_steps;
+    double* ring[2];                             // this rank's partial rings (two parities; equal when there are no peers)
+    int world;
+    double* peer_ring[2][XESN_MAX_WORLD];        // the peers' rings as mapped here
+};
+static int flow_run(xesn_reservoir* h, const FlowRun& f, uint32_t* launches_done, cudaStream_t st) {
+    const int N = h->N;
+    PredictFlowArgs a = {};
+    a.indptr = h->d_indptr, a.indices = h->d_indices, a.values = h->d_values, a.Win = h->d_win, a.bias = h->d_bias;
+    a.values_gs = h->values_gs, a.win_gs = h->win_gs, a.bias_gs = h->bias_gs, a.param_groups = h->n_param_groups;
+    a.alpha_g = h->d_alpha_g, a.alpha = h->alpha, a.Wout = f.wout;
+    a.N = N, a.I = h->I, a.O = f.O, a.G = f.G, a.team = f.team, a.upc = f.upc, a.ring_steps = XESN_FLOW_CHUNK;
+    a.src = f.src, a.in_map = f.in_map, a.fill = f.fill, a.out_map = f.out_map;
+    a.import_cell = f.import_cell, a.n_import = f.n_import;
+    a.r_ring = f.r_ring, a.pred = f.pred, a.ldp = f.ldp;
+    a.exp_ptr = f.exp_ptr, a.exp_peer = f.exp_peer, a.exp_slot = f.exp_slot;
+    a.mask_nan = h->mask_nan_inputs, a.status = h->d_status;
+    const size_t ring_bytes = sizeof(double) * (size_t)((long long)f.G * f.O + f.n_import) * XESN_FLOW_CHUNK * f.team;
+    double* fbuf[2] = {f.field, f.field_alt};
+    double* rbuf[2] = {f.r, f.r_alt};
+    int cur = 0;
+    uint32_t local_count = 0;
+    uint32_t* count = launches_done ? launches_done : &local_count;
+    const bool shared_ring = f.ring[0] == f.ring[1];
+    for (int s0 = 0; s0 < f.n_steps; s0 += XESN_FLOW_CHUNK, cur ^= 1) {
+        const int steps = std::min(XESN_FLOW_CHUNK, f.n_steps - s0);
+        const int par = (int)(*count & 1u);
+        if (shared_ring) XESN_CUDA_OK(cudaMemsetAsync(f.ring[0], 0xFF, ring_bytes, st));
+        XESN_CUDA_OK(cudaMemset2DAsync(f.r_ring, sizeof(double) * (size_t)XESN_FLOW_CHUNK * N, 0xFF,
+                                       sizeof(double) * (size_t)steps * N, f.G, st));
+        // cells nobody produces keep their value in the field leaving the launch
+        XESN_CUDA_OK(cudaMemcpyAsync(fbuf[cur ^ 1], fbuf[cur], sizeof(double) * (size_t)f.n_cells, cudaMemcpyDeviceToDevice, st));
+        a.steps = steps, a.col0 = s0;
+        a.field = fbuf[cur], a.field_out = fbuf[cur ^ 1], a.r_in = rbuf[cur], a.r_out = rbuf[cur ^ 1];
+        a.part_ring = f.ring[par];
+        for (int k = 0; k < f.world && k < XESN_MAX_WORLD; ++k) a.peer_ring[k] = f.peer_ring[par][k];
+        if (int rc = launch_predict_flow(a, st)) return rc;
+        if (!shared_ring) XESN_CUDA_OK(cudaMemsetAsync(f.ring[par], 0xFF, ring_bytes, st));
+        ++*count;
+    }
+    if (cur) {  // results live in the alternates
+        XESN_CUDA_OK(cudaMemcpyAsync(f.r, f.r_alt, sizeof(double) * (size_t)f.G * N, cudaMemcpyDeviceToDevice, st));
+        XESN_CUDA_OK(cudaMemcpyAsync(f.field, f.field_alt, sizeof(double) * (size_t)f.n_cells, cudaMemcpyDeviceToDevice, st));
+    }
+    return 0;
 }
 
 int xesn_predict_step(xesn_reservoir* h, const double* wout, int32_t O, int32_t G, const int32_t* in_map,
@@ -849,6 +927,21 @@ int xesn_predict(xesn_reservoir* h, const double* wout, int32_t O, int32_t G, in
             if ((rc = launch_predict_pull(a, st))) return rc;
         }
         return 0;
+    }
+    int fteam = 0, fupc = 0;
+    if (predict_flow_eligible(h, O, G, &fteam, &fupc)) {
+        // several reservoirs on one GPU: dataflow kernel, every produced cell is local (no imports / exports)
+        const FlowLayout L = flow_layout(h, O, G, n_cells, fteam, true);
+        double* area = field_alt + round_up(n_cells, 2);
+        int* src = reinterpret_cast<int*>(area + L.src);
+        int* owner = reinterpret_cast<int*>(area + L.owner);
+        if ((rc = launch_flow_src(in_map, out_map, owner, src, n_cells, (long long)G * O, (long long)G * I, st))) return rc;
+        FlowRun f = {};
+        f.wout = wout, f.O = O, f.G = G, f.n_cells = n_cells, f.in_map = in_map, f.fill = fill, f.out_map = out_map;
+        f.src = src, f.team = fteam, f.upc = fupc;
+        f.field = field, f.field_alt = field_alt, f.r = r, f.r_alt = r_alt, f.n_steps = n_steps, f.pred = pred, f.ldp = ldp;
+        f.r_ring = area + L.r_ring, f.ring[0] = f.ring[1] = area + L.part_ring, f.world = 1;
+        return flow_run(h, f, nullptr, st);
     }
     if (predict_loop_eligible(h, G)) {
         PredictLoopArgs a = predict_loop_args(h, wout, O, G, in_map, fill, out_map, fbuf, rbuf, pred, ldp, n_steps, S);
@@ -937,6 +1030,63 @@ int xesn_predict_p2p(xesn_reservoir* h, const double* wout, int32_t O, int32_t G
     }
     if ((rc = launch_predict_loop(a, h->num_sms, st))) return rc;
     if (n_steps & 1) XESN_CUDA_OK(cudaMemcpyAsync(r, r_alt, sizeof(double) * (size_t)G * N, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+// ---- dataflow forecast with neighbour-only exchange (predict_flow.cu) ----
+int xesn_flow_geometry(xesn_reservoir* h, int32_t O, int32_t G, int32_t* team_out, int32_t* ring_steps_out) {
+    XESN_REQUIRE(h && team_out && ring_steps_out, "null pointer");
+    int team = 0, upc = 0;
+    if (!predict_flow_eligible(h, O, G, &team, &upc)) {
+        set_error("dataflow forecast: %d groups of n_reservoir=%d, n_input=%d, n_output=%d do not fit (use xesn_predict_p2p)", G,
+                  h->N, h->I, O);
+        return -2;
+    }
+    *team_out = team, *ring_steps_out = XESN_FLOW_CHUNK;
+    return 0;
+}
+
+int xesn_predict_flow(xesn_reservoir* h, xesn_flow_plan* plan, const double* wout, int32_t O, int32_t G, int64_t n_cells,
+                      const int32_t* in_map, const double* fill, const int32_t* out_map, double* field, double* r,
+                      int32_t n_steps, double* pred, void* scratch, int64_t scratch_bytes, void* stream) {
+    XESN_REQUIRE(h && plan && wout && in_map && field && r && pred && scratch, "null pointer");
+    XESN_REQUIRE(plan->world >= 1 && plan->world <= XESN_MAX_WORLD && plan->rank >= 0 && plan->rank < plan->world, "bad world/rank");
+    XESN_REQUIRE(plan->src_dev && (plan->n_import == 0 || plan->import_cell_dev), "plan lacks tables");
+    XESN_REQUIRE(scratch_bytes >= xesn_predict_scratch_bytes(h, O, G, n_cells), "scratch too small");
+    XESN_REQUIRE_GROUPS(h, G);
+    int team = 0, upc = 0;
+    XESN_REQUIRE(predict_flow_eligible(h, O, G, &team, &upc), "configuration does not fit the dataflow forecast");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = h->N, I = h->I;
+    double* Ug = (double*)scratch;
+    double* drive = Ug + round_up((long long)G * I, 2);
+    double* r_alt = drive + round_up((long long)G * N, 2);
+    double* field_alt = r_alt + round_up((long long)G * N, 2);
+    double* area = field_alt + round_up(n_cells, 2);
+    const FlowLayout L = flow_layout(h, O, G, n_cells, team, true);
+    const long long ldp = (long long)n_steps + 1;
+    ProfScope prof(PROF_PREDICT, st);
+    strided_copy_kernel<<<(unsigned)((n_cells + 255) / 256), 256, 0, st>>>(field, pred, ldp, n_cells);
+    XESN_CUDA_OK(cudaGetLastError());
+    count_launch();
+    FlowRun f = {};
+    f.wout = wout, f.O = O, f.G = G, f.n_cells = n_cells, f.in_map = in_map, f.fill = fill, f.out_map = out_map;
+    f.src = plan->src_dev, f.import_cell = plan->import_cell_dev, f.n_import = plan->n_import;
+    f.exp_ptr = plan->exp_ptr_dev, f.exp_peer = plan->exp_peer_dev, f.exp_slot = plan->exp_slot_dev;
+    f.team = team, f.upc = upc;
+    f.field = field, f.field_alt = field_alt, f.r = r, f.r_alt = r_alt, f.n_steps = n_steps, f.pred = pred, f.ldp = ldp;
+    f.r_ring = area + L.r_ring, f.world = plan->world;
+    for (int par = 0; par < 2; ++par) {
+        f.ring[par] = reinterpret_cast<double*>(plan->ring_ptrs[par * plan->world + plan->rank]);
+        XESN_REQUIRE(f.ring[par], "plan lacks this rank's ring");
+        for (int k = 0; k < plan->world; ++k) f.peer_ring[par][k] = reinterpret_cast<double*>(plan->ring_ptrs[par * plan->world + k]);
+    }
+    XESN_REQUIRE(f.ring[0] != f.ring[1], "the two ring parities must be different buffers");
+    return flow_run(h, f, &plan->launches_done, st);
+}
+
+int xesn_memset_async(void* dst, int32_t byte_value, int64_t bytes, void* stream) {
+    XESN_CUDA_OK(cudaMemsetAsync(dst, byte_value, (size_t)bytes, (cudaStream_t)stream));
     return 0;
 }
 

@@ -133,6 +133,51 @@ struct PredictLoopArgs {
 };
 int launch_predict_loop(const PredictLoopArgs& a, int num_sms, cudaStream_t stream);
 
+// ---- dataflow closed loop of several reservoirs (predict_flow.cu) ------------------------------
+constexpr int XESN_FLOW_MAX_TEAM = 16;   // CTAs per reservoir
+constexpr int XESN_FLOW_CHUNK = 256;     // steps per launch = rows of the rings
+struct PredictFlowArgs {
+    const int* indptr;
+    const int* indices;
+    const double* values;
+    const double* Win;
+    const double* bias;
+    long long values_gs, win_gs, bias_gs;
+    int param_groups;
+    const double* alpha_g;
+    double alpha;
+    const double* Wout;       // [G][O][N]
+    int N, I, O, G;
+    int team, upc;            // CTAs per group, units per CTA
+    int steps, ring_steps;    // steps of this launch (<= ring_steps)
+    int col0;                 // step n of this launch is trajectory column col0 + n
+    const int* src;           // [G][I] ring slot feeding the input | -1-k: fill[k] | INT_MIN: static cell of `field`
+    const int* in_map;        // [G][I] cell index (step 1 of a launch reads `field`)
+    const double* fill;
+    const double* field;      // [n_cells] field entering the launch
+    double* field_out;        // [n_cells] field leaving it (local outputs + imported cells written)
+    const int* out_map;       // [G][O] cell of every local output (nullptr: g*O+o)
+    const int* import_cell;   // [n_import] cell of every imported ring slot (slots G*O ..)
+    int n_import;
+    const double* r_in;       // [G][N] states entering the launch
+    double* r_out;            // [G][N] states leaving it
+    double* r_ring;           // [G][ring_steps][N]              pre-filled "unset"
+    double* part_ring;        // [G*O + n_import][ring_steps][team] pre-filled "unset"
+    double* pred;             // [n_cells][ldp]
+    long long ldp;
+    const int* exp_ptr;       // [G*O + 1] exports of every local output (nullptr: none)
+    const int* exp_peer;      // peer index of an export
+    const int* exp_slot;      // ring slot in that peer's ring
+    double* peer_ring[XESN_MAX_WORLD];  // the peers' partial rings (current parity) as mapped in this process
+    int mask_nan;
+    int* status;
+};
+size_t predict_flow_smem(int N, int I, int O, int upc);
+bool predict_flow_geometry(int N, int I, int O, int G, int num_sms, int* team_out, int* upc_out);
+int launch_flow_src(const int* in_map, const int* out_map, int* owner, int* src, long long n_cells, long long n_slots,
+                    long long n_inputs, cudaStream_t stream);
+int launch_predict_flow(const PredictFlowArgs& a, cudaStream_t stream);
+
 // ---- barrier-free closed loop of one reservoir (predict_pull.cu) --------------------------------
 struct PredictPullArgs {
     const int* indptr;

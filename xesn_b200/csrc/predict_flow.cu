@@ -1,0 +1,325 @@
+// Dataflow closed-loop forecast of SEVERAL reservoirs (LazyESN groups, ensemble members) -- sm_100a.
+//
+//      for n = 1 .. n_steps:   r_g <- update(r_g, gather_g(field));   field[out_map_g] <- Wout_g r_g
+//      (reference xesn/lazyesn.py:226-236: _update_nd, _readout and the re-halo `overlap` per step)
+//
+// predict_loop.cu runs the same loop with two software grid barriers per step (all 148 CTAs meet twice,
+// ~8-11 us per step for 16 groups of N=2000) and, across GPUs, stores every predicted cell to every rank
+// behind a system-scope fence and a flag handshake.  But a step of group g only depends on
+//   (1) the new state of g itself, spread over the `team` CTAs that own g, and
+//   (2) the new outputs of the few cells g reads: its own and the halo cells of its neighbours.
+// So nothing here is a barrier.  A team of CTAs owns one group; a CTA keeps its rows of Win and its COLUMNS of
+// Wout in shared memory, and after updating its units it forms its contribution to every output of the
+// group,  part[o][c] = sum_{i in slice c} Wout[o][i] r[i],  and publishes it together with its slice of r.
+// Rings in global memory pre-filled with the "unset" pattern carry both (the data is its own flag,
+// recur_body.cuh): a consumer polls exactly the values it needs and adds the `team` contributions of an
+// output in CTA order (deterministic).  One store -> poll hop per step instead of two grid barriers.
+//
+// Multi-GPU (one process per GPU, groups split in slabs): a cell that a group on ANOTHER rank reads is
+// pushed, contribution by contribution, into that rank's ring with plain 8-byte NVLink P2P stores
+// (peer-mapped memory, CUDA IPC) -- only those cells, only to the ranks that read them (the `overlap`-deep
+// strips of SURVEY.md section 8e), no fence and no flag: the imported slot is polled like a local one.
+#include <algorithm>
+#include <climits>
+
+#include "common.cuh"
+#include "kernels.cuh"
+#include "recur_body.cuh"
+
+namespace xesn {
+namespace {
+
+using namespace recur;
+
+constexpr int PF_THREADS = 512;
+constexpr int PF_WARPS = PF_THREADS / 32;
+constexpr int PF_IO_THREADS = 64;                       // the last two warps poll inputs / trajectory values
+constexpr int PF_R_THREADS = PF_THREADS - PF_IO_THREADS;  // the others refresh the state copy
+constexpr int PF_KREG = 8, PF_KTAIL = 4;
+constexpr int PF_POLL_BATCH = 4;
+
+__device__ __forceinline__ double ld_flag_sys(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];\n" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_flag_sys(double* p, double v) {
+    v = publishable(v);
+    asm volatile("st.relaxed.sys.global.f64 [%0], %1;\n" ::"l"(p), "d"(v) : "memory");
+}
+
+// sum over the team of the contributions to ring slot `slot` at ring row `row`, in CTA order
+__device__ __forceinline__ double team_sum(const PredictFlowArgs& p, long long slot, int row, bool& aborted) {
+    const double* q = p.part_ring + (slot * p.ring_steps + row) * p.team;
+    double v[XESN_FLOW_MAX_TEAM];
+    unsigned pend = (p.team >= 32) ? 0xffffffffu : ((1u << p.team) - 1u);
+    int spins = 0;
+    while (true) {
+#pragma unroll
+        for (int c = 0; c < XESN_FLOW_MAX_TEAM; ++c)
+            if (pend & (1u << c)) v[c] = ld_flag_sys(q + c);
+#pragma unroll
+        for (int c = 0; c < XESN_FLOW_MAX_TEAM; ++c)
+            if ((pend & (1u << c)) && !unset(v[c])) pend &= ~(1u << c);
+        if (!pend || aborted) break;
+        aborted = poll_expired(spins, p.status);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < XESN_FLOW_MAX_TEAM; ++c)
+        if (c < p.team) s += v[c];
+    return s;
+}
+
+__global__ void __launch_bounds__(PF_THREADS, 1) predict_flow_kernel(PredictFlowArgs p) {
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = blockIdx.x / p.team, c = blockIdx.x % p.team;
+    const int N = p.N, I = p.I, O = p.O, upc = p.upc;
+    const int u0 = c * upc, u1 = min(N, u0 + upc), nu = u1 - u0;
+    const int ldw = I + 1 + (I & 1);  // odd row pitch (in doubles): conflict-free reads of one row per lane
+    const int n_pad = (N + 1) & ~1;
+    double* s_r = smem;                              // [n_pad] copy of r_{n-1}
+    double* s_win = s_r + n_pad;                     // [upc][ldw]
+    double* s_wout = s_win + (size_t)upc * ldw;      // [O][upc]
+    double* s_u = s_wout + (size_t)O * upc;          // [I + (I & 1)]
+    double* s_rnew = s_u + I + (I & 1);              // [upc]
+    int* s_src = reinterpret_cast<int*>(s_rnew + upc);  // [I]
+
+    const int pg = g % max(p.param_groups, 1);
+    const double* win = p.Win + (long long)pg * p.win_gs;
+    const double* wout = p.Wout + (long long)g * O * N;
+    for (int e = tid; e < nu * I; e += PF_THREADS) s_win[(e / I) * ldw + (e % I)] = win[(long long)(u0 + e / I) * I + e % I];
+    for (int e = tid; e < O * upc; e += PF_THREADS) {
+        const int o = e / upc, il = e % upc;
+        s_wout[e] = il < nu ? wout[(long long)o * N + u0 + il] : 0.0;
+    }
+    for (int k = tid; k < I; k += PF_THREADS) s_src[k] = p.src[(long long)g * I + k];
+    const double* r_g = p.r_in + (long long)g * N;   // in/out are different arrays: a fast CTA may finish before a team mate has loaded
+    for (int i = tid; i < n_pad; i += PF_THREADS) s_r[i] = i < N ? r_g[i] : 0.0;
+
+    // ---- owners: one unit per thread, head of its row of W in registers ----
+    const bool owner = tid < nu;
+    const int unit = u0 + tid;
+    int row_lo = 0, row_len = 0;
+    double r_cur = 0.0, bias = 0.0;
+    double hv[PF_KREG];
+    int ho[PF_KREG];
+    if (owner) {
+        row_lo = p.indptr[unit];
+        row_len = p.indptr[unit + 1] - row_lo;
+        r_cur = r_g[unit];
+        bias = p.bias[(long long)pg * p.bias_gs + unit];
+    }
+    const double* w_values = p.values + (long long)pg * p.values_gs;
+#pragma unroll
+    for (int k = 0; k < PF_KREG; ++k) {
+        const bool in = k < row_len;
+        hv[k] = in ? w_values[row_lo + k] : 0.0;
+        ho[k] = in ? p.indices[row_lo + k] : 0;
+    }
+    const double alpha = p.alpha_g ? p.alpha_g[pg] : p.alpha, oma = 1.0 - alpha;
+    const bool leader = c == 0;
+    const long long slot0 = (long long)g * O;      // ring slots of this group's outputs
+    double* r_ring = p.r_ring + (long long)g * p.ring_steps * N;
+    const bool vec2 = (N % 2 == 0) && ((reinterpret_cast<uintptr_t>(r_ring) & 15) == 0);
+    bool aborted = false;
+    __syncthreads();
+
+    for (int n = 1; n <= p.steps; ++n) {
+        // ================= phase A: everything step n consumes =================
+        if (tid >= PF_R_THREADS) {
+            // inputs of step n: the outputs of step n-1 (ring row n-2), or the field entering the launch
+            const int t = tid - PF_R_THREADS;
+            for (int k = t; k < I; k += PF_IO_THREADS) {
+                const int src = s_src[k];
+                double x;
+                if (src < 0 && src != INT_MIN) {
+                    x = p.fill[-1 - src];
+                } else if (n == 1 || src == INT_MIN) {
+                    x = p.field[p.in_map[(long long)g * I + k]];
+                } else {
+                    x = team_sum(p, src, n - 2, aborted);
+                }
+                s_u[k] = (p.mask_nan && x != x) ? 0.0 : x;
+            }
+            // leader: trajectory column of step n-1
+            if (leader && n >= 2)
+                for (int o = t; o < O; o += PF_IO_THREADS) {
+                    const long long cell = p.out_map ? (long long)p.out_map[slot0 + o] : slot0 + o;
+                    p.pred[cell * p.ldp + p.col0 + n - 1] = team_sum(p, slot0 + o, n - 2, aborted);
+                }
+        } else if (n >= 2) {
+            // the other slices of r_{n-1} (ring row n-2): coalesced data-as-flag polling
+            const double* row = r_ring + (long long)(n - 2) * N;
+            if (owner) s_r[unit] = r_cur;
+            if (vec2) {
+                const int n2 = N >> 1;
+                for (int q0 = tid; q0 < n2; q0 += PF_R_THREADS * PF_POLL_BATCH) {
+                    double2 v[PF_POLL_BATCH];
+                    unsigned pend = 0;
+#pragma unroll
+                    for (int b = 0; b < PF_POLL_BATCH; ++b) {
+                        const int q = q0 + b * PF_R_THREADS;
+                        if (q < n2 && !(2 * q >= u0 && 2 * q + 1 < u1)) pend |= 1u << b;
+                    }
+                    const unsigned mine = pend;
+                    int spins = 0;
+                    while (pend && !aborted) {
+#pragma unroll
+                        for (int b = 0; b < PF_POLL_BATCH; ++b)
+                            if (pend & (1u << b)) v[b] = ld_flag2(row + 2 * (q0 + b * PF_R_THREADS));
+#pragma unroll
+                        for (int b = 0; b < PF_POLL_BATCH; ++b)
+                            if ((pend & (1u << b)) && !unset(v[b].x) && !unset(v[b].y)) pend &= ~(1u << b);
+                        if (pend) aborted = poll_expired(spins, p.status);
+                    }
+#pragma unroll
+                    for (int b = 0; b < PF_POLL_BATCH; ++b)
+                        if (mine & (1u << b)) {
+                            const int q = q0 + b * PF_R_THREADS;
+                            // a piece that straddles the edge of my slice: keep my own (newer) half
+                            if (!(2 * q >= u0 && 2 * q < u1)) s_r[2 * q] = v[b].x;
+                            if (!(2 * q + 1 >= u0 && 2 * q + 1 < u1)) s_r[2 * q + 1] = v[b].y;
+                        }
+                }
+            } else {
+                for (int q = tid; q < N; q += PF_R_THREADS) {
+                    if (q >= u0 && q < u1) continue;
+                    double v = ld_flag(row + q);
+                    int spins = 0;
+                    while (unset(v) && !aborted) {
+                        aborted = poll_expired(spins, p.status);
+                        v = ld_flag(row + q);
+                    }
+                    s_r[q] = v;
+                }
+            }
+        }
+        if (tid >= PF_R_THREADS && n >= 2 && owner) s_r[unit] = r_cur;  // owners among the I/O threads (upc > 448)
+        __syncthreads();
+
+        // ================= phase B: update of the owned units =================
+        if (owner) {
+            double gth[PF_KREG];
+#pragma unroll
+            for (int k = 0; k < PF_KREG; ++k) gth[k] = s_r[ho[k]];
+            double wr = 0.0;
+#pragma unroll
+            for (int k = 0; k < PF_KREG; ++k)
+                if (k < row_len) wr = __dadd_rn(wr, __dmul_rn(hv[k], gth[k]));
+            for (int k = PF_KREG; k < row_len; ++k)
+                wr = __dadd_rn(wr, __dmul_rn(__ldg(w_values + row_lo + k), s_r[__ldg(p.indices + row_lo + k)]));
+            const double* wrow = s_win + (size_t)tid * ldw;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int k = 0;
+#pragma unroll 2
+            for (; k + 3 < I; k += 4) {
+                a0 = fma(wrow[k], s_u[k], a0);
+                a1 = fma(wrow[k + 1], s_u[k + 1], a1);
+                a2 = fma(wrow[k + 2], s_u[k + 2], a2);
+                a3 = fma(wrow[k + 3], s_u[k + 3], a3);
+            }
+            for (; k < I; ++k) a0 = fma(wrow[k], s_u[k], a0);
+            const double pre = __dadd_rn(__dadd_rn(wr, (a0 + a1) + (a2 + a3)), bias);
+            r_cur = leaky(pre, r_cur, alpha, oma);
+            st_flag(r_ring + (long long)(n - 1) * N + unit, r_cur);
+            s_rnew[tid] = r_cur;
+        } else if (tid < upc) {
+            s_rnew[tid] = 0.0;
+        }
+        __syncthreads();
+
+        // ================= phase C: this CTA's contribution to every output of the group =================
+        for (int o = warp; o < O; o += PF_WARPS) {
+            const double* w = s_wout + (size_t)o * upc;
+            double a = 0.0;
+            for (int il = lane; il < upc; il += 32) a = fma(w[il], s_rnew[il], a);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+            if (lane == 0) {
+                const long long slot = slot0 + o;
+                st_flag_sys(p.part_ring + (slot * p.ring_steps + (n - 1)) * p.team + c, a);
+                // cells that groups on other ranks read: the same contribution, into their rings (NVLink P2P store)
+                if (p.exp_ptr)
+                    for (int e = p.exp_ptr[slot]; e < p.exp_ptr[slot + 1]; ++e)
+                        st_flag_sys(p.peer_ring[p.exp_peer[e]] + ((long long)p.exp_slot[e] * p.ring_steps + (n - 1)) * p.team + c, a);
+            }
+        }
+    }
+
+    // ================= epilogue: last trajectory column, the field leaving the launch, the states =================
+    if (tid >= PF_R_THREADS) {
+        const int t = tid - PF_R_THREADS;
+        if (leader)
+            for (int o = t; o < O; o += PF_IO_THREADS) {
+                const long long cell = p.out_map ? (long long)p.out_map[slot0 + o] : slot0 + o;
+                const double v = team_sum(p, slot0 + o, p.steps - 1, aborted);
+                p.pred[cell * p.ldp + p.col0 + p.steps] = v;
+                p.field_out[cell] = v;
+            }
+        if (blockIdx.x == 0)  // imported cells: what this rank's groups read at step 1 of the next launch
+            for (int j = t; j < p.n_import; j += PF_IO_THREADS)
+                p.field_out[p.import_cell[j]] = team_sum(p, (long long)p.G * O + j, p.steps - 1, aborted);
+    }
+    if (owner) p.r_out[(long long)g * N + unit] = r_cur;
+}
+
+// src[g][k]: ring slot that feeds input k of group g (single GPU: every produced cell is local)
+__global__ void flow_owner_kernel(const int* __restrict__ out_map, int* __restrict__ owner, long long n_slots) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n_slots) owner[out_map ? out_map[s] : s] = (int)s;
+}
+__global__ void flow_src_kernel(const int* __restrict__ in_map, const int* __restrict__ owner, int* __restrict__ src,
+                                long long n) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int m = in_map[k];
+    src[k] = m < 0 ? m : (owner[m] >= 0 ? owner[m] : INT_MIN);
+}
+
+}  // namespace
+
+size_t predict_flow_smem(int N, int I, int O, int upc) {
+    const int ldw = I + 1 + (I & 1);
+    const size_t n_pad = (size_t)((N + 1) & ~1);
+    return sizeof(double) * (n_pad + (size_t)upc * ldw + (size_t)O * upc + (size_t)(I + (I & 1)) + upc) +
+           sizeof(int) * (size_t)(I + 2);
+}
+
+// team size / units per CTA of the dataflow forecast; false when the configuration does not fit (caller falls back)
+bool predict_flow_geometry(int N, int I, int O, int G, int num_sms, int* team_out, int* upc_out) {
+    if (G < 1 || G > num_sms) return false;
+    int team = std::min(num_sms / G, XESN_FLOW_MAX_TEAM);
+    if (team < 1) return false;
+    const int upc = ((N + team - 1) / team + 7) & ~7;
+    team = (N + upc - 1) / upc;
+    if (upc > PF_THREADS) return false;
+    if (predict_flow_smem(N, I, O, upc) > 200 * 1024) return false;
+    *team_out = team, *upc_out = upc;
+    return true;
+}
+
+int launch_flow_src(const int* in_map, const int* out_map, int* owner, int* src, long long n_cells, long long n_slots,
+                    long long n_inputs, cudaStream_t stream) {
+    XESN_CUDA_OK(cudaMemsetAsync(owner, 0xFF, sizeof(int) * (size_t)n_cells, stream));
+    flow_owner_kernel<<<(unsigned)((n_slots + 255) / 256), 256, 0, stream>>>(out_map, owner, n_slots);
+    flow_src_kernel<<<(unsigned)((n_inputs + 255) / 256), 256, 0, stream>>>(in_map, owner, src, n_inputs);
+    XESN_CUDA_OK(cudaGetLastError());
+    count_launch(2);
+    return 0;
+}
+
+int launch_predict_flow(const PredictFlowArgs& a, cudaStream_t stream) {
+    if (a.steps <= 0) return 0;
+    const size_t smem = predict_flow_smem(a.N, a.I, a.O, a.upc);
+    XESN_CUDA_OK(cudaFuncSetAttribute(predict_flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    PredictFlowArgs args = a;
+    void* kargs[] = {&args};
+    XESN_CUDA_OK(cudaLaunchCooperativeKernel((void*)predict_flow_kernel, dim3(a.G * a.team), dim3(PF_THREADS), kargs, smem,
+                                             stream));
+    count_launch();
+    return 0;
+}
+
+}  // namespace xesn

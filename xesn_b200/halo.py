@@ -119,3 +119,64 @@ def blocks_to_wout(blocks, grid, O, N):
     else:
         raise NotImplementedError("LazyESN: Wout block layout is defined for 1 to 3 space axes")
     return np.ascontiguousarray(w.reshape(-1, O, N))
+
+
+SRC_STATIC = -2**31   # src entry of an input cell that no group produces (its value never changes)
+
+
+def flow_tables(in_map, out_map, n_cells, world, rank):
+    """Tables of the dataflow forecast kernel (csrc/predict_flow.cu) for rank `rank` of `world` ranks that own
+    contiguous, equally sized slabs of the group list (`partition_groups`).  Replaces the whole-field re-halo of
+    xesn/lazyesn.py:235 by neighbour-only traffic: a rank IMPORTS exactly the cells its groups read that groups of
+    other ranks produce, and EXPORTS exactly the cells other ranks import from it.
+
+    in_map (G_all, I) / out_map (G_all, O): global cell indices (in_map < 0: constant fill).  Ring slots of a rank:
+    s < G*O = its local output (g, o); G*O + j = its j-th imported cell (sorted by cell index).  Returns a dict:
+      src (G, I) int32        ring slot feeding input k of local group g | negative fill code | SRC_STATIC
+      import_cell (n_imp,)    cell of every import slot
+      import_owner (n_imp,)   rank that produces it
+      exp_ptr (G*O+1,), exp_peer, exp_slot : CSR over the local slots of (importing rank, slot in its ring)
+      n_import_all (world,)   number of import slots of every rank (ring sizes)
+    Every rank can compute every rank's tables: no communication is needed to build them."""
+    G_all, O = out_map.shape
+    if G_all % world:
+        raise ValueError(f"flow_tables: {G_all} groups do not divide over {world} ranks")
+    per = G_all // world
+    owner = np.full(n_cells, -1, dtype=np.int64)          # global slot g*O + o producing a cell
+    owner[out_map.reshape(-1)] = np.arange(G_all * O)
+
+    def imports_of(p):
+        m = in_map[p * per:(p + 1) * per]
+        cells = np.unique(m[m >= 0])
+        own = owner[cells]
+        return cells[(own >= 0) & ((own // O < p * per) | (own // O >= (p + 1) * per))]
+
+    imports = [imports_of(p) for p in range(world)]
+    mine = imports[rank]
+    g0 = rank * per
+    m = in_map[g0:g0 + per].astype(np.int64)
+    own = owner[np.maximum(m, 0)]
+    local = (own >= g0 * O) & (own < (g0 + per) * O)
+    src = np.where(m < 0, m, np.where(own < 0, SRC_STATIC,
+                                      np.where(local, own - g0 * O, per * O + np.searchsorted(mine, np.maximum(m, 0)))))
+    entries = []          # (local slot, peer, slot in the peer's ring)
+    for p in range(world):
+        if p == rank:
+            continue
+        own_p = owner[imports[p]]
+        sel = np.nonzero((own_p >= g0 * O) & (own_p < (g0 + per) * O))[0]
+        entries += [(int(own_p[j] - g0 * O), p, per * O + int(j)) for j in sel]
+    entries.sort()
+    exp_ptr = np.zeros(per * O + 1, dtype=np.int32)
+    for s_, _, _ in entries:
+        exp_ptr[s_ + 1] += 1
+    exp_ptr = np.cumsum(exp_ptr).astype(np.int32)
+    return {
+        "src": np.ascontiguousarray(src.astype(np.int32)),
+        "import_cell": np.ascontiguousarray(mine.astype(np.int32)),
+        "import_owner": (owner[mine] // O // per).astype(np.int32),
+        "exp_ptr": exp_ptr,
+        "exp_peer": np.asarray([e[1] for e in entries], dtype=np.int32),
+        "exp_slot": np.asarray([e[2] for e in entries], dtype=np.int32),
+        "n_import_all": np.asarray([len(i) for i in imports], dtype=np.int64),
+    }

@@ -253,27 +253,39 @@ class LazyESN(ESN):
 
     def _upload_local(self, y, in_map, out_map, tslice):
         """Upload only the cells this rank's groups touch; returns the device rows, the maps
-        re-indexed to those rows and the per-row mask `isnan(first time sample)`."""
+        re-indexed to those rows and the per-row mask `isnan(first time sample)`.
+
+        Host inputs are copied run by run: the cells of a slab of groups are a few runs of consecutive rows
+        of the flattened field (the slab itself plus its halo strips), so every run is one strided
+        host-to-device copy straight from the caller's (ideally pinned) buffer -- no gathered host copy."""
         torch = _torch()
         dev = self._device_reservoir().device
+        used = np.unique(np.concatenate([in_map[in_map >= 0].ravel(), out_map.ravel()]))
         if isinstance(y, torch.Tensor):
             flat = y.reshape(-1, y.shape[-1])[:, tslice]
-            used = np.unique(np.concatenate([in_map[in_map >= 0].ravel(), out_map.ravel()]))
-            rows = flat[torch.from_numpy(used).to(flat.device)].to(device=dev, dtype=torch.float64).contiguous()
-            masked_rows = torch.isnan(rows[:, 0]).cpu().numpy()
         else:
             data = getattr(y, "data", y) if getattr(y, "dims", None) is not None else y
             if hasattr(data, "compute"):
                 data = data.compute()
-            flat = np.asarray(data, dtype=np.float64).reshape(-1, data.shape[-1])[:, tslice]
-            used = np.unique(np.concatenate([in_map[in_map >= 0].ravel(), out_map.ravel()]))
-            host = torch.from_numpy(np.ascontiguousarray(flat[used]))
-            try:
-                host = host.pin_memory()
-            except Exception:  # pragma: no cover
-                pass
-            rows = host.to(dev, non_blocking=True)
-            masked_rows = np.isnan(flat[used, 0])
+            arr = np.asarray(data)
+            if arr.dtype != np.float64:
+                arr = arr.astype(np.float64)
+            flat = torch.from_numpy(arr.reshape(-1, arr.shape[-1]))[:, tslice]
+        if flat.is_cuda:
+            rows = flat[torch.from_numpy(used).to(flat.device)].to(device=dev, dtype=torch.float64).contiguous()
+            masked_rows = torch.isnan(rows[:, 0]).cpu().numpy()
+        else:
+            breaks = np.nonzero(np.diff(used) != 1)[0] + 1
+            starts = np.concatenate([[0], breaks])
+            ends = np.concatenate([breaks, [used.size]])
+            if flat.dtype != torch.float64 or len(starts) > 64:
+                host = flat[torch.from_numpy(used)].to(torch.float64).contiguous()
+                rows = host.to(dev, non_blocking=True)
+            else:
+                rows = torch.empty((used.size, flat.shape[1]), dtype=torch.float64, device=dev)
+                for a, b in zip(starts, ends):
+                    rows[a:b].copy_(flat[int(used[a]):int(used[b - 1]) + 1], non_blocking=True)
+            masked_rows = torch.isnan(flat[torch.from_numpy(used), 0]).numpy() if flat.shape[1] else np.zeros(used.size, bool)
         lookup = np.full(int(used.max()) + 1 if used.size else 1, -1, dtype=np.int64)
         lookup[used] = np.arange(used.size)
         in_l = np.where(in_map >= 0, lookup[np.maximum(in_map, 0)], in_map).astype(np.int32)
@@ -335,11 +347,22 @@ class LazyESN(ESN):
             else:
                 # latency-bound shapes: one persistent kernel per rank with the exchange inside (P2P);
                 # bandwidth-bound shapes (huge Win/Wout traffic per step): per-step launches + NCCL
-                small = (G * N * I * 8 <= (64 << 20) and world <= 8
-                         and os.environ.get("XESN_B200_EXCHANGE", "p2p") == "p2p")
-                multi = self._predict_multi if small else self._predict_multi_nccl
-                multi(lib, res, wout, G, g0, n_cells, t_in, t_fill, t_out, out_map, field, r,
-                      n_steps, pred, scratch, nb, st)
+                # engines: "flow" (default) = dataflow kernel, neighbour-only P2P stores of the halo cells;
+                # "p2p" = persistent kernel with grid barriers, every cell to every rank; "nccl" = per-step launches
+                # and an NCCL exchange (also the fallback for shapes whose Win/Wout traffic per step is HBM-sized)
+                engine = os.environ.get("XESN_B200_EXCHANGE", "flow")
+                small = G * N * I * 8 <= (64 << 20) and world <= 8
+                team, ring_steps = ctypes.c_int32(0), ctypes.c_int32(0)
+                if engine == "flow" and lib.xesn_flow_geometry(res.handle, O, G, ctypes.byref(team),
+                                                               ctypes.byref(ring_steps)) != 0:
+                    engine = "p2p"
+                if engine == "flow":
+                    self._predict_multi_flow(lib, res, wout, G, n_cells, in_map, out_map, t_in, t_fill, t_out, field, r,
+                                             n_steps, pred, scratch, nb, st, team.value, ring_steps.value)
+                else:
+                    multi = self._predict_multi if (small and engine == "p2p") else self._predict_multi_nccl
+                    multi(lib, res, wout, G, g0, n_cells, t_in, t_fill, t_out, out_map, field, r,
+                          n_steps, pred, scratch, nb, st)
         return pred
 
     def _initial_field(self, y, n_spinup, dev):
@@ -390,11 +413,93 @@ class LazyESN(ESN):
             dist.all_gather_into_tensor(gathered, rows)
             pred[owned.reshape(-1)] = gathered.reshape(-1, rows.shape[-1])
 
+    def _predict_multi_flow(self, lib, res, wout, G, n_cells, in_map, out_map, t_in, t_fill, t_out, field, r, n_steps,
+                            pred, scratch, nb, st, team, ring_steps):
+        """One process per GPU, dataflow forecast (csrc/predict_flow.cu): every rank runs its slab of groups; per step a
+        rank pushes exactly the cells that groups of OTHER ranks read (the `overlap`-deep halo strips) into the rings
+        of exactly those ranks with NVLink P2P stores -- the neighbour exchange of lazyesn.py:235 without a fence, a
+        flag or a collective.  The trajectory rows are gathered once at the end."""
+        torch = _torch()
+        rank, world = _dist()
+        O = self.n_output
+        dev = res.device
+        plan = self._flow_plan(lib, in_map, out_map, n_cells, world, rank, G, team, ring_steps, dev, st)
+        _lib.check(lib.xesn_predict_flow(res.handle, ctypes.byref(plan["c"]), _ptr(wout), O, G, n_cells, _ptr(t_in),
+                                         _ptr(t_fill), _ptr(t_out), _ptr(field), _ptr(r), n_steps, _ptr(pred),
+                                         _ptr(scratch), nb, st))
+        self._gather_owned_rows(pred, out_map, world, rank, dev)
+
+    def _gather_owned_rows(self, pred, out_map, world, rank, dev):
+        """Assemble the trajectory on every rank: each rank contributes the rows (cells) its groups predict."""
+        torch = _torch()
+        import torch.distributed as dist
+        per = out_map.shape[0] // world * out_map.shape[1]
+        owned_np = out_map.reshape(world, -1)
+        contiguous = all(np.array_equal(np.sort(owned_np[k]), np.arange(k * per, (k + 1) * per)) for k in range(world))
+        if contiguous:
+            lo, hi = rank * per, (rank + 1) * per
+            dist.all_gather_into_tensor(pred, pred[lo:hi])
+        else:
+            owned = torch.from_numpy(owned_np.astype(np.int64)).to(dev)
+            rows = pred[owned[rank]].contiguous()
+            gathered = torch.empty((world,) + tuple(rows.shape), dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(gathered, rows)
+            pred[owned.reshape(-1)] = gathered.reshape(-1, rows.shape[-1])
+
+    def _flow_plan(self, lib, in_map, out_map, n_cells, world, rank, G, team, ring_steps, dev, st):
+        """Tables + peer-mapped rings of the dataflow forecast, cached per geometry.  Building them is collective
+        (CUDA IPC handles go through torch.distributed once)."""
+        torch = _torch()
+        import torch.distributed as dist
+        key = ("flow", n_cells, world, int(in_map.shape[0]), team, ring_steps)
+        if self._p2p is not None and self._p2p.get("key") == key:
+            return self._p2p
+        self._p2p_release()
+        tb = _halo.flow_tables(in_map, out_map, n_cells, world, rank)
+        O = out_map.shape[1]
+        n_imp = tb["n_import_all"]
+        dev_t = {k: torch.from_numpy(tb[k]).to(dev) for k in ("src", "import_cell", "exp_ptr", "exp_peer", "exp_slot")}
+        ring_bytes = lambda p: int((G * O + int(n_imp[p])) * ring_steps * team * 8)  # noqa: E731
+        own, handles = {}, {}
+        for par in range(2):
+            ptr = ctypes.c_void_p()
+            h = (ctypes.c_uint8 * 64)()
+            _lib.check(lib.xesn_p2p_alloc(ring_bytes(rank), ctypes.byref(ptr), ctypes.cast(h, ctypes.c_void_p)))
+            _lib.check(lib.xesn_memset_async(ptr, 0xFF, ring_bytes(rank), st))
+            own[par], handles[par] = ptr.value, bytes(h)
+        torch.cuda.synchronize(dev)
+        everyone = [None] * world
+        dist.all_gather_object(everyone, handles)
+        importers = set(int(p) for p in tb["exp_peer"])
+        plan = _lib.FlowPlan()
+        plan.n_import = int(n_imp[rank])
+        plan.src_dev, plan.import_cell_dev = _ptr(dev_t["src"]), _ptr(dev_t["import_cell"])
+        has_exports = len(tb["exp_peer"]) > 0
+        plan.exp_ptr_dev = _ptr(dev_t["exp_ptr"]) if has_exports else None
+        plan.exp_peer_dev = _ptr(dev_t["exp_peer"]) if has_exports else None
+        plan.exp_slot_dev = _ptr(dev_t["exp_slot"]) if has_exports else None
+        plan.world, plan.rank, plan.launches_done = world, rank, 0
+        opened = []
+        for par in range(2):
+            for k in range(world):
+                if k == rank:
+                    plan.ring_ptrs[par * world + k] = own[par]
+                elif k in importers:            # only the ranks that read cells of mine are mapped
+                    ptr = ctypes.c_void_p()
+                    buf = (ctypes.c_uint8 * 64).from_buffer_copy(everyone[k][par])
+                    _lib.check(lib.xesn_p2p_open(ctypes.cast(buf, ctypes.c_void_p), ctypes.byref(ptr)))
+                    plan.ring_ptrs[par * world + k] = ptr.value
+                    opened.append(ptr.value)
+        dist.barrier()   # every ring is armed ("unset") and mapped before any rank launches
+        self._p2p = {"key": key, "c": plan, "tables": dev_t, "own_flow": list(own.values()), "opened_flow": opened,
+                     "importers": sorted(importers), "n_import": int(n_imp[rank])}
+        return self._p2p
+
     def _p2p_buffers(self, lib, n_cells, world, rank):
         """Peer-mapped field buffers (2 parities) and step flags of every rank, opened through CUDA
         IPC handles exchanged with torch.distributed; cached per domain size."""
         import torch.distributed as dist
-        if self._p2p is not None and self._p2p["n_cells"] == n_cells and self._p2p["world"] == world:
+        if self._p2p is not None and self._p2p.get("key") == ("p2p", n_cells, world):
             return self._p2p
         self._p2p_release()  # other geometry: unmap the peers' buffers and free our own before allocating anew
         mine = {}
@@ -419,7 +524,8 @@ class LazyESN(ESN):
                 _lib.check(lib.xesn_p2p_open(ctypes.cast(buf, ctypes.c_void_p), ctypes.byref(ptr)))
                 slot[0][slot[1]] = ptr.value
         dist.barrier()
-        self._p2p = {"n_cells": n_cells, "world": world, "field": field, "flags": flags, "steps": 0, "own": mine}
+        self._p2p = {"key": ("p2p", n_cells, world), "n_cells": n_cells, "world": world, "field": field, "flags": flags,
+                     "steps": 0, "own": mine}
         return self._p2p
 
     def _p2p_release(self):
@@ -429,6 +535,12 @@ class LazyESN(ESN):
         if not p2p:
             return
         lib = _lib.load()
+        if "own_flow" in p2p:
+            for ptr in p2p["opened_flow"]:
+                lib.xesn_p2p_close(ptr)
+            for ptr in p2p["own_flow"]:
+                lib.xesn_p2p_free(ptr)
+            return
         own = set(p2p["own"].values())
         for ptr in set(p2p["field"][0]) | set(p2p["field"][1]) | set(p2p["flags"]):
             if ptr and ptr not in own:
