@@ -46,11 +46,12 @@ def case(shape, chunks, overlap, boundary, N, rank, engine):
     if rank == 0:
         depth = {a: overlap[a] for a in range(len(shape))}
         depth[len(shape)] = 0
+        ob = {names.index(k): v for k, v in boundary.items()} if isinstance(boundary, dict) else boundary  # oracle: by axis
         W = sp.csr_matrix(esn.W)
-        ref = oc.lazy_train(field[..., :350], chunks, depth, boundary, 5, 128, W, esn.Win, esn.bias_vector, 0.6, 1e-4)
+        ref = oc.lazy_train(field[..., :350], chunks, depth, ob, 5, 128, W, esn.Win, esn.bias_vector, 0.6, 1e-4)
         ref = ref.reshape(wg.shape)
         e1 = oc.max_normalised_err(wg, ref)
-        refp = oc.lazy_predict(field[..., 350:], chunks, depth, boundary, 15, 40, W, esn.Win, esn.bias_vector, 0.6, wg.reshape(ref.shape).reshape((-1,) + ref.shape[1:]).reshape(tuple(s // c for s, c in zip(shape, chunks)) + ref.shape[1:]))
+        refp = oc.lazy_predict(field[..., 350:], chunks, depth, ob, 15, 40, W, esn.Win, esn.bias_vector, 0.6, wg.reshape(ref.shape).reshape((-1,) + ref.shape[1:]).reshape(tuple(s // c for s, c in zip(shape, chunks)) + ref.shape[1:]))
         # white-noise data makes the closed loop unstable: compare per step, relative to the step's scale
         ax = tuple(range(pred.ndim - 1))
         rel = np.abs(pred - refp).max(axis=ax) / np.maximum(np.abs(refp).max(axis=ax), 1.0)
