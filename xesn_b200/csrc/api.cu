@@ -130,6 +130,8 @@ struct xesn_reservoir {
     // closed loop: NaN inputs read as 0 (LazyESN, xesn/lazyesn.py:362-364) instead of propagating (eager ESN)
     int mask_nan_inputs = 0;
     SolveCtx solve;  // side stream + events of the look-ahead Cholesky, per handle (= per device)
+    int* d_flow_tail_ptr = nullptr;  // predict_flow.cu: offsets of the rows' tails, cached for one (team, upc)
+    int flow_tail_team = 0, flow_tail_upc = 0;
 };
 static inline int gram_mode_effective(const xesn_reservoir* h) { return (h->gram_mode == 1 && h->leak_unit_range) ? 1 : 0; }
 
@@ -262,6 +264,7 @@ int xesn_reservoir_destroy(xesn_reservoir* h) {
     cudaFree(h->d_ro_partial);
     cudaFree(h->d_ro_counters);
     solve_ctx_destroy(h->solve);
+    cudaFree(h->d_flow_tail_ptr);
     delete h;
     return 0;
 }
@@ -777,8 +780,12 @@ static bool predict_pull_eligible(xesn_reservoir* h, int O, int G, long long n_c
 }
 
 // dataflow forecast (predict_flow.cu): several reservoirs, no grid barrier
-static bool predict_flow_eligible(xesn_reservoir* h, int O, int G, int* team, int* upc) {
-    return h->persistent_predict == 1 && G > 1 && predict_flow_geometry(h->N, h->I, O, G, h->num_sms, team, upc);
+static bool predict_flow_eligible(xesn_reservoir* h, int O, int G, int* team, int* upc, int* tail_cap = nullptr) {
+    int tc = 0;
+    const bool ok = h->persistent_predict == 1 && G > 1 &&
+                    predict_flow_geometry(h->N, h->I, O, G, h->num_sms, h->h_indptr.data(), team, upc, &tc);
+    if (ok && tail_cap) *tail_cap = tc;
+    return ok;
 }
 struct FlowLayout {
     long long r_ring, part_ring, src, owner, total;  // offsets in doubles from the start of the flow area
@@ -813,7 +820,7 @@ struct FlowRun {
     long long n_cells;
     const int32_t *in_map, *out_map, *src, *import_cell, *exp_ptr, *exp_peer, *exp_slot;
     const double* fill;
-    int n_import, team, upc;
+    int n_import, team, upc, tail_cap;
     double *field, *field_alt, *r, *r_alt, *pred, *r_ring;
     long long ldp;
     int n_steps;
@@ -823,7 +830,17 @@ struct FlowRun {
 };
 static int flow_run(xesn_reservoir* h, const FlowRun& f, uint32_t* launches_done, cudaStream_t st) {
     const int N = h->N;
+    if (h->flow_tail_team != f.team || h->flow_tail_upc != f.upc) {
+        std::vector<int> tp((size_t)f.team * (f.upc + 1));
+        predict_flow_tail_ptr(N, f.team, f.upc, h->h_indptr.data(), tp.data());
+        if (h->d_flow_tail_ptr) XESN_CUDA_OK(cudaFree(h->d_flow_tail_ptr));
+        h->d_flow_tail_ptr = nullptr;
+        XESN_CUDA_OK(cudaMalloc(&h->d_flow_tail_ptr, sizeof(int) * tp.size()));
+        XESN_CUDA_OK(cudaMemcpy(h->d_flow_tail_ptr, tp.data(), sizeof(int) * tp.size(), cudaMemcpyHostToDevice));
+        h->flow_tail_team = f.team, h->flow_tail_upc = f.upc;
+    }
     PredictFlowArgs a = {};
+    a.tail_cap = f.tail_cap, a.tail_ptr = h->d_flow_tail_ptr;
     a.indptr = h->d_indptr, a.indices = h->d_indices, a.values = h->d_values, a.Win = h->d_win, a.bias = h->d_bias;
     a.values_gs = h->values_gs, a.win_gs = h->win_gs, a.bias_gs = h->bias_gs, a.param_groups = h->n_param_groups;
     a.alpha_g = h->d_alpha_g, a.alpha = h->alpha, a.Wout = f.wout;
@@ -928,8 +945,8 @@ int xesn_predict(xesn_reservoir* h, const double* wout, int32_t O, int32_t G, in
         }
         return 0;
     }
-    int fteam = 0, fupc = 0;
-    if (predict_flow_eligible(h, O, G, &fteam, &fupc)) {
+    int fteam = 0, fupc = 0, ftail = 0;
+    if (predict_flow_eligible(h, O, G, &fteam, &fupc, &ftail)) {
         // several reservoirs on one GPU: dataflow kernel, every produced cell is local (no imports / exports)
         const FlowLayout L = flow_layout(h, O, G, n_cells, fteam, true);
         double* area = field_alt + round_up(n_cells, 2);
@@ -938,7 +955,7 @@ int xesn_predict(xesn_reservoir* h, const double* wout, int32_t O, int32_t G, in
         if ((rc = launch_flow_src(in_map, out_map, owner, src, n_cells, (long long)G * O, (long long)G * I, st))) return rc;
         FlowRun f = {};
         f.wout = wout, f.O = O, f.G = G, f.n_cells = n_cells, f.in_map = in_map, f.fill = fill, f.out_map = out_map;
-        f.src = src, f.team = fteam, f.upc = fupc;
+        f.src = src, f.team = fteam, f.upc = fupc, f.tail_cap = ftail;
         f.field = field, f.field_alt = field_alt, f.r = r, f.r_alt = r_alt, f.n_steps = n_steps, f.pred = pred, f.ldp = ldp;
         f.r_ring = area + L.r_ring, f.ring[0] = f.ring[1] = area + L.part_ring, f.world = 1;
         return flow_run(h, f, nullptr, st);
@@ -1054,8 +1071,8 @@ int xesn_predict_flow(xesn_reservoir* h, xesn_flow_plan* plan, const double* wou
     XESN_REQUIRE(plan->src_dev && (plan->n_import == 0 || plan->import_cell_dev), "plan lacks tables");
     XESN_REQUIRE(scratch_bytes >= xesn_predict_scratch_bytes(h, O, G, n_cells), "scratch too small");
     XESN_REQUIRE_GROUPS(h, G);
-    int team = 0, upc = 0;
-    XESN_REQUIRE(predict_flow_eligible(h, O, G, &team, &upc), "configuration does not fit the dataflow forecast");
+    int team = 0, upc = 0, tail_cap = 0;
+    XESN_REQUIRE(predict_flow_eligible(h, O, G, &team, &upc, &tail_cap), "configuration does not fit the dataflow forecast");
     cudaStream_t st = (cudaStream_t)stream;
     const int N = h->N, I = h->I;
     double* Ug = (double*)scratch;
@@ -1073,7 +1090,7 @@ int xesn_predict_flow(xesn_reservoir* h, xesn_flow_plan* plan, const double* wou
     f.wout = wout, f.O = O, f.G = G, f.n_cells = n_cells, f.in_map = in_map, f.fill = fill, f.out_map = out_map;
     f.src = plan->src_dev, f.import_cell = plan->import_cell_dev, f.n_import = plan->n_import;
     f.exp_ptr = plan->exp_ptr_dev, f.exp_peer = plan->exp_peer_dev, f.exp_slot = plan->exp_slot_dev;
-    f.team = team, f.upc = upc;
+    f.team = team, f.upc = upc, f.tail_cap = tail_cap;
     f.field = field, f.field_alt = field_alt, f.r = r, f.r_alt = r_alt, f.n_steps = n_steps, f.pred = pred, f.ldp = ldp;
     f.r_ring = area + L.r_ring, f.world = plan->world;
     for (int par = 0; par < 2; ++par) {

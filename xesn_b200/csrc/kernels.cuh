@@ -171,9 +171,13 @@ struct PredictFlowArgs {
     double* peer_ring[XESN_MAX_WORLD];  // the peers' partial rings (current parity) as mapped in this process
     int mask_nan;
     int* status;
+    int tail_cap;             // shared-memory capacity (entries) for the rows' tails beyond the register-resident head
+    const int* tail_ptr;      // [team][upc+1] offsets of every owned row's tail in that staging area
 };
-size_t predict_flow_smem(int N, int I, int O, int upc);
-bool predict_flow_geometry(int N, int I, int O, int G, int num_sms, int* team_out, int* upc_out);
+size_t predict_flow_smem(int N, int I, int O, int upc, int tail_cap);
+bool predict_flow_geometry(int N, int I, int O, int G, int num_sms, const int* indptr, int* team_out, int* upc_out,
+                           int* tail_cap_out);
+void predict_flow_tail_ptr(int N, int team, int upc, const int* indptr, int* out);
 int launch_flow_src(const int* in_map, const int* out_map, int* owner, int* src, long long n_cells, long long n_slots,
                     long long n_inputs, cudaStream_t stream);
 int launch_predict_flow(const PredictFlowArgs& a, cudaStream_t stream);

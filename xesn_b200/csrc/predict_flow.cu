@@ -49,15 +49,17 @@ __device__ __forceinline__ void st_flag_sys(double* p, double v) {
 }
 
 // sum over the team of the contributions to ring slot `slot` at ring row `row`, in CTA order
+// (slots written by peer GPUs are polled at system scope, local ones at GPU scope)
 __device__ __forceinline__ double team_sum(const PredictFlowArgs& p, long long slot, int row, bool& aborted) {
     const double* q = p.part_ring + (slot * p.ring_steps + row) * p.team;
+    const bool imported = slot >= (long long)p.G * p.O;
     double v[XESN_FLOW_MAX_TEAM];
     unsigned pend = (p.team >= 32) ? 0xffffffffu : ((1u << p.team) - 1u);
     int spins = 0;
     while (true) {
 #pragma unroll
         for (int c = 0; c < XESN_FLOW_MAX_TEAM; ++c)
-            if (pend & (1u << c)) v[c] = ld_flag_sys(q + c);
+            if (pend & (1u << c)) v[c] = imported ? ld_flag_sys(q + c) : ld_flag(q + c);
 #pragma unroll
         for (int c = 0; c < XESN_FLOW_MAX_TEAM; ++c)
             if ((pend & (1u << c)) && !unset(v[c])) pend &= ~(1u << c);
@@ -71,68 +73,56 @@ __device__ __forceinline__ double team_sum(const PredictFlowArgs& p, long long s
     return s;
 }
 
-__global__ void __launch_bounds__(PF_THREADS, 1) predict_flow_kernel(PredictFlowArgs p) {
-    extern __shared__ __align__(16) double smem[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = blockIdx.x / p.team, c = blockIdx.x % p.team;
-    const int N = p.N, I = p.I, O = p.O, upc = p.upc;
-    const int u0 = c * upc, u1 = min(N, u0 + upc), nu = u1 - u0;
-    const int ldw = I + 1 + (I & 1);  // odd row pitch (in doubles): conflict-free reads of one row per lane
-    const int n_pad = (N + 1) & ~1;
-    double* s_r = smem;                              // [n_pad] copy of r_{n-1}
-    double* s_win = s_r + n_pad;                     // [upc][ldw]
-    double* s_wout = s_win + (size_t)upc * ldw;      // [O][upc]
-    double* s_u = s_wout + (size_t)O * upc;          // [I + (I & 1)]
-    double* s_rnew = s_u + I + (I & 1);              // [upc]
-    int* s_src = reinterpret_cast<int*>(s_rnew + upc);  // [I]
+// CTA-wide meeting points of the two warp roles (named barriers: the roles run different loops, so they cannot
+// share __syncthreads call sites)
+__device__ __forceinline__ void bar_inputs_ready() { asm volatile("bar.sync 1, %0;\n" ::"n"(PF_THREADS) : "memory"); }
+__device__ __forceinline__ void bar_states_ready() { asm volatile("bar.sync 2, %0;\n" ::"n"(PF_THREADS) : "memory"); }
 
-    const int pg = g % max(p.param_groups, 1);
-    const double* win = p.Win + (long long)pg * p.win_gs;
-    const double* wout = p.Wout + (long long)g * O * N;
-    for (int e = tid; e < nu * I; e += PF_THREADS) s_win[(e / I) * ldw + (e % I)] = win[(long long)(u0 + e / I) * I + e % I];
-    for (int e = tid; e < O * upc; e += PF_THREADS) {
-        const int o = e / upc, il = e % upc;
-        s_wout[e] = il < nu ? wout[(long long)o * N + u0 + il] : 0.0;
-    }
-    for (int k = tid; k < I; k += PF_THREADS) s_src[k] = p.src[(long long)g * I + k];
-    const double* r_g = p.r_in + (long long)g * N;   // in/out are different arrays: a fast CTA may finish before a team mate has loaded
-    for (int i = tid; i < n_pad; i += PF_THREADS) s_r[i] = i < N ? r_g[i] : 0.0;
+struct FlowSmem {
+    double* s_r;     // [n_pad] copy of r_{n-1}
+    double* s_win;   // [upc][ldw]
+    double* s_wout;  // [O][upc]
+    double* s_u;     // [I + (I & 1)]
+    double* s_rnew;  // [upc]
+    double* s_tval;  // [tail_cap] entries of W beyond the register-resident head of each owned row ...
+    int* s_toff;     // [tail_cap] ... and their columns
+    int* s_src;      // [I]
+    int ldw;
+};
 
-    // ---- owners: one unit per thread, head of its row of W in registers ----
-    const bool owner = tid < nu;
-    const int unit = u0 + tid;
-    int row_lo = 0, row_len = 0;
-    double r_cur = 0.0, bias = 0.0;
-    double hv[PF_KREG];
-    int ho[PF_KREG];
-    if (owner) {
-        row_lo = p.indptr[unit];
-        row_len = p.indptr[unit + 1] - row_lo;
-        r_cur = r_g[unit];
-        bias = p.bias[(long long)pg * p.bias_gs + unit];
-    }
-    const double* w_values = p.values + (long long)pg * p.values_gs;
+// phase C: this CTA's contribution to every output of the group (all 16 warps)
+__device__ __forceinline__ void flow_contributions(const PredictFlowArgs& p, const FlowSmem& sm, int n, int c, long long slot0,
+                                                   int warp, int lane) {
+    const int upc = p.upc;
+    for (int o = warp; o < p.O; o += PF_WARPS) {
+        const double* w = sm.s_wout + (size_t)o * upc;
+        double a = 0.0;
+        for (int il = lane; il < upc; il += 32) a = fma(w[il], sm.s_rnew[il], a);
 #pragma unroll
-    for (int k = 0; k < PF_KREG; ++k) {
-        const bool in = k < row_len;
-        hv[k] = in ? w_values[row_lo + k] : 0.0;
-        ho[k] = in ? p.indices[row_lo + k] : 0;
+        for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+        if (lane == 0) {
+            const long long slot = slot0 + o;
+            st_flag(p.part_ring + (slot * p.ring_steps + (n - 1)) * p.team + c, a);
+            // cells that groups on other ranks read: the same contribution, into their rings (NVLink P2P store)
+            if (p.exp_ptr)
+                for (int e = p.exp_ptr[slot]; e < p.exp_ptr[slot + 1]; ++e)
+                    st_flag_sys(p.peer_ring[p.exp_peer[e]] + ((long long)p.exp_slot[e] * p.ring_steps + (n - 1)) * p.team + c, a);
+        }
     }
-    const double alpha = p.alpha_g ? p.alpha_g[pg] : p.alpha, oma = 1.0 - alpha;
-    const bool leader = c == 0;
-    const long long slot0 = (long long)g * O;      // ring slots of this group's outputs
-    double* r_ring = p.r_ring + (long long)g * p.ring_steps * N;
-    const bool vec2 = (N % 2 == 0) && ((reinterpret_cast<uintptr_t>(r_ring) & 15) == 0);
-    bool aborted = false;
-    __syncthreads();
+}
 
+// warps 14 and 15: the values the step consumes that come through the partial rings
+__device__ __forceinline__ void flow_io_role(const PredictFlowArgs& p, const FlowSmem& sm, int g, int c, int t /*0..63*/) {
+    const int I = p.I, O = p.O;
+    const int warp = PF_R_THREADS / 32 + (t >> 5), lane = t & 31;
+    const bool leader = c == 0;
+    const long long slot0 = (long long)g * O;
+    bool aborted = false;
     for (int n = 1; n <= p.steps; ++n) {
-        // ================= phase A: everything step n consumes =================
-        if (tid >= PF_R_THREADS) {
+        if (t < 32) {
             // inputs of step n: the outputs of step n-1 (ring row n-2), or the field entering the launch
-            const int t = tid - PF_R_THREADS;
-            for (int k = t; k < I; k += PF_IO_THREADS) {
-                const int src = s_src[k];
+            for (int k = t; k < I; k += 32) {
+                const int src = sm.s_src[k];
                 double x;
                 if (src < 0 && src != INT_MIN) {
                     x = p.fill[-1 - src];
@@ -141,18 +131,121 @@ __global__ void __launch_bounds__(PF_THREADS, 1) predict_flow_kernel(PredictFlow
                 } else {
                     x = team_sum(p, src, n - 2, aborted);
                 }
-                s_u[k] = (p.mask_nan && x != x) ? 0.0 : x;
+                sm.s_u[k] = (p.mask_nan && x != x) ? 0.0 : x;
             }
-            // leader: trajectory column of step n-1
-            if (leader && n >= 2)
-                for (int o = t; o < O; o += PF_IO_THREADS) {
-                    const long long cell = p.out_map ? (long long)p.out_map[slot0 + o] : slot0 + o;
-                    p.pred[cell * p.ldp + p.col0 + n - 1] = team_sum(p, slot0 + o, n - 2, aborted);
-                }
-        } else if (n >= 2) {
-            // the other slices of r_{n-1} (ring row n-2): coalesced data-as-flag polling
+        } else if (leader && n >= 2) {
+            // trajectory column of step n-1 (beside the input polls, not after them)
+            for (int o = t - 32; o < O; o += 32) {
+                const long long cell = p.out_map ? (long long)p.out_map[slot0 + o] : slot0 + o;
+                p.pred[cell * p.ldp + p.col0 + n - 1] = team_sum(p, slot0 + o, n - 2, aborted);
+            }
+        }
+        bar_inputs_ready();
+        bar_states_ready();
+        flow_contributions(p, sm, n, c, slot0, warp, lane);
+    }
+    // last trajectory column, the field leaving the launch
+    if (leader)
+        for (int o = t; o < O; o += PF_IO_THREADS) {
+            const long long cell = p.out_map ? (long long)p.out_map[slot0 + o] : slot0 + o;
+            const double v = team_sum(p, slot0 + o, p.steps - 1, aborted);
+            p.pred[cell * p.ldp + p.col0 + p.steps] = v;
+            p.field_out[cell] = v;
+        }
+    if (blockIdx.x == 0)  // imported cells: what this rank's groups read at step 1 of the next launch
+        for (int j = t; j < p.n_import; j += PF_IO_THREADS)
+            p.field_out[p.import_cell[j]] = team_sum(p, (long long)p.G * O + j, p.steps - 1, aborted);
+}
+
+__global__ void __launch_bounds__(PF_THREADS, 1) predict_flow_kernel(PredictFlowArgs p) {
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = blockIdx.x / p.team, c = blockIdx.x % p.team;
+    const int N = p.N, I = p.I, O = p.O, upc = p.upc;
+    const int u0 = c * upc, u1 = min(N, u0 + upc), nu = u1 - u0;
+    const int n_pad = (N + 1) & ~1;
+    FlowSmem sm;
+    sm.ldw = I + 1 + (I & 1);  // odd row pitch (in doubles): conflict-free reads of one row per lane
+    sm.s_r = smem;
+    sm.s_win = sm.s_r + n_pad;
+    sm.s_wout = sm.s_win + (size_t)upc * sm.ldw;
+    sm.s_u = sm.s_wout + (size_t)O * upc;
+    sm.s_rnew = sm.s_u + I + (I & 1);
+    sm.s_tval = sm.s_rnew + upc;
+    sm.s_toff = reinterpret_cast<int*>(sm.s_tval + p.tail_cap);
+    sm.s_src = sm.s_toff + p.tail_cap + (p.tail_cap & 1);
+
+    const int pg = g % max(p.param_groups, 1);
+    {
+        const double* win = p.Win + (long long)pg * p.win_gs;
+        const double* wout = p.Wout + (long long)g * O * N;
+        for (int e = tid; e < nu * I; e += PF_THREADS) sm.s_win[(e / I) * sm.ldw + (e % I)] = win[(long long)(u0 + e / I) * I + e % I];
+        for (int e = tid; e < O * upc; e += PF_THREADS) {
+            const int o = e / upc, il = e % upc;
+            sm.s_wout[e] = il < nu ? wout[(long long)o * N + u0 + il] : 0.0;
+        }
+        for (int k = tid; k < I; k += PF_THREADS) sm.s_src[k] = p.src[(long long)g * I + k];
+    }
+    // in/out states are different arrays: a fast CTA may finish before a team mate has loaded
+    const double* r_g = p.r_in + (long long)g * N;
+    for (int i = tid; i < n_pad; i += PF_THREADS) sm.s_r[i] = i < N ? r_g[i] : 0.0;
+    const double* w_values = p.values + (long long)pg * p.values_gs;
+    // tails of the long rows of this CTA (entries beyond PF_KREG), packed row after row
+    const int* tail_ptr = p.tail_ptr + (long long)c * (upc + 1);
+    for (int il = tid; il < nu; il += PF_THREADS) {
+        const int lo = p.indptr[u0 + il], len = p.indptr[u0 + il + 1] - lo;
+        for (int k = PF_KREG; k < len; ++k) {
+            const int dst = tail_ptr[il] + (k - PF_KREG);
+            sm.s_tval[dst] = w_values[lo + k];
+            sm.s_toff[dst] = p.indices[lo + k];
+        }
+    }
+    __syncthreads();
+
+    if (tid >= PF_R_THREADS) {
+        flow_io_role(p, sm, g, c, tid - PF_R_THREADS);
+        return;
+    }
+
+    // ---- owners: one unit per thread, head of its row of W in registers ----
+    const bool owner = tid < nu;
+    const int unit = u0 + tid;
+    int row_len = 0, tail_lo = 0;
+    double r_cur = 0.0, bias = 0.0;
+    double hv[PF_KREG];
+    int ho[PF_KREG];
+    {
+        int row_lo = 0;
+        if (owner) {
+            row_lo = p.indptr[unit];
+            row_len = p.indptr[unit + 1] - row_lo;
+            tail_lo = tail_ptr[tid];
+            r_cur = r_g[unit];
+            bias = p.bias[(long long)pg * p.bias_gs + unit];
+        }
+#pragma unroll
+        for (int k = 0; k < PF_KREG; ++k) {
+            const bool in = k < row_len;
+            hv[k] = in ? w_values[row_lo + k] : 0.0;
+            ho[k] = in ? p.indices[row_lo + k] * (int)sizeof(double) : 0;
+        }
+    }
+    const unsigned s_r_addr = (unsigned)__cvta_generic_to_shared(sm.s_r);
+    const double alpha = p.alpha_g ? p.alpha_g[pg] : p.alpha, oma = 1.0 - alpha;
+    const long long slot0 = (long long)g * O;      // ring slots of this group's outputs
+    double* r_ring = p.r_ring + (long long)g * p.ring_steps * N;
+    const bool vec2 = (N % 2 == 0) && ((reinterpret_cast<uintptr_t>(r_ring) & 15) == 0);
+    bool aborted = false;
+#ifdef XESN_RECUR_TRACE
+    long long tr_sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tr_last = trace_clock();
+#endif
+
+    for (int n = 1; n <= p.steps; ++n) {
+        // ================= phase A: the other slices of r_{n-1} (ring row n-2), coalesced data-as-flag polling =================
+        if (n >= 2) {
             const double* row = r_ring + (long long)(n - 2) * N;
-            if (owner) s_r[unit] = r_cur;
+            if (owner) sm.s_r[unit] = r_cur;
             if (vec2) {
                 const int n2 = N >> 1;
                 for (int q0 = tid; q0 < n2; q0 += PF_R_THREADS * PF_POLL_BATCH) {
@@ -176,12 +269,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) predict_flow_kernel(PredictFlow
                     }
 #pragma unroll
                     for (int b = 0; b < PF_POLL_BATCH; ++b)
-                        if (mine & (1u << b)) {
-                            const int q = q0 + b * PF_R_THREADS;
-                            // a piece that straddles the edge of my slice: keep my own (newer) half
-                            if (!(2 * q >= u0 && 2 * q < u1)) s_r[2 * q] = v[b].x;
-                            if (!(2 * q + 1 >= u0 && 2 * q + 1 < u1)) s_r[2 * q + 1] = v[b].y;
-                        }
+                        if (mine & (1u << b)) *reinterpret_cast<double2*>(sm.s_r + 2 * (q0 + b * PF_R_THREADS)) = v[b];
                 }
             } else {
                 for (int q = tid; q < N; q += PF_R_THREADS) {
@@ -192,76 +280,58 @@ __global__ void __launch_bounds__(PF_THREADS, 1) predict_flow_kernel(PredictFlow
                         aborted = poll_expired(spins, p.status);
                         v = ld_flag(row + q);
                     }
-                    s_r[q] = v;
+                    sm.s_r[q] = v;
                 }
             }
         }
-        if (tid >= PF_R_THREADS && n >= 2 && owner) s_r[unit] = r_cur;  // owners among the I/O threads (upc > 448)
-        __syncthreads();
+        XESN_TRACE_MARK(0);  // [0] refresh of the state copy (thread 0's pieces)
+        bar_inputs_ready();
+        XESN_TRACE_MARK(1);  // [1] waiting for the other warps: their pieces, the inputs
 
         // ================= phase B: update of the owned units =================
         if (owner) {
+            // all gathers of the row head in flight before the first use (volatile asm keeps them batched)
             double gth[PF_KREG];
 #pragma unroll
-            for (int k = 0; k < PF_KREG; ++k) gth[k] = s_r[ho[k]];
+            for (int k = 0; k < PF_KREG; ++k)
+                asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(gth[k]) : "r"(s_r_addr + (unsigned)ho[k]));
             double wr = 0.0;
 #pragma unroll
             for (int k = 0; k < PF_KREG; ++k)
                 if (k < row_len) wr = __dadd_rn(wr, __dmul_rn(hv[k], gth[k]));
+            XESN_TRACE_MARK(2);  // [2] head of the row dot
             for (int k = PF_KREG; k < row_len; ++k)
-                wr = __dadd_rn(wr, __dmul_rn(__ldg(w_values + row_lo + k), s_r[__ldg(p.indices + row_lo + k)]));
-            const double* wrow = s_win + (size_t)tid * ldw;
+                wr = __dadd_rn(wr, __dmul_rn(sm.s_tval[tail_lo + k - PF_KREG], sm.s_r[sm.s_toff[tail_lo + k - PF_KREG]]));
+            XESN_TRACE_MARK(3);  // [3] tail of long rows
+            const double* wrow = sm.s_win + (size_t)tid * sm.ldw;
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
             int k = 0;
 #pragma unroll 2
             for (; k + 3 < I; k += 4) {
-                a0 = fma(wrow[k], s_u[k], a0);
-                a1 = fma(wrow[k + 1], s_u[k + 1], a1);
-                a2 = fma(wrow[k + 2], s_u[k + 2], a2);
-                a3 = fma(wrow[k + 3], s_u[k + 3], a3);
+                a0 = fma(wrow[k], sm.s_u[k], a0);
+                a1 = fma(wrow[k + 1], sm.s_u[k + 1], a1);
+                a2 = fma(wrow[k + 2], sm.s_u[k + 2], a2);
+                a3 = fma(wrow[k + 3], sm.s_u[k + 3], a3);
             }
-            for (; k < I; ++k) a0 = fma(wrow[k], s_u[k], a0);
+            for (; k < I; ++k) a0 = fma(wrow[k], sm.s_u[k], a0);
             const double pre = __dadd_rn(__dadd_rn(wr, (a0 + a1) + (a2 + a3)), bias);
+            XESN_TRACE_MARK(4);  // [4] Win u
             r_cur = leaky(pre, r_cur, alpha, oma);
+            XESN_TRACE_MARK(5);  // [5] tanh + leak
             st_flag(r_ring + (long long)(n - 1) * N + unit, r_cur);
-            s_rnew[tid] = r_cur;
+            sm.s_rnew[tid] = r_cur;
         } else if (tid < upc) {
-            s_rnew[tid] = 0.0;
+            sm.s_rnew[tid] = 0.0;
         }
-        __syncthreads();
-
-        // ================= phase C: this CTA's contribution to every output of the group =================
-        for (int o = warp; o < O; o += PF_WARPS) {
-            const double* w = s_wout + (size_t)o * upc;
-            double a = 0.0;
-            for (int il = lane; il < upc; il += 32) a = fma(w[il], s_rnew[il], a);
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
-            if (lane == 0) {
-                const long long slot = slot0 + o;
-                st_flag_sys(p.part_ring + (slot * p.ring_steps + (n - 1)) * p.team + c, a);
-                // cells that groups on other ranks read: the same contribution, into their rings (NVLink P2P store)
-                if (p.exp_ptr)
-                    for (int e = p.exp_ptr[slot]; e < p.exp_ptr[slot + 1]; ++e)
-                        st_flag_sys(p.peer_ring[p.exp_peer[e]] + ((long long)p.exp_slot[e] * p.ring_steps + (n - 1)) * p.team + c, a);
-            }
-        }
+        bar_states_ready();
+        XESN_TRACE_MARK(6);  // [6] state store + waiting for the other owners
+        flow_contributions(p, sm, n, c, slot0, warp, lane);
+        XESN_TRACE_MARK(7);  // [7] contributions
     }
-
-    // ================= epilogue: last trajectory column, the field leaving the launch, the states =================
-    if (tid >= PF_R_THREADS) {
-        const int t = tid - PF_R_THREADS;
-        if (leader)
-            for (int o = t; o < O; o += PF_IO_THREADS) {
-                const long long cell = p.out_map ? (long long)p.out_map[slot0 + o] : slot0 + o;
-                const double v = team_sum(p, slot0 + o, p.steps - 1, aborted);
-                p.pred[cell * p.ldp + p.col0 + p.steps] = v;
-                p.field_out[cell] = v;
-            }
-        if (blockIdx.x == 0)  // imported cells: what this rank's groups read at step 1 of the next launch
-            for (int j = t; j < p.n_import; j += PF_IO_THREADS)
-                p.field_out[p.import_cell[j]] = team_sum(p, (long long)p.G * O + j, p.steps - 1, aborted);
-    }
+#ifdef XESN_RECUR_TRACE
+    if (tid == 0 && blockIdx.x < 64)
+        for (int i = 0; i < 8; ++i) g_recur_trace[blockIdx.x * 8 + i] = tr_sum[i];
+#endif
     if (owner) p.r_out[(long long)g * N + unit] = r_cur;
 }
 
@@ -280,24 +350,44 @@ __global__ void flow_src_kernel(const int* __restrict__ in_map, const int* __res
 
 }  // namespace
 
-size_t predict_flow_smem(int N, int I, int O, int upc) {
+size_t predict_flow_smem(int N, int I, int O, int upc, int tail_cap) {
     const int ldw = I + 1 + (I & 1);
     const size_t n_pad = (size_t)((N + 1) & ~1);
-    return sizeof(double) * (n_pad + (size_t)upc * ldw + (size_t)O * upc + (size_t)(I + (I & 1)) + upc) +
-           sizeof(int) * (size_t)(I + 2);
+    return sizeof(double) * (n_pad + (size_t)upc * ldw + (size_t)O * upc + (size_t)(I + (I & 1)) + upc + (size_t)tail_cap) +
+           sizeof(int) * (size_t)(tail_cap + (tail_cap & 1) + I + 2);
 }
 
 // team size / units per CTA of the dataflow forecast; false when the configuration does not fit (caller falls back)
-bool predict_flow_geometry(int N, int I, int O, int G, int num_sms, int* team_out, int* upc_out) {
+bool predict_flow_geometry(int N, int I, int O, int G, int num_sms, const int* indptr, int* team_out, int* upc_out,
+                           int* tail_cap_out) {
     if (G < 1 || G > num_sms) return false;
     int team = std::min(num_sms / G, XESN_FLOW_MAX_TEAM);
     if (team < 1) return false;
     const int upc = ((N + team - 1) / team + 7) & ~7;
     team = (N + upc - 1) / upc;
-    if (upc > PF_THREADS) return false;
-    if (predict_flow_smem(N, I, O, upc) > 200 * 1024) return false;
-    *team_out = team, *upc_out = upc;
+    if (upc > PF_R_THREADS) return false;   // one unit per thread of the owner warps
+    // entries of W beyond the register-resident head of each row, per CTA slice (shared-memory staging)
+    int tail_cap = 0;
+    for (int c = 0; c < team; ++c) {
+        int t = 0;
+        for (int i = c * upc; i < std::min(N, (c + 1) * upc); ++i) t += std::max(0, indptr[i + 1] - indptr[i] - PF_KREG);
+        tail_cap = std::max(tail_cap, t);
+    }
+    if (predict_flow_smem(N, I, O, upc, tail_cap) > 200 * 1024) return false;
+    *team_out = team, *upc_out = upc, *tail_cap_out = tail_cap;
     return true;
+}
+
+// tail_ptr[c][il] = offset of unit (c*upc + il)'s tail inside its CTA's staging area, [team][upc+1] ints (host array)
+void predict_flow_tail_ptr(int N, int team, int upc, const int* indptr, int* out) {
+    for (int c = 0; c < team; ++c) {
+        int t = 0;
+        for (int il = 0; il <= upc; ++il) {
+            out[(long long)c * (upc + 1) + il] = t;
+            const int i = c * upc + il;
+            if (il < upc && i < N) t += std::max(0, indptr[i + 1] - indptr[i] - PF_KREG);
+        }
+    }
 }
 
 int launch_flow_src(const int* in_map, const int* out_map, int* owner, int* src, long long n_cells, long long n_slots,
@@ -312,7 +402,7 @@ int launch_flow_src(const int* in_map, const int* out_map, int* owner, int* src,
 
 int launch_predict_flow(const PredictFlowArgs& a, cudaStream_t stream) {
     if (a.steps <= 0) return 0;
-    const size_t smem = predict_flow_smem(a.N, a.I, a.O, a.upc);
+    const size_t smem = predict_flow_smem(a.N, a.I, a.O, a.upc, a.tail_cap);
     XESN_CUDA_OK(cudaFuncSetAttribute(predict_flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     PredictFlowArgs args = a;
     void* kargs[] = {&args};
@@ -323,3 +413,9 @@ int launch_predict_flow(const PredictFlowArgs& a, cudaStream_t stream) {
 }
 
 }  // namespace xesn
+
+#ifdef XESN_RECUR_TRACE
+extern "C" int xesn_debug_trace_flow(long long* out) {
+    return (int)cudaMemcpyFromSymbol(out, xesn::recur::g_recur_trace, sizeof(long long) * 64 * 8);
+}
+#endif
