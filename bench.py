@@ -577,16 +577,17 @@ def make_workload(ctx, name, w, world):
 
 
 def multi_gpu_parity(ctx, w, esn, names, test_dev, n_steps=48, n_spinup=32):
-    """Forecast `n_steps` steps of the trained sharded model through BOTH exchange engines -- the in-kernel P2P
-    stores (xesn_predict_p2p) and the per-step NCCL exchange -- and compare each with the same forecast run on
-    rank 0 alone (all groups on one GPU through xesn_predict, no exchange).  Collective: every rank calls this."""
+    """Forecast `n_steps` steps of the trained sharded model through EVERY exchange engine -- the dataflow kernel with
+    neighbour-only P2P stores of the halo cells (xesn_predict_flow, the default), the persistent kernel that stores
+    every cell to every rank (xesn_predict_p2p) and the per-step NCCL exchange -- and compare each with the same
+    forecast run on rank 0 alone (all groups on one GPU through xesn_predict, no exchange).  Collective."""
     import xesn_b200.lazyesn as lz
     from xesn_b200 import LazyESN
     torch, dist = ctx.torch, ctx.dist
     y = test_dev[..., :n_spinup + n_steps + 1].contiguous()
     preds = {}
     prev = os.environ.get("XESN_B200_EXCHANGE")
-    for engine in ("p2p", "nccl"):
+    for engine in ("flow", "p2p", "nccl"):
         os.environ["XESN_B200_EXCHANGE"] = engine
         preds[engine] = esn._predict_core(y, n_steps, n_spinup).clone()
     if prev is None:
@@ -616,7 +617,8 @@ def multi_gpu_parity(ctx, w, esn, names, test_dev, n_steps=48, n_spinup=32):
         result = {"what": (f"{n_steps}-step forecast after {n_spinup} spin-up steps of the trained workload model, sharded over "
                            f"{ctx.world} ranks, against the same forecast on rank 0 alone (xesn_predict, all "
                            f"{w['groups_per_gpu'] * ctx.world} groups on one GPU)"),
-                  "max_abs_err": max(errs.values()), "max_abs_err_p2p": errs["p2p"], "max_abs_err_nccl": errs["nccl"],
+                  "max_abs_err": max(errs.values()), "max_abs_err_flow": errs["flow"], "max_abs_err_p2p": errs["p2p"],
+                  "max_abs_err_nccl": errs["nccl"], "engine_timed": os.environ.get("XESN_B200_EXCHANGE", "flow"),
                   "field_scale": scale, "tolerance": tol, "ok": bool(max(errs.values()) <= tol)}
         solo._drop_device_state()
     ctx.barrier()

@@ -29,6 +29,9 @@ from .matrix import RandomMatrix, SparseRandomMatrix, _dense_scale, _sparse_scal
 
 
 class ESNEnsemble:
+    # unscaled random matrices + their normalisation scalars per (kind, shape, options incl. seed); see build_host
+    _MATRIX_CACHE = {}
+
     def __init__(self, members, device=None):
         members = list(members)
         assert members, "ESNEnsemble: at least one member"
@@ -61,7 +64,9 @@ class ESNEnsemble:
         distinct (shape, distribution, normalization, density, format, seed) and every member then applies its own
         `factor / scale * A` -- the reference's expression (matrix.py:183-193, :296-316), hence the same matrices
         up to ARPACK's ~1e-15 run-to-run jitter in `scale`, which the cache removes."""
-        cache = {}
+        cache = ESNEnsemble._MATRIX_CACHE     # kept across calls: successive batches of a search reuse the draws
+        while len(cache) > 16:
+            cache.pop(next(iter(cache)))
 
         def make(kwargs, n_rows, n_cols):
             kw = dict(kwargs)
