@@ -113,6 +113,14 @@ int xesn_ridge_solve(xesn_reservoir* h, int32_t n_output, int32_t n_groups, cons
                      double beta_scalar, double* gram_dev, double* wout_dev, int32_t* info_dev,
                      void* scratch_dev, int64_t scratch_bytes, void* stream);
 
+/* Pivoted fallback for ONE system (n_groups == 1 layout: gram_dev [N][N] with the lower triangle valid and WITHOUT beta,
+ *      wout_dev [O][N] = Y R^T) whose Cholesky factorisation reported info > 0: blocked LU with partial pivoting, the
+ *      factorisation the reference's GPU path uses (cupy getrf/getrs; scipy's assume_a="sym" is the pivoted LDL^T),
+ *      xesn/esn.py:516-520.  The caller re-runs xesn_train_accumulate for that group first (the failed factorisation
+ *      destroyed the Gram matrix).  info_dev: one int, 0 or j+1 when column j has no usable pivot (exactly singular). */
+int xesn_ridge_solve_pivoted(xesn_reservoir* h, int32_t n_output, double beta, double* gram_dev, double* wout_dev,
+                             int32_t* info_dev, void* scratch_dev, int64_t scratch_bytes, void* stream);
+
 /* ---- a3/a6: closed-loop forecast                            xesn/esn.py:264-268 (ESN.predict),
  *      xesn/lazyesn.py:226-236 (+ _update_nd, _readout, overlap per step).
  *      The domain is a flat vector of `n_cells` values.  in_map [G][I] gathers every group's
@@ -226,6 +234,16 @@ int xesn_cost_nrmse(const double* pred_dev, const double* truth_dev, int64_t tru
  * the terms (cost.py:204-210: factor-weighted sum per window), averages over the windows and clamps. */
 int xesn_cost_psd_nrmse(const double* pred_dev, const double* truth_dev, int64_t truth_ld, int64_t t0, int32_t n_windows,
                         int32_t n_groups, int32_t n_output, int32_t n_times, double* psd_nrmse_fg_dev, void* stream);
+/* Radially binned power spectrum of fields with two or three spatial axes (xesn/psd.py:42-65): spec_dev holds the
+ * 2-D FFT of every image as interleaved (re, im) doubles, [n_images][n_z][n_pix]; out[img][b] = factor[b] * mean over
+ * the spectral cells pix_idx[bin_ptr[b] .. bin_ptr[b+1]) of (mean over z of |spec|^2); NaN for an annulus without cells
+ * (scipy.stats.binned_statistic).  The cell lists depend only on the grid size and come from the host. */
+int xesn_psd_radial(const double* spec_dev, int64_t n_images, int32_t n_z, int32_t n_pix, const int32_t* bin_ptr_dev,
+                    const int32_t* pix_idx_dev, const double* factor_dev, int32_t n_bins, double* out_dev, void* stream);
+/* NRMSE with xarray's skip-NaN reductions between pred [n_windows][n_groups][n_rows][n_times] and truth
+ * [n_windows][n_rows][n_times] (the psd_nrmse of xesn/cost.py:257-272 applied to spectra that may hold NaN bins). */
+int xesn_nrmse_skipnan(const double* pred_dev, const double* truth_dev, int32_t n_windows, int32_t n_groups,
+                       int32_t n_rows, int32_t n_times, double* nrmse_fg_dev, void* stream);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 int64_t xesn_launch_count(void);
 /* per-phase device timers (CUDA events on the launching stream).  enable(1) clears and starts

@@ -335,19 +335,52 @@ def psd_1d(x):
     return out
 
 
-def psd_nrmse_fg(preds, truths):
+def psd_nd(x):
+    """1-D power spectral density of a time-varying field with one, two or three spatial axes (time last).  Restates
+    xesn/psd.py:12-70 (`psd`): FFT over the first axis (one spatial axis) or 2-D FFT over the first two (which must be
+    equally long, psd.py:42-49 builds both wavenumber axes from n_x), |.|^2, mean over a third spatial axis (psd.py:59),
+    mean over the cells of every unit-width wavenumber annulus (`scipy.stats.binned_statistic`, bins .5, 1.5, ...,
+    n_x//2 + .5) times the annulus area factor pi (k2^2 - k1^2).  Returns (n_x // 2, n_time); empty bins are NaN.
+    PINNED against the reference's own function on seeded inputs (tests/golden/psd.npz, oracle/make_golden.py)."""
+    from scipy.fft import fft, fft2, fftfreq
+    from scipy.stats import binned_statistic
+    x = np.asarray(x, dtype=np.float64)
+    if x.ndim == 2:
+        return psd_1d(x)
+    if x.ndim not in (3, 4):
+        raise NotImplementedError("psd will only work for up to 3D time varying arrays (i.e., 4 dims total)")
+    n_x, n_time = x.shape[0], x.shape[-1]
+    psi = np.abs(fft2(x.T)) ** 2                       # (n_time, [n_z,] n_y, n_x)
+    n_k = n_x // 2 + 1
+    k = n_x * fftfreq(n_x)
+    k2d = np.meshgrid(k, k)
+    k_tot = np.sqrt(k2d[0] ** 2 + k2d[1] ** 2)
+    k_bins = np.arange(.5, n_k, 1.)
+    out = np.zeros((n_x // 2, n_time))
+    for n in range(n_time):
+        arr = psi[n].mean(axis=0) if psi.ndim > 3 else psi[n]
+        tmp1d, *_ = binned_statistic(k_tot.flatten(), arr.flatten(), statistic="mean", bins=k_bins)
+        out[:, n] = tmp1d * np.pi * (k_bins[1:] ** 2 - k_bins[:-1] ** 2)
+    return out
+
+
+def psd_nrmse_fg(preds, truths, space_shape=None):
     """NRMSE of the PSD per window and candidate.  Restates xesn/cost.py:257-272 (`psd_nrmse` = `nrmse` of the two
-    spectra, cost.py:227-254) with xarray's skip-NaN reductions.  preds: (F, G, O, S), truths: (F, O, S) -> (F, G)."""
+    spectra, cost.py:227-254) with xarray's skip-NaN reductions.  preds: (F, G, O, S), truths: (F, O, S) -> (F, G);
+    `space_shape`: the spatial shape the O cells unflatten to (C order), default one spatial axis.
+    The spectra are pinned (psd_nd); the NRMSE reductions on top are PARITY UNPINNED (xarray absent here)."""
     preds, truths = np.asarray(preds, dtype=np.float64), np.asarray(truths, dtype=np.float64)
     F, G = preds.shape[:2]
+    S = preds.shape[-1]
+    shape = tuple(space_shape) if space_shape is not None else (preds.shape[2],)
     out = np.zeros((F, G))
     import warnings
     with np.errstate(all="ignore"), warnings.catch_warnings():
         warnings.simplefilter("ignore", RuntimeWarning)   # the empty last bin of an even n_x is all-NaN by design
         for f in range(F):
-            pt = psd_1d(truths[f])
+            pt = psd_nd(truths[f].reshape(shape + (S,)))
             w = 1.0 / np.nanstd(pt, axis=-1, keepdims=True)
             for g in range(G):
-                err = (psd_1d(preds[f, g]) - pt) * w
+                err = (psd_nd(preds[f, g].reshape(shape + (S,))) - pt) * w
                 out[f, g] = np.sqrt(np.nanmean(err ** 2))
     return out

@@ -258,11 +258,36 @@ def lazy_cases():
         )
 
 
+def psd_cases():
+    """Power spectral densities from the reference's own `psd` (xesn/psd.py:12-70, run unmodified over a stub
+    DataArray): one, two and three spatial axes, even and odd sizes."""
+    psd = ref_shim.load_psd()
+    rs = np.random.RandomState(11)
+    out = {}
+    for name, shape, dims in (("x12", (12, 6), ("x", "time")), ("x13", (13, 5), ("x", "ftime")),
+                              ("xy8", (8, 8, 5), ("x", "y", "time")), ("xy9", (9, 9, 4), ("x", "y", "time")),
+                              ("xyz8", (8, 8, 3, 4), ("x", "y", "z", "time"))):
+        x = rs.normal(size=shape)
+        with np.errstate(all="ignore"):
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                res = psd(ref_shim.field_array(x, dims))
+        out[f"in_{name}"] = x
+        out[f"psd_{name}"] = np.asarray(res.data)
+        out[f"k_{name}"] = np.asarray(res["k1d"].data)
+    np.savez_compressed(os.path.join(OUT, "psd.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if "--only-psd" in sys.argv:
+        psd_cases()
+        sys.exit(0)
     matrices()
     eager_small()
     eager_l96()
     lazy_cases()
+    psd_cases()
     total = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print("golden fixtures written to", OUT, f"({total/1e6:.2f} MB)")

@@ -698,3 +698,55 @@ def test_gram_i8_bounds(torch, lib, case):
         assert err <= K * 2.0 ** -50, (err, K * 2.0 ** -50)
     if case == "k16384":
         assert float(G[0, 0]) == K and float(G[1, 0]) == -K and float(G[1, 1]) == K
+
+
+# --------------------------------------------------------------------------- pivoted fallback of the ridge solve
+@pytest.mark.parametrize("N,T,beta", [(300, 200, 1e-13), (700, 450, 0.0)])
+def test_ridge_pivoted_fallback_matches_symmetric_solver(torch, N, T, beta):
+    """A rank-deficient Gram matrix with a negligible tikhonov_parameter is not positive definite in double precision:
+    Cholesky stops (info > 0).  The reference's scipy.linalg.solve(assume_a="sym") still returns a (huge, ill-conditioned)
+    solution; so must we -- through the pivoted LU fallback -- and it must satisfy the oracle's normal equations as well
+    as the oracle's own solution does, and fit the training targets equally well."""
+    from xesn_b200.synthetic import lorenz96
+    data = lorenz96(6, T)
+    esn = make_esn(6, 6, N, beta=beta)
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        esn.train(data, n_spinup=0)
+    assert any("partial pivoting" in str(w.message) for w in caught), [str(w.message) for w in caught]
+    w = np.array(esn.Wout)
+    assert np.isfinite(w).all()
+    W = sp.csr_matrix(esn.W)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")     # scipy's LinAlgWarning: ill-conditioned
+        ref, rr, yr = oc.ridge_train(data, data, 0, None, W, esn.Win, esn.bias_vector, 0.5, beta, return_gram=True)
+    scale = np.abs(yr).max()
+    res = np.abs(w @ rr - yr).max() / scale
+    res_ref = np.abs(ref @ rr - yr).max() / scale
+    assert res < max(10 * res_ref, 1e-9), (res, res_ref)
+    states = oc.forced_states(data, T, W, esn.Win, esn.bias_vector, 0.5)[:T]      # row t pairs with data[:, t]
+    fit = np.abs(w @ states.T - data).max()
+    fit_ref = np.abs(ref @ states.T - data).max()
+    assert fit < max(10 * fit_ref, 1e-6), (fit, fit_ref)
+
+
+def test_ridge_fallback_only_touches_the_failed_members(torch):
+    """Batched systems: one member with an indefinite system, the others fine -- the good members keep their Cholesky
+    readouts bit for bit, the bad one gets the pivoted solve."""
+    from xesn_b200 import ESNEnsemble
+    from xesn_b200.synthetic import lorenz96
+    data = lorenz96(40, 300)
+    members = _macro_candidates(3, 500)
+    members[1].tikhonov_parameter = 0.0            # T = 300 < N = 500: singular without regularisation
+    ens = ESNEnsemble(members)
+    ens.build()
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        ens.train(data, n_spinup=10)
+    assert any("partial pivoting" in str(w.message) for w in caught)
+    w = ens.Wout
+    assert np.isfinite(w).all()
+    for g in (0, 2):
+        m = members[g]
+        ref = oc.ridge_train(data, data, 10, None, sp.csr_matrix(m.W), m.Win, m.bias_vector, m.leak_rate, m.tikhonov_parameter)
+        assert oc.max_normalised_err(w[g], ref) < 1e-4

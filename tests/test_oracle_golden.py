@@ -136,3 +136,18 @@ def test_cost_oracle_known_answers():
     # the PSD error of a perfect forecast is 0
     tr = rs.normal(size=(1, 16, 30))
     np.testing.assert_allclose(oc.psd_nrmse_fg(tr[:, None], tr), [[0.0]], atol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["x12", "x13", "xy8", "xy9", "xyz8"])
+def test_psd_matches_reference(name):
+    """oracle.psd_nd against the reference's own `psd` (xesn/psd.py:12-70, executed unmodified by oracle/make_golden.py):
+    one, two and three spatial axes; the empty last bin of an even 1-D size is NaN on both sides."""
+    import warnings
+    z = load_golden("psd.npz")
+    with warnings.catch_warnings(), np.errstate(all="ignore"):
+        warnings.simplefilter("ignore")
+        got = oc.psd_nd(z[f"in_{name}"])
+    ref = z[f"psd_{name}"]
+    assert got.shape == ref.shape == (z[f"in_{name}"].shape[0] // 2, z[f"in_{name}"].shape[-1])
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    np.testing.assert_allclose(np.nan_to_num(got), np.nan_to_num(ref), rtol=1e-13)

@@ -61,6 +61,8 @@ SIGNATURES = {
                                         C.c_int64, C.c_void_p]),
     "xesn_ridge_solve": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "xesn_ridge_solve_pivoted": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_int64, C.c_void_p]),
     "xesn_predict_scratch_bytes": (C.c_int64, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64]),
     "xesn_predict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
@@ -88,6 +90,9 @@ SIGNATURES = {
                                       C.c_void_p, C.c_void_p]),
     "xesn_cost_nrmse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "xesn_psd_radial": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                  C.c_void_p, C.c_void_p]),
+    "xesn_nrmse_skipnan": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "xesn_reservoir_set_group_params": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "xesn_set_recur_mode": (C.c_int, [C.c_void_p, C.c_int32]),
     "xesn_set_gram_mode": (C.c_int, [C.c_void_p, C.c_int32]),

@@ -74,8 +74,8 @@ class CostFunction:
     __slots__ = ("ESN", "train_data", "macro_data", "config", "test_data", "max_batch")
 
     def __init__(self, ESN, train_data, macro_data, config, test_data=None, max_batch=None):
-        if not (isinstance(ESN, type) and issubclass(ESN, _ESN)) or issubclass(ESN, _LazyESN):
-            raise NotImplementedError("xesn_b200.CostFunction batches the eager ESN; evaluate LazyESN candidates one by one")
+        if not (isinstance(ESN, type) and issubclass(ESN, _ESN)):
+            raise TypeError("CostFunction: ESN must be xesn_b200.ESN or xesn_b200.LazyESN")
         for key in config["macro_training"].get("cost_terms", {}):
             if key not in _TERMS:
                 raise NotImplementedError(f"CostFunction.__init__: found '{key}' in config['macro_training']['cost_terms'], "
@@ -123,10 +123,60 @@ class CostFunction:
                             cost_terms=mt.get("cost_terms", {"nrmse": 1.0}))
         return np.asarray(costs, dtype=np.float64)
 
+    # ------------------------------------------------------------------ LazyESN candidates: one model at a time
+    def _terms_device(self, pred, truth, space_shape):
+        """Per-window total of the cost terms (cost.py:204-210) of ONE model: pred / truth (F, O, S) device tensors."""
+        import torch
+        lib = _lib.load()
+        terms = self.config["macro_training"].get("cost_terms", {"nrmse": 1.0})
+        F, O, S = (int(n) for n in pred.shape)
+        total = torch.zeros((F, 1), dtype=torch.float64, device=pred.device)
+        with torch.cuda.device(pred.device):
+            st = torch.cuda.current_stream().cuda_stream
+            if "nrmse" in terms:
+                fg = torch.empty((F, 1), dtype=torch.float64, device=pred.device)
+                scratch = torch.empty(1, dtype=torch.float64, device=pred.device)
+                tr = truth.reshape(F * O, S).contiguous()
+                _lib.check(lib.xesn_cost_nrmse(pred.contiguous().data_ptr(), tr.data_ptr(), S, 0, F, 1, O, S, 1e300,
+                                               fg.data_ptr(), scratch.data_ptr(), st))
+                total = total + float(terms["nrmse"]) * fg
+            if "psd_nrmse" in terms:
+                from .psd import psd_nrmse_device
+                total = total + float(terms["psd_nrmse"]) * psd_nrmse_device(pred.reshape(F, 1, O, S), truth, space_shape)
+        return total[:, 0]
+
+    def _evaluate_lazy(self, kwargs):
+        """`_cost` (cost.py:175-225) of one LazyESN parameter set: build, train, forecast every macro sample, cost terms
+        on the device.  Under torch.distributed the groups of the model are sharded over the ranks (LazyESN does
+        that itself), so every rank evaluates every set."""
+        import torch
+        mt = self.config["macro_training"]
+        fc = mt["forecast"]
+        esn = self.ESN(**copy.deepcopy(kwargs))
+        esn.build()
+        esn.train(self.train_data, **self.config.get("training", {}))
+        preds, truths = [], []
+        for truth in self.macro_data:
+            pred = esn._predict_core(truth, fc["n_steps"], fc["n_spinup"])              # (n_cells, n_steps + 1) on the device
+            t = truth if isinstance(truth, torch.Tensor) else torch.from_numpy(
+                np.ascontiguousarray(np.asarray(getattr(truth, "data", truth), dtype=np.float64)))
+            space_shape = tuple(int(n) for n in t.shape[:-1])
+            t = t.reshape(-1, t.shape[-1])[:, fc["n_spinup"]:fc["n_spinup"] + fc["n_steps"] + 1].to(pred.device)
+            preds.append(pred)
+            truths.append(t)
+        per_window = self._terms_device(torch.stack(preds), torch.stack(truths).contiguous(), space_shape)
+        cost = float(per_window.mean().item())
+        ub = mt.get("cost_upper_bound", 1e9)
+        ub = 1e9 if ub is None else ub
+        esn._drop_device_state()
+        return ub if (math.isnan(cost) or math.isinf(cost) or cost > ub) else cost
+
     def __call__(self, macro_param_sets, is_transformed=True):
         """Cost of every parameter set, shape (n_sets, 1) like the reference (cost.py:94-122)."""
         kwargs = self.candidate_kwargs(macro_param_sets, is_transformed)
         n_sets = len(kwargs)
+        if issubclass(self.ESN, _LazyESN):
+            return np.asarray([self._evaluate_lazy(kw) for kw in kwargs], dtype=np.float64).reshape(-1, 1)
         rank, world, dist = 0, 1, None
         try:
             import torch.distributed as dist_mod
@@ -147,3 +197,61 @@ class CostFunction:
             for idx, vals in gathered:
                 local[idx] = vals
         return local.reshape(-1, 1)
+
+
+    # ------------------------------------------------------------------ diagnostics of one parameter set
+    def evaluate(self, parameters, use_test_data=False):
+        """`CostFunction.evaluate` of the reference (cost.py:124-172): build and train one model from `parameters`
+        (names as in the config, untransformed), forecast every sample of `macro_data` (or `test_data`), and return
+        per sample the prediction, the truth and the time-resolved terms named in `cost_terms`: "nrmse" (cost.py:227-254
+        with drop_time=False: RMS over space of the error normalised by the truth's temporal standard deviation) and
+        "psd_truth" / "psd_prediction" / "psd_nrmse" (psd.py, cost.py:257-272).  Returns an `xarray.Dataset`
+        concatenated along "sample" when xarray is importable and the data are DataArrays, else a dict of numpy arrays
+        with a leading sample axis."""
+        from .esn import _host_array, _is_dataarray, xr
+        from .psd import psd as psd_fn
+        kwargs = update_esn_kwargs(parameters, self.config[self.ESN.__name__.lower()])
+        esn = self.ESN(**kwargs)
+        esn.build()
+        esn.train(self.train_data, **self.config.get("training", {}))
+        if not use_test_data:
+            datasets = self.macro_data
+            n_spinup = self.config["macro_training"]["forecast"]["n_spinup"]
+            n_steps = self.config["macro_training"]["forecast"]["n_steps"]
+        else:
+            datasets = self.test_data
+            n_spinup, n_steps = self.config["testing"]["n_spinup"], self.config["testing"]["n_steps"]
+        terms = self.config["macro_training"].get("cost_terms", {"nrmse": 1.0})
+        results = []
+        for i, truth in enumerate(datasets):
+            result = esn.test(truth, n_steps=n_steps, n_spinup=n_spinup)
+            if _is_dataarray(truth):
+                pred, tr = result["prediction"].values, result["truth"].values
+            else:
+                pred, tr = np.asarray(result["prediction"]), np.asarray(_host_array(truth))[..., n_spinup:n_spinup + n_steps + 1]
+            out = {"prediction": pred, "truth": tr}
+            space_axes = tuple(range(pred.ndim - 1))
+            if "nrmse" in terms:
+                w = 1.0 / np.nanstd(tr, axis=-1, keepdims=True)
+                out["nrmse"] = np.sqrt(np.nanmean(((pred - tr) * w) ** 2, axis=space_axes))
+            if "psd_nrmse" in terms:
+                out["psd_truth"], out["psd_prediction"] = psd_fn(tr), psd_fn(pred)
+                with np.errstate(all="ignore"):
+                    w = 1.0 / np.nanstd(out["psd_truth"], axis=-1, keepdims=True)
+                    out["psd_nrmse"] = np.sqrt(np.nanmean(((out["psd_prediction"] - out["psd_truth"]) * w) ** 2, axis=0))
+            if _is_dataarray(truth):
+                ds = result
+                tdim = "ftime"
+                if "nrmse" in out:
+                    ds["nrmse"] = xr.DataArray(out["nrmse"], coords={tdim: ds[tdim]}, dims=(tdim,))
+                if "psd_nrmse" in out:
+                    k = np.arange(1.0, out["psd_truth"].shape[0] + 1)
+                    for name in ("psd_truth", "psd_prediction"):
+                        ds[name] = xr.DataArray(out[name], coords={"k1d": k, tdim: ds[tdim]}, dims=("k1d", tdim))
+                    ds["psd_nrmse"] = xr.DataArray(out["psd_nrmse"], coords={tdim: ds[tdim]}, dims=(tdim,))
+                results.append(ds.expand_dims({"sample": [i]}))
+            else:
+                results.append(out)
+        if results and not isinstance(results[0], dict):
+            return xr.concat(results, dim="sample")
+        return {key: np.stack([r[key] for r in results]) for key in results[0]} if results else {}

@@ -473,7 +473,7 @@ static TrainLayout train_layout(xesn_reservoir* h, int O, int G, int chunk, int 
 int64_t xesn_train_scratch_bytes(xesn_reservoir* h, int32_t O, int32_t G, int32_t chunk, int32_t gu, int32_t gy) {
     if (!h || chunk <= 0) return -1;
     long long train = train_layout(h, O, G, chunk, gu, gy).total;
-    long long solve = cholesky_workspace_doubles(h->N, O, G);
+    long long solve = std::max(cholesky_workspace_doubles(h->N, O, G), lu_workspace_doubles(h->N));
     return (train > solve ? train : solve) * 8 + 256;
 }
 
@@ -675,6 +675,20 @@ int xesn_ridge_solve(xesn_reservoir* h, int32_t O, int32_t G, const double* beta
     if (rc) return rc;
     return launch_cholesky_solve_ws(h->solve, gram, N, (long long)N * N, wout, N, (long long)O * N, N, O, G, info,
                                     (double*)scratch, st);
+}
+
+// Pivoted fallback for ONE system whose Cholesky factorisation failed (info > 0 from xesn_ridge_solve): the caller
+// re-accumulates gram/wout of that group (xesn_train_accumulate) and hands them here.  LU with partial pivoting,
+// the factorisation the reference's own GPU path uses (cupy.linalg.solve; scipy's assume_a="sym" is pivoted LDL^T).
+int xesn_ridge_solve_pivoted(xesn_reservoir* h, int32_t O, double beta, double* gram, double* wout, int32_t* info,
+                             void* scratch, int64_t scratch_bytes, void* stream) {
+    XESN_REQUIRE(h && gram && wout && info && scratch, "null pointer");
+    XESN_REQUIRE(scratch_bytes >= lu_workspace_doubles(h->N) * 8, "scratch too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = h->N;
+    ProfScope prof(PROF_SOLVE, st);
+    if (int rc = launch_add_diag(gram, N, (long long)N * N, N, 1, nullptr, beta, st)) return rc;
+    return launch_lu_solve(gram, N, wout, N, N, O, info, (double*)scratch, st);
 }
 
 // ---------------------------------------------------------------------------------------------

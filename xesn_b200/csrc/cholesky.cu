@@ -178,6 +178,40 @@ __global__ void add_diag_kernel(double* A, long long lda, long long strideA, int
 
 }  // namespace
 
+// Backward sweep  X T = Z  for the block-lower-triangular T stored in A (row-major, 128-wide blocks whose explicit
+// inverses are in linv, [block][128][128] per matrix), Z = B (nrhs x n rows) overwritten with X: block columns
+// jb_first down to the one starting at `stop_col`.  Shared by the Cholesky path (T = L) and the pivoted LU fallback
+// (T = U^T: the upper factor in the column-major view of the symmetric matrix, lu_solve.cu).
+int backward_sweep_128(double* A, long long lda, long long strideA, double* B, long long ldb, long long strideB, int n,
+                       int nrhs, int batch, const double* linv, long long strideLinv, int jb_first, cudaStream_t stream,
+                       int stop_col = 0) {
+    for (int jb = jb_first; jb >= 0 && jb * NB >= stop_col; --jb) {
+        const int j0 = jb * NB;
+        const int nbj = min(NB, n - j0);
+        const double* Linv_j = linv + (long long)jb * NB * NB;
+        GemmArgs g = {};
+        g.A = B + j0, g.lda = ldb, g.strideA = strideB;
+        g.B = Linv_j, g.ldb = NB, g.strideB = strideLinv;  // B(k,n) = Linv[k][n]
+        g.C = B + j0, g.ldc = ldb, g.strideC = strideB;
+        g.M = nrhs, g.N = nbj, g.K = nbj;
+        g.batch = batch, g.alpha = 1.0, g.beta = 0.0;
+        g.flags = GEMM_A_KMAJOR;
+        int rc = launch_gemm_f64(g, stream);
+        if (rc) return rc;
+        if (j0 == 0) break;
+        GemmArgs u = {};
+        u.A = B + j0, u.lda = ldb, u.strideA = strideB;
+        u.B = A + (long long)j0 * lda, u.ldb = lda, u.strideB = strideA;  // B(k,n) = T[j0+k][n]
+        u.C = B, u.ldc = ldb, u.strideC = strideB;
+        u.M = nrhs, u.N = j0, u.K = nbj;
+        u.batch = batch, u.alpha = -1.0, u.beta = 1.0;
+        u.flags = GEMM_A_KMAJOR;
+        rc = launch_gemm_f64(u, stream);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
 int launch_add_diag(double* A, long long lda, long long strideA, int n, int batch, const double* beta_dev,
                     double beta_scalar, cudaStream_t stream) {
     dim3 grid((n + 255) / 256, batch);
@@ -456,30 +490,9 @@ static int cholesky_solve_body(SolveCtx& ctx, double* A, long long lda, long lon
         if ((rc = level(2 * NB, 1))) return rc;
     }
     // columns beyond the full wide blocks (and everything when there are none): 128-wide steps
-    for (int jb = nblk - 1; jb >= 0 && jb * NB >= n_wide * WB; --jb) {
-        const int j0 = jb * NB;
-        const int nbj = min(NB, n - j0);
-        double* Linv_j = work + (long long)jb * NB * NB;
-        GemmArgs g = {};
-        g.A = B + j0, g.lda = ldb, g.strideA = strideB;
-        g.B = Linv_j, g.ldb = NB, g.strideB = strideLinv;  // B(k,n) = Linv[k][n]
-        g.C = B + j0, g.ldc = ldb, g.strideC = strideB;
-        g.M = nrhs, g.N = nbj, g.K = nbj;
-        g.batch = batch, g.alpha = 1.0, g.beta = 0.0;
-        g.flags = GEMM_A_KMAJOR;
-        int rc = launch_gemm_f64(g, stream);
-        if (rc) return rc;
-        if (j0 == 0) break;
-        GemmArgs u = {};
-        u.A = B + j0, u.lda = ldb, u.strideA = strideB;
-        u.B = A + (long long)j0 * lda, u.ldb = lda, u.strideB = strideA;  // B(k,n) = L[j0+k][n]
-        u.C = B, u.ldc = ldb, u.strideC = strideB;
-        u.M = nrhs, u.N = j0, u.K = nbj;
-        u.batch = batch, u.alpha = -1.0, u.beta = 1.0;
-        u.flags = GEMM_A_KMAJOR;
-        rc = launch_gemm_f64(u, stream);
-        if (rc) return rc;
-    }
+    if ((rc = backward_sweep_128(A, lda, strideA, B, ldb, strideB, n, nrhs, batch, work, strideLinv, nblk - 1, stream,
+                                 n_wide * WB)))
+        return rc;
     for (int J = n_wide - 1; J >= 0; --J) {
         const int j0 = J * WB;
         GemmArgs g = {};  // X_J = Z_J * inv(L_JJ)   (four column tiles read all of Z_J: not in place)

@@ -106,6 +106,71 @@ __global__ void __launch_bounds__(CT) psd_nrmse_kernel(const double* __restrict_
     if (threadIdx.x == 0) out_fg[blockIdx.x] = kmax > 0 ? sqrt(total / ((double)kmax * S)) : 0.0;
 }
 
+// Radially binned power spectrum of fields with two or three spatial axes (xesn/psd.py:42-65): for image `img` (one
+// forecast time of one field) out[img][b] = factor[b] * mean over the spectral cells p of annulus b of
+// (mean over z of |spec[img][z][p]|^2); an annulus without cells gives NaN like scipy's binned_statistic.  The cell
+// lists per annulus come from the host (they depend only on the grid size); a warp owns an annulus and adds its
+// cells in a fixed order, so the result is deterministic.  spec: interleaved (re, im) pairs.
+__global__ void __launch_bounds__(CT) psd_radial_kernel(const double2* __restrict__ spec, int n_z, int n_pix,
+                                                        const int* __restrict__ bin_ptr, const int* __restrict__ pix_idx,
+                                                        const double* __restrict__ factor, int n_bins,
+                                                        double* __restrict__ out) {
+    const long long img = blockIdx.x;
+    const double2* base = spec + img * (long long)n_z * n_pix;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int b = warp; b < n_bins; b += CT / 32) {
+        const int lo = bin_ptr[b], hi = bin_ptr[b + 1];
+        double acc = 0.0;
+        for (int e = lo + lane; e < hi; e += 32) {
+            const int p = pix_idx[e];
+            double zsum = 0.0;
+            for (int z = 0; z < n_z; ++z) {
+                const double2 c = base[(long long)z * n_pix + p];
+                zsum += c.x * c.x + c.y * c.y;
+            }
+            acc += zsum / n_z;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (lane == 0) out[img * n_bins + b] = hi > lo ? acc / (hi - lo) * factor[b] : __longlong_as_double(0x7FF8000000000000LL);
+    }
+}
+
+// NRMSE between two sets of rows with xarray's skip-NaN reductions (xesn/cost.py:227-254 applied to spectra,
+// :257-272): per row k the truth's temporal mean / variance over its non-NaN samples, the squared normalised error
+// over the samples where both are numbers, then the mean over every such (k, s) and the square root.
+// pred [F][G][K][S], truth [F][K][S]; one CTA per (f, g).
+__global__ void __launch_bounds__(CT) nrmse_skipnan_kernel(const double* __restrict__ pred, const double* __restrict__ truth,
+                                                           int G, int K, int S, double* __restrict__ out_fg) {
+    __shared__ double s_red[CT / 32];
+    const int f = blockIdx.x / G, g = blockIdx.x % G;
+    double total = 0.0, count = 0.0;
+    for (int k = 0; k < K; ++k) {
+        const double* tr = truth + ((long long)f * K + k) * S;
+        const double* pr = pred + (((long long)f * G + g) * K + k) * S;
+        double a = 0.0, n = 0.0;
+        for (int s = threadIdx.x; s < S; s += CT) {
+            const double t = tr[s];
+            if (t == t) a += t, n += 1.0;
+        }
+        const double nt = block_sum(n, s_red);
+        const double mean = block_sum(a, s_red) / nt;
+        double v = 0.0, e = 0.0, m = 0.0;
+        for (int s = threadIdx.x; s < S; s += CT) {
+            const double t = tr[s], q = pr[s];
+            if (t == t) {
+                v += (t - mean) * (t - mean);
+                if (q == q) e += (q - t) * (q - t), m += 1.0;
+            }
+        }
+        const double var = block_sum(v, s_red) / nt;
+        const double err = block_sum(e, s_red);
+        const double cnt = block_sum(m, s_red);
+        if (nt > 0.0 && cnt > 0.0) total += err / var, count += cnt;   // an all-NaN row has NaN weights: skipped
+    }
+    if (threadIdx.x == 0) out_fg[blockIdx.x] = sqrt(total / count);
+}
+
 __global__ void cost_mean_kernel(const double* __restrict__ fg, int F, int G, double upper, double* __restrict__ cost) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= G) return;
@@ -148,6 +213,29 @@ extern "C" int xesn_cost_psd_nrmse(const double* pred_dev, const double* truth_d
     XESN_CUDA_OK(cudaFuncSetAttribute(psd_nrmse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     psd_nrmse_kernel<<<(unsigned)(n_windows * n_groups), CT, smem, (cudaStream_t)stream>>>(
         pred_dev, truth_dev, truth_ld, t0, n_groups, n_output, n_times, psd_nrmse_fg_dev);
+    XESN_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+extern "C" int xesn_psd_radial(const double* spec_dev, int64_t n_images, int32_t n_z, int32_t n_pix, const int32_t* bin_ptr_dev,
+                               const int32_t* pix_idx_dev, const double* factor_dev, int32_t n_bins, double* out_dev,
+                               void* stream) {
+    XESN_REQUIRE(spec_dev && bin_ptr_dev && pix_idx_dev && factor_dev && out_dev, "null pointer");
+    XESN_REQUIRE(n_images > 0 && n_z > 0 && n_pix > 0 && n_bins > 0 && n_images < (1LL << 31), "bad sizes");
+    psd_radial_kernel<<<(unsigned)n_images, CT, 0, (cudaStream_t)stream>>>(reinterpret_cast<const double2*>(spec_dev), n_z, n_pix,
+                                                                          bin_ptr_dev, pix_idx_dev, factor_dev, n_bins, out_dev);
+    XESN_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+extern "C" int xesn_nrmse_skipnan(const double* pred_dev, const double* truth_dev, int32_t n_windows, int32_t n_groups,
+                                  int32_t n_rows, int32_t n_times, double* nrmse_fg_dev, void* stream) {
+    XESN_REQUIRE(pred_dev && truth_dev && nrmse_fg_dev, "null pointer");
+    XESN_REQUIRE(n_windows > 0 && n_groups > 0 && n_rows > 0 && n_times > 0, "bad sizes");
+    nrmse_skipnan_kernel<<<(unsigned)(n_windows * n_groups), CT, 0, (cudaStream_t)stream>>>(pred_dev, truth_dev, n_groups, n_rows,
+                                                                                           n_times, nrmse_fg_dev);
     XESN_CUDA_OK(cudaGetLastError());
     count_launch();
     return 0;

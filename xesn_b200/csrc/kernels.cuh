@@ -228,6 +228,10 @@ struct SolveCtx {
 void solve_ctx_destroy(SolveCtx& c);
 int launch_cholesky_solve_ws(SolveCtx& ctx, double* A, long long lda, long long strideA, double* B, long long ldb, long long strideB,
                              int n, int nrhs, int batch, int* info, double* work, cudaStream_t stream);
+// pivoted fallback (lu_solve.cu): one system, lower triangle of A valid (beta on the diagonal), B = nrhs x n rows
+long long lu_workspace_doubles(int n);
+int launch_lu_solve(double* A, long long lda, double* B, long long ldb, int n, int nrhs, int* info, double* work,
+                    cudaStream_t stream);
 int launch_add_diag(double* A, long long lda, long long strideA, int n, int batch, const double* beta_dev,
                     double beta_scalar, cudaStream_t stream);
 

@@ -24,7 +24,7 @@ import numpy as np
 import scipy.sparse
 
 from . import _lib
-from .esn import ESN, DeviceReservoir, _ptr, _time_last, _torch, auto_chunk
+from .esn import ESN, DeviceReservoir, _ptr, _time_last, _torch, auto_chunk, pivoted_fallback
 from .matrix import RandomMatrix, SparseRandomMatrix, _dense_scale, _sparse_scale
 
 
@@ -170,11 +170,16 @@ class ESNEnsemble:
             info = torch.zeros(G, dtype=torch.int32, device=res.device)
             beta = torch.tensor([float(m.tikhonov_parameter) for m in self.members], dtype=torch.float64,
                                 device=res.device)
-            _lib.check(lib.xesn_train_accumulate(
-                res.handle, ctypes.byref(u_series), ctypes.byref(y_series), O, G, n_time, n_spinup, chunk,
-                _ptr(gram), _ptr(wout), _ptr(scratch), nbytes, st))
+            def accumulate():
+                _lib.check(lib.xesn_train_accumulate(
+                    res.handle, ctypes.byref(u_series), ctypes.byref(y_series), O, G, n_time, n_spinup, chunk,
+                    _ptr(gram), _ptr(wout), _ptr(scratch), nbytes, st))
+
+            accumulate()
             _lib.check(lib.xesn_ridge_solve(res.handle, O, G, _ptr(beta), 0.0, _ptr(gram), _ptr(wout), _ptr(info),
                                             _ptr(scratch), nbytes, st))
+            pivoted_fallback(lib, res.handle, accumulate, O, [float(m.tikhonov_parameter) for m in self.members], gram,
+                             wout, info, scratch, nbytes, st, "ESNEnsemble")
             del gram, ku, ky
         self._wout_dev = wout
         self.last_info = info
@@ -217,12 +222,14 @@ class ESNEnsemble:
         stacked = torch.cat(ws, dim=0) if F > 1 else ws[0]          # rows f*O + o
         return self._predict_device(stacked, n_steps, n_spinup, F).cpu().numpy()
 
-    def cost(self, windows, n_steps, n_spinup, cost_upper_bound=1e9, cost_terms=None):
+    def cost(self, windows, n_steps, n_spinup, cost_upper_bound=1e9, cost_terms=None, space_shape=None):
         """The reference's macro-training cost of every member (`cost._cost`, xesn/cost.py:195-225): forecast the F
         windows, per window the factor-weighted sum of the cost terms -- "nrmse" (cost.py:227-254) and, for fields with
         one spatial axis, "psd_nrmse" (cost.py:257-272 over psd.py:12-65); default {"nrmse": 1} like the reference --
         then the average over the windows and the clamp to `cost_upper_bound`.  Forecasts, spectra and errors stay on
-        the device; returns (costs (G,), per-window totals (F, G)) as numpy arrays."""
+        the device; returns (costs (G,), per-window totals (F, G)) as numpy arrays.  `space_shape`: the spatial shape the
+        n_output variables unflatten to (C order) when the field has two or three spatial axes -- the PSD term is then
+        the radially binned spectrum of psd.py:42-65 (xesn_b200/psd.py); default: one spatial axis."""
         torch = _torch()
         res = self._device_reservoir()
         terms = {"nrmse": 1.0} if cost_terms is None else dict(cost_terms)
@@ -245,9 +252,14 @@ class ESNEnsemble:
             if terms != {"nrmse": 1.0}:
                 total = float(terms.get("nrmse", 0.0)) * fg if "nrmse" in terms else torch.zeros_like(fg)
                 if "psd_nrmse" in terms:
-                    pfg = torch.empty((F, G), dtype=torch.float64, device=res.device)
-                    _lib.check(res._lib.xesn_cost_psd_nrmse(_ptr(pred), _ptr(stacked), stacked.stride(0), n_spinup, F, G,
-                                                            O, n_steps + 1, _ptr(pfg), st))
+                    if space_shape is not None and len(tuple(space_shape)) > 1:
+                        from .psd import psd_nrmse_device
+                        truth = stacked.view(F, O, -1)[:, :, n_spinup:n_spinup + n_steps + 1].contiguous()
+                        pfg = psd_nrmse_device(pred.view(F, G, O, n_steps + 1), truth, space_shape)
+                    else:
+                        pfg = torch.empty((F, G), dtype=torch.float64, device=res.device)
+                        _lib.check(res._lib.xesn_cost_psd_nrmse(_ptr(pred), _ptr(stacked), stacked.stride(0), n_spinup, F,
+                                                                G, O, n_steps + 1, _ptr(pfg), st))
                     total = total + float(terms["psd_nrmse"]) * pfg
                 fg = total
                 cost = fg.mean(dim=0)

@@ -323,12 +323,18 @@ class ESN:
                 wout = torch.empty((G, O, N), dtype=torch.float64, device=res.device)
             info = torch.zeros(G, dtype=torch.int32, device=res.device)
             st = self._stream()
-            _lib.check(lib.xesn_train_accumulate(
-                res.handle, ctypes.byref(u_series), ctypes.byref(y_series), O, G, n_time, n_spinup, chunk,
-                _ptr(gram), _ptr(wout), _ptr(scratch), nbytes, st))
+
+            def accumulate():
+                _lib.check(lib.xesn_train_accumulate(
+                    res.handle, ctypes.byref(u_series), ctypes.byref(y_series), O, G, n_time, n_spinup, chunk,
+                    _ptr(gram), _ptr(wout), _ptr(scratch), nbytes, st))
+
+            accumulate()
             _lib.check(lib.xesn_ridge_solve(
                 res.handle, O, G, None, float(self.tikhonov_parameter), _ptr(gram), _ptr(wout), _ptr(info),
                 _ptr(scratch), nbytes, st))
+            pivoted_fallback(lib, res.handle, accumulate, O, [float(self.tikhonov_parameter)] * G, gram, wout, info,
+                             scratch, nbytes, st, type(self).__name__)
             if G == 1:
                 wout = wout.clone()  # do not keep the 8 N^2 bytes of the Gram matrix alive through a view
                 del gram, both
@@ -460,6 +466,33 @@ class ESN:
         if "units" in time.attrs:
             attrs["units"] = time.attrs["units"]
         return xr.DataArray(ftime, coords={"ftime": ftime}, dims="ftime", attrs=attrs)
+
+
+def pivoted_fallback(lib, handle, accumulate, n_output, betas, gram, wout, info, scratch, nbytes, stream, who):
+    """Systems whose Cholesky factorisation failed (info > 0: numerically not positive definite -- tiny
+    tikhonov_parameter, rank-deficient Gram) are solved again with partial pivoting, as the reference does on every
+    system (scipy `assume_a="sym"` = pivoted LDL^T, cupy = LU; xesn/esn.py:516-520).  The failed factorisation
+    destroyed the Gram matrices, so the accumulation is repeated first (rare path; nothing is paid when every system
+    is positive definite, apart from reading `info`).  gram (G, N, N), wout (G, O, N), info (G,) device tensors.
+    XESN_B200_SOLVE_FALLBACK=0 disables it (the readout of such systems is then NaN)."""
+    import os
+    torch = _torch()
+    bad = torch.nonzero(info).flatten().tolist()
+    if not bad or os.environ.get("XESN_B200_SOLVE_FALLBACK", "1") == "0":
+        return bad
+    warnings.warn(f"{who}.train: {len(bad)} ridge system(s) are not positive definite in double precision "
+                  f"(ill-conditioned: tikhonov_parameter too small for this Gram matrix); solved with partial pivoting "
+                  f"like scipy.linalg.solve(assume_a='sym')", RuntimeWarning)
+    good = wout.clone() if len(bad) < wout.shape[0] else None
+    accumulate()
+    for g in bad:
+        _lib.check(lib.xesn_ridge_solve_pivoted(handle, n_output, float(betas[g]), gram[g].data_ptr(), wout[g].data_ptr(),
+                                                info[g:g + 1].data_ptr(), _ptr(scratch), nbytes, stream))
+    if good is not None:
+        keep = torch.ones(wout.shape[0], dtype=torch.bool, device=wout.device)
+        keep[torch.as_tensor(bad, device=wout.device)] = False
+        wout[keep] = good[keep]
+    return bad
 
 
 def torch_index(idx, like):
