@@ -750,3 +750,95 @@ def test_ridge_fallback_only_touches_the_failed_members(torch):
         m = members[g]
         ref = oc.ridge_train(data, data, 10, None, sp.csr_matrix(m.W), m.Win, m.bias_vector, m.leak_rate, m.tikhonov_parameter)
         assert oc.max_normalised_err(w[g], ref) < 1e-4
+
+
+# --------------------------------------------------------------------------- spectra, cost, CostFunction
+@pytest.mark.parametrize("name", ["x12", "x13", "xy8", "xy9", "xyz8"])
+def test_psd_device_matches_reference(torch, name):
+    """xesn_b200.psd (cuFFT + the radial-binning kernel of libxesn_b200.so) against the reference's own `psd`
+    (tests/golden/psd.npz, generated from xesn/psd.py unmodified): 1, 2 and 3 spatial axes."""
+    import xesn_b200
+    z = load_golden("psd.npz")
+    got = xesn_b200.psd(z[f"in_{name}"])
+    ref = z[f"psd_{name}"]
+    assert got.shape == ref.shape
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    np.testing.assert_allclose(np.nan_to_num(got), np.nan_to_num(ref), rtol=1e-11, atol=1e-12 * np.nanmax(np.abs(ref)))
+
+
+def test_ensemble_cost_with_radial_psd_term(torch):
+    """Macro-training cost of candidates on a field with TWO spatial axes (8 x 8 cells flattened to 64 variables):
+    nrmse + 0.5 * psd_nrmse with the radially binned spectrum of psd.py:42-65, on the device, against the oracle."""
+    from xesn_b200 import ESN, ESNEnsemble
+    from xesn_b200.synthetic import wave_field_2d
+    field = wave_field_2d(8, 8, 700).reshape(64, 700)
+    rs = np.random.RandomState(2)
+    members = []
+    for _ in range(3):
+        kw = {k: dict(v) for k, v in ESN_KW.items()}
+        kw["input_kwargs"]["factor"], kw["bias_kwargs"]["factor"] = rs.uniform(0.2, 1.0), rs.uniform(0.1, 1.0)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            members.append(ESN(64, 64, 400, rs.uniform(0.3, 1.0), 10.0 ** rs.uniform(-6, -2), **kw))
+    ens = ESNEnsemble(members)
+    ens.build()
+    ens.train(field[:, :500], n_spinup=10)
+    wins = [field[:, 500:600], field[:, 560:660]]
+    many = ens.predict_windows(wins, n_steps=30, n_spinup=40)
+    truths = np.stack([w[:, 40:71] for w in wins])
+    cost, fg = ens.cost(wins, n_steps=30, n_spinup=40, cost_upper_bound=1e9, cost_terms={"nrmse": 1.0, "psd_nrmse": 0.5},
+                        space_shape=(8, 8))
+    _, ref_n = oc.nrmse_cost(many, truths)
+    ref_fg = ref_n + 0.5 * oc.psd_nrmse_fg(many, truths, space_shape=(8, 8))
+    np.testing.assert_allclose(fg, ref_fg, rtol=1e-9)
+    np.testing.assert_allclose(cost, ref_fg.mean(axis=0), rtol=1e-9)
+
+
+def _macro_config(n_reservoir, model, extra):
+    cfg = {model: dict(n_reservoir=n_reservoir, leak_rate=0.5, tikhonov_parameter=1e-6,
+                       **{k: dict(v) for k, v in ESN_KW.items()}, **extra),
+           "training": {"n_spinup": 5},
+           "macro_training": {"parameters": {"input_factor": None, "leak_rate": None, "tikhonov_parameter": None},
+                              "transformations": {"tikhonov_parameter": "log10"},
+                              "forecast": {"n_samples": 2, "n_spinup": 30, "n_steps": 25},
+                              "cost_terms": {"nrmse": 1.0, "psd_nrmse": 1.0}, "cost_upper_bound": 1e6},
+           "testing": {"n_spinup": 20, "n_steps": 15}}
+    return cfg
+
+
+def test_costfunction_lazy_candidates_and_evaluate(torch):
+    """CostFunction (xesn/cost.py:23-172) with LazyESN candidates -- one model per parameter set, cost terms on the
+    device -- against the oracle's step-by-step restatement; `evaluate` returns the time-resolved diagnostics."""
+    from xesn_b200 import CostFunction, LazyESN
+    from xesn_b200.synthetic import lorenz96
+    data = lorenz96(24, 900)
+    cfg = _macro_config(200, "lazyesn", dict(esn_chunks={"x": 6}, overlap={"x": 1}, boundary="periodic"))
+    train = data[:, :600]
+    macro = [data[:, 600:700], data[:, 700:800]]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        cf = CostFunction(LazyESN, train, macro, cfg, test_data=[data[:, 800:900]])
+        X = np.array([[0.4, 0.6, -4.0], [0.9, 0.3, -2.0]])
+        costs = cf(X, is_transformed=True)
+        assert costs.shape == (2, 1) and np.isfinite(costs).all()
+        depth = {0: 1, 1: 0}
+        for row, got in zip(X, costs[:, 0]):
+            f_in, leak, beta = row[0], row[1], 10.0 ** row[2]
+            kw = {k: dict(v) for k, v in ESN_KW.items()}
+            kw["input_kwargs"]["factor"] = f_in
+            esn = LazyESN({"x": 6}, {"x": 1}, "periodic", 200, leak, beta, **kw)
+            esn.build()
+            W = sp.csr_matrix(esn.W)
+            wout = oc.lazy_train(train, (6,), depth, "periodic", 5, None, W, esn.Win, esn.bias_vector, leak, beta)
+            per_window = []
+            for tr in macro:
+                pred = oc.lazy_predict(tr, (6,), depth, "periodic", 25, 30, W, esn.Win, esn.bias_vector, leak, wout)
+                truth = tr[:, 30:56]
+                _, n_fg = oc.nrmse_cost(pred[None, None], truth[None])
+                per_window.append(n_fg[0, 0] + oc.psd_nrmse_fg(pred[None, None], truth[None])[0, 0])
+            assert abs(got - np.mean(per_window)) <= 1e-5 * np.mean(per_window), (got, np.mean(per_window))
+        out = cf.evaluate({"input_factor": 0.4, "leak_rate": 0.6, "tikhonov_parameter": 1e-4}, use_test_data=True)
+    assert out["prediction"].shape == (1, 24, 16) and out["truth"].shape == (1, 24, 16)
+    assert out["nrmse"].shape == (1, 16) and out["nrmse"][0, 0] == 0.0           # step 0 is the truth
+    assert out["psd_truth"].shape == (1, 12, 16) and out["psd_nrmse"].shape == (1, 16)
+    np.testing.assert_allclose(np.nan_to_num(out["psd_truth"][0]), np.nan_to_num(oc.psd_nd(out["truth"][0])), rtol=1e-10)

@@ -463,3 +463,70 @@ def test_flow_tables_route_every_input(shape, chunks, depth, boundary, world):
         assert total_imports == 0
     else:
         assert 0 < total_imports < n_cells                             # halo strips, not the whole field
+
+
+# --------------------------------------------------------------------------- checkpoint round trip (io.py)
+def test_checkpoint_roundtrip_npz_and_zarr_gate(tmp_path):
+    """`to_xds` content (readout + constructor kwargs incl. seeds) through the dependency-free .npz twin: the rebuilt
+    model has the same matrices (the seeds are the checkpoint, xesn/esn.py:309-338, io.py:13-53) and readout; LazyESN
+    readouts travel in the reference's block layout with the singleton axis re-appended (io.py:46-49)."""
+    import warnings
+    import xesn_b200 as xb
+    from xesn_b200 import halo
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        esn = xb.ESN(3, 3, 60, 0.4, 1e-5, **{k: dict(v) for k, v in ESN_KW.items()})
+        esn.build()
+        esn.Wout = np.random.RandomState(0).normal(size=(3, 60))
+        path = str(tmp_path / "eager.npz")
+        xb.to_npz(esn, path)
+        back = xb.from_npz(path)
+        assert type(back) is xb.ESN and back.leak_rate == 0.4 and back.adjacency_kwargs == esn.adjacency_kwargs
+        np.testing.assert_allclose(back.Win, esn.Win, rtol=1e-12)
+        np.testing.assert_allclose(back.W.toarray(), esn.W.toarray(), rtol=1e-12)
+        np.testing.assert_array_equal(back.Wout, esn.Wout)
+
+        lazy = xb.LazyESN({"x": 2, "y": 3, "z": 2}, {"x": 1, "y": 1, "z": 0}, {"x": "periodic", "y": 0.0}, 30, 0.5, 1e-6,
+                          **{k: dict(v) for k, v in ESN_KW.items()})
+        lazy.build()
+        grid = (4, 2, 1)
+        wg = np.random.RandomState(1).normal(size=(8, lazy.n_output, 30))
+        lazy._grid = grid
+        lazy.Wout = halo.wout_to_blocks(wg, grid)
+        assert lazy.Wout.shape == (4 * 12, 2 * 30, 1)
+        path = str(tmp_path / "lazy.npz")
+        xb.to_npz(lazy, path)
+        assert np.load(path)["Wout"].shape == (48, 60)          # stored squeezed, like to_xds
+        back = xb.from_npz(path)
+        assert type(back) is xb.LazyESN and back.boundary == {"x": "periodic", "y": 0.0} and back.overlap["z"] == 0
+        np.testing.assert_array_equal(back.Wout, lazy.Wout)
+        np.testing.assert_array_equal(halo.blocks_to_wout(back.Wout, back._grid, 12, 30), wg)
+        untrained = xb.ESN(3, 3, 60, 0.4, 1e-5, **{k: dict(v) for k, v in ESN_KW.items()})
+        with pytest.raises(Exception):
+            xb.to_npz(untrained, str(tmp_path / "no.npz"))
+    try:
+        import xarray  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError):
+            xb.from_zarr(str(tmp_path / "store.zarr"))
+
+
+def test_psd_bin_tables_match_binned_statistic():
+    """The annulus cell lists the device kernel uses against scipy.stats.binned_statistic on the same wavenumbers
+    (xesn/psd.py:42-65)."""
+    from scipy.fft import fftfreq
+    from scipy.stats import binned_statistic
+    from xesn_b200.psd import bin_tables
+    for n_x, nd in ((12, 1), (13, 1), (8, 2), (9, 2), (32, 2)):
+        bin_ptr, pix_idx, factor, k_vals = bin_tables(n_x, nd)
+        k = n_x * fftfreq(n_x)
+        k_tot = np.abs(k) if nd == 1 else np.sqrt(sum(a ** 2 for a in np.meshgrid(k, k))).reshape(-1)
+        k_bins = np.arange(.5, n_x // 2 + 1, 1.)
+        values = np.random.RandomState(n_x).rand(k_tot.size)
+        with np.errstate(all="ignore"):
+            ref, _, _ = binned_statistic(k_tot, values, statistic="mean", bins=k_bins)
+        got = np.array([values[pix_idx[bin_ptr[b]:bin_ptr[b + 1]]].mean() if bin_ptr[b + 1] > bin_ptr[b] else np.nan
+                        for b in range(len(factor))])
+        np.testing.assert_allclose(np.nan_to_num(got), np.nan_to_num(ref), rtol=1e-13)
+        assert np.array_equal(np.isnan(got), np.isnan(ref))
+        np.testing.assert_allclose(factor, np.pi * (k_bins[1:] ** 2 - k_bins[:-1] ** 2))

@@ -11,7 +11,10 @@ from .esn import ESN
 from .lazyesn import LazyESN
 from .ensemble import ESNEnsemble
 from .cost import CostFunction
+from .io import from_zarr, from_npz, to_npz
+from .psd import psd
 from ._lib import XesnError, LIB_PATH, launch_count
 
-__all__ = ["ESN", "LazyESN", "ESNEnsemble", "CostFunction", "RandomMatrix", "SparseRandomMatrix", "XesnError", "LIB_PATH", "launch_count"]
+__all__ = ["ESN", "LazyESN", "ESNEnsemble", "CostFunction", "RandomMatrix", "SparseRandomMatrix", "from_zarr", "from_npz", "to_npz",
+           "psd", "XesnError", "LIB_PATH", "launch_count"]
 __version__ = "0.1.0"
