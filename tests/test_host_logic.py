@@ -520,7 +520,7 @@ def test_psd_bin_tables_match_binned_statistic():
     for n_x, nd in ((12, 1), (13, 1), (8, 2), (9, 2), (32, 2)):
         bin_ptr, pix_idx, factor, k_vals = bin_tables(n_x, nd)
         k = n_x * fftfreq(n_x)
-        k_tot = np.abs(k) if nd == 1 else np.sqrt(sum(a ** 2 for a in np.meshgrid(k, k))).reshape(-1)
+        k_tot = k if nd == 1 else np.sqrt(sum(a ** 2 for a in np.meshgrid(k, k))).reshape(-1)
         k_bins = np.arange(.5, n_x // 2 + 1, 1.)
         values = np.random.RandomState(n_x).rand(k_tot.size)
         with np.errstate(all="ignore"):

@@ -27,7 +27,7 @@ def bin_tables(n_x, ndim_space):
     if key not in _TABLES:
         k = np.fft.fftfreq(n_x) * n_x
         if ndim_space == 1:
-            k_tot = np.abs(k)
+            k_tot = k            # signed, as psd.py:45-46 has it: only the positive half of the spectrum is binned
         else:
             kx, ky = np.meshgrid(k, k)
             k_tot = np.sqrt(kx ** 2 + ky ** 2).reshape(-1)
