@@ -172,7 +172,7 @@ int fused_recur_geometry(int N, int n_groups, int threads, int* team_out, int* u
 int fused_smem_bytes(const RecurArgs& a, int team, bool* w_in_smem) {
     const int upc = (a.N + team - 1) / team;
     (void)upc;
-    const long long n_pad = (a.N + 1) & ~1;
+    const long long n_pad = ((a.N + 1) & ~1) + 2;
     const long long smem_r = n_pad * 8;
     const long long smem_w = (long long)(a.smem_nnz + (a.smem_nnz & 1)) * 12 + 16;
     const long long limit = 227 * 1024;
@@ -190,7 +190,7 @@ int launch_fused_chunk(RecurArgs rp, int n_groups, int team, int upt, int max_sl
     const bool has_rec = rp.steps > 0;
     rp.units_per_cta = recur_units_per_cta(rp.N, team);
     rp.smem_nnz = max_slice_nnz + (max_slice_nnz & 1);
-    rp.n_pad = (rp.N + 1) & ~1;
+    rp.n_pad = ((rp.N + 1) & ~1) + 2;
     bool w_in_smem = false;
     const int smem = fused_smem_bytes(rp, team, &w_in_smem);
     if (smem < 0) {
@@ -239,7 +239,7 @@ int launch_fused_chunk_i8(RecurArgs rp, int n_groups, int team, int upt, int max
     const bool has_rec = rp.steps > 0;
     rp.units_per_cta = recur_units_per_cta(rp.N, team);
     rp.smem_nnz = max_slice_nnz + (max_slice_nnz & 1);
-    rp.n_pad = (rp.N + 1) & ~1;
+    rp.n_pad = ((rp.N + 1) & ~1) + 2;
     bool w_in_smem = false;
     const int smem = fused_smem_bytes(rp, team, &w_in_smem);
     if (smem < 0) {

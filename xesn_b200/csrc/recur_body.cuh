@@ -188,6 +188,44 @@ __device__ __forceinline__ void put_digits(signed char* planes, const RecurArgs&
     }
 }
 
+// Refresh of the shared-memory state copy with coalesced polling loads: PB 16-byte pieces in flight per thread and
+// round.  PB is chosen per launch (the smallest that covers the state vector in one round, at most PollCfg::BATCH):
+// an unrolled batch of 8 costs ~50 predicated instructions per retry even when a thread has one piece to fetch, and
+// the recurrence role is instruction-issue bound.  `mine_all`: bit (round * PB + b) = piece b of that round is this
+// thread's to fetch (pieces inside the own slice are already in the copy).
+template <int PB, int RC_THREADS>
+__device__ __forceinline__ void refresh_copy(const double* r_next, double* s_r, int n2, int tid, unsigned mine_all,
+                                             bool packed_masks, int u0, int u1, int* status, bool& aborted) {
+    int it = 0;
+    for (int q0 = tid; q0 < n2; q0 += RC_THREADS * PB, ++it) {
+        double2 v[PB];
+        unsigned pending = 0;  // bit b: piece b still has an unset half
+        if (packed_masks) {
+            pending = (mine_all >> (it * PB)) & ((1u << PB) - 1u);
+        } else {
+#pragma unroll
+            for (int b = 0; b < PB; ++b) {
+                const int q = q0 + b * RC_THREADS;
+                if ((q < n2) && !(2 * q >= u0 && 2 * q + 1 < u1)) pending |= 1u << b;
+            }
+        }
+        const unsigned mine = pending;
+        int spins = 0;
+        while (pending && !aborted) {
+#pragma unroll
+            for (int b = 0; b < PB; ++b)
+                if (pending & (1u << b)) v[b] = ld_flag2(r_next + 2 * (q0 + b * RC_THREADS));
+#pragma unroll
+            for (int b = 0; b < PB; ++b)
+                if ((pending & (1u << b)) && !unset(v[b].x) && !unset(v[b].y)) pending &= ~(1u << b);
+            if (pending) aborted = poll_expired(spins, status);
+        }
+#pragma unroll
+        for (int b = 0; b < PB; ++b)
+            if (mine & (1u << b)) *reinterpret_cast<double2*>(s_r + 2 * (q0 + b * RC_THREADS)) = v[b];
+    }
+}
+
 // The CTA `c` of the `C` CTAs that own reservoir `g` runs the whole chunk.  RC_THREADS = threads
 // taking part (the calling CTA's size); all C CTAs must be co-resident (cluster or cooperative launch).
 template <int UPT, int RC_THREADS, bool WS>
@@ -237,10 +275,14 @@ __device__ __forceinline__ void recur_body(const RecurArgs& p, const unsigned c,
         r_cur[j] = ok ? carry[unit] : 0.0;
         d_next[j] = (ok && p.steps > 0) ? drive[unit] : 0.0;
     }
-    // register-resident head of each owned row
+    // register-resident head of each owned row.  Padding entries (rows shorter than KREG) carry weight 0 and point at a
+    // dedicated slot of the copy that always holds 0: the row dot then needs no predication (0 * 0 added to the
+    // running sum changes nothing, bit for bit), which saves three instructions per entry in an issue-bound loop
     constexpr int KREG = RowRegs<UPT, RC_THREADS>::K;
     constexpr int POLL_BATCH = PollCfg<RC_THREADS, UPT>::BATCH;
     const unsigned s_r_addr = (unsigned)__cvta_generic_to_shared(s_r);
+    const int zero_off = (p.n_pad - 1) * (int)sizeof(double);  // launchers reserve n_pad >= N + 1 entries
+    if (tid == 0) s_r[p.n_pad - 1] = 0.0;
     double hv[UPT][KREG];
     int ho[UPT][KREG];
 #pragma unroll
@@ -249,20 +291,20 @@ __device__ __forceinline__ void recur_body(const RecurArgs& p, const unsigned c,
         for (int k = 0; k < KREG; ++k) {
             const bool in = k < row_len[j];
             hv[j][k] = in ? w_values[row_lo[j] + k] : 0.0;
-            ho[j][k] = in ? p.indices[row_lo[j] + k] * (int)sizeof(double) : 0;
+            ho[j][k] = in ? p.indices[row_lo[j] + k] * (int)sizeof(double) : zero_off;
         }
     // pieces of the state copy this thread refreshes per polling round (own slice excluded); constant over
-    // the chunk, packed POLL_BATCH bits per round when all rounds fit one word
+    // the chunk, packed poll_batch bits per round when all rounds fit one word
     const int n2_all = N >> 1;
-    const int poll_rounds = (n2_all + RC_THREADS * POLL_BATCH - 1) / (RC_THREADS * POLL_BATCH);
-    const bool packed_masks = poll_rounds * POLL_BATCH <= 32;
+    const int poll_batch = RC_THREADS * 2 >= n2_all ? 2 : POLL_BATCH;   // small reservoirs: two pieces per thread cover the copy
+    const int poll_rounds = (n2_all + RC_THREADS * poll_batch - 1) / (RC_THREADS * poll_batch);
+    const bool packed_masks = poll_rounds * poll_batch <= 32;
     unsigned mine_all = 0;
     if (packed_masks)
         for (int it = 0; it < poll_rounds; ++it)
-#pragma unroll
-            for (int b = 0; b < POLL_BATCH; ++b) {
-                const int q = tid + (it * POLL_BATCH + b) * RC_THREADS;
-                if ((q < n2_all) && !(2 * q >= u0 && 2 * q + 1 < u1)) mine_all |= 1u << (it * POLL_BATCH + b);
+            for (int b = 0; b < poll_batch; ++b) {
+                const int q = tid + (it * poll_batch + b) * RC_THREADS;
+                if ((q < n2_all) && !(2 * q >= u0 && 2 * q + 1 < u1)) mine_all |= 1u << (it * poll_batch + b);
             }
     put_states<UPT>(states + ubase, r_cur, nvalid);  // row 0 = state entering the chunk (read by the Gram kernel)
     if (digits && p.steps > 0) put_digits<UPT>(digits, p, 0, ubase, r_cur, nvalid);
@@ -293,8 +335,7 @@ __device__ __forceinline__ void recur_body(const RecurArgs& p, const unsigned c,
         for (int j = 0; j < UPT; ++j) {
             double acc = 0.0;
 #pragma unroll
-            for (int k = 0; k < KREG; ++k)
-                if (k < row_len[j]) acc = __dadd_rn(acc, __dmul_rn(hv[j][k], gth[j][k]));
+            for (int k = 0; k < KREG; ++k) acc = __dadd_rn(acc, __dmul_rn(hv[j][k], gth[j][k]));  // padding: + 0 * 0
             hsum[j] = acc;
         }
         // long rows: the next KTAIL entries are staged together (offsets and values from the CSR slice, then
@@ -378,35 +419,10 @@ __device__ __forceinline__ void recur_body(const RecurArgs& p, const unsigned c,
         if (C > 1 && !p.debug_no_exchange) {
             if (vec2) {
                 const int n2 = N >> 1;
-                int it = 0;
-                for (int q0 = tid; q0 < n2; q0 += RC_THREADS * POLL_BATCH, ++it) {
-                    double2 v[POLL_BATCH];
-                    unsigned pending = 0;  // bit b: piece b still has an unset half
-                    if (packed_masks) {
-                        pending = (mine_all >> (it * POLL_BATCH)) & ((1u << POLL_BATCH) - 1u);
-                    } else {
-#pragma unroll
-                        for (int b = 0; b < POLL_BATCH; ++b) {
-                            const int q = q0 + b * RC_THREADS;
-                            // pieces lying entirely inside my own slice are already in the copy
-                            if ((q < n2) && !(2 * q >= u0 && 2 * q + 1 < u1)) pending |= 1u << b;
-                        }
-                    }
-                    const unsigned mine = pending;
-                    int spins = 0;
-                    while (pending && !aborted) {
-#pragma unroll
-                        for (int b = 0; b < POLL_BATCH; ++b)
-                            if (pending & (1u << b)) v[b] = ld_flag2(r_next + 2 * (q0 + b * RC_THREADS));
-#pragma unroll
-                        for (int b = 0; b < POLL_BATCH; ++b)
-                            if ((pending & (1u << b)) && !unset(v[b].x) && !unset(v[b].y)) pending &= ~(1u << b);
-                        if (pending) aborted = poll_expired(spins, p.status);
-                    }
-#pragma unroll
-                    for (int b = 0; b < POLL_BATCH; ++b)
-                        if (mine & (1u << b)) *reinterpret_cast<double2*>(s_r + 2 * (q0 + b * RC_THREADS)) = v[b];
-                }
+                if (poll_batch <= 2)
+                    refresh_copy<2, RC_THREADS>(r_next, s_r, n2, tid, mine_all, packed_masks, u0, u1, p.status, aborted);
+                else
+                    refresh_copy<POLL_BATCH, RC_THREADS>(r_next, s_r, n2, tid, mine_all, packed_masks, u0, u1, p.status, aborted);
             } else {
                 for (int q = tid; q < N; q += RC_THREADS) {
                     if (q >= u0 && q < u1) continue;

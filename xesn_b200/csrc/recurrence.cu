@@ -247,7 +247,7 @@ int launch_recur_forced(RecurArgs a, int n_groups, int max_slice_nnz, cudaStream
     }
     a.units_per_cta = recur_units_per_cta(a.N, C);
     a.smem_nnz = max_slice_nnz + (max_slice_nnz & 1);
-    a.n_pad = (a.N + 1) & ~1;
+    a.n_pad = ((a.N + 1) & ~1) + 2;
     // shared memory: full state copy (always) + this CTA's CSR slice of W (if it fits)
     const long long smem_r = (long long)a.n_pad * 8;
     const long long smem_w = (long long)a.smem_nnz * 12 + 16;
