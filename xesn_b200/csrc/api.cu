@@ -510,12 +510,13 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
         if ((rc = forced_launch(h, r, G, st))) return rc;
     }
     // accumulate: xesn/esn.py:502-513
-    int team = 0, upt = 0;
+    int team = 0, upt = 0, halves = 1;
     int pull_upc = 0, pull_upt = 0;
     const bool pull = h->recur_pull == 2 && gram_mode_effective(h) == 1 && pull_geometry(N, G, h->num_sms, &pull_upc, &pull_upt) == 0;
     const bool fuse = h->fused_enabled && (N % 2 == 0) && T > n_spinup &&
-                      (pull || (fused_recur_geometry(N, G, fused_threads(gram_mode_effective(h) == 1), &team, &upt) == 0 &&
-                                (long long)team * G < h->num_sms));
+                      (pull || (fused_recur_geometry(N, G, fused_threads(gram_mode_effective(h) == 1), &team, &upt,
+                                                     gram_mode_effective(h) == 1 ? &halves : nullptr) == 0 &&
+                                (long long)team * G / halves < h->num_sms));
     if (fuse) {
         // software pipeline over chunks: launch c runs recurrence(c) || Gram(c-1) in one cooperative kernel
         const int upc = pull ? N : recur_units_per_cta(N, team);
@@ -581,7 +582,7 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
             {
                 ProfScope prof(PROF_FUSED, st);
                 rc = pull ? launch_fused_pull_i8(r, G, g8, h->d_tiles_i8, ntiles, h->num_sms, st)
-                     : i8 ? launch_fused_chunk_i8(r, G, team, upt, slice_nnz, g8, h->d_tiles_i8, ntiles, h->num_sms, st)
+                     : i8 ? launch_fused_chunk_i8(r, G, team, upt, halves, slice_nnz, g8, h->d_tiles_i8, ntiles, h->num_sms, st)
                           : launch_fused_chunk(r, G, team, upt, slice_nnz, g, h->d_tiles, ntiles, h->num_sms, st);
                 if (rc) return rc;
             }

@@ -70,14 +70,31 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     } while (0)
 #endif
 
+// member_bytes > 0: every recurrence CTA hosts TWO 256-thread team members of different reservoirs (virtual member
+// v = half * rec_ctas + blockIdx.x; reservoirs [0, G/2) in half 0, [G/2, G) in half 1).  A member spends more than
+// half of a step waiting for its peers' states; the other member computes meanwhile, so each reservoir's chain sees
+// a half-size slice (shorter arithmetic, less skew between its warps) on the same number of SMs.
 template <int UPT, bool WS>
 __global__ void __launch_bounds__(FUSED_I8_THREADS, 1)
-fused_chunk_i8_kernel(RecurArgs rp, int rec_ctas, int team, gi8::GramI8Args gp, const __grid_constant__ CUtensorMap tmA,
-                      const __grid_constant__ CUtensorMap tmB, const int2* __restrict__ tiles, int ntiles) {
+fused_chunk_i8_kernel(RecurArgs rp, int rec_ctas, int team, int member_bytes, gi8::GramI8Args gp,
+                      const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const int2* __restrict__ tiles, int ntiles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     XESN_CTA_STAMP(0);
     if ((int)blockIdx.x < rec_ctas) {
-        recur::recur_body<UPT, FUSED_I8_THREADS, WS>(rp, blockIdx.x % team, team, blockIdx.x / team, smem_raw);
+        bool done = false;
+        if constexpr (UPT == 1) {   // the launcher pairs members only for one unit per thread
+            if (member_bytes > 0) {
+                const int half = threadIdx.x >> 8, v = half * rec_ctas + blockIdx.x;
+                if (half == 0)
+                    recur::recur_body<UPT, FUSED_I8_THREADS / 2, WS, 1>(rp, v % team, team, v / team, smem_raw, threadIdx.x & 255);
+                else
+                    recur::recur_body<UPT, FUSED_I8_THREADS / 2, WS, 2>(rp, v % team, team, v / team, smem_raw + member_bytes,
+                                                                        threadIdx.x & 255);
+                done = true;
+            }
+        }
+        if (!done) recur::recur_body<UPT, FUSED_I8_THREADS, WS>(rp, blockIdx.x % team, team, blockIdx.x / team, smem_raw);
         XESN_CTA_STAMP(1);
         return;
     }
@@ -130,7 +147,8 @@ __global__ void __launch_bounds__(recur::PULL_THREADS, 1) pull_forced_kernel(Rec
 }  // namespace
 
 // team size / units per thread of the recurrence role for FUSED_THREADS-wide CTAs
-int fused_recur_geometry(int N, int n_groups, int threads, int* team_out, int* upt_out) {
+int fused_recur_geometry(int N, int n_groups, int threads, int* team_out, int* upt_out, int* halves_out) {
+    if (halves_out) *halves_out = 1;
     // The recurrence role wants many thin CTAs (its per-step cost grows with the units per CTA: the
     // shared-memory gathers of W r are bank-conflict bound), the Gram role wants the SMs.  Default: `threads`
     // x UPT units per CTA with the smallest UPT whose total CTA count stays within the cap (48 CTAs for one
@@ -166,6 +184,15 @@ int fused_recur_geometry(int N, int n_groups, int threads, int* team_out, int* u
         if ((long long)threads * upt >= upc) best_team = want_team, best_upt = upt;
     }
     *team_out = best_team, *upt_out = best_upt;
+    // several small reservoirs on the int8 pipeline: two 256-thread members of different reservoirs per SM
+    // (fused_chunk_i8_kernel); same SM count, twice the team size.  XESN_B200_REC_SPLIT=0 keeps whole-CTA members.
+    const char* e = getenv("XESN_B200_REC_SPLIT");
+    if (halves_out && threads == 512 && n_groups >= 2 && n_groups % 2 == 0 && best_upt == 1 && !(e && e[0] == '0')) {
+        const int team_v = (N + 255) / 256;
+        const int upc_v = recur_units_per_cta(N, team_v);
+        if (upc_v <= 256 && (long long)team_v * n_groups / 2 <= cap && (N + upc_v - 1) / upc_v == team_v)
+            *team_out = team_v, *halves_out = 2;
+    }
     return 0;
 }
 
@@ -234,20 +261,33 @@ namespace xesn {
 int fused_threads(int i8) { return i8 ? FUSED_I8_THREADS : FUSED_THREADS; }
 
 
-int launch_fused_chunk_i8(RecurArgs rp, int n_groups, int team, int upt, int max_slice_nnz,
+int launch_fused_chunk_i8(RecurArgs rp, int n_groups, int team, int upt, int halves, int max_slice_nnz,
                           const gi8::GramI8Args& gp, const int2* tiles, int ntiles, int num_sms, cudaStream_t stream) {
     const bool has_rec = rp.steps > 0;
     rp.units_per_cta = recur_units_per_cta(rp.N, team);
     rp.smem_nnz = max_slice_nnz + (max_slice_nnz & 1);
     rp.n_pad = ((rp.N + 1) & ~1) + 2;
     bool w_in_smem = false;
-    const int smem = fused_smem_bytes(rp, team, &w_in_smem);
+    int smem = fused_smem_bytes(rp, team, &w_in_smem);
     if (smem < 0) {
         set_error("fused chunk: n_reservoir=%d does not fit the shared-memory state copy", rp.N);
         return -2;
     }
+    int member_bytes = 0;
+    if (halves == 2) {
+        // two members per CTA: each gets its own state copy (+ slice of W if both fit)
+        const long long smem_r = (long long)rp.n_pad * 8;
+        const long long smem_w = (long long)rp.smem_nnz * 12 + 16;
+        w_in_smem = 2 * (smem_r + smem_w) + 32 <= 227 * 1024;
+        member_bytes = (int)(((w_in_smem ? smem_r + smem_w : smem_r) + 15) & ~15LL);
+        if (2LL * member_bytes > 227 * 1024) {
+            set_error("fused chunk: two members of n_reservoir=%d do not fit one SM", rp.N);
+            return -2;
+        }
+        smem = std::max(smem, 2 * member_bytes);
+    }
     rp.w_in_smem = w_in_smem;
-    int rec_ctas = has_rec ? team * n_groups : 0;
+    int rec_ctas = has_rec ? team * n_groups / halves : 0;
     if (has_rec) {
         XESN_CUDA_OK(cudaMemset2DAsync(rp.states, sizeof(double) * rp.state_group_stride, 0xFF,
                                        sizeof(double) * (size_t)(rp.steps + 1) * rp.N, n_groups, stream));
@@ -259,7 +299,7 @@ int launch_fused_chunk_i8(RecurArgs rp, int n_groups, int team, int upt, int max
         set_error("fused chunk: recurrence role needs %d CTAs, device has %d SMs", rec_ctas, num_sms);
         return -2;
     }
-    void (*kern)(RecurArgs, int, int, gi8::GramI8Args, const CUtensorMap, const CUtensorMap, const int2*, int);
+    void (*kern)(RecurArgs, int, int, int, gi8::GramI8Args, const CUtensorMap, const CUtensorMap, const int2*, int);
     if (w_in_smem)
         kern = upt == 1 ? fused_chunk_i8_kernel<1, true>
                         : (upt == 2 ? fused_chunk_i8_kernel<2, true>
@@ -275,7 +315,7 @@ int launch_fused_chunk_i8(RecurArgs rp, int n_groups, int team, int upt, int max
     memset(&tm_b, 0, sizeof(tm_b));
     if (ntiles > 0)
         if (int rc = gram_i8_make_maps(g, &tm_a, &tm_b)) return rc;
-    void* args[] = {&rp, &rec_ctas, &team, &g, &tm_a, &tm_b, (void*)&tiles, &ntiles};
+    void* args[] = {&rp, &rec_ctas, &team, &member_bytes, &g, &tm_a, &tm_b, (void*)&tiles, &ntiles};
     XESN_CUDA_OK(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(FUSED_I8_THREADS), args, (size_t)smem, stream));
     count_launch();
     return 0;

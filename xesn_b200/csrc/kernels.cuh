@@ -76,13 +76,13 @@ int recur_cluster_size(int N);
 inline int recur_units_per_cta(int N, int team) { return ((N + team - 1) / team + 7) & ~7; }
 // fused recurrence(c) || Gram(c-1) chunk kernel (fused_train.cu)
 int fused_threads(int i8);  // CTA width of the fused chunk kernel (256 FP64-Gram, 512 int8-Gram)
-int fused_recur_geometry(int N, int n_groups, int threads, int* team_out, int* upt_out);
+int fused_recur_geometry(int N, int n_groups, int threads, int* team_out, int* upt_out, int* halves_out = nullptr);
 int launch_fused_chunk(RecurArgs rp, int n_groups, int team, int upt, int max_slice_nnz, const GemmArgs& gp,
                        const int2* tiles, int ntiles, int num_sms, cudaStream_t stream);
 namespace gi8 { struct GramI8Args; }
 // same, with the Gram role on the int8 tensor cores (tcgen05 kind::i8) reading digit planes
 int gram_i8_make_maps(const gi8::GramI8Args& a, void* map_a, void* map_b);  // two CUtensorMap (64-byte aligned)
-int launch_fused_chunk_i8(RecurArgs rp, int n_groups, int team, int upt, int max_slice_nnz,
+int launch_fused_chunk_i8(RecurArgs rp, int n_groups, int team, int upt, int halves, int max_slice_nnz,
                           const gi8::GramI8Args& gp, const int2* tiles, int ntiles, int num_sms, cudaStream_t stream);
 // pull-model recurrence (pull_body.cuh): spread over all SMs, beside the Gram role in every CTA
 int pull_geometry(int N, int n_groups, int n_ctas, int* upc_out, int* upt_out);

@@ -228,10 +228,19 @@ __device__ __forceinline__ void refresh_copy(const double* r_next, double* s_r, 
 
 // The CTA `c` of the `C` CTAs that own reservoir `g` runs the whole chunk.  RC_THREADS = threads
 // taking part (the calling CTA's size); all C CTAs must be co-resident (cluster or cooperative launch).
-template <int UPT, int RC_THREADS, bool WS>
+// SUB > 0: the caller is one of several independent RC_THREADS-wide sub-blocks of a wider CTA (fused_train.cu hosts
+// two 256-thread team members of DIFFERENT reservoirs per SM so that one computes while the other waits for its
+// peers); it passes its thread index inside the sub-block and synchronises on named barrier SUB instead of barrier 0.
+template <int SUB>
+__device__ __forceinline__ void sub_block_sync(int n_threads) {
+    if (SUB == 0) __syncthreads();
+    else asm volatile("bar.sync %0, %1;\n" ::"n"(SUB), "r"(n_threads) : "memory");
+}
+
+template <int UPT, int RC_THREADS, bool WS, int SUB = 0>
 __device__ __forceinline__ void recur_body(const RecurArgs& p, const unsigned c, const unsigned C, const int g,
-                                           unsigned char* smem_raw) {
-    const int tid = threadIdx.x;
+                                           unsigned char* smem_raw, const int sub_tid = -1) {
+    const int tid = SUB == 0 ? (int)threadIdx.x : sub_tid;
     const int N = p.N;
     const int upc = p.units_per_cta;
     const int u0 = c * upc;
@@ -279,7 +288,7 @@ __device__ __forceinline__ void recur_body(const RecurArgs& p, const unsigned c,
     // dedicated slot of the copy that always holds 0: the row dot then needs no predication (0 * 0 added to the
     // running sum changes nothing, bit for bit), which saves three instructions per entry in an issue-bound loop
     constexpr int KREG = RowRegs<UPT, RC_THREADS>::K;
-    constexpr int POLL_BATCH = PollCfg<RC_THREADS, UPT>::BATCH;
+    constexpr int POLL_BATCH = SUB ? 8 : PollCfg<RC_THREADS, UPT>::BATCH;  // sub-blocks live under a 128-register cap
     const unsigned s_r_addr = (unsigned)__cvta_generic_to_shared(s_r);
     const int zero_off = (p.n_pad - 1) * (int)sizeof(double);  // launchers reserve n_pad >= N + 1 entries
     if (tid == 0) s_r[p.n_pad - 1] = 0.0;
@@ -296,7 +305,8 @@ __device__ __forceinline__ void recur_body(const RecurArgs& p, const unsigned c,
     // pieces of the state copy this thread refreshes per polling round (own slice excluded); constant over
     // the chunk, packed poll_batch bits per round when all rounds fit one word
     const int n2_all = N >> 1;
-    const int poll_batch = RC_THREADS * 2 >= n2_all ? 2 : POLL_BATCH;   // small reservoirs: two pieces per thread cover the copy
+    // small reservoirs: two (or four) pieces per thread cover the copy in one round
+    const int poll_batch = RC_THREADS * 2 >= n2_all ? 2 : ((SUB && RC_THREADS * 4 >= n2_all) ? 4 : POLL_BATCH);
     const int poll_rounds = (n2_all + RC_THREADS * poll_batch - 1) / (RC_THREADS * poll_batch);
     const bool packed_masks = poll_rounds * poll_batch <= 32;
     unsigned mine_all = 0;
@@ -311,7 +321,7 @@ __device__ __forceinline__ void recur_body(const RecurArgs& p, const unsigned c,
     const double alpha = p.alpha_g ? p.alpha_g[pg] : p.alpha, oma = 1.0 - alpha;
     const bool vec2 = (N % 2 == 0) && ((reinterpret_cast<uintptr_t>(states) & 15) == 0);
     bool aborted = false;
-    __syncthreads();
+    sub_block_sync<SUB>(RC_THREADS);
 
 #ifdef XESN_RECUR_TRACE
     long long tr_sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -410,7 +420,7 @@ __device__ __forceinline__ void recur_body(const RecurArgs& p, const unsigned c,
         for (int j = 0; j < UPT; ++j)
             if (j < nvalid) d_next[j] = __ldg(drive + (long long)(t + 1) * N + ubase + j);
         XESN_TRACE_MARK(0);
-        __syncthreads();  // every gather of r_t is done: the shared copy may be overwritten
+        sub_block_sync<SUB>(RC_THREADS);  // every gather of r_t is done: the shared copy may be overwritten
         XESN_TRACE_MARK(1);
 #pragma unroll
         for (int j = 0; j < UPT; ++j)
@@ -421,6 +431,8 @@ __device__ __forceinline__ void recur_body(const RecurArgs& p, const unsigned c,
                 const int n2 = N >> 1;
                 if (poll_batch <= 2)
                     refresh_copy<2, RC_THREADS>(r_next, s_r, n2, tid, mine_all, packed_masks, u0, u1, p.status, aborted);
+                else if (SUB && poll_batch == 4)
+                    refresh_copy<4, RC_THREADS>(r_next, s_r, n2, tid, mine_all, packed_masks, u0, u1, p.status, aborted);
                 else
                     refresh_copy<POLL_BATCH, RC_THREADS>(r_next, s_r, n2, tid, mine_all, packed_masks, u0, u1, p.status, aborted);
             } else {
@@ -437,7 +449,7 @@ __device__ __forceinline__ void recur_body(const RecurArgs& p, const unsigned c,
             }
         }
         XESN_TRACE_MARK(2);
-        __syncthreads();
+        sub_block_sync<SUB>(RC_THREADS);
         XESN_TRACE_MARK(3);
     }
 #ifdef XESN_RECUR_TRACE
