@@ -579,25 +579,33 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
                 g8.batch = G;
                 ntiles = i8 ? h->n_tiles_i8 : h->n_tiles;
             }
-            {
-                ProfScope prof(PROF_FUSED, st);
-                rc = pull ? launch_fused_pull_i8(r, G, g8, h->d_tiles_i8, ntiles, h->num_sms, st)
-                     : i8 ? launch_fused_chunk_i8(r, G, team, upt, halves, slice_nnz, g8, h->d_tiles_i8, ntiles, h->num_sms, st)
-                          : launch_fused_chunk(r, G, team, upt, slice_nnz, g, h->d_tiles, ntiles, h->num_sms, st);
-                if (rc) return rc;
-            }
+            // ybar += Y R of chunk c-1: skinny targets ride in the Gram role of the int8 fused kernel, else a launch of
+            // their own after it
+            GemmArgs q = {};
+            bool yr_in_kernel = false;
             if (c >= 1) {
                 const int mp = chunk_m(c - 1);
                 const double* yb;
                 long long ldy, ygs;
                 if ((rc = chunk_inputs(h, y, O, G, chunk_t0(c - 1), mp, Yc, L.cld, &yb, &ldy, &ygs, st))) return rc;
-                GemmArgs q = {};
                 q.A = yb, q.lda = ldy, q.strideA = ygs;
                 q.B = Rbuf[(c - 1) & 1], q.ldb = N, q.strideB = (long long)(mp + 1) * N;
                 q.C = wout, q.ldc = N, q.strideC = (long long)O * N;
                 q.M = O, q.N = N, q.K = mp, q.batch = G, q.alpha = 1.0, q.beta = 1.0, q.flags = GEMM_A_KMAJOR;
+                yr_in_kernel = i8 && !pull && O <= YR_SKINNY_MAX_ROWS && !getenv("XESN_B200_YR_SEPARATE");
+            }
+            GemmArgs q_none = {};
+            {
+                ProfScope prof(PROF_FUSED, st);
+                rc = pull ? launch_fused_pull_i8(r, G, g8, h->d_tiles_i8, ntiles, h->num_sms, st)
+                     : i8 ? launch_fused_chunk_i8(r, G, team, upt, halves, slice_nnz, g8, h->d_tiles_i8, ntiles,
+                                                  yr_in_kernel ? q : q_none, h->num_sms, st)
+                          : launch_fused_chunk(r, G, team, upt, slice_nnz, g, h->d_tiles, ntiles, h->num_sms, st);
+                if (rc) return rc;
+            }
+            if (c >= 1 && !yr_in_kernel) {
                 ProfScope prof(PROF_YR, st);
-                if ((rc = launch_gemm_f64(q, st))) return rc;
+                if ((rc = (O <= YR_SKINNY_MAX_ROWS ? launch_yr_skinny(q, st) : launch_gemm_f64(q, st)))) return rc;
             }
         }
         return 0;
@@ -636,7 +644,7 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
         q.M = O, q.N = N, q.K = m, q.batch = G, q.alpha = 1.0, q.beta = 1.0, q.flags = GEMM_A_KMAJOR;
         {
             ProfScope prof(PROF_YR, st);
-            if ((rc = launch_gemm_f64(q, st))) return rc;
+            if ((rc = (O <= YR_SKINNY_MAX_ROWS ? launch_yr_skinny(q, st) : launch_gemm_f64(q, st)))) return rc;
         }
     }
     return 0;

@@ -64,5 +64,8 @@ struct GemmArgs {
 
 // C = alpha * op(A) op(B) + beta * C (+ bias), FP64 on the tensor pipe (DMMA m8n8k4)
 int launch_gemm_f64(const GemmArgs& a, cudaStream_t stream);
+// the same contraction for a skinny A (n_output <= 64 target rows, time-contiguous) and B[k*ldb + n]: yr_skinny.cuh
+int launch_yr_skinny(const GemmArgs& a, cudaStream_t stream);
+constexpr int YR_SKINNY_MAX_ROWS = 64;
 
 }  // namespace xesn

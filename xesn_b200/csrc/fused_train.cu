@@ -26,6 +26,7 @@
 #include "kernels.cuh"
 #include "recur_body.cuh"
 #include "pull_body.cuh"
+#include "yr_skinny.cuh"
 
 namespace xesn {
 namespace {
@@ -78,7 +79,7 @@ template <int UPT, bool WS>
 __global__ void __launch_bounds__(FUSED_I8_THREADS, 1)
 fused_chunk_i8_kernel(RecurArgs rp, int rec_ctas, int team, int member_bytes, gi8::GramI8Args gp,
                       const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                      const int2* __restrict__ tiles, int ntiles) {
+                      const int2* __restrict__ tiles, int ntiles, GemmArgs yrp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     XESN_CTA_STAMP(0);
     if ((int)blockIdx.x < rec_ctas) {
@@ -100,11 +101,20 @@ fused_chunk_i8_kernel(RecurArgs rp, int rec_ctas, int team, int member_bytes, gi
     }
     const int worker = blockIdx.x - rec_ctas, nworkers = gridDim.x - rec_ctas;
     const long long total = (long long)ntiles * gp.batch;
-    if (worker >= total) return;
-    gi8::GramI8Ctx ctx;
-    gi8::gram_i8_setup(ctx, smem_raw);
-    gi8::gram_i8_run<FUSED_I8_THREADS>(ctx, gp, &tmA, &tmB, tiles, ntiles, worker, nworkers);
-    gi8::gram_i8_teardown(ctx);
+    if (worker < total) {
+        gi8::GramI8Ctx ctx;
+        gi8::gram_i8_setup(ctx, smem_raw);
+        gi8::gram_i8_run<FUSED_I8_THREADS>(ctx, gp, &tmA, &tmB, tiles, ntiles, worker, nworkers);
+        gi8::gram_i8_teardown(ctx);
+    }
+    // ybar += Y R of the same (previous) chunk: skinny work items taken by the Gram CTAs as they run out of tiles --
+    // free in recurrence-bound configurations, where the Gram role ends long before the recurrence role
+    if (yrp.M > 0) {
+        __syncthreads();
+        const long long items = yr::n_items(yrp);
+        for (long long it = worker; it < items; it += nworkers)
+            yr::yr_item<FUSED_I8_THREADS>(yrp, it, reinterpret_cast<double*>(smem_raw));
+    }
     XESN_CTA_STAMP(1);
 }
 
@@ -262,7 +272,8 @@ int fused_threads(int i8) { return i8 ? FUSED_I8_THREADS : FUSED_THREADS; }
 
 
 int launch_fused_chunk_i8(RecurArgs rp, int n_groups, int team, int upt, int halves, int max_slice_nnz,
-                          const gi8::GramI8Args& gp, const int2* tiles, int ntiles, int num_sms, cudaStream_t stream) {
+                          const gi8::GramI8Args& gp, const int2* tiles, int ntiles, const GemmArgs& yr_args, int num_sms,
+                          cudaStream_t stream) {
     const bool has_rec = rp.steps > 0;
     rp.units_per_cta = recur_units_per_cta(rp.N, team);
     rp.smem_nnz = max_slice_nnz + (max_slice_nnz & 1);
@@ -299,7 +310,7 @@ int launch_fused_chunk_i8(RecurArgs rp, int n_groups, int team, int upt, int hal
         set_error("fused chunk: recurrence role needs %d CTAs, device has %d SMs", rec_ctas, num_sms);
         return -2;
     }
-    void (*kern)(RecurArgs, int, int, int, gi8::GramI8Args, const CUtensorMap, const CUtensorMap, const int2*, int);
+    void (*kern)(RecurArgs, int, int, int, gi8::GramI8Args, const CUtensorMap, const CUtensorMap, const int2*, int, GemmArgs);
     if (w_in_smem)
         kern = upt == 1 ? fused_chunk_i8_kernel<1, true>
                         : (upt == 2 ? fused_chunk_i8_kernel<2, true>
@@ -315,7 +326,10 @@ int launch_fused_chunk_i8(RecurArgs rp, int n_groups, int team, int upt, int hal
     memset(&tm_b, 0, sizeof(tm_b));
     if (ntiles > 0)
         if (int rc = gram_i8_make_maps(g, &tm_a, &tm_b)) return rc;
-    void* args[] = {&rp, &rec_ctas, &team, &member_bytes, &g, &tm_a, &tm_b, (void*)&tiles, &ntiles};
+    GemmArgs yr_copy = yr_args;
+    if (ntiles == 0) yr_copy.M = 0;   // no Gram CTAs in this launch: the caller runs the Y R pass itself
+    smem = std::max(smem, yr::smem_bytes<FUSED_I8_THREADS>());
+    void* args[] = {&rp, &rec_ctas, &team, &member_bytes, &g, &tm_a, &tm_b, (void*)&tiles, &ntiles, &yr_copy};
     XESN_CUDA_OK(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(FUSED_I8_THREADS), args, (size_t)smem, stream));
     count_launch();
     return 0;

@@ -15,8 +15,11 @@
 //
 // CTA tile 128x128x16, 256 threads = 8 warps (2 x 4), warp tile 64x32 -> 32 DMMA per k4 step
 // against 12 LDS.64 (shared memory padded so fragment loads are bank-conflict free).
+#include <algorithm>
+
 #include "common.cuh"
 #include "gemm_tile.cuh"
+#include "yr_skinny.cuh"
 
 namespace xesn {
 namespace {
@@ -38,7 +41,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_f64_kernel(GemmArgs p, int t
 
 inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
+constexpr int YR_THREADS = 256;
+__global__ void __launch_bounds__(YR_THREADS) yr_skinny_kernel(GemmArgs p) {
+    extern __shared__ __align__(16) double smem[];
+    const long long items = yr::n_items(p);
+    for (long long it = blockIdx.x; it < items; it += gridDim.x) yr::yr_item<YR_THREADS>(p, it, smem);
+}
+
 }  // namespace
+
+// C += alpha * A B for a skinny A (few target rows, time-contiguous) and B = state ring rows; see yr_skinny.cuh
+int launch_yr_skinny(const GemmArgs& a, cudaStream_t stream) {
+    if (a.M <= 0 || a.N <= 0 || a.K <= 0 || a.batch <= 0) return 0;
+    const int smem = yr::smem_bytes<YR_THREADS>();
+    XESN_CUDA_OK(cudaFuncSetAttribute(yr_skinny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const long long items = yr::n_items(a);
+    yr_skinny_kernel<<<(unsigned)std::min<long long>(items, 4 * 148), YR_THREADS, smem, stream>>>(a);
+    count_launch();
+    XESN_CUDA_OK(cudaGetLastError());
+    return 0;
+}
 
 int launch_gemm_f64(const GemmArgs& a, cudaStream_t stream) {
     if (a.M <= 0 || a.N <= 0 || a.batch <= 0) return 0;
@@ -65,11 +87,8 @@ int launch_gemm_f64(const GemmArgs& a, cudaStream_t stream) {
     };
     const int which = (ak ? 4 : 0) + (bk ? 2 : 0) + (vec ? 1 : 0);
     void (*kern)(GemmArgs, int) = table[which];
-    static bool attr_done[8] = {false, false, false, false, false, false, false, false};
-    if (!attr_done[which]) {
-        XESN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr_done[which] = true;
-    }
+    // per device, so on every launch rather than once per process (two handles may live on two GPUs)
+    XESN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     kern<<<grid, NTHREADS, SMEM_BYTES, stream>>>(a, tiles_n);
     count_launch();
     XESN_CUDA_OK(cudaGetLastError());
