@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "kernels.cuh"
 #include "gram_i8.cuh"
+#include "yr_skinny.cuh"
 
 namespace xesn {
 
@@ -546,8 +547,27 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
         };
         int rc = drive_for(0);
         if (rc) return rc;
+        // few inputs: the drive of chunk c+1 is computed by the Gram CTAs of launch c (yr_skinny.cuh) instead of a
+        // GEMM launch of its own between the fused launches
+        // ... when the Gram role has time to spare: small reservoirs, whose chunk is bounded by the serial recurrence
+        // (measured: 16 x N=2000 gains 3 ms of 57; N=16000, bounded by the Gram role, loses 6 of 125)
+        const bool drive_in_kernel = i8 && !pull && upt == 1 && h->I <= drv::MAX_INPUTS && (double)G * N * N <= 1.0e8 &&
+                                     !getenv("XESN_B200_DRIVE_SEPARATE");
         for (long long c = 0; c <= nch; ++c) {
-            if (c + 1 < nch && (rc = drive_for(c + 1))) return rc;
+            drv::DriveArgs dv = {};
+            if (c + 1 < nch) {
+                if (drive_in_kernel) {
+                    const double* ub;
+                    long long ldu, ugs;
+                    if ((rc = chunk_inputs(h, u, h->I, G, chunk_t0(c + 1), chunk_m(c + 1), Uc, L.cld, &ub, &ldu, &ugs, st))) return rc;
+                    dv.U = ub, dv.ldu = ldu, dv.ugs = ugs;
+                    dv.Win = h->d_win, dv.bias = h->d_bias, dv.win_gs = h->win_gs, dv.bias_gs = h->bias_gs;
+                    dv.param_groups = h->n_param_groups, dv.D = Dbuf[(c + 1) & 1];
+                    dv.m = chunk_m(c + 1), dv.N = N, dv.I = h->I, dv.G = G;
+                } else if ((rc = drive_for(c + 1))) {
+                    return rc;
+                }
+            }
             RecurArgs r = recur_args(h);
             if (c < nch) {
                 const int m = chunk_m(c);
@@ -599,7 +619,7 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
                 ProfScope prof(PROF_FUSED, st);
                 rc = pull ? launch_fused_pull_i8(r, G, g8, h->d_tiles_i8, ntiles, h->num_sms, st)
                      : i8 ? launch_fused_chunk_i8(r, G, team, upt, halves, slice_nnz, g8, h->d_tiles_i8, ntiles,
-                                                  yr_in_kernel ? q : q_none, h->num_sms, st)
+                                                  yr_in_kernel ? q : q_none, dv, h->num_sms, st)
                           : launch_fused_chunk(r, G, team, upt, slice_nnz, g, h->d_tiles, ntiles, h->num_sms, st);
                 if (rc) return rc;
             }

@@ -75,11 +75,13 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 // v = half * rec_ctas + blockIdx.x; reservoirs [0, G/2) in half 0, [G/2, G) in half 1).  A member spends more than
 // half of a step waiting for its peers' states; the other member computes meanwhile, so each reservoir's chain sees
 // a half-size slice (shorter arithmetic, less skew between its warps) on the same number of SMs.
-template <int UPT, bool WS>
+// DRV: the variant whose Gram CTAs can also compute the next chunk's drive (kept out of the plain variant: its
+// registers would spill in the Gram role, which bounds the large-reservoir configurations)
+template <int UPT, bool WS, bool DRV>
 __global__ void __launch_bounds__(FUSED_I8_THREADS, 1)
 fused_chunk_i8_kernel(RecurArgs rp, int rec_ctas, int team, int member_bytes, gi8::GramI8Args gp,
                       const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                      const int2* __restrict__ tiles, int ntiles, GemmArgs yrp) {
+                      const int2* __restrict__ tiles, int ntiles, GemmArgs yrp, drv::DriveArgs dvp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     XESN_CTA_STAMP(0);
     if ((int)blockIdx.x < rec_ctas) {
@@ -114,6 +116,14 @@ fused_chunk_i8_kernel(RecurArgs rp, int rec_ctas, int team, int member_bytes, gi
         const long long items = yr::n_items(yrp);
         for (long long it = worker; it < items; it += nworkers)
             yr::yr_item<FUSED_I8_THREADS>(yrp, it, reinterpret_cast<double*>(smem_raw));
+    }
+    // Win u + b of the NEXT chunk (few inputs): likewise taken by the Gram CTAs when their tiles are done
+    if constexpr (DRV) {
+        if (dvp.m > 0) {
+            const long long items = drv::n_items(dvp);
+            for (long long it = worker; it < items; it += nworkers)
+                drv::drive_item<FUSED_I8_THREADS>(dvp, it, reinterpret_cast<double*>(smem_raw));
+        }
     }
     XESN_CTA_STAMP(1);
 }
@@ -272,8 +282,8 @@ int fused_threads(int i8) { return i8 ? FUSED_I8_THREADS : FUSED_THREADS; }
 
 
 int launch_fused_chunk_i8(RecurArgs rp, int n_groups, int team, int upt, int halves, int max_slice_nnz,
-                          const gi8::GramI8Args& gp, const int2* tiles, int ntiles, const GemmArgs& yr_args, int num_sms,
-                          cudaStream_t stream) {
+                          const gi8::GramI8Args& gp, const int2* tiles, int ntiles, const GemmArgs& yr_args,
+                          const drv::DriveArgs& drive_args, int num_sms, cudaStream_t stream) {
     const bool has_rec = rp.steps > 0;
     rp.units_per_cta = recur_units_per_cta(rp.N, team);
     rp.smem_nnz = max_slice_nnz + (max_slice_nnz & 1);
@@ -304,21 +314,27 @@ int launch_fused_chunk_i8(RecurArgs rp, int n_groups, int team, int upt, int hal
                                        sizeof(double) * (size_t)(rp.steps + 1) * rp.N, n_groups, stream));
     }
     int grid = num_sms;
-    if (ntiles == 0) grid = rec_ctas;
+    if (ntiles == 0 && drive_args.m <= 0) grid = rec_ctas;
     if (grid <= 0) return 0;
-    if (rec_ctas >= grid && ntiles > 0) {
+    if (rec_ctas >= grid && (ntiles > 0 || drive_args.m > 0)) {
         set_error("fused chunk: recurrence role needs %d CTAs, device has %d SMs", rec_ctas, num_sms);
         return -2;
     }
-    void (*kern)(RecurArgs, int, int, int, gi8::GramI8Args, const CUtensorMap, const CUtensorMap, const int2*, int, GemmArgs);
+    void (*kern)(RecurArgs, int, int, int, gi8::GramI8Args, const CUtensorMap, const CUtensorMap, const int2*, int, GemmArgs,
+                 drv::DriveArgs);
+    const bool drv_on = drive_args.m > 0;
+    if (drv_on && upt != 1) {
+        set_error("fused chunk: the in-kernel drive is built for one unit per thread");
+        return -2;
+    }
     if (w_in_smem)
-        kern = upt == 1 ? fused_chunk_i8_kernel<1, true>
-                        : (upt == 2 ? fused_chunk_i8_kernel<2, true>
-                                    : (upt == 4 ? fused_chunk_i8_kernel<4, true> : fused_chunk_i8_kernel<8, true>));
+        kern = upt == 1 ? (drv_on ? fused_chunk_i8_kernel<1, true, true> : fused_chunk_i8_kernel<1, true, false>)
+                        : (upt == 2 ? fused_chunk_i8_kernel<2, true, false>
+                                    : (upt == 4 ? fused_chunk_i8_kernel<4, true, false> : fused_chunk_i8_kernel<8, true, false>));
     else
-        kern = upt == 1 ? fused_chunk_i8_kernel<1, false>
-                        : (upt == 2 ? fused_chunk_i8_kernel<2, false>
-                                    : (upt == 4 ? fused_chunk_i8_kernel<4, false> : fused_chunk_i8_kernel<8, false>));
+        kern = upt == 1 ? (drv_on ? fused_chunk_i8_kernel<1, false, true> : fused_chunk_i8_kernel<1, false, false>)
+                        : (upt == 2 ? fused_chunk_i8_kernel<2, false, false>
+                                    : (upt == 4 ? fused_chunk_i8_kernel<4, false, false> : fused_chunk_i8_kernel<8, false, false>));
     XESN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     gi8::GramI8Args g = gp;
     alignas(64) CUtensorMap tm_a, tm_b;
@@ -329,7 +345,8 @@ int launch_fused_chunk_i8(RecurArgs rp, int n_groups, int team, int upt, int hal
     GemmArgs yr_copy = yr_args;
     if (ntiles == 0) yr_copy.M = 0;   // no Gram CTAs in this launch: the caller runs the Y R pass itself
     smem = std::max(smem, yr::smem_bytes<FUSED_I8_THREADS>());
-    void* args[] = {&rp, &rec_ctas, &team, &member_bytes, &g, &tm_a, &tm_b, (void*)&tiles, &ntiles, &yr_copy};
+    drv::DriveArgs dv = drive_args;
+    void* args[] = {&rp, &rec_ctas, &team, &member_bytes, &g, &tm_a, &tm_b, (void*)&tiles, &ntiles, &yr_copy, &dv};
     XESN_CUDA_OK(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(FUSED_I8_THREADS), args, (size_t)smem, stream));
     count_launch();
     return 0;

@@ -82,10 +82,12 @@ int launch_fused_chunk(RecurArgs rp, int n_groups, int team, int upt, int max_sl
 namespace gi8 { struct GramI8Args; }
 // same, with the Gram role on the int8 tensor cores (tcgen05 kind::i8) reading digit planes
 int gram_i8_make_maps(const gi8::GramI8Args& a, void* map_a, void* map_b);  // two CUtensorMap (64-byte aligned)
-// yr_args.M > 0: the Gram CTAs also run ybar += Y R of the previous chunk (skinny targets, yr_skinny.cuh)
+// yr_args.M > 0: the Gram CTAs also run ybar += Y R of the previous chunk (skinny targets, yr_skinny.cuh);
+// drive_args.m > 0: and the input projection Win u + b of the next chunk (few inputs)
+namespace drv { struct DriveArgs; }
 int launch_fused_chunk_i8(RecurArgs rp, int n_groups, int team, int upt, int halves, int max_slice_nnz,
-                          const gi8::GramI8Args& gp, const int2* tiles, int ntiles, const GemmArgs& yr_args, int num_sms,
-                          cudaStream_t stream);
+                          const gi8::GramI8Args& gp, const int2* tiles, int ntiles, const GemmArgs& yr_args,
+                          const drv::DriveArgs& drive_args, int num_sms, cudaStream_t stream);
 // pull-model recurrence (pull_body.cuh): spread over all SMs, beside the Gram role in every CTA
 int pull_geometry(int N, int n_groups, int n_ctas, int* upc_out, int* upt_out);
 int launch_pull_forced(RecurArgs rp, int n_groups, int num_sms, cudaStream_t stream);

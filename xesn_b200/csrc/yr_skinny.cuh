@@ -90,3 +90,69 @@ __device__ __forceinline__ void yr_item(const GemmArgs& p, long long item, doubl
 
 }  // namespace yr
 }  // namespace xesn
+
+// ---- drive of a chunk, D[g][t][n] = sum_i U_g[i][t] Win[n][i] + b[n], for a SMALL number of inputs -----------------
+// (xesn/esn.py:459 `Win @ u` for every step of the chunk).  With 18 ... 64 inputs this is an outer-product-like pass
+// bound by writing D (m x N x 8 bytes per reservoir), not a GEMM worth 128 x 128 tiles.  A work item is (reservoir,
+// block of 16 time steps): the inputs of the block sit in shared memory, a thread owns a column n and keeps the 16
+// sums in registers, streaming its row of Win once; stores are coalesced along n.  Run by the Gram CTAs of the fused
+// training kernel for chunk c+1 while the recurrence role works on chunk c.
+namespace xesn {
+namespace drv {
+
+constexpr int TB = 16;          // time steps per work item (16 sums in registers: the fused kernel lives under a 128-register cap)
+constexpr int MAX_INPUTS = 64;  // shared-memory tile [I][TB]
+
+struct DriveArgs {
+    const double* U;      // row i of reservoir g, time t: U[g*ugs + i*ldu + t]
+    long long ldu, ugs;
+    const double* Win;    // [N][I] per parameter set
+    const double* bias;   // [N]
+    long long win_gs, bias_gs;
+    int param_groups;     // reservoir g uses parameter set g % param_groups (0 / 1: shared)
+    double* D;            // [G][m][N]
+    int m, N, I, G;
+};
+
+__host__ __device__ inline long long n_items(const DriveArgs& p) { return (long long)p.G * ((p.m + TB - 1) / TB); }
+
+template <int NTHREADS>
+__device__ __forceinline__ void drive_item(const DriveArgs& p, long long item, double* smem) {
+    const int blocks = (p.m + TB - 1) / TB;
+    const int g = (int)(item / blocks), t0 = (int)(item % blocks) * TB;
+    const int nt = min(TB, p.m - t0);
+    const int pg = g % max(p.param_groups, 1);
+    const double* U = p.U + (long long)g * p.ugs + t0;
+    const double* Win = p.Win + (long long)pg * p.win_gs;
+    const double* bias = p.bias + (long long)pg * p.bias_gs;
+    double* D = p.D + ((long long)g * p.m + t0) * p.N;
+    __syncthreads();
+    for (int e = threadIdx.x; e < p.I * TB; e += NTHREADS) {
+        const int i = e / TB, t = e % TB;
+        smem[e] = t < nt ? U[(long long)i * p.ldu + t] : 0.0;
+    }
+    __syncthreads();
+    for (int n = threadIdx.x; n < p.N; n += NTHREADS) {
+        double acc[TB];
+#pragma unroll
+        for (int t = 0; t < TB; ++t) acc[t] = 0.0;
+        const double* w = Win + (long long)n * p.I;
+        for (int i = 0; i < p.I; ++i) {
+            const double wi = __ldg(w + i);
+            const double2* u2 = reinterpret_cast<const double2*>(smem + i * TB);
+#pragma unroll
+            for (int t = 0; t < TB / 2; ++t) {
+                const double2 u = u2[t];
+                acc[2 * t] = fma(u.x, wi, acc[2 * t]);
+                acc[2 * t + 1] = fma(u.y, wi, acc[2 * t + 1]);
+            }
+        }
+        const double b = __ldg(bias + n);
+#pragma unroll
+        for (int t = 0; t < TB; ++t)
+            if (t < nt) D[(long long)t * p.N + n] = acc[t] + b;
+    }
+}
+
+}  // namespace drv
+}  // namespace xesn
