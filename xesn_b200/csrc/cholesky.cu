@@ -41,7 +41,6 @@ potrf_diag_kernel(double* A, long long lda, long long strideA, int j0, int nbj, 
     double* S = sm;                      // [NB][LDS] the factor, for the inversion phase
     double* colbuf = sm + NB * LDS;      // [NB]
     double* rowbuf = colbuf + NB;        // [2][NB]
-    __shared__ double s_piv[2];  // sqrt(pivot) and its reciprocal, computed once by the owner thread
     const int tid = threadIdx.x;
     const int ty = tid >> 4, tx = tid & 15;
     const int b = blockIdx.x;
@@ -60,39 +59,41 @@ potrf_diag_kernel(double* A, long long lda, long long strideA, int j0, int nbj, 
             a[x][y] = v;
         }
 
-    // ---- factorisation (right-looking, one column per step) ----
+    // ---- factorisation (right-looking, one column per step, ONE CTA barrier per step) ----
+    // After the update of step k-1 the owners of column k (tx == k % 16) publish it RAW -- pivot included -- and every
+    // thread scales it itself with rsqrt(pivot) computed redundantly: no owner-only sqrt/divide between two barriers
+    // (the first version spent ~1400 cycles per column on sqrt + divide + two barriers; the chain of 125 such blocks
+    // is what the look-ahead of the blocked factorisation has to hide).
+    // column buffers, double-buffered: colbuf for even k, the first half of rowbuf (free in this phase) for odd k
+    if (tx == 0) {
+#pragma unroll
+        for (int x = 0; x < 8; ++x) colbuf[ty + 16 * x] = a[x][0];
+    }
+    __syncthreads();
 #pragma unroll
     for (int ka = 0; ka < 8; ++ka) {
         for (int kx = 0; kx < 16; ++kx) {
             const int k = ka * 16 + kx;
-            if (ty == kx && tx == kx) {
-                const double piv = a[ka][ka];
-                if (!(piv > 0.0) || !(piv < 1.7e308)) atomicCAS(&info[b], 0, j0 + k + 1);  // not positive definite
-                const double dd = sqrt(piv);
-                s_piv[0] = dd;
-                s_piv[1] = 1.0 / dd;
-            }
-            __syncthreads();
-            const double d = s_piv[0], rinv = s_piv[1];
-            if (tx == kx) {
-#pragma unroll
-                for (int x = 0; x < 8; ++x) {
-                    const int i = ty + 16 * x;
-                    if (i > k) {
-                        a[x][ka] *= rinv;
-                        colbuf[i] = a[x][ka];
-                    } else if (i == k) {
-                        a[x][ka] = d;
-                    }
-                }
-            }
-            __syncthreads();
-            // only register blocks that can still change: x >= ka (rows > k), ka <= y <= x
+            const double* col = (k & 1) ? rowbuf : colbuf;
+            const double piv = col[k];
+            if (tid == 0 && (!(piv > 0.0) || !(piv < 1.7e308))) atomicCAS(&info[b], 0, j0 + k + 1);  // not positive definite
+            const double rinv = rsqrt(piv);
+            const double d = piv * rinv;
+            // scaled column entries this thread needs: rows of its register blocks and columns of its register blocks
             double li[8], lj[8];
 #pragma unroll
-            for (int x = ka; x < 8; ++x) li[x] = colbuf[ty + 16 * x];
+            for (int x = ka; x < 8; ++x) li[x] = col[ty + 16 * x] * rinv;
 #pragma unroll
-            for (int y = ka; y < 8; ++y) lj[y] = colbuf[tx + 16 * y];
+            for (int y = ka; y < 8; ++y) lj[y] = col[tx + 16 * y] * rinv;
+            if (tx == kx) {   // owners of column k keep the final values
+#pragma unroll
+                for (int x = ka; x < 8; ++x) {
+                    const int i = ty + 16 * x;
+                    if (i > k) a[x][ka] = li[x];
+                    else if (i == k) a[x][ka] = d;
+                }
+            }
+            // only register blocks that can still change: x >= ka (rows > k), ka <= y <= x
 #pragma unroll
             for (int x = ka; x < 8; ++x)
 #pragma unroll
@@ -100,6 +101,21 @@ potrf_diag_kernel(double* A, long long lda, long long strideA, int j0, int nbj, 
                     const int i = ty + 16 * x, j = tx + 16 * y;
                     if (j > k && j <= i) a[x][y] = fma(-li[x], lj[y], a[x][y]);
                 }
+            // publish column k+1 (final after this update) for the next step
+            // (register arrays need compile-time indices: the two cases of "next column" are spelled out)
+            double* nxt = (k & 1) ? colbuf : rowbuf;
+            if (kx < 15) {
+                if (tx == kx + 1) {
+#pragma unroll
+                    for (int x = ka; x < 8; ++x) nxt[ty + 16 * x] = a[x][ka];
+                }
+            } else if (ka + 1 < 8) {
+                if (tx == 0) {
+#pragma unroll
+                    for (int x = ka + 1; x < 8; ++x) nxt[ty + 16 * x] = a[x][(ka + 1) & 7];
+                }
+            }
+            __syncthreads();
         }
     }
 #pragma unroll
@@ -112,19 +128,24 @@ potrf_diag_kernel(double* A, long long lda, long long strideA, int j0, int nbj, 
             if (i < nbj && j <= i) Ab[(long long)i * lda + j] = v;
         }
     __syncthreads();
+    // reciprocals of the diagonal, once, instead of a divide inside every step of the substitution below
+    double* dinv_all = colbuf;
+    if (tid < NB) dinv_all[tid] = 1.0 / S[tid * LDS + tid];
+    __syncthreads();
 
     // ---- inverse: L X = I by forward substitution, one row per step ----
 #pragma unroll
     for (int x = 0; x < 8; ++x)
 #pragma unroll
         for (int y = 0; y < 8; ++y) a[x][y] = (ty + 16 * x == tx + 16 * y) ? 1.0 : 0.0;
+    double* rowbufs = rowbuf;  // [2][NB]
 #pragma unroll
     for (int ka = 0; ka < 8; ++ka) {
         for (int kx = 0; kx < 16; ++kx) {
             const int k = ka * 16 + kx;
-            double* rb = rowbuf + (k & 1) * NB;
+            double* rb = rowbufs + (k & 1) * NB;
             if (ty == kx) {
-                const double dinv = 1.0 / S[k * LDS + k];
+                const double dinv = dinv_all[k];
 #pragma unroll
                 for (int y = 0; y < 8; ++y) {
                     const int j = tx + 16 * y;

@@ -208,9 +208,10 @@ int fused_recur_geometry(int N, int n_groups, int threads, int* team_out, int* u
     // (fused_chunk_i8_kernel); same SM count, twice the team size.  XESN_B200_REC_SPLIT=0 keeps whole-CTA members.
     const char* e = getenv("XESN_B200_REC_SPLIT");
     if (halves_out && threads == 512 && n_groups >= 2 && n_groups % 2 == 0 && best_upt == 1 && !(e && e[0] == '0')) {
-        const int team_v = (N + 255) / 256;
+        int team_v = (N + 255) / 256, cap_v = cap;
+        if (const char* t = getenv("XESN_B200_REC_TEAM_V")) team_v = atoi(t), cap_v = 100;   // experiments: thinner members
         const int upc_v = recur_units_per_cta(N, team_v);
-        if (upc_v <= 256 && (long long)team_v * n_groups / 2 <= cap && (N + upc_v - 1) / upc_v == team_v)
+        if (team_v >= 1 && upc_v <= 256 && (long long)team_v * n_groups / 2 <= cap_v && (N + upc_v - 1) / upc_v == team_v)
             *team_out = team_v, *halves_out = 2;
     }
     return 0;
