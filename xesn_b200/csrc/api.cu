@@ -133,6 +133,8 @@ struct xesn_reservoir {
     SolveCtx solve;  // side stream + events of the look-ahead Cholesky, per handle (= per device)
     int* d_flow_tail_ptr = nullptr;  // predict_flow.cu: offsets of the rows' tails, cached for one (team, upc)
     int flow_tail_team = 0, flow_tail_upc = 0;
+    int* d_cl_tail_ptr = nullptr;    // recur_cluster.cuh: the same for the cluster recurrence, cached for one team size
+    int cl_tail_team = 0;
 };
 static inline int gram_mode_effective(const xesn_reservoir* h) { return (h->gram_mode == 1 && h->leak_unit_range) ? 1 : 0; }
 
@@ -266,6 +268,7 @@ int xesn_reservoir_destroy(xesn_reservoir* h) {
     cudaFree(h->d_ro_counters);
     solve_ctx_destroy(h->solve);
     cudaFree(h->d_flow_tail_ptr);
+    cudaFree(h->d_cl_tail_ptr);
     delete h;
     return 0;
 }
@@ -514,15 +517,29 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
     int team = 0, upt = 0, halves = 1;
     int pull_upc = 0, pull_upt = 0;
     const bool pull = h->recur_pull == 2 && gram_mode_effective(h) == 1 && pull_geometry(N, G, h->num_sms, &pull_upc, &pull_upt) == 0;
+    // small reservoirs: the team of a reservoir is a thread-block cluster that exchanges states through distributed
+    // shared memory (recur_cluster.cuh); XESN_B200_REC_CLUSTER=0 keeps the L2-polling teams
+    int cteam = 0, ctail = 0;
+    const bool cluster = !pull && gram_mode_effective(h) == 1 &&
+                         cluster_recur_geometry(N, G, h->h_indptr.data(), h->num_sms, &cteam, &ctail);
+    if (cluster && h->cl_tail_team != cteam) {
+        std::vector<int> tp((size_t)cteam * (recur_units_per_cta(N, cteam) + 1));
+        cluster_tail_ptr(N, cteam, h->h_indptr.data(), tp.data());
+        if (h->d_cl_tail_ptr) XESN_CUDA_OK(cudaFree(h->d_cl_tail_ptr));
+        h->d_cl_tail_ptr = nullptr;
+        XESN_CUDA_OK(cudaMalloc(&h->d_cl_tail_ptr, sizeof(int) * tp.size()));
+        XESN_CUDA_OK(cudaMemcpy(h->d_cl_tail_ptr, tp.data(), sizeof(int) * tp.size(), cudaMemcpyHostToDevice));
+        h->cl_tail_team = cteam;
+    }
     const bool fuse = h->fused_enabled && (N % 2 == 0) && T > n_spinup &&
-                      (pull || (fused_recur_geometry(N, G, fused_threads(gram_mode_effective(h) == 1), &team, &upt,
+                      (pull || cluster || (fused_recur_geometry(N, G, fused_threads(gram_mode_effective(h) == 1), &team, &upt,
                                                      gram_mode_effective(h) == 1 ? &halves : nullptr) == 0 &&
                                 (long long)team * G / halves < h->num_sms));
     if (fuse) {
         // software pipeline over chunks: launch c runs recurrence(c) || Gram(c-1) in one cooperative kernel
-        const int upc = pull ? N : recur_units_per_cta(N, team);
+        const int upc = (pull || cluster) ? N : recur_units_per_cta(N, team);
         int slice_nnz = 0;
-        for (int c = 0; c < (pull ? 0 : team); ++c) {
+        for (int c = 0; c < ((pull || cluster) ? 0 : team); ++c) {
             const int lo = c * upc < N ? c * upc : N, hi = (c + 1) * upc < N ? (c + 1) * upc : N;
             slice_nnz = std::max(slice_nnz, h->h_indptr[hi] - h->h_indptr[lo]);
         }
@@ -551,7 +568,7 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
         // GEMM launch of its own between the fused launches
         // ... when the Gram role has time to spare: small reservoirs, whose chunk is bounded by the serial recurrence
         // (measured: 16 x N=2000 gains 3 ms of 57; N=16000, bounded by the Gram role, loses 6 of 125)
-        const bool drive_in_kernel = i8 && !pull && upt == 1 && h->I <= drv::MAX_INPUTS && (double)G * N * N <= 1.0e8 &&
+        const bool drive_in_kernel = i8 && !pull && (cluster || upt == 1) && h->I <= drv::MAX_INPUTS && (double)G * N * N <= 1.0e8 &&
                                      !getenv("XESN_B200_DRIVE_SEPARATE");
         for (long long c = 0; c <= nch; ++c) {
             drv::DriveArgs dv = {};
@@ -618,6 +635,8 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
             {
                 ProfScope prof(PROF_FUSED, st);
                 rc = pull ? launch_fused_pull_i8(r, G, g8, h->d_tiles_i8, ntiles, h->num_sms, st)
+                     : cluster ? launch_fused_cluster_i8(r, G, cteam, h->d_cl_tail_ptr, ctail, g8, h->d_tiles_i8, ntiles,
+                                                         yr_in_kernel ? q : q_none, dv, h->num_sms, st)
                      : i8 ? launch_fused_chunk_i8(r, G, team, upt, halves, slice_nnz, g8, h->d_tiles_i8, ntiles,
                                                   yr_in_kernel ? q : q_none, dv, h->num_sms, st)
                           : launch_fused_chunk(r, G, team, upt, slice_nnz, g, h->d_tiles, ntiles, h->num_sms, st);

@@ -27,6 +27,7 @@
 #include "recur_body.cuh"
 #include "pull_body.cuh"
 #include "yr_skinny.cuh"
+#include "recur_cluster.cuh"
 
 namespace xesn {
 namespace {
@@ -128,6 +129,44 @@ fused_chunk_i8_kernel(RecurArgs rp, int rec_ctas, int team, int member_bytes, gi
     XESN_CTA_STAMP(1);
 }
 
+
+// The same SM-specialised chunk kernel with the recurrence role on THREAD-BLOCK CLUSTERS (recur_cluster.cuh): the
+// team of a reservoir is one cluster and exchanges its states through distributed shared memory (st.async +
+// mbarrier) instead of polling the L2.  The grid is a whole number of clusters; clusters [0, G) run the recurrence,
+// the CTAs of the others are Gram / Y R / drive workers exactly as in fused_chunk_i8_kernel.  Not a cooperative
+// launch: a cluster is co-scheduled by the hardware and nothing else in the grid waits for anything.
+template <bool DRV>
+__global__ void __launch_bounds__(FUSED_I8_THREADS, 1)
+fused_cluster_i8_kernel(RecurArgs rp, int rec_ctas, int team, const int* __restrict__ tail_ptr, int tail_cap,
+                        gi8::GramI8Args gp, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                        const int2* __restrict__ tiles, int ntiles, GemmArgs yrp, drv::DriveArgs dvp) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    if ((int)blockIdx.x < rec_ctas) {
+        recur::recur_cluster_body(rp, recur::cluster_ctarank(), team, blockIdx.x / team, smem_raw, tail_ptr, tail_cap);
+        return;
+    }
+    const int worker = blockIdx.x - rec_ctas, nworkers = gridDim.x - rec_ctas;
+    const long long total = (long long)ntiles * gp.batch;
+    if (worker < total) {
+        gi8::GramI8Ctx ctx;
+        gi8::gram_i8_setup(ctx, smem_raw);
+        gi8::gram_i8_run<FUSED_I8_THREADS>(ctx, gp, &tmA, &tmB, tiles, ntiles, worker, nworkers);
+        gi8::gram_i8_teardown(ctx);
+    }
+    if (yrp.M > 0) {
+        __syncthreads();
+        const long long items = yr::n_items(yrp);
+        for (long long it = worker; it < items; it += nworkers)
+            yr::yr_item<FUSED_I8_THREADS>(yrp, it, reinterpret_cast<double*>(smem_raw));
+    }
+    if constexpr (DRV) {
+        if (dvp.m > 0) {
+            const long long items = drv::n_items(dvp);
+            for (long long it = worker; it < items; it += nworkers)
+                drv::drive_item<FUSED_I8_THREADS>(dvp, it, reinterpret_cast<double*>(smem_raw));
+        }
+    }
+}
 
 // Pull-model fusion: no SM specialisation.  EVERY CTA runs the Gram role (producer warp 4, issuer warp 0,
 // epilogue warps 8..15 -- gram_i8.cuh) and its otherwise idle warps 1-3 and 5-7 run the recurrence of
@@ -353,6 +392,89 @@ int launch_fused_chunk_i8(RecurArgs rp, int n_groups, int team, int upt, int hal
     return 0;
 }
 
+
+// cluster geometry of the recurrence role: team (= cluster size, <= 8) and tail staging capacity; false if the
+// reservoir does not fit (one unit per thread, three state copies in shared memory)
+bool cluster_recur_geometry(int N, int n_groups, const int* indptr, int num_sms, int* team_out, int* tail_cap_out) {
+    const char* e = getenv("XESN_B200_REC_CLUSTER");
+    if (e && e[0] == '0') return false;
+    int team = (N + recur::CL_THREADS - 1) / recur::CL_THREADS;
+    if (const char* t = getenv("XESN_B200_REC_CLUSTER_TEAM")) team = atoi(t);
+    if (team < 1 || team > 8) return false;
+    const int upc = recur_units_per_cta(N, team);
+    if (upc > recur::CL_THREADS) return false;
+    if ((long long)team * n_groups > num_sms - team) return false;   // at least one cluster of workers must remain
+    int tail_cap = 0;
+    for (int c = 0; c < team; ++c) {
+        int t = 0;
+        for (int i = c * upc; i < std::min(N, (c + 1) * upc); ++i) t += std::max(0, indptr[i + 1] - indptr[i] - recur::CL_KREG);
+        tail_cap = std::max(tail_cap, t);
+    }
+    const long long n_pad = ((N + 1) & ~1) + 2;
+    if (recur::cluster_smem_bytes((int)n_pad, tail_cap) > 227 * 1024) return false;
+    *team_out = team, *tail_cap_out = tail_cap;
+    return true;
+}
+
+void cluster_tail_ptr(int N, int team, const int* indptr, int* out) {
+    const int upc = recur_units_per_cta(N, team);
+    for (int c = 0; c < team; ++c) {
+        int t = 0;
+        for (int il = 0; il <= upc; ++il) {
+            out[(long long)c * (upc + 1) + il] = t;
+            const int i = c * upc + il;
+            if (il < upc && i < N) t += std::max(0, indptr[i + 1] - indptr[i] - recur::CL_KREG);
+        }
+    }
+}
+
+// rp.steps == 0 -> no recurrence role; ntiles == 0 -> no Gram role
+int launch_fused_cluster_i8(RecurArgs rp, int n_groups, int team, const int* tail_ptr_dev, int tail_cap,
+                            const gi8::GramI8Args& gp, const int2* tiles, int ntiles, const GemmArgs& yr_args,
+                            const drv::DriveArgs& drive_args, int num_sms, cudaStream_t stream) {
+    const bool has_rec = rp.steps > 0;
+    rp.units_per_cta = recur_units_per_cta(rp.N, team);
+    rp.n_pad = ((rp.N + 1) & ~1) + 2;
+    int smem = (int)recur::cluster_smem_bytes(rp.n_pad, tail_cap);
+    smem = std::max(smem, gi8::SMEM_BYTES);
+    smem = std::max(smem, yr::smem_bytes<FUSED_I8_THREADS>());
+    const bool drv_on = drive_args.m > 0;
+    auto kern = drv_on ? fused_cluster_i8_kernel<true> : fused_cluster_i8_kernel<false>;
+    XESN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    int rec_ctas = has_rec ? team * n_groups : 0;
+    // how many clusters of this size the device holds at once (GPC boundaries: fewer than num_sms / team)
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(FUSED_I8_THREADS);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = team, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    cfg.gridDim = dim3((unsigned)(num_sms / team * team));
+    int max_clusters = 0;
+    XESN_CUDA_OK(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
+    if (max_clusters * team <= rec_ctas && (ntiles > 0 || drv_on)) {
+        set_error("fused cluster chunk: %d clusters of %d fit, the recurrence role needs %d", max_clusters, team, n_groups);
+        return -2;
+    }
+    int grid = max_clusters * team;
+    if (ntiles == 0 && !drv_on) grid = rec_ctas;
+    if (grid <= 0) return 0;
+    cfg.gridDim = dim3((unsigned)grid);
+    gi8::GramI8Args g = gp;
+    alignas(64) CUtensorMap tm_a, tm_b;
+    memset(&tm_a, 0, sizeof(tm_a));
+    memset(&tm_b, 0, sizeof(tm_b));
+    if (ntiles > 0)
+        if (int rc = gram_i8_make_maps(g, &tm_a, &tm_b)) return rc;
+    GemmArgs yr_copy = yr_args;
+    if (ntiles == 0) yr_copy.M = 0;
+    drv::DriveArgs dv = drive_args;
+    XESN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, rp, rec_ctas, team, tail_ptr_dev, tail_cap, g, tm_a, tm_b, tiles, ntiles, yr_copy, dv));
+    count_launch();
+    return 0;
+}
 
 // units per CTA (multiple of 8) and units per thread of the pull-model recurrence spread over n_ctas CTAs
 int pull_geometry(int N, int n_groups, int n_ctas, int* upc_out, int* upt_out) {

@@ -88,6 +88,12 @@ namespace drv { struct DriveArgs; }
 int launch_fused_chunk_i8(RecurArgs rp, int n_groups, int team, int upt, int halves, int max_slice_nnz,
                           const gi8::GramI8Args& gp, const int2* tiles, int ntiles, const GemmArgs& yr_args,
                           const drv::DriveArgs& drive_args, int num_sms, cudaStream_t stream);
+// recurrence role on thread-block clusters (recur_cluster.cuh): state exchange through distributed shared memory
+bool cluster_recur_geometry(int N, int n_groups, const int* indptr, int num_sms, int* team_out, int* tail_cap_out);
+void cluster_tail_ptr(int N, int team, const int* indptr, int* out);   // host table [team][units_per_cta + 1]
+int launch_fused_cluster_i8(RecurArgs rp, int n_groups, int team, const int* tail_ptr_dev, int tail_cap,
+                            const gi8::GramI8Args& gp, const int2* tiles, int ntiles, const GemmArgs& yr_args,
+                            const drv::DriveArgs& drive_args, int num_sms, cudaStream_t stream);
 // pull-model recurrence (pull_body.cuh): spread over all SMs, beside the Gram role in every CTA
 int pull_geometry(int N, int n_groups, int n_ctas, int* upc_out, int* upt_out);
 int launch_pull_forced(RecurArgs rp, int n_groups, int num_sms, cudaStream_t stream);
