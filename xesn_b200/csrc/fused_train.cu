@@ -398,9 +398,17 @@ int launch_fused_chunk_i8(RecurArgs rp, int n_groups, int team, int upt, int hal
 bool cluster_recur_geometry(int N, int n_groups, const int* indptr, int num_sms, int* team_out, int* tail_cap_out) {
     const char* e = getenv("XESN_B200_REC_CLUSTER");
     if (e && e[0] == '0') return false;
-    int team = (N + recur::CL_THREADS - 1) / recur::CL_THREADS;
+    // the thinner the members the shorter a step (less arithmetic per CTA between two exchanges), within what is left
+    // of the machine after the Gram role's share: at most 8 CTAs per cluster (portable size), at most ~64 SMs in all,
+    // at least a warp of units per member
+    int team = std::min(8, std::max(1, 64 / std::max(n_groups, 1)));
+    team = std::min(team, std::max(1, (N + 31) / 32));
+    team = std::max(team, (N + recur::CL_THREADS - 1) / recur::CL_THREADS);
     if (const char* t = getenv("XESN_B200_REC_CLUSTER_TEAM")) team = atoi(t);
     if (team < 1 || team > 8) return false;
+    // clusters cost resident CTAs (GPC boundaries: 132 of 148 at size 4, 128 at size 8): only where the chunk is
+    // bounded by the recurrence, not by the Gram role (measured: 8 x N=4000 loses 23 ms of 50 with clusters)
+    if ((double)n_groups * N * N > 1.0e8 && !getenv("XESN_B200_REC_CLUSTER_TEAM")) return false;
     const int upc = recur_units_per_cta(N, team);
     if (upc > recur::CL_THREADS) return false;
     if ((long long)team * n_groups > num_sms - team) return false;   // at least one cluster of workers must remain

@@ -164,10 +164,22 @@ __device__ __forceinline__ void recur_cluster_body(const RecurArgs& p, const uns
             double acc = 0.0;
 #pragma unroll
             for (int k = 0; k < CL_KREG; ++k) acc = __dadd_rn(acc, __dmul_rn(hv[k], gth[k]));  // padding: + 0 * 0
-            for (int k = 0; k < n_tail; ++k) {
-                double gv;
-                asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(gv) : "r"(src + (unsigned)s_toff[tail_lo + k]));
-                acc = __dadd_rn(acc, __dmul_rn(s_tval[tail_lo + k], gv));
+            // long rows: CL_KTAIL more entries per round, staged together (offsets and values, then the gathers) so the
+            // longest row of the warp costs one more round of loads, not one per entry; padding -> 0 * 0 again
+            for (int k0 = 0; k0 < n_tail; k0 += CL_KTAIL) {
+                int to[CL_KTAIL];
+                double tv[CL_KTAIL], tg[CL_KTAIL];
+#pragma unroll
+                for (int k = 0; k < CL_KTAIL; ++k) {
+                    const bool in = k0 + k < n_tail;
+                    to[k] = in ? s_toff[tail_lo + k0 + k] : zero_off;
+                    tv[k] = in ? s_tval[tail_lo + k0 + k] : 0.0;
+                }
+#pragma unroll
+                for (int k = 0; k < CL_KTAIL; ++k)
+                    asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(tg[k]) : "r"(src + (unsigned)to[k]));
+#pragma unroll
+                for (int k = 0; k < CL_KTAIL; ++k) acc = __dadd_rn(acc, __dmul_rn(tv[k], tg[k]));
             }
             XESN_TRACE_MARK(4);
             r_new = leaky(__dadd_rn(acc, d_next), r_cur, alpha, oma);

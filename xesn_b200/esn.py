@@ -125,8 +125,11 @@ def auto_chunk(n_reservoir, n_groups, n_time, batch_size, budget_bytes=3 << 30):
     """Internal time-chunk length: bounds the (chunk+1, N) state ring + drive buffers
     (the reference's `batch_size` has the same purpose, esn.py:479-489).  Only the
     floating-point summation order of the Gram terms depends on it."""
+    import os
     per_step = 48 * n_reservoir * n_groups  # drive + state ring + int8 digit planes, double-buffered
-    c = max(64, min(2048, budget_bytes // max(per_step, 1)))
+    cap = int(os.environ.get("XESN_B200_CHUNK_MAX", 2048))
+    budget_bytes = int(os.environ.get("XESN_B200_CHUNK_BUDGET", budget_bytes))
+    c = max(64, min(cap, budget_bytes // max(per_step, 1)))
     c = (c // 64) * 64
     if batch_size is not None:
         c = min(c, max(int(batch_size), 1))
