@@ -212,7 +212,8 @@ int xesn_memset_async(void* dst_dev, int32_t byte_value, int64_t bytes, void* st
 int xesn_gemm_f64(const double* a_dev, int64_t lda, const double* b_dev, int64_t ldb, double* c_dev, int64_t ldc,
                   int32_t m, int32_t n, int32_t k, double alpha, double beta, int32_t flags, void* stream);
 /* gram_dev (N x N, lower triangle) += S^T S for S = states_dev [n_rows][N], |S| <= 1, computed
- * error-free on the int8 tensor cores (tcgen05 kind::i8) from the fixed-point digits of S.  Allocates
+ * on the int8 tensor cores (tcgen05 kind::i8) from the fixed-point digits of S: absolute error <= n_rows * 2^-50
+ * per entry (FP64-DGEMM level for |S| ~ 1, exact for S on a 2^-42 grid), whatever the magnitude of S.  Allocates
  * its own scratch and synchronises: a test / measurement entry (the training pipeline runs the same
  * device code inside the fused chunk kernel).  Replaces xesn/esn.py:510. */
 int xesn_gram_i8(const double* states_dev, int64_t lds, int32_t n_rows, int32_t n_reservoir, double* gram_dev,

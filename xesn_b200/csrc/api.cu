@@ -120,7 +120,7 @@ struct xesn_reservoir {
     int n_tiles = 0;
     int2* d_tiles_i8 = nullptr;  // 128 x 64 tiles of the int8 tensor-core Gram role
     int n_tiles_i8 = 0;
-    int gram_mode = 1;  // 0 = FP64 DMMA, 1 = error-free int8 on tcgen05
+    int gram_mode = 1;  // 0 = FP64 DMMA, 1 = fixed-point int8 digit planes on tcgen05 (absolute error <= K 2^-50 per entry)
     int fused_enabled = 1;
     // recurrence engine: 0 = team model everywhere (recur_body.cuh), 1 = pull model (pull_body.cuh) for forced runs and
     // spin-up, team model inside the fused training kernel (default: measured fastest), 2 = pull model everywhere
@@ -689,7 +689,7 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
     return 0;
 }
 
-// 0 = FP64 DMMA Gram, 1 = error-free int8 tensor-core Gram (default; fused pipeline only)
+// 0 = FP64 DMMA Gram, 1 = fixed-point int8 tensor-core Gram (default; fused pipeline only)
 int xesn_set_gram_mode(xesn_reservoir* h, int32_t mode) {
     XESN_REQUIRE(h && (mode == 0 || mode == 1), "bad arguments");
     h->gram_mode = mode;

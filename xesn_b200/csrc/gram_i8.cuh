@@ -8,10 +8,12 @@
 // Every plane product is an int8 x int8 -> int32 GEMM that the tensor cores compute EXACTLY
 // (|d| <= 128, at most 7 pairs per accumulator: K <= 16384 steps per launch keeps the int32 sums below
 // 2^31).  Pairs with a+b = s share one TMEM accumulator (same weight 2^(-12-8s)); the 28 pairs with
-// a+b <= 6 are kept.  Roundings: the fixed-point image (2^-55 absolute: exact for |r| >= 2^-2 given
-// FP64's own spacing), the dropped pairs (a+b >= 7: below 2^-51 per product in the worst case, ~2^-54
-// typical, zero-mean) and the seven FP64 adds that combine the levels -- the same order as the
-// rounding of each FP64 product in a DGEMM, and exact when the states live on a 2^-42 grid.
+// a+b <= 6 are kept.  Roundings: the fixed-point image (2^-55 absolute), the 21 dropped pairs (a+b >= 7:
+// below 2^-51 per product in the worst case, ~2^-54 typical, zero-mean) and the seven FP64 adds that combine
+// the levels.  GUARANTEE: an ABSOLUTE error <= K 2^-50 per Gram entry over K steps, whatever the magnitude of
+// the states -- the accuracy of an FP64 DGEMM for |r| ~ 1, a relative accuracy that degrades for states near
+// 0 (the ridge system's beta on the diagonal is an absolute scale too); exact when the states live on a
+// 2^-42 grid.  Non-finite states are digitised as 0 (the FP64 ring keeps them, so ybar and Wout become NaN).
 // 28 int8 MMAs replace the FP64 FMAs: 28 * 2 N^2 K int-ops at 4.5 Pop/s vs 2 N^2 K flops at 37 TFLOP/s.
 // (First version: 8 balanced base-128 digits, 36 pairs, 8 levels = all of TMEM; base 256 needs 22 % fewer
 // MMAs and one plane less for the same 2^-55..2^-56 resolution.)
