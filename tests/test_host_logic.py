@@ -347,8 +347,7 @@ def test_update_esn_kwargs_and_candidates():
     assert cf.batch_size(4000, 64) >= 8 and cf.batch_size(16000, 64) >= 1
     with pytest.raises(NotImplementedError):
         CostFunction(ESN, None, None, {"macro_training": {"cost_terms": {"mae": 1.0}}})
-    with pytest.raises(NotImplementedError):
-        CostFunction(LazyESN, None, None, MACRO_CONFIG)
+    assert CostFunction(LazyESN, None, None, MACRO_CONFIG).ESN is LazyESN   # LazyESN candidates are accepted since round 2
 
 
 def test_cost_function_batches_and_orders_the_sets():
