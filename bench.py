@@ -722,6 +722,7 @@ def run_ours(ctx, args, name, steps, warmup, with_cpu=True, peaks_int8=None):
     with ClockSampler(ctx.local_rank) as clocks:
         ms_total = ctx.timed(step_device, steps)
     prof = _lib.profile_read()
+    fused_ms = _lib.profile_regions("fused_chunk")
     _lib.profile_enable(False)
     launches = launch_count() - launches0
     ms_per_step = ms_total / steps
@@ -737,6 +738,14 @@ def run_ours(ctx, args, name, steps, warmup, with_cpu=True, peaks_int8=None):
     sub = argparse.Namespace(steps=steps)
     roofline, i8 = roofline_of(ctx, sub, name, w, prof, wl["g_local"], peaks_int8)
     phases = {k: {"regions": v[0], "ms_per_step": v[1] / steps} for k, v in prof.items() if v[0]}
+    if len(fused_ms) >= 3 * steps and len(fused_ms) % steps == 0:
+        # launches of one training pass: the first runs the recurrence role alone (nothing to accumulate yet), the last
+        # the Gram role alone (on every SM), the others both side by side
+        per = len(fused_ms) // steps
+        one = fused_ms[-per:]
+        phases["fused_chunk"]["launches_ms"] = {"recurrence_only_first": round(one[0], 3),
+                                                "both_median": round(float(np.median(one[1:-1])), 3) if per > 2 else None,
+                                                "gram_only_last": round(one[-1], 3), "per_pass": per}
 
     cpu = None
     # the CPU baseline is a single-process measurement: rank 0 at N=1 only (torchrun also pins OMP_NUM_THREADS to 1)

@@ -218,6 +218,14 @@ int xesn_gemm_f64(const double* a_dev, int64_t lda, const double* b_dev, int64_t
  * device code inside the fused chunk kernel).  Replaces xesn/esn.py:510. */
 int xesn_gram_i8(const double* states_dev, int64_t lds, int32_t n_rows, int32_t n_reservoir, double* gram_dev,
                  int64_t ldg, void* stream);
+/* Host-side helper (no GPU needed): the placement of the reservoir state in shared memory that the recurrence
+ * kernels use.  slot_out[j] (a permutation into [0, n_slots), n_slots a multiple of 16 and >= n_reservoir) is chosen so
+ * that the states one half-warp gathers for W r (xesn/esn.py:459, one row of W per thread, rows of a CTA in order,
+ * `units_per_cta` rows per CTA) fall into different banks.  Returns the shared-memory wavefronts of those gathers per
+ * time step, summed over the CTAs, for the chosen placement and (in *natural_out) for slot[j] = j; negative on error.
+ * The arithmetic does not depend on the placement.  Exposed for tests and measurements. */
+int64_t xesn_bank_layout(int32_t n_reservoir, const int32_t* indptr, const int32_t* indices, int32_t units_per_cta,
+                         int32_t n_slots, int32_t* slot_out, int64_t* natural_out);
 /* readout v[g][o] = Wout[g][o][:] . r[g][:]   (xesn/esn.py:268, xesn/lazyesn.py:325-327) */
 int xesn_readout(const double* wout_dev, const double* r_dev, double* v_dev, int32_t n_reservoir,
                  int32_t n_output, int32_t n_groups, void* stream);
@@ -268,6 +276,8 @@ int xesn_set_gram_mode(xesn_reservoir* h, int32_t mode);
 int xesn_get_gram_mode(xesn_reservoir* h, int32_t* mode_out);
 int xesn_profile_enable(int32_t on);
 int xesn_profile_read(int32_t cls, int64_t* n_regions, double* total_ms);
+/* the same, region by region in launch order: fills ms_out[0 .. min(n, capacity)) and returns n (or a negative code) */
+int64_t xesn_profile_regions(int32_t cls, double* ms_out, int64_t capacity);
 
 #ifdef __cplusplus
 }

@@ -529,3 +529,64 @@ def test_psd_bin_tables_match_binned_statistic():
         np.testing.assert_allclose(np.nan_to_num(got), np.nan_to_num(ref), rtol=1e-13)
         assert np.array_equal(np.isnan(got), np.isnan(ref))
         np.testing.assert_allclose(factor, np.pi * (k_bins[1:] ** 2 - k_bins[:-1] ** 2))
+
+
+def _gather_wavefronts(indptr, indices, slot, upc, zero_slot):
+    """Independent count of the shared-memory wavefronts of the row gathers (8-byte loads: a half-warp at a time, one
+    wavefront per distinct address that shares a 16-wide bank pair with another): 8 rounds per warp plus rounds of 4
+    while the warp's longest row lasts -- the access pattern of recur_cluster.cuh."""
+    n = len(indptr) - 1
+    total = n_sets = 0
+    for u0 in range(0, n, upc):
+        u1 = min(n, u0 + upc)
+        for w0 in range(u0, u1, 32):
+            rows = range(w0, min(w0 + 32, u1))
+            longest = max(indptr[r + 1] - indptr[r] for r in rows)
+            rounds = 8 + (0 if longest <= 8 else -(-(longest - 8) // 4) * 4)
+            for h0 in range(w0, min(w0 + 32, u1), 16):
+                half = range(h0, min(h0 + 16, u1))
+                for k in range(rounds):
+                    cols = {indices[indptr[r] + k] for r in half if k < indptr[r + 1] - indptr[r]}
+                    if not cols:
+                        continue
+                    addr = {slot[c] for c in cols}
+                    if any(k >= indptr[r + 1] - indptr[r] for r in half):
+                        addr.add(zero_slot)
+                    total += np.bincount([a % 16 for a in addr], minlength=16).max()
+                    n_sets += 1
+    return total, n_sets
+
+
+@pytest.mark.parametrize("n,team", [(1000, 8), (2000, 4), (333, 2)])
+def test_bank_layout_is_a_permutation_and_removes_conflicts(n, team):
+    """xesn_bank_layout (host code of the library): the placement is a permutation into the slots, the reported
+    wavefront counts agree with an independent count, and the search removes most of the bank conflicts of the natural
+    placement (conflict-free = one wavefront per non-empty half-warp gather)."""
+    import scipy.sparse as sp
+    from xesn_b200 import SparseRandomMatrix
+    W = sp.csr_matrix(SparseRandomMatrix(n_rows=n, n_cols=n, factor=0.9, distribution="uniform", normalization="multiply",
+                                         connectedness=5, format="csr", random_seed=1)())
+    indptr, indices = W.indptr.astype(np.int32), W.indices.astype(np.int32)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    lib.xesn_bank_layout.restype = ctypes.c_int64
+    lib.xesn_bank_layout.argtypes = _lib.SIGNATURES["xesn_bank_layout"][1]
+    upc = ((n + team - 1) // team + 7) & ~7
+    n_slots = (n + 15) // 16 * 16 + 32
+    slot = np.zeros(n, np.int32)
+    natural = ctypes.c_int64()
+    after = lib.xesn_bank_layout(n, indptr.ctypes.data, indices.ctypes.data, upc, n_slots, slot.ctypes.data,
+                                 ctypes.byref(natural))
+    assert after > 0
+    assert len(np.unique(slot)) == n and slot.min() >= 0 and slot.max() < n_slots
+    # a warp's states stay inside the warp's own run of 32 slots (remote stores of a warp: one 256-byte segment)
+    for u0 in range(0, n, upc):
+        for w0 in range(u0, min(n, u0 + upc), 32):
+            w1 = min(n, u0 + upc, w0 + 32)
+            assert sorted(slot[w0:w1]) == list(range(w0, w1))
+    assert _gather_wavefronts(indptr, indices, np.arange(n), upc, n_slots + 1)[0] == natural.value
+    count, floor = _gather_wavefronts(indptr, indices, slot, upc, n_slots + 1)   # floor: one wavefront per gather
+    assert count == after
+    assert after <= natural.value
+    assert after - floor <= 0.6 * (natural.value - floor), (floor, after, natural.value)
+    # bad arguments are refused
+    assert lib.xesn_bank_layout(n, indptr.ctypes.data, indices.ctypes.data, upc, n_slots + 1, slot.ctypes.data, None) < 0

@@ -20,6 +20,7 @@ from xesn_b200.synthetic import lorenz96  # noqa: E402
 KIND = os.environ.get("PROF_KIND", "lazy")
 N = int(os.environ.get("PROF_N", 2000))
 STEPS = int(os.environ.get("PROF_STEPS", 2048))
+CHUNKS = int(os.environ.get("PROF_CHUNKS", 3))   # 1: the traced launch runs the recurrence role alone (no Gram role beside it)
 lib = _lib.load()
 
 
@@ -39,10 +40,10 @@ with warnings.catch_warnings():
     if KIND == "lazy":
         G = int(os.environ.get("PROF_G", 16))
         esn = LazyESN({"x": 16}, {"x": 1}, "periodic", N, 0.5, 1e-6, **{k: dict(v) for k, v in ESN_KW.items()})
-        data = torch.from_numpy(lorenz96(16 * G, 3 * STEPS)).cuda()
+        data = torch.from_numpy(lorenz96(16 * G, CHUNKS * STEPS)).cuda()
     else:
         esn = ESN(40, 40, N, 0.5, 1e-6, **{k: dict(v) for k, v in ESN_KW.items()})
-        data = torch.from_numpy(lorenz96(40, 3 * STEPS)).cuda()
+        data = torch.from_numpy(lorenz96(40, CHUNKS * STEPS)).cuda()
     esn.build()
 for _ in range(2):
     esn.train(data, n_spinup=0, batch_size=STEPS)
@@ -55,6 +56,7 @@ e1.record()
 torch.cuda.synchronize()
 prof = _lib.profile_read()
 _lib.profile_enable(False)
-print(f"{KIND} N={N}: train of {3 * STEPS} steps {e0.elapsed_time(e1):.2f} ms; fused kernels {prof['fused_chunk'][1]:.2f} ms "
-      f"= {prof['fused_chunk'][1] * 1e3 / (3 * STEPS):.3f} us per step")
-show("xesn_debug_trace_fused", STEPS, f"fused {KIND} N={N} (last chunk)")
+print(f"{KIND} N={N}: train of {CHUNKS * STEPS} steps {e0.elapsed_time(e1):.2f} ms; fused kernels {prof['fused_chunk'][1]:.2f} ms "
+      f"= {prof['fused_chunk'][1] * 1e3 / (CHUNKS * STEPS):.3f} us per step")
+print("fused launches, ms: " + " ".join(f"{x:.3f}" for x in _lib.profile_regions("fused_chunk"))) if hasattr(_lib, "profile_regions") else None
+show("xesn_debug_trace_fused", STEPS, f"fused {KIND} N={N} (last chunk{', recurrence role alone' if CHUNKS == 1 else ''})")

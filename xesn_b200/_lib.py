@@ -51,6 +51,8 @@ SIGNATURES = {
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]),
     "xesn_reservoir_destroy": (C.c_int, [C.c_void_p]),
     "xesn_reservoir_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
+    "xesn_bank_layout": (C.c_int64, [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
+                                     C.POINTER(C.c_int64)]),
     "xesn_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "xesn_forced_scratch_bytes": (C.c_int64, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
     "xesn_forced_run": (C.c_int, [C.c_void_p, C.POINTER(Series), C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
@@ -101,6 +103,7 @@ SIGNATURES = {
     "xesn_set_nan_input_mask": (C.c_int, [C.c_void_p, C.c_int32]),
     "xesn_profile_enable": (C.c_int, [C.c_int32]),
     "xesn_profile_read": (C.c_int, [C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
+    "xesn_profile_regions": (C.c_int64, [C.c_int32, C.POINTER(C.c_double), C.c_int64]),
     "xesn_gram_i8": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
     "xesn_readout": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
 }
@@ -145,6 +148,15 @@ PROFILE_CLASSES = ("drive_gemm", "recurrence", "gram_syrk", "yr_gemm", "ridge_so
 
 def profile_enable(on=True):
     check(load().xesn_profile_enable(1 if on else 0))
+
+
+def profile_regions(name, capacity=4096):
+    """ms of every timed region of one class, in launch order."""
+    buf = (C.c_double * capacity)()
+    n = int(load().xesn_profile_regions(PROFILE_CLASSES.index(name), buf, capacity))
+    if n < 0:
+        check(n)
+    return [float(buf[i]) for i in range(min(n, capacity))]
 
 
 def profile_read():

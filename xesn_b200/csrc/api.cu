@@ -115,7 +115,7 @@ struct xesn_reservoir {
     int cluster = 1;
     int max_slice_nnz = 0;
     int num_sms = 0;
-    std::vector<int> h_indptr;
+    std::vector<int> h_indptr, h_indices;
     int2* d_tiles = nullptr;  // Gram tile order of the fused chunk kernel
     int n_tiles = 0;
     int2* d_tiles_i8 = nullptr;  // 128 x 64 tiles of the int8 tensor-core Gram role
@@ -133,8 +133,17 @@ struct xesn_reservoir {
     SolveCtx solve;  // side stream + events of the look-ahead Cholesky, per handle (= per device)
     int* d_flow_tail_ptr = nullptr;  // predict_flow.cu: offsets of the rows' tails, cached for one (team, upc)
     int flow_tail_team = 0, flow_tail_upc = 0;
-    int* d_cl_tail_ptr = nullptr;    // recur_cluster.cuh: the same for the cluster recurrence, cached for one team size
-    int cl_tail_team = 0;
+    // recur_cluster.cuh: per team size, the offsets of the rows' tails and the shared-memory placement of the states
+    // (bank_layout.cu: slot of every state, byte offset of the slot of every entry of W)
+    struct ClusterPlan {
+        int* d_tail_ptr = nullptr;
+        int* d_slot = nullptr;
+        int* d_col_off = nullptr;
+    };
+    ClusterPlan cl_plan[9];   // index = team size (1..8)
+    // low-priority stream + fork/join events of the worker grid that runs beside the recurrence clusters
+    cudaStream_t worker_stream = nullptr;
+    cudaEvent_t ev_wfork = nullptr, ev_wjoin = nullptr;
 };
 static inline int gram_mode_effective(const xesn_reservoir* h) { return (h->gram_mode == 1 && h->leak_unit_range) ? 1 : 0; }
 
@@ -143,6 +152,18 @@ extern "C" {
 const char* xesn_last_error(void) { return g_error.c_str(); }
 int xesn_abi_version(void) { return 1; }
 int64_t xesn_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int64_t xesn_bank_layout(int32_t n_reservoir, const int32_t* indptr, const int32_t* indices, int32_t units_per_cta,
+                         int32_t n_slots, int32_t* slot_out, int64_t* natural_out) {
+    XESN_REQUIRE(indptr && slot_out && n_reservoir > 0 && units_per_cta > 0, "bad arguments");
+    XESN_REQUIRE(n_slots >= n_reservoir && n_slots % 16 == 0, "n_slots: a multiple of 16, at least n_reservoir");
+    XESN_REQUIRE(indptr[n_reservoir] == 0 || indices, "null CSR indices");
+    long long before = 0;
+    const long long after = plan_bank_layout(n_reservoir, indptr, indices, units_per_cta, recur::CL_KHEAD, recur::CL_KTAIL,
+                                             n_slots, n_slots + 1, slot_out, &before);
+    if (natural_out) *natural_out = before;
+    return after;
+}
 
 int xesn_profile_enable(int on) {
     for (auto& r : g_prof) {
@@ -167,6 +188,22 @@ int xesn_profile_read(int cls, int64_t* n_regions, double* total_ms) {
     }
     *n_regions = n, *total_ms = ms;
     return 0;
+}
+
+int64_t xesn_profile_regions(int32_t cls, double* ms_out, int64_t capacity) {
+    XESN_REQUIRE(cls >= 0 && cls < PROF_N && (ms_out || capacity == 0), "bad arguments");
+    long long n = 0;
+    for (auto& r : g_prof) {
+        if (r.cls != cls) continue;
+        if (n < capacity) {
+            XESN_CUDA_OK(cudaEventSynchronize(r.b));
+            float t = 0.f;
+            XESN_CUDA_OK(cudaEventElapsedTime(&t, r.a, r.b));
+            ms_out[n] = t;
+        }
+        ++n;
+    }
+    return n;
 }
 
 int xesn_reservoir_create(xesn_reservoir** out, int device, int32_t N, int32_t I, const int32_t* indptr,
@@ -230,6 +267,7 @@ int xesn_reservoir_create(xesn_reservoir** out, int device, int32_t N, int32_t I
     h->max_slice_nnz = mx;
     h->num_sms = prop.multiProcessorCount;
     h->h_indptr.assign(indptr, indptr + N + 1);
+    h->h_indices.assign(indices, indices + nnz);
     {
         // lower-triangle tile list in super-rows of 12 tile rows, column by column (L2 locality)
         const int T = (N + 127) / 128, H = 12;
@@ -268,7 +306,10 @@ int xesn_reservoir_destroy(xesn_reservoir* h) {
     cudaFree(h->d_ro_counters);
     solve_ctx_destroy(h->solve);
     cudaFree(h->d_flow_tail_ptr);
-    cudaFree(h->d_cl_tail_ptr);
+    for (auto& pl : h->cl_plan) cudaFree(pl.d_tail_ptr), cudaFree(pl.d_slot), cudaFree(pl.d_col_off);
+    if (h->worker_stream) cudaStreamDestroy(h->worker_stream);
+    if (h->ev_wfork) cudaEventDestroy(h->ev_wfork);
+    if (h->ev_wjoin) cudaEventDestroy(h->ev_wjoin);
     delete h;
     return 0;
 }
@@ -376,8 +417,46 @@ static int drive_gemm(xesn_reservoir* h, const double* ubase, long long ldu, lon
     return launch_gemm_f64(g, st);
 }
 
+// tables of the cluster recurrence for one team size, built on first use
+static int ensure_cluster_plan(xesn_reservoir* h, int team) {
+    XESN_REQUIRE(team >= 1 && team <= 8, "cluster team size");
+    auto& pl = h->cl_plan[team];
+    if (pl.d_tail_ptr) return 0;
+    const int N = h->N, upc = recur_units_per_cta(N, team);
+    std::vector<int> tp((size_t)team * (upc + 1));
+    cluster_tail_ptr(N, team, h->h_indptr.data(), tp.data());
+    // placement of the state copies: banks chosen against the gathers of this geometry
+    std::vector<int> slot(N), col_off((size_t)std::max<long long>(h->nnz, 1));
+    const int n_slots = cluster_state_slots(N);
+    if (getenv("XESN_B200_NATURAL_SLOTS")) {   // A/B measurements
+        for (int j = 0; j < N; ++j) slot[j] = j;
+    } else {
+        plan_bank_layout(N, h->h_indptr.data(), h->h_indices.data(), upc, recur::CL_KHEAD, recur::CL_KTAIL, n_slots,
+                         n_slots + 1, slot.data(), nullptr);
+    }
+    for (long long k = 0; k < h->nnz; ++k) col_off[k] = slot[h->h_indices[k]] * (int)sizeof(double);
+    XESN_CUDA_OK(cudaMalloc(&pl.d_slot, sizeof(int) * slot.size()));
+    XESN_CUDA_OK(cudaMalloc(&pl.d_col_off, sizeof(int) * col_off.size()));
+    XESN_CUDA_OK(cudaMemcpy(pl.d_slot, slot.data(), sizeof(int) * slot.size(), cudaMemcpyHostToDevice));
+    XESN_CUDA_OK(cudaMemcpy(pl.d_col_off, col_off.data(), sizeof(int) * col_off.size(), cudaMemcpyHostToDevice));
+    XESN_CUDA_OK(cudaMalloc(&pl.d_tail_ptr, sizeof(int) * tp.size()));
+    XESN_CUDA_OK(cudaMemcpy(pl.d_tail_ptr, tp.data(), sizeof(int) * tp.size(), cudaMemcpyHostToDevice));
+    return 0;
+}
+
 // teacher-forced recurrence without a Gram role (spin-up, forced runs)
 static int forced_launch(xesn_reservoir* h, const RecurArgs& r, int G, cudaStream_t st) {
+    // small reservoirs: clusters exchanging states through distributed shared memory, as thin as the machine allows
+    // (no Gram role to leave SMs to); needs |r| bookkeeping of nothing but the ring, so every Gram mode can use it
+    int cteam = 0, ctail = 0;
+    if (h->recur_pull != 2 && cluster_forced_geometry(h->N, G, h->h_indptr.data(), h->num_sms, &cteam, &ctail)) {
+        if (int rc = ensure_cluster_plan(h, cteam)) return rc;
+        RecurArgs rc_args = r;
+        rc_args.slot = h->cl_plan[cteam].d_slot, rc_args.col_off = h->cl_plan[cteam].d_col_off;
+        rc_args.planes = nullptr;
+        return launch_fused_cluster_i8(rc_args, G, cteam, h->cl_plan[cteam].d_tail_ptr, ctail, gi8::GramI8Args{}, nullptr, 0,
+                                       GemmArgs{}, drv::DriveArgs{}, h->num_sms, st);
+    }
     int upc = 0, upt = 0;
     if (h->recur_pull && pull_geometry(h->N, G, h->num_sms, &upc, &upt) == 0) return launch_pull_forced(r, G, h->num_sms, st);
     return launch_recur_forced(r, G, h->max_slice_nnz, st);
@@ -522,14 +601,15 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
     int cteam = 0, ctail = 0;
     const bool cluster = !pull && gram_mode_effective(h) == 1 &&
                          cluster_recur_geometry(N, G, h->h_indptr.data(), h->num_sms, &cteam, &ctail);
-    if (cluster && h->cl_tail_team != cteam) {
-        std::vector<int> tp((size_t)cteam * (recur_units_per_cta(N, cteam) + 1));
-        cluster_tail_ptr(N, cteam, h->h_indptr.data(), tp.data());
-        if (h->d_cl_tail_ptr) XESN_CUDA_OK(cudaFree(h->d_cl_tail_ptr));
-        h->d_cl_tail_ptr = nullptr;
-        XESN_CUDA_OK(cudaMalloc(&h->d_cl_tail_ptr, sizeof(int) * tp.size()));
-        XESN_CUDA_OK(cudaMemcpy(h->d_cl_tail_ptr, tp.data(), sizeof(int) * tp.size(), cudaMemcpyHostToDevice));
-        h->cl_tail_team = cteam;
+    if (cluster)
+        if (int rc = ensure_cluster_plan(h, cteam)) return rc;
+    const bool split = cluster && !getenv("XESN_B200_CLUSTER_SINGLE");
+    if (split && !h->worker_stream) {
+        int lo = 0, hi = 0;
+        XESN_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        XESN_CUDA_OK(cudaStreamCreateWithPriority(&h->worker_stream, cudaStreamNonBlocking, lo));
+        XESN_CUDA_OK(cudaEventCreateWithFlags(&h->ev_wfork, cudaEventDisableTiming));
+        XESN_CUDA_OK(cudaEventCreateWithFlags(&h->ev_wjoin, cudaEventDisableTiming));
     }
     const bool fuse = h->fused_enabled && (N % 2 == 0) && T > n_spinup &&
                       (pull || cluster || (fused_recur_geometry(N, G, fused_threads(gram_mode_effective(h) == 1), &team, &upt,
@@ -552,9 +632,12 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
             XESN_CUDA_OK(cudaMemsetAsync(Pbuf[0], 0, (size_t)G * plane_group, st));
             XESN_CUDA_OK(cudaMemsetAsync(Pbuf[1], 0, (size_t)G * plane_group, st));
         }
+        // chunks of equal length (a multiple of the Gram role's K-block): a short last chunk would still cost a launch
+        // as long as the Gram pass of the full chunk before it
         const long long nch = (T - n_spinup + chunk - 1) / chunk;
-        auto chunk_t0 = [&](long long c) { return n_spinup + c * chunk; };
-        auto chunk_m = [&](long long c) { return (int)std::min<long long>(chunk, T - chunk_t0(c)); };
+        const long long chunk_eq = std::min<long long>(chunk, round_up((T - n_spinup + nch - 1) / nch, gi8::KB));
+        auto chunk_t0 = [&](long long c) { return n_spinup + c * chunk_eq; };
+        auto chunk_m = [&](long long c) { return (int)std::max<long long>(0, std::min<long long>(chunk_eq, T - chunk_t0(c))); };
         auto drive_for = [&](long long c) -> int {
             const double* ub;
             long long ldu, ugs;
@@ -586,6 +669,7 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
                 }
             }
             RecurArgs r = recur_args(h);
+            if (cluster) r.slot = h->cl_plan[cteam].d_slot, r.col_off = h->cl_plan[cteam].d_col_off;
             if (c < nch) {
                 const int m = chunk_m(c);
                 r.drive = Dbuf[c & 1], r.drive_group_stride = (long long)m * N, r.steps = m, r.carry = carry;
@@ -635,7 +719,10 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
             {
                 ProfScope prof(PROF_FUSED, st);
                 rc = pull ? launch_fused_pull_i8(r, G, g8, h->d_tiles_i8, ntiles, h->num_sms, st)
-                     : cluster ? launch_fused_cluster_i8(r, G, cteam, h->d_cl_tail_ptr, ctail, g8, h->d_tiles_i8, ntiles,
+                     : split ? launch_fused_cluster_split_i8(r, G, cteam, h->cl_plan[cteam].d_tail_ptr, ctail, g8, h->d_tiles_i8,
+                                                             ntiles, yr_in_kernel ? q : q_none, dv, h->num_sms, st,
+                                                             h->worker_stream, h->ev_wfork, h->ev_wjoin)
+                     : cluster ? launch_fused_cluster_i8(r, G, cteam, h->cl_plan[cteam].d_tail_ptr, ctail, g8, h->d_tiles_i8, ntiles,
                                                          yr_in_kernel ? q : q_none, dv, h->num_sms, st)
                      : i8 ? launch_fused_chunk_i8(r, G, team, upt, halves, slice_nnz, g8, h->d_tiles_i8, ntiles,
                                                   yr_in_kernel ? q : q_none, dv, h->num_sms, st)

@@ -418,10 +418,39 @@ bool cluster_recur_geometry(int N, int n_groups, const int* indptr, int num_sms,
         for (int i = c * upc; i < std::min(N, (c + 1) * upc); ++i) t += std::max(0, indptr[i + 1] - indptr[i] - recur::CL_KREG);
         tail_cap = std::max(tail_cap, t);
     }
-    const long long n_pad = ((N + 1) & ~1) + 2;
+    const long long n_pad = cluster_state_slots(N) + 2;
     if (recur::cluster_smem_bytes((int)n_pad, tail_cap) > 227 * 1024) return false;
     *team_out = team, *tail_cap_out = tail_cap;
     return true;
+}
+
+static int cluster_tail_cap(int N, int team, const int* indptr) {
+    const int upc = recur_units_per_cta(N, team);
+    int tail_cap = 0;
+    for (int c = 0; c < team; ++c) {
+        int t = 0;
+        for (int i = c * upc; i < std::min(N, (c + 1) * upc); ++i) t += std::max(0, indptr[i + 1] - indptr[i] - recur::CL_KREG);
+        tail_cap = std::max(tail_cap, t);
+    }
+    return tail_cap;
+}
+
+bool cluster_forced_geometry(int N, int n_groups, const int* indptr, int num_sms, int* team_out, int* tail_cap_out) {
+    const char* e = getenv("XESN_B200_REC_CLUSTER");
+    if (e && e[0] == '0') return false;
+    // clusters of 8 keep 128 CTAs resident on a B200, clusters of 4 132 (GPC boundaries); more clusters than that would
+    // simply queue (nothing waits across clusters), but then the pull model over all SMs is the better engine
+    for (int team = 8; team >= 1; team >>= 1) {
+        if (team > 1 && (N + team - 1) / team < 32) continue;   // at least a warp of units per member
+        const int upc = recur_units_per_cta(N, team);
+        if (upc > recur::CL_THREADS) return false;               // thinner teams only get fatter members
+        if ((long long)team * n_groups > (team >= 8 ? 128 : (team >= 4 ? 132 : num_sms))) continue;
+        const int tail_cap = cluster_tail_cap(N, team, indptr);
+        if (recur::cluster_smem_bytes(cluster_state_slots(N) + 2, tail_cap) > 227 * 1024) return false;
+        *team_out = team, *tail_cap_out = tail_cap;
+        return true;
+    }
+    return false;
 }
 
 void cluster_tail_ptr(int N, int team, const int* indptr, int* out) {
@@ -442,7 +471,11 @@ int launch_fused_cluster_i8(RecurArgs rp, int n_groups, int team, const int* tai
                             const drv::DriveArgs& drive_args, int num_sms, cudaStream_t stream) {
     const bool has_rec = rp.steps > 0;
     rp.units_per_cta = recur_units_per_cta(rp.N, team);
-    rp.n_pad = ((rp.N + 1) & ~1) + 2;
+    rp.n_pad = cluster_state_slots(rp.N) + 2;   // the last slot of a copy always holds 0
+    if (has_rec && (!rp.slot || !rp.col_off)) {
+        set_error("fused cluster chunk: no shared-memory placement");
+        return -1;
+    }
     int smem = (int)recur::cluster_smem_bytes(rp.n_pad, tail_cap);
     smem = std::max(smem, gi8::SMEM_BYTES);
     smem = std::max(smem, yr::smem_bytes<FUSED_I8_THREADS>());
@@ -482,6 +515,58 @@ int launch_fused_cluster_i8(RecurArgs rp, int n_groups, int team, const int* tai
     XESN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, rp, rec_ctas, team, tail_ptr_dev, tail_cap, g, tm_a, tm_b, tiles, ntiles, yr_copy, dv));
     count_launch();
     return 0;
+}
+
+// Gram / Y R / drive workers alone, as an ordinary (non-cluster, non-cooperative) launch of `n_workers` CTAs: the
+// companion of a recurrence-only cluster launch (below), and the last launch of a training pass
+static int launch_gram_workers_i8(const gi8::GramI8Args& gp, const int2* tiles, int ntiles, const GemmArgs& yr_args,
+                                  const drv::DriveArgs& drive_args, int n_workers, cudaStream_t stream) {
+    const bool drv_on = drive_args.m > 0;
+    if (n_workers <= 0 || (ntiles == 0 && !drv_on)) return 0;
+    auto kern = drv_on ? fused_chunk_i8_kernel<1, false, true> : fused_chunk_i8_kernel<1, false, false>;
+    XESN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    gi8::GramI8Args g = gp;
+    alignas(64) CUtensorMap tm_a, tm_b;
+    memset(&tm_a, 0, sizeof(tm_a));
+    memset(&tm_b, 0, sizeof(tm_b));
+    if (ntiles > 0)
+        if (int rc = gram_i8_make_maps(g, &tm_a, &tm_b)) return rc;
+    GemmArgs yr_copy = yr_args;
+    if (ntiles == 0) yr_copy.M = 0;
+    drv::DriveArgs dv = drive_args;
+    RecurArgs none = {};
+    int rec_ctas = 0, team = 1, member_bytes = 0;
+    const int smem = std::max(gi8::SMEM_BYTES, yr::smem_bytes<FUSED_I8_THREADS>());
+    void* args[] = {&none, &rec_ctas, &team, &member_bytes, &g, &tm_a, &tm_b, (void*)&tiles, &ntiles, &yr_copy, &dv};
+    XESN_CUDA_OK(cudaLaunchKernel((void*)kern, dim3(n_workers), dim3(FUSED_I8_THREADS), args, (size_t)smem, stream));
+    count_launch();
+    return 0;
+}
+
+// One chunk launch of the cluster engine as TWO kernels side by side: the recurrence clusters on `stream`, the
+// workers as a plain grid on `side`.  A single cluster launch keeps only 132 (cluster size 4) or 128 (size 8) of the 148
+// SMs busy -- clusters cannot straddle GPCs -- which costs the Gram role a fifth of its SMs where it shares the chunk
+// with many recurrence clusters; a plain grid has no such limit, and nothing in either kernel waits for the other.
+// The recurrence kernel is enqueued first and `side` has the lower priority, so the clusters are placed before the
+// workers fill the remaining SMs.
+int launch_fused_cluster_split_i8(RecurArgs rp, int n_groups, int team, const int* tail_ptr_dev, int tail_cap,
+                                  const gi8::GramI8Args& gp, const int2* tiles, int ntiles, const GemmArgs& yr_args,
+                                  const drv::DriveArgs& drive_args, int num_sms, cudaStream_t stream, cudaStream_t side,
+                                  cudaEvent_t ev_fork, cudaEvent_t ev_join) {
+    const bool has_rec = rp.steps > 0, has_work = ntiles > 0 || drive_args.m > 0;
+    if (!has_rec) return launch_gram_workers_i8(gp, tiles, ntiles, yr_args, drive_args, num_sms, stream);
+    const int rec_ctas = team * n_groups;
+    if (!has_work || rec_ctas >= num_sms)
+        return launch_fused_cluster_i8(rp, n_groups, team, tail_ptr_dev, tail_cap, gp, tiles, ntiles, yr_args, drive_args, num_sms, stream);
+    XESN_CUDA_OK(cudaEventRecord(ev_fork, stream));
+    XESN_CUDA_OK(cudaStreamWaitEvent(side, ev_fork, 0));
+    if (int rc = launch_fused_cluster_i8(rp, n_groups, team, tail_ptr_dev, tail_cap, gi8::GramI8Args{}, nullptr, 0, GemmArgs{},
+                                         drv::DriveArgs{}, num_sms, stream))
+        return rc;
+    int rc = launch_gram_workers_i8(gp, tiles, ntiles, yr_args, drive_args, num_sms - rec_ctas, side);
+    XESN_CUDA_OK(cudaEventRecord(ev_join, side));
+    XESN_CUDA_OK(cudaStreamWaitEvent(stream, ev_join, 0));
+    return rc;
 }
 
 // units per CTA (multiple of 8) and units per thread of the pull-model recurrence spread over n_ctas CTAs

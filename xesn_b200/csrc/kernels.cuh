@@ -30,6 +30,9 @@ struct RecurArgs {
     int debug_no_exchange;   // timing experiments only: skip the refresh of the other CTAs' slices (wrong results)
     int poll_sleep_retry;    // pull model, experiments: nanoseconds to sleep between polls
     unsigned* hint;          // pull model: device counter of CTAs that have published their part of a row (zeroed per launch)
+    // cluster engine: conflict-avoiding placement of the state copies in shared memory (bank_layout.cu)
+    const int* slot;         // [N] 8-byte slot of state j
+    const int* col_off;      // [nnz] byte offset of the slot of indices[k]
     int n_active_ctas;       // filled by the launcher
 };
 
@@ -90,10 +93,27 @@ int launch_fused_chunk_i8(RecurArgs rp, int n_groups, int team, int upt, int hal
                           const drv::DriveArgs& drive_args, int num_sms, cudaStream_t stream);
 // recurrence role on thread-block clusters (recur_cluster.cuh): state exchange through distributed shared memory
 bool cluster_recur_geometry(int N, int n_groups, const int* indptr, int num_sms, int* team_out, int* tail_cap_out);
+// the same engine for runs without a Gram role (spin-up, forced runs): the thinnest clusters that are all resident
+bool cluster_forced_geometry(int N, int n_groups, const int* indptr, int num_sms, int* team_out, int* tail_cap_out);
 void cluster_tail_ptr(int N, int team, const int* indptr, int* out);   // host table [team][units_per_cta + 1]
 int launch_fused_cluster_i8(RecurArgs rp, int n_groups, int team, const int* tail_ptr_dev, int tail_cap,
                             const gi8::GramI8Args& gp, const int2* tiles, int ntiles, const GemmArgs& yr_args,
                             const drv::DriveArgs& drive_args, int num_sms, cudaStream_t stream);
+// placement of the states in shared memory that avoids bank conflicts of the row gathers (bank_layout.cu): slot_out[N]
+// in [0, n_slots), n_slots % 16 == 0; returns the gather wavefronts per step over all CTAs, *before = natural placement
+long long plan_bank_layout(int N, const int* indptr, const int* indices, int upc, int kreg, int ktail, int n_slots,
+                           int zero_slot, int* slot_out, long long* before);
+namespace recur {
+constexpr int CL_KREG = 12;   // entries of a row of W held in registers by the cluster engine ...
+constexpr int CL_KHEAD = 8;   // ... of which the last CL_KREG - CL_KHEAD are skipped by warps whose rows are all shorter
+constexpr int CL_KTAIL = 4;   // entries per round of the rows' tails (shared memory)
+}
+inline int cluster_state_slots(int N) { return (N + 15) / 16 * 16 + 32; }   // two spare slots per bank pair
+// the same chunk as two kernels side by side (recurrence clusters on `stream`, plain worker grid on `side`)
+int launch_fused_cluster_split_i8(RecurArgs rp, int n_groups, int team, const int* tail_ptr_dev, int tail_cap,
+                                  const gi8::GramI8Args& gp, const int2* tiles, int ntiles, const GemmArgs& yr_args,
+                                  const drv::DriveArgs& drive_args, int num_sms, cudaStream_t stream, cudaStream_t side,
+                                  cudaEvent_t ev_fork, cudaEvent_t ev_join);
 // pull-model recurrence (pull_body.cuh): spread over all SMs, beside the Gram role in every CTA
 int pull_geometry(int N, int n_groups, int n_ctas, int* upc_out, int* upt_out);
 int launch_pull_forced(RecurArgs rp, int n_groups, int num_sms, cudaStream_t stream);

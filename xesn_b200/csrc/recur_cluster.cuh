@@ -16,6 +16,9 @@
 //   * one mbarrier per copy: the owner posts "expect (N - own units) x 8 bytes" once per use, every thread waits on it
 //     (try_wait sleeps in hardware: no polling loop, no "unset" pattern, no memset of rings), then ONE CTA barrier
 //     orders the local stores -- one barrier and no global-memory round trip on the per-step critical path;
+//   * inside a copy, state j sits in slot p.slot[j], chosen on the host so that the gathers of a half-warp fall into
+//     different banks (bank_layout.cu): the gather phase is bound by shared-memory wavefronts, and the natural
+//     placement costs ~1.6x the conflict-free count;
 //   * the state ring in global memory is still written (plain stores: FP64 values for Y R and the next chunk, int8
 //     digit planes for the Gram role), but nobody waits for it.
 // The arithmetic (CSR order, separately rounded multiply and add, FP64 tanh) is recur_body's, bit for bit.
@@ -26,8 +29,6 @@ namespace xesn {
 namespace recur {
 
 constexpr int CL_THREADS = 512;
-constexpr int CL_KREG = 8;
-constexpr int CL_KTAIL = 4;
 
 __device__ __forceinline__ unsigned cl_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ unsigned cl_mapa(unsigned addr, unsigned rank) {
@@ -100,7 +101,7 @@ __device__ __forceinline__ void recur_cluster_body(const RecurArgs& p, const uns
 
     // copy 0 <- the state entering the chunk (every CTA reads the whole vector: no exchange for step 0);
     // every copy ends with a slot that always holds 0 (padding entries of short rows point there)
-    for (int i = tid; i < N; i += CL_THREADS) s_buf[i] = carry[i];
+    for (int i = tid; i < N; i += CL_THREADS) s_buf[p.slot[i]] = carry[i];
     if (tid < 3) {
         s_buf[(long long)tid * n_pad + n_pad - 1] = 0.0;
         cl_mbar_init(bar_addr + 8u * tid, 1);
@@ -118,7 +119,7 @@ __device__ __forceinline__ void recur_cluster_body(const RecurArgs& p, const uns
         d_next = p.steps > 0 ? drive[unit] : 0.0;
         for (int k = CL_KREG; k < row_len; ++k) {
             s_tval[tail_lo + k - CL_KREG] = w_values[row_lo + k];
-            s_toff[tail_lo + k - CL_KREG] = p.indices[row_lo + k] * (int)sizeof(double);
+            s_toff[tail_lo + k - CL_KREG] = p.col_off[row_lo + k];
         }
     }
     const int zero_off = (n_pad - 1) * (int)sizeof(double);
@@ -128,9 +129,11 @@ __device__ __forceinline__ void recur_cluster_body(const RecurArgs& p, const uns
     for (int k = 0; k < CL_KREG; ++k) {
         const bool in = k < row_len;
         hv[k] = in ? w_values[row_lo + k] : 0.0;
-        ho[k] = in ? p.indices[row_lo + k] * (int)sizeof(double) : zero_off;
+        ho[k] = in ? p.col_off[row_lo + k] : zero_off;
     }
     const int n_tail = max(row_len - CL_KREG, 0);
+    const bool warp_long = __any_sync(0xffffffffu, row_len > CL_KHEAD);
+    const unsigned own_off = owner ? (unsigned)p.slot[unit] * 8u : 0u;   // where this unit's state lives in every copy
     if (owner) {
         states[unit] = r_cur;  // row 0 = state entering the chunk (read by the Gram role / Y R of this chunk)
         if (digits && p.steps > 0) {
@@ -159,11 +162,20 @@ __device__ __forceinline__ void recur_cluster_body(const RecurArgs& p, const uns
         if (owner) {
             double gth[CL_KREG];
 #pragma unroll
-            for (int k = 0; k < CL_KREG; ++k)
+            for (int k = 0; k < CL_KHEAD; ++k)
                 asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(gth[k]) : "r"(src + (unsigned)ho[k]));
+            if (warp_long) {   // warp-uniform
+#pragma unroll
+                for (int k = CL_KHEAD; k < CL_KREG; ++k)
+                    asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(gth[k]) : "r"(src + (unsigned)ho[k]));
+            }
             double acc = 0.0;
 #pragma unroll
-            for (int k = 0; k < CL_KREG; ++k) acc = __dadd_rn(acc, __dmul_rn(hv[k], gth[k]));  // padding: + 0 * 0
+            for (int k = 0; k < CL_KHEAD; ++k) acc = __dadd_rn(acc, __dmul_rn(hv[k], gth[k]));  // padding: + 0 * 0
+            if (warp_long) {
+#pragma unroll
+                for (int k = CL_KHEAD; k < CL_KREG; ++k) acc = __dadd_rn(acc, __dmul_rn(hv[k], gth[k]));
+            }
             // long rows: CL_KTAIL more entries per round, staged together (offsets and values, then the gathers) so the
             // longest row of the warp costs one more round of loads, not one per entry; padding -> 0 * 0 again
             for (int k0 = 0; k0 < n_tail; k0 += CL_KTAIL) {
@@ -186,7 +198,7 @@ __device__ __forceinline__ void recur_cluster_body(const RecurArgs& p, const uns
             r_cur = r_new;
             XESN_TRACE_MARK(5);
             // home copy, then the peers' copies (each store signs off 8 bytes on the receiver's barrier)
-            const unsigned off = (unsigned)unit * 8u;
+            const unsigned off = own_off;
             asm volatile("st.shared.f64 [%0], %1;\n" ::"r"(dst + off), "d"(r_new) : "memory");
             for (unsigned q = 0; q < C; ++q)
                 if (q != c) cl_st_async(cl_mapa(dst + off, q), r_new, cl_mapa(bar_addr + 8u * nxt, q));
