@@ -467,6 +467,7 @@ static RecurArgs recur_args(xesn_reservoir* h) {
     r.indptr = h->d_indptr, r.indices = h->d_indices, r.values = h->d_values;
     r.values_gs = h->values_gs, r.alpha_g = h->d_alpha_g, r.param_groups = h->n_param_groups;
     r.N = h->N, r.alpha = h->alpha, r.smem_nnz = h->max_slice_nnz, r.status = h->d_status;
+    r.stagger = getenv("XESN_B200_NO_STAGGER") ? 0 : 1;
     r.debug_no_exchange = getenv("XESN_B200_DEBUG_NO_EXCHANGE") != nullptr;
     r.hint = getenv("XESN_B200_NO_HINT") ? nullptr : h->d_bar + 2;
     if (const char* e = getenv("XESN_B200_POLL_SLEEP1")) r.poll_sleep_retry = atoi(e);
@@ -633,11 +634,22 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
             XESN_CUDA_OK(cudaMemsetAsync(Pbuf[1], 0, (size_t)G * plane_group, st));
         }
         // chunks of equal length (a multiple of the Gram role's K-block): a short last chunk would still cost a launch
-        // as long as the Gram pass of the full chunk before it
-        const long long nch = (T - n_spinup + chunk - 1) / chunk;
-        const long long chunk_eq = std::min<long long>(chunk, round_up((T - n_spinup + nch - 1) / nch, gi8::KB));
-        auto chunk_t0 = [&](long long c) { return n_spinup + c * chunk_eq; };
-        auto chunk_m = [&](long long c) { return (int)std::max<long long>(0, std::min<long long>(chunk_eq, T - chunk_t0(c))); };
+        // as long as the Gram pass of the full chunk before it.  (A ramp of short first chunks was measured too: the
+        // first launch has no Gram pass beside it, but the recurrence runs in it all the same -- no gain.)
+        std::vector<long long> sched_t0;
+        std::vector<int> sched_m;
+        {
+            long long t = n_spinup, left = T - n_spinup;
+            const long long n_eq = (left + chunk - 1) / chunk;
+            const long long m_eq = n_eq ? std::min<long long>(chunk, round_up((left + n_eq - 1) / n_eq, gi8::KB)) : 0;
+            for (long long k = 0; k < n_eq && left > 0; ++k) {
+                const long long m = std::min(m_eq, left);
+                sched_t0.push_back(t), sched_m.push_back((int)m), t += m, left -= m;
+            }
+        }
+        const long long nch = (long long)sched_m.size();
+        auto chunk_t0 = [&](long long c) { return sched_t0[(size_t)c]; };
+        auto chunk_m = [&](long long c) { return sched_m[(size_t)c]; };
         auto drive_for = [&](long long c) -> int {
             const double* ub;
             long long ldu, ugs;

@@ -440,7 +440,10 @@ bool cluster_forced_geometry(int N, int n_groups, const int* indptr, int num_sms
     if (e && e[0] == '0') return false;
     // clusters of 8 keep 128 CTAs resident on a B200, clusters of 4 132 (GPC boundaries); more clusters than that would
     // simply queue (nothing waits across clusters), but then the pull model over all SMs is the better engine
-    for (int team = 8; team >= 1; team >>= 1) {
+    int first = 8;
+    while (first > 1 && first * n_groups > 64) first >>= 1;   // as in training: at most ~64 SMs of clusters side by side
+    if (const char* t = getenv("XESN_B200_FORCED_TEAM")) first = atoi(t);
+    for (int team = first; team >= 1; team >>= 1) {
         if (team > 1 && (N + team - 1) / team < 32) continue;   // at least a warp of units per member
         const int upc = recur_units_per_cta(N, team);
         if (upc > recur::CL_THREADS) return false;               // thinner teams only get fatter members

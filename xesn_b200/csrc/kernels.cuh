@@ -33,6 +33,7 @@ struct RecurArgs {
     // cluster engine: conflict-avoiding placement of the state copies in shared memory (bank_layout.cu)
     const int* slot;         // [N] 8-byte slot of state j
     const int* col_off;      // [nnz] byte offset of the slot of indices[k]
+    int stagger;             // cluster engine: the second half of a CTA's warps runs a few hundred cycles behind the first
     int n_active_ctas;       // filled by the launcher
 };
 

@@ -133,6 +133,10 @@ __device__ __forceinline__ void recur_cluster_body(const RecurArgs& p, const uns
     }
     const int n_tail = max(row_len - CL_KREG, 0);
     const bool warp_long = __any_sync(0xffffffffu, row_len > CL_KHEAD);
+    // staggered halves (warp-uniform): see the step loop
+    const int owner_warps = (u1 - u0 + 31) >> 5;
+    const bool late = p.stagger && owner_warps >= 4 && (tid >> 5) >= (owner_warps + 1) / 2;
+    double d_after = 0.0;
     const unsigned own_off = owner ? (unsigned)p.slot[unit] * 8u : 0u;   // where this unit's state lives in every copy
     if (owner) {
         states[unit] = r_cur;  // row 0 = state entering the chunk (read by the Gram role / Y R of this chunk)
@@ -160,6 +164,19 @@ __device__ __forceinline__ void recur_cluster_body(const RecurArgs& p, const uns
         const unsigned src = buf_addr + cur * copy_bytes, dst = buf_addr + nxt * copy_bytes;
         double r_new = 0.0;
         if (owner) {
+            if (late) {
+                // late half of the warps: the bookkeeping of the PREVIOUS step (ring, digit planes, prefetch) comes first,
+                // so these warps reach their gathers -- and, at the other end, their sends -- a few hundred cycles after
+                // the early half: the early half's states are on the wire while the late half still computes
+                if (t > 0) {
+                    states[(long long)t * N + unit] = r_cur;
+                    if (digits) {
+                        double one[1] = {r_cur};
+                        put_digits<1>(digits, p, t, unit, one, 1);
+                    }
+                }
+                d_after = t + 1 < p.steps ? __ldg(drive + (long long)(t + 1) * N + unit) : 0.0;
+            }
             double gth[CL_KREG];
 #pragma unroll
             for (int k = 0; k < CL_KHEAD; ++k)
@@ -204,12 +221,16 @@ __device__ __forceinline__ void recur_cluster_body(const RecurArgs& p, const uns
                 if (q != c) cl_st_async(cl_mapa(dst + off, q), r_new, cl_mapa(bar_addr + 8u * nxt, q));
             XESN_TRACE_MARK(6);
             // global ring + digit planes: for the Gram role and Y R (nobody polls them)
-            states[(long long)(t + 1) * N + unit] = r_new;
-            if (digits && t + 1 < p.steps) {
-                double one[1] = {r_new};
-                put_digits<1>(digits, p, t + 1, unit, one, 1);
+            if (!late) {
+                states[(long long)(t + 1) * N + unit] = r_new;
+                if (digits && t + 1 < p.steps) {
+                    double one[1] = {r_new};
+                    put_digits<1>(digits, p, t + 1, unit, one, 1);
+                }
+                if (t + 1 < p.steps) d_next = __ldg(drive + (long long)(t + 1) * N + unit);
+            } else {
+                d_next = d_after;
             }
-            if (t + 1 < p.steps) d_next = __ldg(drive + (long long)(t + 1) * N + unit);
         }
         XESN_TRACE_MARK(0);
         if (C > 1 && ok) ok = cl_mbar_wait(bar_addr + 8u * nxt, (phase_bits >> nxt) & 1u, p.status);
@@ -223,7 +244,10 @@ __device__ __forceinline__ void recur_cluster_body(const RecurArgs& p, const uns
     if (tid == 0 && c < 64)
         for (int i = 0; i < 8; ++i) g_recur_trace[c * 8 + i] = tr_sum[i];
 #endif
-    if (owner) p.carry[(long long)g * N + unit] = r_cur;
+    if (owner) {
+        if (late && p.steps > 0) states[(long long)p.steps * N + unit] = r_cur;   // the last row of the late half
+        p.carry[(long long)g * N + unit] = r_cur;
+    }
     cl_cluster_sync();   // nobody leaves while a peer may still store into its shared memory
 }
 
