@@ -42,7 +42,14 @@ if hasattr(lib, "xesn_debug_trace_flow"):
     lib.xesn_debug_trace_flow(buf)
     last = STEPS % 256 or 256
     a = np.array(buf[:], dtype=np.float64).reshape(64, 8) / last
+    io = a[32:]
+    io = io[io.sum(1) > 0]
+    a = a[:32]
     live = a[a.sum(1) > 0]
+    print(f"input-polling warp of {len(io)} CTAs, cycles per step: [0] polling the inputs | [1] waiting for the owners at the "
+          f"inputs barrier | [2] the owners' update | [3] contributions | total")
+    for name, v in (("mean", io.mean(0)), ("min", io.min(0)), ("max", io.max(0))):
+        print(f"   {name:5s} " + " ".join(f"{x:8.0f}" for x in v[:4]) + f" {v.sum():8.0f}")
     print(f"{len(live)} CTAs (last launch, {last} steps), cycles per step: [0] state refresh | [1] wait inputs/other warps | "
           f"[2] row-dot head | [3] row tails | [4] Win u | [5] tanh+leak | [6] store + wait owners | [7] contributions | total")
     for name, v in (("mean", live.mean(0)), ("min", live.min(0)), ("max", live.max(0))):

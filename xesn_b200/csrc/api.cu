@@ -941,11 +941,13 @@ static bool predict_pull_eligible(xesn_reservoir* h, int O, int G, long long n_c
 }
 
 // dataflow forecast (predict_flow.cu): several reservoirs, no grid barrier
-static bool predict_flow_eligible(xesn_reservoir* h, int O, int G, int* team, int* upc, int* tail_cap = nullptr) {
-    int tc = 0;
+static bool predict_flow_eligible(xesn_reservoir* h, int O, int G, int* team, int* upc, int* tail_cap = nullptr,
+                                  int* cluster = nullptr) {
+    int tc = 0, cl = 0;
     const bool ok = h->persistent_predict == 1 && G > 1 &&
-                    predict_flow_geometry(h->N, h->I, O, G, h->num_sms, h->h_indptr.data(), team, upc, &tc);
+                    predict_flow_geometry(h->N, h->I, O, G, h->num_sms, h->h_indptr.data(), team, upc, &tc, &cl);
     if (ok && tail_cap) *tail_cap = tc;
+    if (ok && cluster) *cluster = cl;
     return ok;
 }
 struct FlowLayout {
@@ -981,7 +983,7 @@ struct FlowRun {
     long long n_cells;
     const int32_t *in_map, *out_map, *src, *import_cell, *exp_ptr, *exp_peer, *exp_slot;
     const double* fill;
-    int n_import, team, upc, tail_cap;
+    int n_import, team, upc, tail_cap, cluster;
     double *field, *field_alt, *r, *r_alt, *pred, *r_ring;
     long long ldp;
     int n_steps;
@@ -1006,6 +1008,7 @@ static int flow_run(xesn_reservoir* h, const FlowRun& f, uint32_t* launches_done
     a.values_gs = h->values_gs, a.win_gs = h->win_gs, a.bias_gs = h->bias_gs, a.param_groups = h->n_param_groups;
     a.alpha_g = h->d_alpha_g, a.alpha = h->alpha, a.Wout = f.wout;
     a.N = N, a.I = h->I, a.O = f.O, a.G = f.G, a.team = f.team, a.upc = f.upc, a.ring_steps = XESN_FLOW_CHUNK;
+    a.cluster = f.cluster;
     a.src = f.src, a.in_map = f.in_map, a.fill = f.fill, a.out_map = f.out_map;
     a.import_cell = f.import_cell, a.n_import = f.n_import;
     a.r_ring = f.r_ring, a.pred = f.pred, a.ldp = f.ldp;
@@ -1022,8 +1025,9 @@ static int flow_run(xesn_reservoir* h, const FlowRun& f, uint32_t* launches_done
         const int steps = std::min(XESN_FLOW_CHUNK, f.n_steps - s0);
         const int par = (int)(*count & 1u);
         if (shared_ring) XESN_CUDA_OK(cudaMemsetAsync(f.ring[0], 0xFF, ring_bytes, st));
-        XESN_CUDA_OK(cudaMemset2DAsync(f.r_ring, sizeof(double) * (size_t)XESN_FLOW_CHUNK * N, 0xFF,
-                                       sizeof(double) * (size_t)steps * N, f.G, st));
+        if (!f.cluster)   // the cluster variant moves the states through distributed shared memory, not this ring
+            XESN_CUDA_OK(cudaMemset2DAsync(f.r_ring, sizeof(double) * (size_t)XESN_FLOW_CHUNK * N, 0xFF,
+                                           sizeof(double) * (size_t)steps * N, f.G, st));
         // cells nobody produces keep their value in the field leaving the launch
         XESN_CUDA_OK(cudaMemcpyAsync(fbuf[cur ^ 1], fbuf[cur], sizeof(double) * (size_t)f.n_cells, cudaMemcpyDeviceToDevice, st));
         a.steps = steps, a.col0 = s0;
@@ -1106,8 +1110,8 @@ int xesn_predict(xesn_reservoir* h, const double* wout, int32_t O, int32_t G, in
         }
         return 0;
     }
-    int fteam = 0, fupc = 0, ftail = 0;
-    if (predict_flow_eligible(h, O, G, &fteam, &fupc, &ftail)) {
+    int fteam = 0, fupc = 0, ftail = 0, fcluster = 0;
+    if (predict_flow_eligible(h, O, G, &fteam, &fupc, &ftail, &fcluster)) {
         // several reservoirs on one GPU: dataflow kernel, every produced cell is local (no imports / exports)
         const FlowLayout L = flow_layout(h, O, G, n_cells, fteam, true);
         double* area = field_alt + round_up(n_cells, 2);
@@ -1116,7 +1120,7 @@ int xesn_predict(xesn_reservoir* h, const double* wout, int32_t O, int32_t G, in
         if ((rc = launch_flow_src(in_map, out_map, owner, src, n_cells, (long long)G * O, (long long)G * I, st))) return rc;
         FlowRun f = {};
         f.wout = wout, f.O = O, f.G = G, f.n_cells = n_cells, f.in_map = in_map, f.fill = fill, f.out_map = out_map;
-        f.src = src, f.team = fteam, f.upc = fupc, f.tail_cap = ftail;
+        f.src = src, f.team = fteam, f.upc = fupc, f.tail_cap = ftail, f.cluster = fcluster;
         f.field = field, f.field_alt = field_alt, f.r = r, f.r_alt = r_alt, f.n_steps = n_steps, f.pred = pred, f.ldp = ldp;
         f.r_ring = area + L.r_ring, f.ring[0] = f.ring[1] = area + L.part_ring, f.world = 1;
         return flow_run(h, f, nullptr, st);
@@ -1232,8 +1236,8 @@ int xesn_predict_flow(xesn_reservoir* h, xesn_flow_plan* plan, const double* wou
     XESN_REQUIRE(plan->src_dev && (plan->n_import == 0 || plan->import_cell_dev), "plan lacks tables");
     XESN_REQUIRE(scratch_bytes >= xesn_predict_scratch_bytes(h, O, G, n_cells), "scratch too small");
     XESN_REQUIRE_GROUPS(h, G);
-    int team = 0, upc = 0, tail_cap = 0;
-    XESN_REQUIRE(predict_flow_eligible(h, O, G, &team, &upc, &tail_cap), "configuration does not fit the dataflow forecast");
+    int team = 0, upc = 0, tail_cap = 0, cluster = 0;
+    XESN_REQUIRE(predict_flow_eligible(h, O, G, &team, &upc, &tail_cap, &cluster), "configuration does not fit the dataflow forecast");
     cudaStream_t st = (cudaStream_t)stream;
     const int N = h->N, I = h->I;
     double* Ug = (double*)scratch;
@@ -1251,7 +1255,7 @@ int xesn_predict_flow(xesn_reservoir* h, xesn_flow_plan* plan, const double* wou
     f.wout = wout, f.O = O, f.G = G, f.n_cells = n_cells, f.in_map = in_map, f.fill = fill, f.out_map = out_map;
     f.src = plan->src_dev, f.import_cell = plan->import_cell_dev, f.n_import = plan->n_import;
     f.exp_ptr = plan->exp_ptr_dev, f.exp_peer = plan->exp_peer_dev, f.exp_slot = plan->exp_slot_dev;
-    f.team = team, f.upc = upc, f.tail_cap = tail_cap;
+    f.team = team, f.upc = upc, f.tail_cap = tail_cap, f.cluster = cluster;
     f.field = field, f.field_alt = field_alt, f.r = r, f.r_alt = r_alt, f.n_steps = n_steps, f.pred = pred, f.ldp = ldp;
     f.r_ring = area + L.r_ring, f.world = plan->world;
     for (int par = 0; par < 2; ++par) {

@@ -180,6 +180,7 @@ struct PredictFlowArgs {
     const double* Wout;       // [G][O][N]
     int N, I, O, G;
     int team, upc;            // CTAs per group, units per CTA
+    int cluster;              // the team is a thread-block cluster: states travel through distributed shared memory
     int steps, ring_steps;    // steps of this launch (<= ring_steps)
     int col0;                 // step n of this launch is trajectory column col0 + n
     const int* src;           // [G][I] ring slot feeding the input | -1-k: fill[k] | INT_MIN: static cell of `field`
@@ -205,9 +206,9 @@ struct PredictFlowArgs {
     int tail_cap;             // shared-memory capacity (entries) for the rows' tails beyond the register-resident head
     const int* tail_ptr;      // [team][upc+1] offsets of every owned row's tail in that staging area
 };
-size_t predict_flow_smem(int N, int I, int O, int upc, int tail_cap);
+size_t predict_flow_smem(int N, int I, int O, int upc, int tail_cap, int cluster);
 bool predict_flow_geometry(int N, int I, int O, int G, int num_sms, const int* indptr, int* team_out, int* upc_out,
-                           int* tail_cap_out);
+                           int* tail_cap_out, int* cluster_out);
 void predict_flow_tail_ptr(int N, int team, int upc, const int* indptr, int* out);
 int launch_flow_src(const int* in_map, const int* out_map, int* owner, int* src, long long n_cells, long long n_slots,
                     long long n_inputs, cudaStream_t stream);

@@ -15,6 +15,11 @@
 // recur_body.cuh): a consumer polls exactly the values it needs and adds the `team` contributions of an
 // output in CTA order (deterministic).  One store -> poll hop per step instead of two grid barriers.
 //
+// CLUSTER variant (teams of <= 8 CTAs that are all resident as thread-block clusters): the slices of r travel through
+// distributed shared memory instead of the state ring -- three copies of r per CTA, `st.async` + mbarrier exactly as in
+// recur_cluster.cuh -- so the per-step critical path holds no L2 round trip for the states; the contributions to the
+// outputs still go through the partial rings (they are what other groups, other ranks and the trajectory read).
+//
 // Multi-GPU (one process per GPU, groups split in slabs): a cell that a group on ANOTHER rank reads is
 // pushed, contribution by contribution, into that rank's ring with plain 8-byte NVLink P2P stores
 // (peer-mapped memory, CUDA IPC) -- only those cells, only to the ranks that read them (the `overlap`-deep
@@ -25,6 +30,7 @@
 #include "common.cuh"
 #include "kernels.cuh"
 #include "recur_body.cuh"
+#include "recur_cluster.cuh"
 
 namespace xesn {
 namespace {
@@ -118,6 +124,21 @@ __device__ __forceinline__ void flow_io_role(const PredictFlowArgs& p, const Flo
     const bool leader = c == 0;
     const long long slot0 = (long long)g * O;
     bool aborted = false;
+#ifdef XESN_RECUR_TRACE
+    long long io_sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long io_last = trace_clock();
+#define XESN_IO_MARK(i)                                   \
+    do {                                                  \
+        if (t == 0) {                                     \
+            const long long now_ = trace_clock();         \
+            io_sum[i] += now_ - io_last, io_last = now_;  \
+        }                                                 \
+    } while (0)
+#else
+#define XESN_IO_MARK(i) \
+    do {                \
+    } while (0)
+#endif
     for (int n = 1; n <= p.steps; ++n) {
         if (t < 32) {
             // inputs of step n: the outputs of step n-1 (ring row n-2), or the field entering the launch
@@ -140,10 +161,18 @@ __device__ __forceinline__ void flow_io_role(const PredictFlowArgs& p, const Flo
                 p.pred[cell * p.ldp + p.col0 + n - 1] = team_sum(p, slot0 + o, n - 2, aborted);
             }
         }
+        XESN_IO_MARK(0);   // [0] polling the inputs
         bar_inputs_ready();
+        XESN_IO_MARK(1);   // [1] waiting for the owners to arrive (they were still busy with the previous step)
         bar_states_ready();
+        XESN_IO_MARK(2);   // [2] the owners' update
         flow_contributions(p, sm, n, c, slot0, warp, lane);
+        XESN_IO_MARK(3);   // [3] contributions
     }
+#ifdef XESN_RECUR_TRACE
+    if (t == 0 && blockIdx.x < 32)
+        for (int i = 0; i < 8; ++i) g_recur_trace[(32 + blockIdx.x) * 8 + i] = io_sum[i];
+#endif
     // last trajectory column, the field leaving the launch
     if (leader)
         for (int o = t; o < O; o += PF_IO_THREADS) {
@@ -157,6 +186,7 @@ __device__ __forceinline__ void flow_io_role(const PredictFlowArgs& p, const Flo
             p.field_out[p.import_cell[j]] = team_sum(p, (long long)p.G * O + j, p.steps - 1, aborted);
 }
 
+template <bool CL>
 __global__ void __launch_bounds__(PF_THREADS, 1) predict_flow_kernel(PredictFlowArgs p) {
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -166,8 +196,9 @@ __global__ void __launch_bounds__(PF_THREADS, 1) predict_flow_kernel(PredictFlow
     const int n_pad = (N + 1) & ~1;
     FlowSmem sm;
     sm.ldw = I + 1 + (I & 1);  // odd row pitch (in doubles): conflict-free reads of one row per lane
-    sm.s_r = smem;
-    sm.s_win = sm.s_r + n_pad;
+    sm.s_r = smem;   // CL: three copies of the state vector, then the mbarrier of each copy
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem + 3 * (size_t)n_pad);
+    sm.s_win = CL ? sm.s_r + 3 * (size_t)n_pad + 8 : sm.s_r + n_pad;
     sm.s_wout = sm.s_win + (size_t)upc * sm.ldw;
     sm.s_u = sm.s_wout + (size_t)O * upc;
     sm.s_rnew = sm.s_u + I + (I & 1);
@@ -200,10 +231,17 @@ __global__ void __launch_bounds__(PF_THREADS, 1) predict_flow_kernel(PredictFlow
             sm.s_toff[dst] = p.indices[lo + k];
         }
     }
+    const unsigned bar_addr = CL ? cl_smem_u32(s_bar) : 0u;
+    if (CL) {
+        if (tid < 3) cl_mbar_init(bar_addr + 8u * tid, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
     __syncthreads();
+    if (CL) cl_cluster_sync();   // every CTA's barriers exist before anybody sends
 
     if (tid >= PF_R_THREADS) {
         flow_io_role(p, sm, g, c, tid - PF_R_THREADS);
+        if (CL) cl_cluster_sync();   // nobody leaves while a peer may still store into its shared memory
         return;
     }
 
@@ -241,7 +279,19 @@ __global__ void __launch_bounds__(PF_THREADS, 1) predict_flow_kernel(PredictFlow
     long long tr_last = trace_clock();
 #endif
 
+    const unsigned copy_bytes = (unsigned)n_pad * 8u;
+    const unsigned expect_bytes = (unsigned)(N - nu) * 8u;   // what the peers send me per step
+    unsigned cur = 0, phase_bits = 0;                         // CL: copy holding r_{n-1}; parities of the three barriers
     for (int n = 1; n <= p.steps; ++n) {
+        const unsigned nxt = cur == 2 ? 0u : cur + 1u;
+        if (CL) {
+            // ================= phase A (cluster): r_{n-1} has been stored into copy `cur` by its owners =================
+            if (tid == 0) cl_mbar_expect(bar_addr + 8u * nxt, expect_bytes);
+            if (n >= 2 && p.team > 1 && !aborted) {
+                aborted = !cl_mbar_wait(bar_addr + 8u * cur, (phase_bits >> cur) & 1u, p.status);
+                phase_bits ^= 1u << cur;
+            }
+        } else
         // ================= phase A: the other slices of r_{n-1} (ring row n-2), coalesced data-as-flag polling =================
         if (n >= 2) {
             const double* row = r_ring + (long long)(n - 2) * N;
@@ -294,14 +344,15 @@ __global__ void __launch_bounds__(PF_THREADS, 1) predict_flow_kernel(PredictFlow
             double gth[PF_KREG];
 #pragma unroll
             for (int k = 0; k < PF_KREG; ++k)
-                asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(gth[k]) : "r"(s_r_addr + (unsigned)ho[k]));
+                asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(gth[k]) : "r"(s_r_addr + (CL ? cur * copy_bytes : 0u) + (unsigned)ho[k]));
             double wr = 0.0;
 #pragma unroll
             for (int k = 0; k < PF_KREG; ++k)
                 if (k < row_len) wr = __dadd_rn(wr, __dmul_rn(hv[k], gth[k]));
             XESN_TRACE_MARK(2);  // [2] head of the row dot
             for (int k = PF_KREG; k < row_len; ++k)
-                wr = __dadd_rn(wr, __dmul_rn(sm.s_tval[tail_lo + k - PF_KREG], sm.s_r[sm.s_toff[tail_lo + k - PF_KREG]]));
+                wr = __dadd_rn(wr, __dmul_rn(sm.s_tval[tail_lo + k - PF_KREG],
+                                             sm.s_r[(CL ? (size_t)cur * n_pad : 0) + sm.s_toff[tail_lo + k - PF_KREG]]));
             XESN_TRACE_MARK(3);  // [3] tail of long rows
             const double* wrow = sm.s_win + (size_t)tid * sm.ldw;
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
@@ -318,7 +369,15 @@ __global__ void __launch_bounds__(PF_THREADS, 1) predict_flow_kernel(PredictFlow
             XESN_TRACE_MARK(4);  // [4] Win u
             r_cur = leaky(pre, r_cur, alpha, oma);
             XESN_TRACE_MARK(5);  // [5] tanh + leak
-            st_flag(r_ring + (long long)(n - 1) * N + unit, r_cur);
+            if (CL) {
+                // home copy, then the peers' copies (each store signs off 8 bytes on the receiver's barrier)
+                const unsigned dst = s_r_addr + nxt * copy_bytes + (unsigned)unit * 8u;
+                asm volatile("st.shared.f64 [%0], %1;\n" ::"r"(dst), "d"(r_cur) : "memory");
+                for (unsigned q = 0; q < (unsigned)p.team; ++q)
+                    if (q != (unsigned)c) cl_st_async(cl_mapa(dst, q), r_cur, cl_mapa(bar_addr + 8u * nxt, q));
+            } else {
+                st_flag(r_ring + (long long)(n - 1) * N + unit, r_cur);
+            }
             sm.s_rnew[tid] = r_cur;
         } else if (tid < upc) {
             sm.s_rnew[tid] = 0.0;
@@ -327,12 +386,14 @@ __global__ void __launch_bounds__(PF_THREADS, 1) predict_flow_kernel(PredictFlow
         XESN_TRACE_MARK(6);  // [6] state store + waiting for the other owners
         flow_contributions(p, sm, n, c, slot0, warp, lane);
         XESN_TRACE_MARK(7);  // [7] contributions
+        cur = CL ? nxt : 0u;
     }
 #ifdef XESN_RECUR_TRACE
-    if (tid == 0 && blockIdx.x < 64)
+    if (tid == 0 && blockIdx.x < 32)
         for (int i = 0; i < 8; ++i) g_recur_trace[blockIdx.x * 8 + i] = tr_sum[i];
 #endif
     if (owner) p.r_out[(long long)g * N + unit] = r_cur;
+    if (CL) cl_cluster_sync();
 }
 
 // src[g][k]: ring slot that feeds input k of group g (single GPU: every produced cell is local)
@@ -350,22 +411,38 @@ __global__ void flow_src_kernel(const int* __restrict__ in_map, const int* __res
 
 }  // namespace
 
-size_t predict_flow_smem(int N, int I, int O, int upc, int tail_cap) {
+size_t predict_flow_smem(int N, int I, int O, int upc, int tail_cap, int cluster) {
     const int ldw = I + 1 + (I & 1);
-    const size_t n_pad = (size_t)((N + 1) & ~1);
+    const size_t n_pad = cluster ? 3 * (size_t)((N + 1) & ~1) + 8 : (size_t)((N + 1) & ~1);
     return sizeof(double) * (n_pad + (size_t)upc * ldw + (size_t)O * upc + (size_t)(I + (I & 1)) + upc + (size_t)tail_cap) +
            sizeof(int) * (size_t)(tail_cap + (tail_cap & 1) + I + 2);
 }
 
 // team size / units per CTA of the dataflow forecast; false when the configuration does not fit (caller falls back)
-bool predict_flow_geometry(int N, int I, int O, int G, int num_sms, const int* indptr, int* team_out, int* upc_out,
-                           int* tail_cap_out) {
-    if (G < 1 || G > num_sms) return false;
-    int team = std::min(num_sms / G, XESN_FLOW_MAX_TEAM);
-    if (team < 1) return false;
+// clusters of `team` CTAs with `smem` bytes each that the device keeps resident at once (0 on error)
+static int flow_resident_clusters(int team, size_t smem) {
+    if (cudaFuncSetAttribute(predict_flow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)team), cfg.blockDim = dim3(PF_THREADS), cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)team, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, predict_flow_kernel<true>, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+static bool flow_fits(int N, int I, int O, int team, int cluster, const int* indptr, int* upc_out, int* tail_cap_out) {
     const int upc = ((N + team - 1) / team + 7) & ~7;
-    team = (N + upc - 1) / upc;
-    if (upc > PF_R_THREADS) return false;   // one unit per thread of the owner warps
+    if ((N + upc - 1) / upc != team) return false;   // a team of this size would leave a member without units
+    if (upc > PF_R_THREADS) return false;            // one unit per thread of the owner warps
     // entries of W beyond the register-resident head of each row, per CTA slice (shared-memory staging)
     int tail_cap = 0;
     for (int c = 0; c < team; ++c) {
@@ -373,8 +450,37 @@ bool predict_flow_geometry(int N, int I, int O, int G, int num_sms, const int* i
         for (int i = c * upc; i < std::min(N, (c + 1) * upc); ++i) t += std::max(0, indptr[i + 1] - indptr[i] - PF_KREG);
         tail_cap = std::max(tail_cap, t);
     }
-    if (predict_flow_smem(N, I, O, upc, tail_cap) > 200 * 1024) return false;
-    *team_out = team, *upc_out = upc, *tail_cap_out = tail_cap;
+    if (predict_flow_smem(N, I, O, upc, tail_cap, cluster) > 200 * 1024) return false;
+    *upc_out = upc, *tail_cap_out = tail_cap;
+    return true;
+}
+
+bool predict_flow_geometry(int N, int I, int O, int G, int num_sms, const int* indptr, int* team_out, int* upc_out,
+                           int* tail_cap_out, int* cluster_out) {
+    if (cluster_out) *cluster_out = 0;
+    if (G < 1 || G > num_sms) return false;
+    // cluster variant first: the largest team (<= 8 CTAs) whose clusters are ALL resident -- clusters cannot straddle
+    // GPCs, so the device holds fewer CTAs in clusters than SMs (measured here: 15 clusters of 8) -- because groups
+    // wait for each other's outputs
+    const char* e = getenv("XESN_B200_FLOW_CLUSTER");
+    if (cluster_out && !(e && e[0] == '0')) {
+        for (int team = 8; team >= 2; --team) {   // any size works, not only powers of two
+            if ((long long)team * G > num_sms) continue;
+            if (!flow_fits(N, I, O, team, 1, indptr, upc_out, tail_cap_out)) continue;
+            const int resident = flow_resident_clusters(team, predict_flow_smem(N, I, O, *upc_out, *tail_cap_out, 1));
+            if (getenv("XESN_B200_VERBOSE"))
+                fprintf(stderr, "xesn_b200: dataflow forecast, clusters of %d: %d resident, %d groups\n", team, resident, G);
+            if (resident < G) continue;
+            *team_out = team, *cluster_out = 1;
+            return true;
+        }
+    }
+    int team = std::min(num_sms / G, XESN_FLOW_MAX_TEAM);
+    if (team < 1) return false;
+    const int upc = ((N + team - 1) / team + 7) & ~7;
+    team = (N + upc - 1) / upc;
+    if (!flow_fits(N, I, O, team, 0, indptr, upc_out, tail_cap_out)) return false;
+    *team_out = team;
     return true;
 }
 
@@ -402,12 +508,33 @@ int launch_flow_src(const int* in_map, const int* out_map, int* owner, int* src,
 
 int launch_predict_flow(const PredictFlowArgs& a, cudaStream_t stream) {
     if (a.steps <= 0) return 0;
-    const size_t smem = predict_flow_smem(a.N, a.I, a.O, a.upc, a.tail_cap);
-    XESN_CUDA_OK(cudaFuncSetAttribute(predict_flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    const size_t smem = predict_flow_smem(a.N, a.I, a.O, a.upc, a.tail_cap, a.cluster);
     PredictFlowArgs args = a;
-    void* kargs[] = {&args};
-    XESN_CUDA_OK(cudaLaunchCooperativeKernel((void*)predict_flow_kernel, dim3(a.G * a.team), dim3(PF_THREADS), kargs, smem,
-                                             stream));
+    if (a.cluster) {
+        XESN_CUDA_OK(cudaFuncSetAttribute(predict_flow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(a.G * a.team)), cfg.blockDim = dim3(PF_THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)a.team, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeCooperative;   // every cluster resident: groups poll each other's outputs
+        attr[1].val.cooperative = 1;
+        cfg.attrs = attr, cfg.numAttrs = 2;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, predict_flow_kernel<true>, args);
+        if (e == cudaErrorCooperativeLaunchTooLarge) {
+            // the cooperative bound does not know about cluster placement; the geometry was chosen from
+            // cudaOccupancyMaxActiveClusters, so every cluster is resident when the device is otherwise idle
+            cudaGetLastError();
+            cfg.numAttrs = 1;
+            e = cudaLaunchKernelEx(&cfg, predict_flow_kernel<true>, args);
+        }
+        XESN_CUDA_OK(e);
+    } else {
+        XESN_CUDA_OK(cudaFuncSetAttribute(predict_flow_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        void* kargs[] = {&args};
+        XESN_CUDA_OK(cudaLaunchCooperativeKernel((void*)predict_flow_kernel<false>, dim3(a.G * a.team), dim3(PF_THREADS), kargs,
+                                                 smem, stream));
+    }
     count_launch();
     return 0;
 }
