@@ -680,8 +680,9 @@ def roofline_of(ctx, args, name, w, prof, g_local, peaks_int8):
     ach = int_ops / (ms_gram * 1e-3) / 1e12
     return {
         "bound": "tensor",
-        "kernel": "fused_chunk_i8_kernel (Gram role: tcgen05.mma kind::i8 on fixed-point digit planes, beside the "
-                  "recurrence role)",
+        "kernel": "fused_chunk_i8_kernel (Gram role: tcgen05.mma kind::i8 on fixed-point digit planes) beside the recurrence "
+                  "role -- the same kernel's other CTAs for large reservoirs, the cluster kernel fused_cluster_i8_kernel launched "
+                  "next to it for small ones (DSMEM state exchange)",
         "achieved": ach, "peak": peak, "unit": "TOP/s", "frac": ach / peak, "traffic": traffic, "peak_source": src,
         "int8_peak_measured": None if peaks_int8 is None else {"burst": peaks_int8[0], "sustained": peaks_int8[1]},
         "int8_peak_derived_2x_bf16": derived,
@@ -689,8 +690,8 @@ def roofline_of(ctx, args, name, w, prof, g_local, peaks_int8):
         "fp64_equivalent_tflops": achieved, "fp64_dgemm_peak_tflops": peak_tf,
         "fp64_equivalent_frac_of_dgemm_peak": achieved / peak_tf if peak_tf else None,
         "note": "achieved = 28 x N(N+1) x T x G int8 ops (the digit-pair MMAs of one triangle) / summed event time of the "
-                "fused launches; the same kernel hosts the recurrence on its other SMs and is bounded by whichever role "
-                "finishes last (small reservoirs: the serial recurrence chain, so the fraction is informational there)"}, True
+                "chunk launches (event pair around both roles); a launch is bounded by whichever role finishes last (small "
+                "reservoirs: the serial recurrence chain, so the fraction is informational there)"}, True
 
 
 def run_ours(ctx, args, name, steps, warmup, with_cpu=True, peaks_int8=None):

@@ -1025,9 +1025,9 @@ static int flow_run(xesn_reservoir* h, const FlowRun& f, uint32_t* launches_done
         const int steps = std::min(XESN_FLOW_CHUNK, f.n_steps - s0);
         const int par = (int)(*count & 1u);
         if (shared_ring) XESN_CUDA_OK(cudaMemsetAsync(f.ring[0], 0xFF, ring_bytes, st));
-        if (!f.cluster)   // the cluster variant moves the states through distributed shared memory, not this ring
-            XESN_CUDA_OK(cudaMemset2DAsync(f.r_ring, sizeof(double) * (size_t)XESN_FLOW_CHUNK * N, 0xFF,
-                                           sizeof(double) * (size_t)steps * N, f.G, st));
+        // (the cluster variant moves the states through distributed shared memory, but its fallback polls this ring)
+        XESN_CUDA_OK(cudaMemset2DAsync(f.r_ring, sizeof(double) * (size_t)XESN_FLOW_CHUNK * N, 0xFF,
+                                       sizeof(double) * (size_t)steps * N, f.G, st));
         // cells nobody produces keep their value in the field leaving the launch
         XESN_CUDA_OK(cudaMemcpyAsync(fbuf[cur ^ 1], fbuf[cur], sizeof(double) * (size_t)f.n_cells, cudaMemcpyDeviceToDevice, st));
         a.steps = steps, a.col0 = s0;

@@ -508,29 +508,30 @@ int launch_flow_src(const int* in_map, const int* out_map, int* owner, int* src,
 
 int launch_predict_flow(const PredictFlowArgs& a, cudaStream_t stream) {
     if (a.steps <= 0) return 0;
-    const size_t smem = predict_flow_smem(a.N, a.I, a.O, a.upc, a.tail_cap, a.cluster);
     PredictFlowArgs args = a;
     if (a.cluster) {
+        const size_t smem = predict_flow_smem(a.N, a.I, a.O, a.upc, a.tail_cap, 1);
         XESN_CUDA_OK(cudaFuncSetAttribute(predict_flow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)(a.G * a.team)), cfg.blockDim = dim3(PF_THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
-        cudaLaunchAttribute attr[2];
+        // Not a cooperative launch: that bound ignores cluster placement and refuses grids this one needs (and a refused
+        // launch is fatal under a profiler).  The geometry was chosen from cudaOccupancyMaxActiveClusters, so every
+        // cluster is resident on an otherwise idle device; should the launch be refused all the same, the L2 variant
+        // runs with the same team (the state ring is armed for it in either case).
+        cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = (unsigned)a.team, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-        attr[1].id = cudaLaunchAttributeCooperative;   // every cluster resident: groups poll each other's outputs
-        attr[1].val.cooperative = 1;
-        cfg.attrs = attr, cfg.numAttrs = 2;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, predict_flow_kernel<true>, args);
-        if (e == cudaErrorCooperativeLaunchTooLarge) {
-            // the cooperative bound does not know about cluster placement; the geometry was chosen from
-            // cudaOccupancyMaxActiveClusters, so every cluster is resident when the device is otherwise idle
-            cudaGetLastError();
-            cfg.numAttrs = 1;
-            e = cudaLaunchKernelEx(&cfg, predict_flow_kernel<true>, args);
+        cfg.attrs = attr, cfg.numAttrs = 1;
+        if (cudaLaunchKernelEx(&cfg, predict_flow_kernel<true>, args) == cudaSuccess) {
+            count_launch();
+            return 0;
         }
-        XESN_CUDA_OK(e);
-    } else {
+        cudaGetLastError();
+        args.cluster = 0;
+    }
+    {
         XESN_CUDA_OK(cudaFuncSetAttribute(predict_flow_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        const size_t smem = predict_flow_smem(a.N, a.I, a.O, a.upc, a.tail_cap, 0);
         void* kargs[] = {&args};
         XESN_CUDA_OK(cudaLaunchCooperativeKernel((void*)predict_flow_kernel<false>, dim3(a.G * a.team), dim3(PF_THREADS), kargs,
                                                  smem, stream));
