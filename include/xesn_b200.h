@@ -97,7 +97,10 @@ int xesn_forced_run(xesn_reservoir* h, const xesn_series* u, int64_t t0, int32_t
  *        gram_dev : [G][N][N] workspace (lower triangle = R R^T + beta I on return from
  *                   xesn_train_accumulate; destroyed by xesn_ridge_solve)
  *        wout_dev : [G][O][N]; holds Y R^T after accumulate, Wout after solve
- *        info_dev : [G] ints, 0 = ok, k>0 = leading minor k not positive definite */
+ *        info_dev : [G] ints, 0 = ok, k>0 = leading minor k not positive definite
+ *      INTERLEAVED LAYOUT: when wout_dev == gram_dev + N*N (in doubles) the two are taken as ONE array [G][N+O][N], the
+ *      O readout rows of a group right below its Gram matrix (group stride (N+O)*N for both).  Pass the same two
+ *      pointers to xesn_train_accumulate and xesn_ridge_solve. */
 int64_t xesn_train_scratch_bytes(xesn_reservoir* h, int32_t n_output, int32_t n_groups, int32_t chunk,
                                  int32_t gathered_u, int32_t gathered_y);
 int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_series* y, int32_t n_output,
@@ -106,9 +109,8 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
                           void* stream);
 /* (R R^T + beta I) solve: xesn/esn.py:516-520.  beta_dev: [G] or NULL (then beta_scalar is used).
  *      Blocked Cholesky; for one large system the trailing updates run on the int8 tensor cores (row-scaled
- *      8-digit fixed point, XESN_B200_SOLVE_I8=0 keeps FP64 DMMA).  Layout hint: with n_groups == 1 and
- *      wout_dev == gram_dev + N*N (readout rows stored right below the Gram matrix) the forward substitution
- *      is folded into the factorisation. */
+ *      8-digit fixed point, XESN_B200_SOLVE_I8=0 keeps FP64 DMMA).  With the interleaved layout (above) and
+ *      n_output <= 256 the right-hand sides ride through the factorisation as extra rows: no forward substitution. */
 int xesn_ridge_solve(xesn_reservoir* h, int32_t n_output, int32_t n_groups, const double* beta_dev,
                      double beta_scalar, double* gram_dev, double* wout_dev, int32_t* info_dev,
                      void* scratch_dev, int64_t scratch_bytes, void* stream);

@@ -561,6 +561,11 @@ int64_t xesn_train_scratch_bytes(xesn_reservoir* h, int32_t O, int32_t G, int32_
     return (train > solve ? train : solve) * 8 + 256;
 }
 
+// Group strides of the Gram matrices and readouts.  Separate arrays: [G][N][N] and [G][O][N].  When the readout rows
+// start right below the first Gram matrix (wout == gram + N*N) the two are ONE array [G][N+O][N]: the solve then carries
+// the right-hand sides through the factorisation as extra rows and needs no forward substitution (cholesky.cu, FOLD).
+static inline bool gram_interleaved(const double* gram, const double* wout, int N) { return wout == gram + (long long)N * N; }
+
 int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_series* y, int32_t O, int32_t G,
                           int64_t T, int64_t n_spinup, int32_t chunk, double* gram, double* wout, void* scratch,
                           int64_t scratch_bytes, void* stream) {
@@ -577,8 +582,15 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
     double *carry = base + L.carry, *Uc = base + L.Uc, *Yc = base + L.Yc, *D = base + L.D, *R = base + L.R;
 
     XESN_CUDA_OK(cudaMemsetAsync(carry, 0, sizeof(double) * (size_t)G * N, st));
-    XESN_CUDA_OK(cudaMemsetAsync(gram, 0, sizeof(double) * (size_t)G * N * N, st));
-    XESN_CUDA_OK(cudaMemsetAsync(wout, 0, sizeof(double) * (size_t)G * O * N, st));
+    const bool inter = gram_interleaved(gram, wout, N);
+    const long long gram_gs = inter ? (long long)(N + O) * N : (long long)N * N;
+    const long long wout_gs = inter ? (long long)(N + O) * N : (long long)O * N;
+    if (inter) {
+        XESN_CUDA_OK(cudaMemsetAsync(gram, 0, sizeof(double) * (size_t)G * gram_gs, st));
+    } else {
+        XESN_CUDA_OK(cudaMemsetAsync(gram, 0, sizeof(double) * (size_t)G * N * N, st));
+        XESN_CUDA_OK(cudaMemsetAsync(wout, 0, sizeof(double) * (size_t)G * O * N, st));
+    }
 
     // spin-up (states not stored): xesn/esn.py:498-499
     for (long long t0 = 0; t0 < n_spinup; t0 += chunk) {
@@ -629,9 +641,10 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
         const bool i8 = gram_mode_effective(h) == 1;
         signed char* Pbuf[2] = {reinterpret_cast<signed char*>(base + L.P1), reinterpret_cast<signed char*>(base + L.P2)};
         const long long plane_group = (long long)gi8::NDIG * L.plane_stride;
-        if (i8 && L.ldp > N) {  // padding columns must read as zero digits
-            XESN_CUDA_OK(cudaMemsetAsync(Pbuf[0], 0, (size_t)G * plane_group, st));
-            XESN_CUDA_OK(cudaMemsetAsync(Pbuf[1], 0, (size_t)G * plane_group, st));
+        if (i8 && L.ldp > N) {  // padding columns must read as zero digits (rows of every plane and group are ldp apart)
+            const size_t rows = (size_t)(G * plane_group / L.ldp);
+            XESN_CUDA_OK(cudaMemset2DAsync(Pbuf[0] + N, (size_t)L.ldp, 0, (size_t)(L.ldp - N), rows, st));
+            XESN_CUDA_OK(cudaMemset2DAsync(Pbuf[1] + N, (size_t)L.ldp, 0, (size_t)(L.ldp - N), rows, st));
         }
         // chunks of equal length (a multiple of the Gram role's K-block): a short last chunk would still cost a launch
         // as long as the Gram pass of the full chunk before it.  (A ramp of short first chunks was measured too: the
@@ -704,11 +717,11 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
                 double* Rp = Rbuf[(c - 1) & 1];
                 g.A = Rp, g.lda = N, g.strideA = rgs;
                 g.B = Rp, g.ldb = N, g.strideB = rgs;
-                g.C = gram, g.ldc = N, g.strideC = (long long)N * N;
+                g.C = gram, g.ldc = N, g.strideC = gram_gs;
                 g.M = N, g.N = N, g.K = mp, g.batch = G, g.alpha = 1.0, g.beta = 1.0, g.flags = GEMM_LOWER;
                 g8.planes = reinterpret_cast<const int8_t*>(Pbuf[(c - 1) & 1]);
                 g8.ldp = L.ldp, g8.plane_stride = L.plane_stride, g8.group_stride = plane_group;
-                g8.K = (int)round_up(mp, gi8::KB), g8.N = N, g8.G = gram, g8.ldg = N, g8.strideG = (long long)N * N;
+                g8.K = (int)round_up(mp, gi8::KB), g8.N = N, g8.G = gram, g8.ldg = N, g8.strideG = gram_gs;
                 g8.batch = G;
                 ntiles = i8 ? h->n_tiles_i8 : h->n_tiles;
             }
@@ -723,7 +736,7 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
                 if ((rc = chunk_inputs(h, y, O, G, chunk_t0(c - 1), mp, Yc, L.cld, &yb, &ldy, &ygs, st))) return rc;
                 q.A = yb, q.lda = ldy, q.strideA = ygs;
                 q.B = Rbuf[(c - 1) & 1], q.ldb = N, q.strideB = (long long)(mp + 1) * N;
-                q.C = wout, q.ldc = N, q.strideC = (long long)O * N;
+                q.C = wout, q.ldc = N, q.strideC = wout_gs;
                 q.M = O, q.N = N, q.K = mp, q.batch = G, q.alpha = 1.0, q.beta = 1.0, q.flags = GEMM_A_KMAJOR;
                 yr_in_kernel = i8 && !pull && O <= YR_SKINNY_MAX_ROWS && !getenv("XESN_B200_YR_SEPARATE");
             }
@@ -768,7 +781,7 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
         GemmArgs g = {};
         g.A = R, g.lda = N, g.strideA = rgs;
         g.B = R, g.ldb = N, g.strideB = rgs;
-        g.C = gram, g.ldc = N, g.strideC = (long long)N * N;
+        g.C = gram, g.ldc = N, g.strideC = gram_gs;
         g.M = N, g.N = N, g.K = m, g.batch = G, g.alpha = 1.0, g.beta = 1.0, g.flags = GEMM_LOWER;
         {
             ProfScope prof(PROF_GRAM, st);
@@ -778,7 +791,7 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
         GemmArgs q = {};
         q.A = yb, q.lda = ldy, q.strideA = ygs;
         q.B = R, q.ldb = N, q.strideB = rgs;
-        q.C = wout, q.ldc = N, q.strideC = (long long)O * N;
+        q.C = wout, q.ldc = N, q.strideC = wout_gs;
         q.M = O, q.N = N, q.K = m, q.batch = G, q.alpha = 1.0, q.beta = 1.0, q.flags = GEMM_A_KMAJOR;
         {
             ProfScope prof(PROF_YR, st);
@@ -818,10 +831,12 @@ int xesn_ridge_solve(xesn_reservoir* h, int32_t O, int32_t G, const double* beta
     cudaStream_t st = (cudaStream_t)stream;
     const int N = h->N;
     ProfScope prof(PROF_SOLVE, st);
-    int rc = launch_add_diag(gram, N, (long long)N * N, N, G, beta_dev, beta_scalar, st);
+    const bool inter = gram_interleaved(gram, wout, N);
+    const long long gram_gs = inter ? (long long)(N + O) * N : (long long)N * N;
+    const long long wout_gs = inter ? (long long)(N + O) * N : (long long)O * N;
+    int rc = launch_add_diag(gram, N, gram_gs, N, G, beta_dev, beta_scalar, st);
     if (rc) return rc;
-    return launch_cholesky_solve_ws(h->solve, gram, N, (long long)N * N, wout, N, (long long)O * N, N, O, G, info,
-                                    (double*)scratch, st);
+    return launch_cholesky_solve_ws(h->solve, gram, N, gram_gs, wout, N, wout_gs, N, O, G, info, (double*)scratch, st);
 }
 
 // Pivoted fallback for ONE system whose Cholesky factorisation failed (info > 0 from xesn_ridge_solve): the caller

@@ -330,7 +330,8 @@ static int cholesky_solve_body(SolveCtx& ctx, double* A, long long lda, long lon
     // FOLD: when the right-hand sides are stored as the rows n .. n+nrhs-1 of the same array (B = A + n*lda),
     // every panel operation simply runs over nrhs more rows, which turns B into Z = B L^-T on the way:
     // the forward sweep (125 dependent pairs of small launches at n = 16000) disappears.
-    const bool fold = batch == 1 && nrhs <= FOLD_MAX_RHS && ldb == lda && B == A + (long long)n * lda;
+    const bool fold = nrhs <= FOLD_MAX_RHS && ldb == lda && B == A + (long long)n * lda && (batch == 1 || strideB == strideA) &&
+                      !getenv("XESN_B200_NO_FOLD");
     const int xr = fold ? nrhs : 0;
     cudaStream_t side = ctx.side;
     cudaEvent_t* ev_panel = ctx.ev_panel;

@@ -24,7 +24,7 @@ import numpy as np
 import scipy.sparse
 
 from . import _lib
-from .esn import ESN, DeviceReservoir, _ptr, _time_last, _torch, auto_chunk, pivoted_fallback
+from .esn import ESN, DeviceReservoir, _ptr, _time_last, _torch, auto_chunk, gram_and_readout, pivoted_fallback
 from .matrix import RandomMatrix, SparseRandomMatrix, _dense_scale, _sparse_scale
 
 
@@ -165,8 +165,7 @@ class ESNEnsemble:
             st = torch.cuda.current_stream().cuda_stream
             nbytes = lib.xesn_train_scratch_bytes(res.handle, O, G, chunk, 1, 1)
             scratch = torch.empty(nbytes, dtype=torch.uint8, device=res.device)
-            gram = torch.empty((G, N, N), dtype=torch.float64, device=res.device)
-            wout = torch.empty((G, O, N), dtype=torch.float64, device=res.device)
+            gram, wout, both = gram_and_readout(G, N, O, res.device)
             info = torch.zeros(G, dtype=torch.int32, device=res.device)
             beta = torch.tensor([float(m.tikhonov_parameter) for m in self.members], dtype=torch.float64,
                                 device=res.device)
@@ -180,7 +179,9 @@ class ESNEnsemble:
                                             _ptr(scratch), nbytes, st))
             pivoted_fallback(lib, res.handle, accumulate, O, [float(m.tikhonov_parameter) for m in self.members], gram,
                              wout, info, scratch, nbytes, st, "ESNEnsemble")
-            del gram, ku, ky
+            if both is not None:
+                wout = wout.clone()   # the Gram matrices must not stay alive through a view
+            del gram, both, ku, ky
         self._wout_dev = wout
         self.last_info = info
         bad = np.nonzero(info.cpu().numpy())[0]

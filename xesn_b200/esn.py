@@ -316,14 +316,7 @@ class ESN:
         with torch.cuda.device(res.device):
             nbytes = lib.xesn_train_scratch_bytes(res.handle, O, G, chunk, gu, gy)
             scratch = torch.empty(nbytes, dtype=torch.uint8, device=res.device)
-            if G == 1:
-                # readout rows stored right below the Gram matrix: the solve then carries them through the
-                # factorisation as extra rows and needs no forward substitution (include/xesn_b200.h)
-                both = torch.empty((N + O, N), dtype=torch.float64, device=res.device)
-                gram, wout = both[:N].view(1, N, N), both[N:].view(1, O, N)
-            else:
-                gram = torch.empty((G, N, N), dtype=torch.float64, device=res.device)
-                wout = torch.empty((G, O, N), dtype=torch.float64, device=res.device)
+            gram, wout, both = gram_and_readout(G, N, O, res.device)
             info = torch.zeros(G, dtype=torch.int32, device=res.device)
             st = self._stream()
 
@@ -338,8 +331,8 @@ class ESN:
                 _ptr(scratch), nbytes, st))
             pivoted_fallback(lib, res.handle, accumulate, O, [float(self.tikhonov_parameter)] * G, gram, wout, info,
                              scratch, nbytes, st, type(self).__name__)
-            if G == 1:
-                wout = wout.clone()  # do not keep the 8 N^2 bytes of the Gram matrix alive through a view
+            if both is not None:
+                wout = wout.clone()  # do not keep the 8 N^2 bytes of the Gram matrices alive through a view
                 del gram, both
         self.last_info = info
         del keepalive
@@ -469,6 +462,20 @@ class ESN:
         if "units" in time.attrs:
             attrs["units"] = time.attrs["units"]
         return xr.DataArray(ftime, coords={"ftime": ftime}, dims="ftime", attrs=attrs)
+
+
+def gram_and_readout(n_groups, n_reservoir, n_output, device):
+    """Device buffers of the Gram matrices (G, N, N) and the readouts (G, O, N) of a training call.  With few readout rows
+    both are views of ONE array (G, N + O, N) -- the readout rows of a group right below its Gram matrix -- which the
+    library recognises (wout == gram + N*N elements, include/xesn_b200.h): the solve then carries the right-hand sides
+    through the factorisation as extra rows and needs no forward substitution.  Returns (gram, wout, owner or None)."""
+    torch = _torch()
+    G, N, O = n_groups, n_reservoir, n_output
+    if O <= 256:
+        both = torch.empty((G, N + O, N), dtype=torch.float64, device=device)
+        return both[:, :N, :], both[:, N:, :], both
+    return (torch.empty((G, N, N), dtype=torch.float64, device=device),
+            torch.empty((G, O, N), dtype=torch.float64, device=device), None)
 
 
 def pivoted_fallback(lib, handle, accumulate, n_output, betas, gram, wout, info, scratch, nbytes, stream, who):
