@@ -959,8 +959,14 @@ static bool predict_pull_eligible(xesn_reservoir* h, int O, int G, long long n_c
 static bool predict_flow_eligible(xesn_reservoir* h, int O, int G, int* team, int* upc, int* tail_cap = nullptr,
                                   int* cluster = nullptr) {
     int tc = 0, cl = 0;
-    const bool ok = h->persistent_predict == 1 && G > 1 &&
-                    predict_flow_geometry(h->N, h->I, O, G, h->num_sms, h->h_indptr.data(), team, upc, &tc, &cl);
+    bool ok = h->persistent_predict == 1 && G >= 1 &&
+              predict_flow_geometry(h->N, h->I, O, G, h->num_sms, h->h_indptr.data(), team, upc, &tc, &cl);
+    // one reservoir: only the cluster variant (everything a step needs travels through distributed shared memory); the
+    // L2 variant would lose to the barrier-free kernel of predict_pull.cu.  XESN_B200_FLOW_SINGLE=0 keeps that kernel.
+    if (ok && G == 1) {
+        const char* e = getenv("XESN_B200_FLOW_SINGLE");
+        ok = cl == 1 && !(e && e[0] == '0');
+    }
     if (ok && tail_cap) *tail_cap = tc;
     if (ok && cluster) *cluster = cl;
     return ok;
@@ -1106,7 +1112,9 @@ int xesn_predict(xesn_reservoir* h, const double* wout, int32_t O, int32_t G, in
     double* rbuf[2] = {r, r_alt};
     double* fbuf[2] = {field, field_alt};
     int pp_upc = 0, pp_ctas = 0;
-    if (predict_pull_eligible(h, O, G, n_cells, &pp_upc, &pp_ctas)) {
+    int fteam = 0, fupc = 0, ftail = 0, fcluster = 0;
+    const bool flow_ok = predict_flow_eligible(h, O, G, &fteam, &fupc, &ftail, &fcluster);
+    if (!(G == 1 && flow_ok) && predict_pull_eligible(h, O, G, n_cells, &pp_upc, &pp_ctas)) {
         // one reservoir: barrier-free forecast kernel, PULL_PREDICT_CHUNK steps per launch
         PredictPullArgs a = {};
         a.indptr = h->d_indptr, a.indices = h->d_indices, a.values = h->d_values;
@@ -1125,9 +1133,8 @@ int xesn_predict(xesn_reservoir* h, const double* wout, int32_t O, int32_t G, in
         }
         return 0;
     }
-    int fteam = 0, fupc = 0, ftail = 0, fcluster = 0;
-    if (predict_flow_eligible(h, O, G, &fteam, &fupc, &ftail, &fcluster)) {
-        // several reservoirs on one GPU: dataflow kernel, every produced cell is local (no imports / exports)
+    if (flow_ok) {
+        // several reservoirs on one GPU (or one small reservoir on a cluster): dataflow kernel, every produced cell is local (no imports / exports)
         const FlowLayout L = flow_layout(h, O, G, n_cells, fteam, true);
         double* area = field_alt + round_up(n_cells, 2);
         int* src = reinterpret_cast<int*>(area + L.src);

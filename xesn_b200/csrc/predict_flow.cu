@@ -94,11 +94,16 @@ struct FlowSmem {
     int* s_toff;     // [tail_cap] ... and their columns
     int* s_src;      // [I]
     int ldw;
+    // cluster variant: the team's contributions to this group's outputs, three copies like the states ([3][team][O]),
+    // and the shared-window address of the three mbarriers
+    double* s_part;
+    unsigned bar_addr;
 };
 
 // phase C: this CTA's contribution to every output of the group (all 16 warps)
+template <bool CL>
 __device__ __forceinline__ void flow_contributions(const PredictFlowArgs& p, const FlowSmem& sm, int n, int c, long long slot0,
-                                                   int warp, int lane) {
+                                                   int warp, int lane, unsigned nxt) {
     const int upc = p.upc;
     for (int o = warp; o < p.O; o += PF_WARPS) {
         const double* w = sm.s_wout + (size_t)o * upc;
@@ -106,6 +111,13 @@ __device__ __forceinline__ void flow_contributions(const PredictFlowArgs& p, con
         for (int il = lane; il < upc; il += 32) a = fma(w[il], sm.s_rnew[il], a);
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+        if (CL && lane < p.team) {
+            // cluster variant: lane q hands the contribution to CTA q of the team (itself included) through distributed
+            // shared memory, signed off on the same mbarrier as the states of this step -- the group's own cells reach
+            // the next step's inputs without a round trip through the L2
+            const unsigned dst = cl_smem_u32(sm.s_part + ((size_t)nxt * p.team + c) * p.O + o);
+            cl_st_async(cl_mapa(dst, (unsigned)lane), a, cl_mapa(sm.bar_addr + 8u * nxt, (unsigned)lane));
+        }
         if (lane == 0) {
             const long long slot = slot0 + o;
             st_flag(p.part_ring + (slot * p.ring_steps + (n - 1)) * p.team + c, a);
@@ -118,8 +130,10 @@ __device__ __forceinline__ void flow_contributions(const PredictFlowArgs& p, con
 }
 
 // warps 14 and 15: the values the step consumes that come through the partial rings
+template <bool CL>
 __device__ __forceinline__ void flow_io_role(const PredictFlowArgs& p, const FlowSmem& sm, int g, int c, int t /*0..63*/) {
     const int I = p.I, O = p.O;
+    unsigned cur = 0, phase_bits = 0;   // CL: copy that holds the contributions of step n-1; parities of the mbarriers
     const int warp = PF_R_THREADS / 32 + (t >> 5), lane = t & 31;
     const bool leader = c == 0;
     const long long slot0 = (long long)g * O;
@@ -140,7 +154,12 @@ __device__ __forceinline__ void flow_io_role(const PredictFlowArgs& p, const Flo
     } while (0)
 #endif
     for (int n = 1; n <= p.steps; ++n) {
+        const unsigned nxt = cur == 2 ? 0u : cur + 1u;
         if (t < 32) {
+            if (CL && n >= 2 && !aborted) {   // the team's contributions of step n-1 have landed in copy `cur`
+                aborted = !cl_mbar_wait(sm.bar_addr + 8u * cur, (phase_bits >> cur) & 1u, p.status);
+                phase_bits ^= 1u << cur;
+            }
             // inputs of step n: the outputs of step n-1 (ring row n-2), or the field entering the launch
             for (int k = t; k < I; k += 32) {
                 const int src = sm.s_src[k];
@@ -149,6 +168,11 @@ __device__ __forceinline__ void flow_io_role(const PredictFlowArgs& p, const Flo
                     x = p.fill[-1 - src];
                 } else if (n == 1 || src == INT_MIN) {
                     x = p.field[p.in_map[(long long)g * I + k]];
+                } else if (CL && src >= slot0 && src < slot0 + O) {
+                    // a cell of this group: the contributions are in shared memory, added in CTA order like team_sum
+                    const double* q = sm.s_part + (size_t)cur * p.team * O + (src - slot0);
+                    x = 0.0;
+                    for (int cc = 0; cc < p.team; ++cc) x += q[(size_t)cc * O];
                 } else {
                     x = team_sum(p, src, n - 2, aborted);
                 }
@@ -166,8 +190,9 @@ __device__ __forceinline__ void flow_io_role(const PredictFlowArgs& p, const Flo
         XESN_IO_MARK(1);   // [1] waiting for the owners to arrive (they were still busy with the previous step)
         bar_states_ready();
         XESN_IO_MARK(2);   // [2] the owners' update
-        flow_contributions(p, sm, n, c, slot0, warp, lane);
+        flow_contributions<CL>(p, sm, n, c, slot0, warp, lane, nxt);
         XESN_IO_MARK(3);   // [3] contributions
+        cur = CL ? nxt : 0u;
     }
 #ifdef XESN_RECUR_TRACE
     if (t == 0 && blockIdx.x < 32)
@@ -198,7 +223,8 @@ __global__ void __launch_bounds__(PF_THREADS, 1) predict_flow_kernel(PredictFlow
     sm.ldw = I + 1 + (I & 1);  // odd row pitch (in doubles): conflict-free reads of one row per lane
     sm.s_r = smem;   // CL: three copies of the state vector, then the mbarrier of each copy
     unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(smem + 3 * (size_t)n_pad);
-    sm.s_win = CL ? sm.s_r + 3 * (size_t)n_pad + 8 : sm.s_r + n_pad;
+    sm.s_part = smem + 3 * (size_t)n_pad + 8;
+    sm.s_win = CL ? sm.s_part + 3 * (size_t)p.team * O : sm.s_r + n_pad;
     sm.s_wout = sm.s_win + (size_t)upc * sm.ldw;
     sm.s_u = sm.s_wout + (size_t)O * upc;
     sm.s_rnew = sm.s_u + I + (I & 1);
@@ -232,6 +258,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) predict_flow_kernel(PredictFlow
         }
     }
     const unsigned bar_addr = CL ? cl_smem_u32(s_bar) : 0u;
+    sm.bar_addr = bar_addr;
     if (CL) {
         if (tid < 3) cl_mbar_init(bar_addr + 8u * tid, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -240,7 +267,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) predict_flow_kernel(PredictFlow
     if (CL) cl_cluster_sync();   // every CTA's barriers exist before anybody sends
 
     if (tid >= PF_R_THREADS) {
-        flow_io_role(p, sm, g, c, tid - PF_R_THREADS);
+        flow_io_role<CL>(p, sm, g, c, tid - PF_R_THREADS);
         if (CL) cl_cluster_sync();   // nobody leaves while a peer may still store into its shared memory
         return;
     }
@@ -280,7 +307,8 @@ __global__ void __launch_bounds__(PF_THREADS, 1) predict_flow_kernel(PredictFlow
 #endif
 
     const unsigned copy_bytes = (unsigned)n_pad * 8u;
-    const unsigned expect_bytes = (unsigned)(N - nu) * 8u;   // what the peers send me per step
+    // per step: the peers' slices of r and every team member's contributions (mine included) to the group's outputs
+    const unsigned expect_bytes = (unsigned)(N - nu) * 8u + (unsigned)(p.team * O) * 8u;
     unsigned cur = 0, phase_bits = 0;                         // CL: copy holding r_{n-1}; parities of the three barriers
     for (int n = 1; n <= p.steps; ++n) {
         const unsigned nxt = cur == 2 ? 0u : cur + 1u;
@@ -384,10 +412,12 @@ __global__ void __launch_bounds__(PF_THREADS, 1) predict_flow_kernel(PredictFlow
         }
         bar_states_ready();
         XESN_TRACE_MARK(6);  // [6] state store + waiting for the other owners
-        flow_contributions(p, sm, n, c, slot0, warp, lane);
+        flow_contributions<CL>(p, sm, n, c, slot0, warp, lane, nxt);
         XESN_TRACE_MARK(7);  // [7] contributions
         cur = CL ? nxt : 0u;
     }
+    // what was sent during the last step must have landed before anybody leaves (nobody else waits for it)
+    if (CL && p.steps >= 1 && !aborted) cl_mbar_wait(bar_addr + 8u * cur, (phase_bits >> cur) & 1u, p.status);
 #ifdef XESN_RECUR_TRACE
     if (tid == 0 && blockIdx.x < 32)
         for (int i = 0; i < 8; ++i) g_recur_trace[blockIdx.x * 8 + i] = tr_sum[i];
@@ -413,7 +443,8 @@ __global__ void flow_src_kernel(const int* __restrict__ in_map, const int* __res
 
 size_t predict_flow_smem(int N, int I, int O, int upc, int tail_cap, int cluster) {
     const int ldw = I + 1 + (I & 1);
-    const size_t n_pad = cluster ? 3 * (size_t)((N + 1) & ~1) + 8 : (size_t)((N + 1) & ~1);
+    // cluster variant: three copies of the states, the mbarriers, three copies of the team's contributions (team <= 8)
+    const size_t n_pad = cluster ? 3 * (size_t)((N + 1) & ~1) + 8 + 3 * 8 * (size_t)O : (size_t)((N + 1) & ~1);
     return sizeof(double) * (n_pad + (size_t)upc * ldw + (size_t)O * upc + (size_t)(I + (I & 1)) + upc + (size_t)tail_cap) +
            sizeof(int) * (size_t)(tail_cap + (tail_cap & 1) + I + 2);
 }
