@@ -406,9 +406,11 @@ bool cluster_recur_geometry(int N, int n_groups, const int* indptr, int num_sms,
     team = std::max(team, (N + recur::CL_THREADS - 1) / recur::CL_THREADS);
     if (const char* t = getenv("XESN_B200_REC_CLUSTER_TEAM")) team = atoi(t);
     if (team < 1 || team > 8) return false;
-    // clusters cost resident CTAs (GPC boundaries: 132 of 148 at size 4, 128 at size 8): only where the chunk is
-    // bounded by the recurrence, not by the Gram role (measured: 8 x N=4000 loses 23 ms of 50 with clusters)
-    if ((double)n_groups * N * N > 1.0e8 && !getenv("XESN_B200_REC_CLUSTER_TEAM")) return false;
+    // only where the chunk is bounded by the recurrence rather than by the Gram role.  (With the Gram workers in the
+    // same cluster launch the clusters also cost resident CTAs -- 8 x N=4000 lost 23 ms of 50; as two kernels side by
+    // side they do not, and that shape gains 2 %: bench macro 98.2 -> 96.1 ms.)
+    const double limit = getenv("XESN_B200_CLUSTER_SINGLE") ? 1.0e8 : 1.5e8;
+    if ((double)n_groups * N * N > limit && !getenv("XESN_B200_REC_CLUSTER_TEAM")) return false;
     const int upc = recur_units_per_cta(N, team);
     if (upc > recur::CL_THREADS) return false;
     if ((long long)team * n_groups > num_sms - team) return false;   // at least one cluster of workers must remain
