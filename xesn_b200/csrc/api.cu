@@ -144,6 +144,7 @@ struct xesn_reservoir {
     // low-priority stream + fork/join events of the worker grid that runs beside the recurrence clusters
     cudaStream_t worker_stream = nullptr;
     cudaEvent_t ev_wfork = nullptr, ev_wjoin = nullptr;
+    int* d_tile_counter = nullptr;   // Gram tiles of a chunk launch are drawn from this counter (gram_i8.cuh, DYN)
 };
 static inline int gram_mode_effective(const xesn_reservoir* h) { return (h->gram_mode == 1 && h->leak_unit_range) ? 1 : 0; }
 
@@ -307,6 +308,7 @@ int xesn_reservoir_destroy(xesn_reservoir* h) {
     solve_ctx_destroy(h->solve);
     cudaFree(h->d_flow_tail_ptr);
     for (auto& pl : h->cl_plan) cudaFree(pl.d_tail_ptr), cudaFree(pl.d_slot), cudaFree(pl.d_col_off);
+    cudaFree(h->d_tile_counter);
     if (h->worker_stream) cudaStreamDestroy(h->worker_stream);
     if (h->ev_wfork) cudaEventDestroy(h->ev_wfork);
     if (h->ev_wjoin) cudaEventDestroy(h->ev_wjoin);
@@ -616,6 +618,7 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
                          cluster_recur_geometry(N, G, h->h_indptr.data(), h->num_sms, &cteam, &ctail);
     if (cluster)
         if (int rc = ensure_cluster_plan(h, cteam)) return rc;
+    if (!h->d_tile_counter) XESN_CUDA_OK(cudaMalloc(&h->d_tile_counter, 64));
     const bool split = cluster && !getenv("XESN_B200_CLUSTER_SINGLE");
     if (split && !h->worker_stream) {
         int lo = 0, hi = 0;
@@ -746,11 +749,11 @@ int xesn_train_accumulate(xesn_reservoir* h, const xesn_series* u, const xesn_se
                 rc = pull ? launch_fused_pull_i8(r, G, g8, h->d_tiles_i8, ntiles, h->num_sms, st)
                      : split ? launch_fused_cluster_split_i8(r, G, cteam, h->cl_plan[cteam].d_tail_ptr, ctail, g8, h->d_tiles_i8,
                                                              ntiles, yr_in_kernel ? q : q_none, dv, h->num_sms, st,
-                                                             h->worker_stream, h->ev_wfork, h->ev_wjoin)
+                                                             h->worker_stream, h->ev_wfork, h->ev_wjoin, h->d_tile_counter)
                      : cluster ? launch_fused_cluster_i8(r, G, cteam, h->cl_plan[cteam].d_tail_ptr, ctail, g8, h->d_tiles_i8, ntiles,
-                                                         yr_in_kernel ? q : q_none, dv, h->num_sms, st)
+                                                         yr_in_kernel ? q : q_none, dv, h->num_sms, st, h->d_tile_counter)
                      : i8 ? launch_fused_chunk_i8(r, G, team, upt, halves, slice_nnz, g8, h->d_tiles_i8, ntiles,
-                                                  yr_in_kernel ? q : q_none, dv, h->num_sms, st)
+                                                  yr_in_kernel ? q : q_none, dv, h->num_sms, st, h->d_tile_counter)
                           : launch_fused_chunk(r, G, team, upt, slice_nnz, g, h->d_tiles, ntiles, h->num_sms, st);
                 if (rc) return rc;
             }

@@ -82,9 +82,10 @@ template <int UPT, bool WS, bool DRV>
 __global__ void __launch_bounds__(FUSED_I8_THREADS, 1)
 fused_chunk_i8_kernel(RecurArgs rp, int rec_ctas, int team, int member_bytes, gi8::GramI8Args gp,
                       const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                      const int2* __restrict__ tiles, int ntiles, GemmArgs yrp, drv::DriveArgs dvp) {
+                      const int2* __restrict__ tiles, int ntiles, GemmArgs yrp, drv::DriveArgs dvp, int* tile_counter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     XESN_CTA_STAMP(0);
+    const long long total = (long long)ntiles * gp.batch;
     if ((int)blockIdx.x < rec_ctas) {
         bool done = false;
         if constexpr (UPT == 1) {   // the launcher pairs members only for one unit per thread
@@ -100,14 +101,22 @@ fused_chunk_i8_kernel(RecurArgs rp, int rec_ctas, int team, int member_bytes, gi
         }
         if (!done) recur::recur_body<UPT, FUSED_I8_THREADS, WS>(rp, blockIdx.x % team, team, blockIdx.x / team, smem_raw);
         XESN_CTA_STAMP(1);
+        // the recurrence of this CTA is done: it joins the Gram role for whatever tiles are left (the tiles are drawn from a
+        // counter, so a chunk costs (recurrence + Gram work) / SMs instead of max(recurrence, Gram on the other SMs))
+        if (total > 0) {
+            __syncthreads();
+            gi8::GramI8Ctx ctx;
+            gi8::gram_i8_setup(ctx, smem_raw);
+            gi8::gram_i8_run<FUSED_I8_THREADS, gi8::NDIG, true>(ctx, gp, &tmA, &tmB, tiles, ntiles, 0, 1, tile_counter);
+            gi8::gram_i8_teardown(ctx);
+        }
         return;
     }
     const int worker = blockIdx.x - rec_ctas, nworkers = gridDim.x - rec_ctas;
-    const long long total = (long long)ntiles * gp.batch;
-    if (worker < total) {
+    if (total > 0) {
         gi8::GramI8Ctx ctx;
         gi8::gram_i8_setup(ctx, smem_raw);
-        gi8::gram_i8_run<FUSED_I8_THREADS>(ctx, gp, &tmA, &tmB, tiles, ntiles, worker, nworkers);
+        gi8::gram_i8_run<FUSED_I8_THREADS, gi8::NDIG, true>(ctx, gp, &tmA, &tmB, tiles, ntiles, worker, nworkers, tile_counter);
         gi8::gram_i8_teardown(ctx);
     }
     // ybar += Y R of the same (previous) chunk: skinny work items taken by the Gram CTAs as they run out of tiles --
@@ -139,18 +148,25 @@ template <bool DRV>
 __global__ void __launch_bounds__(FUSED_I8_THREADS, 1)
 fused_cluster_i8_kernel(RecurArgs rp, int rec_ctas, int team, const int* __restrict__ tail_ptr, int tail_cap,
                         gi8::GramI8Args gp, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                        const int2* __restrict__ tiles, int ntiles, GemmArgs yrp, drv::DriveArgs dvp) {
+                        const int2* __restrict__ tiles, int ntiles, GemmArgs yrp, drv::DriveArgs dvp, int* tile_counter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    const long long total = (long long)ntiles * gp.batch;
     if ((int)blockIdx.x < rec_ctas) {
         recur::recur_cluster_body(rp, recur::cluster_ctarank(), team, blockIdx.x / team, smem_raw, tail_ptr, tail_cap);
+        if (total > 0) {   // done with the recurrence: help with the Gram tiles that are left (see fused_chunk_i8_kernel)
+            __syncthreads();
+            gi8::GramI8Ctx ctx;
+            gi8::gram_i8_setup(ctx, smem_raw);
+            gi8::gram_i8_run<FUSED_I8_THREADS, gi8::NDIG, true>(ctx, gp, &tmA, &tmB, tiles, ntiles, 0, 1, tile_counter);
+            gi8::gram_i8_teardown(ctx);
+        }
         return;
     }
     const int worker = blockIdx.x - rec_ctas, nworkers = gridDim.x - rec_ctas;
-    const long long total = (long long)ntiles * gp.batch;
-    if (worker < total) {
+    if (total > 0) {
         gi8::GramI8Ctx ctx;
         gi8::gram_i8_setup(ctx, smem_raw);
-        gi8::gram_i8_run<FUSED_I8_THREADS>(ctx, gp, &tmA, &tmB, tiles, ntiles, worker, nworkers);
+        gi8::gram_i8_run<FUSED_I8_THREADS, gi8::NDIG, true>(ctx, gp, &tmA, &tmB, tiles, ntiles, worker, nworkers, tile_counter);
         gi8::gram_i8_teardown(ctx);
     }
     if (yrp.M > 0) {
@@ -323,7 +339,7 @@ int fused_threads(int i8) { return i8 ? FUSED_I8_THREADS : FUSED_THREADS; }
 
 int launch_fused_chunk_i8(RecurArgs rp, int n_groups, int team, int upt, int halves, int max_slice_nnz,
                           const gi8::GramI8Args& gp, const int2* tiles, int ntiles, const GemmArgs& yr_args,
-                          const drv::DriveArgs& drive_args, int num_sms, cudaStream_t stream) {
+                          const drv::DriveArgs& drive_args, int num_sms, cudaStream_t stream, int* tile_counter) {
     const bool has_rec = rp.steps > 0;
     rp.units_per_cta = recur_units_per_cta(rp.N, team);
     rp.smem_nnz = max_slice_nnz + (max_slice_nnz & 1);
@@ -361,7 +377,7 @@ int launch_fused_chunk_i8(RecurArgs rp, int n_groups, int team, int upt, int hal
         return -2;
     }
     void (*kern)(RecurArgs, int, int, int, gi8::GramI8Args, const CUtensorMap, const CUtensorMap, const int2*, int, GemmArgs,
-                 drv::DriveArgs);
+                 drv::DriveArgs, int*);
     const bool drv_on = drive_args.m > 0;
     if (drv_on && upt != 1) {
         set_error("fused chunk: the in-kernel drive is built for one unit per thread");
@@ -386,7 +402,11 @@ int launch_fused_chunk_i8(RecurArgs rp, int n_groups, int team, int upt, int hal
     if (ntiles == 0) yr_copy.M = 0;   // no Gram CTAs in this launch: the caller runs the Y R pass itself
     smem = std::max(smem, yr::smem_bytes<FUSED_I8_THREADS>());
     drv::DriveArgs dv = drive_args;
-    void* args[] = {&rp, &rec_ctas, &team, &member_bytes, &g, &tm_a, &tm_b, (void*)&tiles, &ntiles, &yr_copy, &dv};
+    if (ntiles > 0) {
+        XESN_REQUIRE(tile_counter, "fused chunk: no tile counter");
+        XESN_CUDA_OK(cudaMemsetAsync(tile_counter, 0, sizeof(int), stream));
+    }
+    void* args[] = {&rp, &rec_ctas, &team, &member_bytes, &g, &tm_a, &tm_b, (void*)&tiles, &ntiles, &yr_copy, &dv, &tile_counter};
     XESN_CUDA_OK(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(FUSED_I8_THREADS), args, (size_t)smem, stream));
     count_launch();
     return 0;
@@ -473,7 +493,8 @@ void cluster_tail_ptr(int N, int team, const int* indptr, int* out) {
 // rp.steps == 0 -> no recurrence role; ntiles == 0 -> no Gram role
 int launch_fused_cluster_i8(RecurArgs rp, int n_groups, int team, const int* tail_ptr_dev, int tail_cap,
                             const gi8::GramI8Args& gp, const int2* tiles, int ntiles, const GemmArgs& yr_args,
-                            const drv::DriveArgs& drive_args, int num_sms, cudaStream_t stream) {
+                            const drv::DriveArgs& drive_args, int num_sms, cudaStream_t stream, int* tile_counter,
+                            bool rec_grid_only, bool zero_counter) {
     const bool has_rec = rp.steps > 0;
     rp.units_per_cta = recur_units_per_cta(rp.N, team);
     rp.n_pad = cluster_state_slots(rp.N) + 2;   // the last slot of a copy always holds 0
@@ -484,7 +505,7 @@ int launch_fused_cluster_i8(RecurArgs rp, int n_groups, int team, const int* tai
     int smem = (int)recur::cluster_smem_bytes(rp.n_pad, tail_cap);
     smem = std::max(smem, gi8::SMEM_BYTES);
     smem = std::max(smem, yr::smem_bytes<FUSED_I8_THREADS>());
-    const bool drv_on = drive_args.m > 0;
+    const bool drv_on = drive_args.m > 0 && !rec_grid_only;
     auto kern = drv_on ? fused_cluster_i8_kernel<true> : fused_cluster_i8_kernel<false>;
     XESN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     int rec_ctas = has_rec ? team * n_groups : 0;
@@ -500,13 +521,19 @@ int launch_fused_cluster_i8(RecurArgs rp, int n_groups, int team, const int* tai
     cfg.gridDim = dim3((unsigned)(num_sms / team * team));
     int max_clusters = 0;
     XESN_CUDA_OK(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
-    if (max_clusters * team <= rec_ctas && (ntiles > 0 || drv_on)) {
+    if (!rec_grid_only && max_clusters * team <= rec_ctas && (ntiles > 0 || drv_on)) {
         set_error("fused cluster chunk: %d clusters of %d fit, the recurrence role needs %d", max_clusters, team, n_groups);
         return -2;
     }
     int grid = max_clusters * team;
-    if (ntiles == 0 && !drv_on) grid = rec_ctas;
+    // rec_grid_only: the workers are a launch of their own (launch_fused_cluster_split_i8); the Gram arguments are only
+    // there for the recurrence CTAs to help with the tiles once their chunk is done
+    if ((ntiles == 0 && !drv_on) || rec_grid_only) grid = rec_ctas;
     if (grid <= 0) return 0;
+    if (ntiles > 0) {
+        XESN_REQUIRE(tile_counter, "fused cluster chunk: no tile counter");
+        if (zero_counter) XESN_CUDA_OK(cudaMemsetAsync(tile_counter, 0, sizeof(int), stream));
+    }
     cfg.gridDim = dim3((unsigned)grid);
     gi8::GramI8Args g = gp;
     alignas(64) CUtensorMap tm_a, tm_b;
@@ -517,7 +544,9 @@ int launch_fused_cluster_i8(RecurArgs rp, int n_groups, int team, const int* tai
     GemmArgs yr_copy = yr_args;
     if (ntiles == 0) yr_copy.M = 0;
     drv::DriveArgs dv = drive_args;
-    XESN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, rp, rec_ctas, team, tail_ptr_dev, tail_cap, g, tm_a, tm_b, tiles, ntiles, yr_copy, dv));
+    if (rec_grid_only) yr_copy.M = 0, dv.m = 0;
+    XESN_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, rp, rec_ctas, team, tail_ptr_dev, tail_cap, g, tm_a, tm_b, tiles, ntiles, yr_copy, dv,
+                                    tile_counter));
     count_launch();
     return 0;
 }
@@ -525,7 +554,8 @@ int launch_fused_cluster_i8(RecurArgs rp, int n_groups, int team, const int* tai
 // Gram / Y R / drive workers alone, as an ordinary (non-cluster, non-cooperative) launch of `n_workers` CTAs: the
 // companion of a recurrence-only cluster launch (below), and the last launch of a training pass
 static int launch_gram_workers_i8(const gi8::GramI8Args& gp, const int2* tiles, int ntiles, const GemmArgs& yr_args,
-                                  const drv::DriveArgs& drive_args, int n_workers, cudaStream_t stream) {
+                                  const drv::DriveArgs& drive_args, int n_workers, cudaStream_t stream, int* tile_counter,
+                                  bool zero_counter) {
     const bool drv_on = drive_args.m > 0;
     if (n_workers <= 0 || (ntiles == 0 && !drv_on)) return 0;
     auto kern = drv_on ? fused_chunk_i8_kernel<1, false, true> : fused_chunk_i8_kernel<1, false, false>;
@@ -542,7 +572,11 @@ static int launch_gram_workers_i8(const gi8::GramI8Args& gp, const int2* tiles, 
     RecurArgs none = {};
     int rec_ctas = 0, team = 1, member_bytes = 0;
     const int smem = std::max(gi8::SMEM_BYTES, yr::smem_bytes<FUSED_I8_THREADS>());
-    void* args[] = {&none, &rec_ctas, &team, &member_bytes, &g, &tm_a, &tm_b, (void*)&tiles, &ntiles, &yr_copy, &dv};
+    if (ntiles > 0) {
+        XESN_REQUIRE(tile_counter, "Gram workers: no tile counter");
+        if (zero_counter) XESN_CUDA_OK(cudaMemsetAsync(tile_counter, 0, sizeof(int), stream));
+    }
+    void* args[] = {&none, &rec_ctas, &team, &member_bytes, &g, &tm_a, &tm_b, (void*)&tiles, &ntiles, &yr_copy, &dv, &tile_counter};
     XESN_CUDA_OK(cudaLaunchKernel((void*)kern, dim3(n_workers), dim3(FUSED_I8_THREADS), args, (size_t)smem, stream));
     count_launch();
     return 0;
@@ -557,18 +591,24 @@ static int launch_gram_workers_i8(const gi8::GramI8Args& gp, const int2* tiles, 
 int launch_fused_cluster_split_i8(RecurArgs rp, int n_groups, int team, const int* tail_ptr_dev, int tail_cap,
                                   const gi8::GramI8Args& gp, const int2* tiles, int ntiles, const GemmArgs& yr_args,
                                   const drv::DriveArgs& drive_args, int num_sms, cudaStream_t stream, cudaStream_t side,
-                                  cudaEvent_t ev_fork, cudaEvent_t ev_join) {
+                                  cudaEvent_t ev_fork, cudaEvent_t ev_join, int* tile_counter) {
     const bool has_rec = rp.steps > 0, has_work = ntiles > 0 || drive_args.m > 0;
-    if (!has_rec) return launch_gram_workers_i8(gp, tiles, ntiles, yr_args, drive_args, num_sms, stream);
+    if (!has_rec) return launch_gram_workers_i8(gp, tiles, ntiles, yr_args, drive_args, num_sms, stream, tile_counter, true);
     const int rec_ctas = team * n_groups;
     if (!has_work || rec_ctas >= num_sms)
-        return launch_fused_cluster_i8(rp, n_groups, team, tail_ptr_dev, tail_cap, gp, tiles, ntiles, yr_args, drive_args, num_sms, stream);
+        return launch_fused_cluster_i8(rp, n_groups, team, tail_ptr_dev, tail_cap, gp, tiles, ntiles, yr_args, drive_args, num_sms,
+                                       stream, tile_counter, false, true);
+    // the tile counter is shared by both kernels: zeroed once, before the fork
+    if (ntiles > 0) {
+        XESN_REQUIRE(tile_counter, "fused cluster chunk: no tile counter");
+        XESN_CUDA_OK(cudaMemsetAsync(tile_counter, 0, sizeof(int), stream));
+    }
     XESN_CUDA_OK(cudaEventRecord(ev_fork, stream));
     XESN_CUDA_OK(cudaStreamWaitEvent(side, ev_fork, 0));
-    if (int rc = launch_fused_cluster_i8(rp, n_groups, team, tail_ptr_dev, tail_cap, gi8::GramI8Args{}, nullptr, 0, GemmArgs{},
-                                         drv::DriveArgs{}, num_sms, stream))
+    if (int rc = launch_fused_cluster_i8(rp, n_groups, team, tail_ptr_dev, tail_cap, gp, tiles, ntiles, GemmArgs{}, drv::DriveArgs{},
+                                         num_sms, stream, tile_counter, true, false))
         return rc;
-    int rc = launch_gram_workers_i8(gp, tiles, ntiles, yr_args, drive_args, num_sms - rec_ctas, side);
+    int rc = launch_gram_workers_i8(gp, tiles, ntiles, yr_args, drive_args, num_sms - rec_ctas, side, tile_counter, false);
     XESN_CUDA_OK(cudaEventRecord(ev_join, side));
     XESN_CUDA_OK(cudaStreamWaitEvent(stream, ev_join, 0));
     return rc;

@@ -153,7 +153,12 @@ struct GramI8Ctx {
     unsigned bar_tfull;    // all MMAs of the tile have completed: accumulators ready for the epilogue
     unsigned bar_tempty;   // the epilogue has read the accumulators
     unsigned tmem;         // TMEM base address (512 columns)
+    // dynamic tile scheduling (gram_i8_run<.., DYN = true>): the producer draws tile numbers from a global counter and
+    // hands them to the MMA issuer and the epilogue through a ring of TILE_RING slots, one mbarrier per slot
+    unsigned bar_tile;     // TILE_RING mbarriers: the slot holds the number of the next tile (or -1: no more tiles)
+    unsigned tile_ids;     // TILE_RING ints
 };
+constexpr int TILE_RING = 8;   // > STAGES + 2: the producer is never that many tiles ahead of the epilogue
 
 // one warp allocates all 512 TMEM columns; every thread learns the base address
 template <int ND = NDIG>
@@ -167,11 +172,14 @@ __device__ __forceinline__ void gram_i8_setup(GramI8Ctx& ctx, unsigned char* sme
     ctx.bar_tfull = ctl + 16 * STAGES;
     ctx.bar_tempty = ctl + 16 * STAGES + 8;
     const unsigned tmem_slot = ctl + 16 * STAGES + 16;
+    ctx.bar_tile = ctl + 16 * STAGES + 24;
+    ctx.tile_ids = ctx.bar_tile + 8 * TILE_RING;    // ends at ctl + 16 STAGES + 24 + 96 <= ctl + 256
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(ctx.bar_full + 8 * s, 1);
             mbar_init(ctx.bar_empty + 8 * s, ISSUERS);
         }
+        for (int s = 0; s < TILE_RING; ++s) mbar_init(ctx.bar_tile + 8 * s, 1);
         mbar_init(ctx.bar_tfull, ISSUERS);
         mbar_init(ctx.bar_tempty, 8 /* EPI_WARPS */);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -250,10 +258,43 @@ __device__ __forceinline__ int2 tile_of(const int2* __restrict__ tiles, long lon
     return make_int2(ti, (int)(t - (long long)ti * (ti + 1)));
 }
 
-template <int NT, int ND = NDIG>
+// tile sequence of one role: static (tile worker, worker + nworkers, ...) or drawn by the producer from *counter
+template <bool DYN>
+struct TileSeq {
+    long long t, step, total;
+    unsigned n = 0;
+    __device__ __forceinline__ TileSeq(long long worker, long long nworkers, long long total_) : t(worker), step(nworkers), total(total_) {}
+    // consumer side (issuer, epilogue): number of the next tile, or -1
+    __device__ __forceinline__ long long next(const GramI8Ctx& ctx) {
+        if (!DYN) {
+            const long long r = t < total ? t : -1;
+            t += step;
+            return r;
+        }
+        const unsigned slot = n % TILE_RING;
+        mbar_wait(ctx.bar_tile + 8 * slot, (n / TILE_RING) & 1u);
+        int id;
+        asm volatile("ld.shared.b32 %0, [%1];\n" : "=r"(id) : "r"(ctx.tile_ids + 4 * slot) : "memory");
+        ++n;
+        return id;
+    }
+    // producer side: draws the next tile and publishes it to the other roles
+    __device__ __forceinline__ long long draw(const GramI8Ctx& ctx, int* counter) {
+        if (!DYN) return next(ctx);
+        const long long got = atomicAdd(counter, 1);
+        const int id = got < total ? (int)got : -1;
+        const unsigned slot = n % TILE_RING;
+        asm volatile("st.shared.b32 [%0], %1;\n" ::"r"(ctx.tile_ids + 4 * slot), "r"(id) : "memory");
+        mbar_arrive(ctx.bar_tile + 8 * slot);
+        ++n;
+        return id;
+    }
+};
+
+template <int NT, int ND = NDIG, bool DYN = false>
 __device__ __forceinline__ void gram_i8_run(GramI8Ctx& ctx, const GramI8Args& p, const void* tmA, const void* tmB,
                                             const int2* __restrict__ tiles, int ntiles, long long worker,
-                                            long long nworkers) {
+                                            long long nworkers, int* counter = nullptr) {
     static_assert(NT == 512, "the Gram role is laid out for 16 warps");
     constexpr int NDIG = ND;  // shadows the 7-digit default inside this function
     constexpr int STAGES = Ring<ND>::STAGES, STAGE_BYTES = Ring<ND>::STAGE_BYTES, A_BYTES = Ring<ND>::A_BYTES;
@@ -264,7 +305,8 @@ __device__ __forceinline__ void gram_i8_run(GramI8Ctx& ctx, const GramI8Args& p,
     if (warp == PRODUCER_WARP) {
         if (lane == 0) {
             unsigned it = 0;
-            for (long long t = worker; t < total; t += nworkers) {
+            TileSeq<DYN> seq(worker, nworkers, total);
+            for (long long t = seq.draw(ctx, counter); t >= 0; t = seq.draw(ctx, counter)) {
                 const int2 ij = tile_of(tiles, t % ntiles);
                 const int bz = (int)(t / ntiles);
                 const int m0 = ij.x * TM, n0 = ij.y * TN;
@@ -282,7 +324,8 @@ __device__ __forceinline__ void gram_i8_run(GramI8Ctx& ctx, const GramI8Args& p,
     } else if (warp < ISSUERS) {
         if (lane == 0) {
             unsigned it = 0, tc = 0;
-            for (long long t = worker; t < total; t += nworkers, ++tc) {
+            TileSeq<DYN> seq(worker, nworkers, total);
+            for (long long t = seq.next(ctx); t >= 0; t = seq.next(ctx), ++tc) {
                 mbar_wait(ctx.bar_tempty, (tc & 1u) ^ 1u);  // the epilogue has drained the previous tile's accumulators
                 tc_fence_after();
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
@@ -317,7 +360,8 @@ __device__ __forceinline__ void gram_i8_run(GramI8Ctx& ctx, const GramI8Args& p,
         constexpr int NC = TN / (EPI_WARPS / 4);
         const int q = warp & 3, part = (warp - EPI_WARP0) >> 2;
         unsigned tc = 0;
-        for (long long t = worker; t < total; t += nworkers, ++tc) {
+        TileSeq<DYN> seq(worker, nworkers, total);
+        for (long long t = seq.next(ctx); t >= 0; t = seq.next(ctx), ++tc) {
             const int2 ij = tile_of(tiles, t % ntiles);
             const int bz = (int)(t / ntiles);
             const int m0 = ij.x * TM, n0 = ij.y * TN;

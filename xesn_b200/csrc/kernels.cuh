@@ -89,9 +89,10 @@ int gram_i8_make_maps(const gi8::GramI8Args& a, void* map_a, void* map_b);  // t
 // yr_args.M > 0: the Gram CTAs also run ybar += Y R of the previous chunk (skinny targets, yr_skinny.cuh);
 // drive_args.m > 0: and the input projection Win u + b of the next chunk (few inputs)
 namespace drv { struct DriveArgs; }
+// tile_counter: device int from which the Gram CTAs -- and the recurrence CTAs once their chunk is done -- draw tiles
 int launch_fused_chunk_i8(RecurArgs rp, int n_groups, int team, int upt, int halves, int max_slice_nnz,
                           const gi8::GramI8Args& gp, const int2* tiles, int ntiles, const GemmArgs& yr_args,
-                          const drv::DriveArgs& drive_args, int num_sms, cudaStream_t stream);
+                          const drv::DriveArgs& drive_args, int num_sms, cudaStream_t stream, int* tile_counter);
 // recurrence role on thread-block clusters (recur_cluster.cuh): state exchange through distributed shared memory
 bool cluster_recur_geometry(int N, int n_groups, const int* indptr, int num_sms, int* team_out, int* tail_cap_out);
 // the same engine for runs without a Gram role (spin-up, forced runs): the thinnest clusters that are all resident
@@ -99,7 +100,8 @@ bool cluster_forced_geometry(int N, int n_groups, const int* indptr, int num_sms
 void cluster_tail_ptr(int N, int team, const int* indptr, int* out);   // host table [team][units_per_cta + 1]
 int launch_fused_cluster_i8(RecurArgs rp, int n_groups, int team, const int* tail_ptr_dev, int tail_cap,
                             const gi8::GramI8Args& gp, const int2* tiles, int ntiles, const GemmArgs& yr_args,
-                            const drv::DriveArgs& drive_args, int num_sms, cudaStream_t stream);
+                            const drv::DriveArgs& drive_args, int num_sms, cudaStream_t stream, int* tile_counter = nullptr,
+                            bool rec_grid_only = false, bool zero_counter = true);
 // placement of the states in shared memory that avoids bank conflicts of the row gathers (bank_layout.cu): slot_out[N]
 // in [0, n_slots), n_slots % 16 == 0; returns the gather wavefronts per step over all CTAs, *before = natural placement
 long long plan_bank_layout(int N, const int* indptr, const int* indices, int upc, int kreg, int ktail, int n_slots,
@@ -114,7 +116,7 @@ inline int cluster_state_slots(int N) { return (N + 15) / 16 * 16 + 32; }   // t
 int launch_fused_cluster_split_i8(RecurArgs rp, int n_groups, int team, const int* tail_ptr_dev, int tail_cap,
                                   const gi8::GramI8Args& gp, const int2* tiles, int ntiles, const GemmArgs& yr_args,
                                   const drv::DriveArgs& drive_args, int num_sms, cudaStream_t stream, cudaStream_t side,
-                                  cudaEvent_t ev_fork, cudaEvent_t ev_join);
+                                  cudaEvent_t ev_fork, cudaEvent_t ev_join, int* tile_counter);
 // pull-model recurrence (pull_body.cuh): spread over all SMs, beside the Gram role in every CTA
 int pull_geometry(int N, int n_groups, int n_ctas, int* upc_out, int* upt_out);
 int launch_pull_forced(RecurArgs rp, int n_groups, int num_sms, cudaStream_t stream);
