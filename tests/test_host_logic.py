@@ -110,7 +110,7 @@ def test_auto_chunk_bounds():
     assert auto_chunk(16000, 1, 20000, 100) == 100
     assert auto_chunk(100, 1, 10, None) == 10
     assert auto_chunk(6000, 256, 4096, None) >= 64
-    assert 16 * 6000 * 256 * auto_chunk(6000, 256, 4096, None) <= (4 << 30)
+    assert 48 * 6000 * 256 * auto_chunk(6000, 256, 4096, None) <= (12 << 30)      # the scratch budget (12 of the 180 GB)
 
 
 # --------------------------------------------------------------------------- LazyESN shell (xesn/test/lazy.py)
