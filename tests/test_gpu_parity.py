@@ -3,6 +3,7 @@ committed reference outputs.  Tolerances: the north star allows states rtol 1e-5
 Wout rtol 1e-4 (max-normalised); the FP64 path is held to much tighter bounds here.
 """
 import ctypes
+import os
 import itertools
 import warnings
 
@@ -848,3 +849,31 @@ def test_costfunction_lazy_candidates_and_evaluate(torch):
     assert out["nrmse"].shape == (1, 16) and out["nrmse"][0, 0] == 0.0           # step 0 is the truth
     assert out["psd_truth"].shape == (1, 12, 16) and out["psd_nrmse"].shape == (1, 16)
     np.testing.assert_allclose(np.nan_to_num(out["psd_truth"][0]), np.nan_to_num(oc.psd_nd(out["truth"][0])), rtol=1e-10)
+
+
+def test_batched_large_systems_int8_trailing_updates(torch):
+    """Several ridge systems with N >= 2048 (the cfg-4 / cfg-5 regime): the trailing updates of the batched Cholesky run on
+    the int8 tensor cores, one SYRK per system and panel, with the right-hand sides folded into the factorisation.
+    Two LazyESN groups of N=2304 against the oracle (scipy's symmetric solve), training series longer than N."""
+    from xesn_b200 import LazyESN
+    from xesn_b200.synthetic import lorenz96
+    data = lorenz96(16, 2700)
+    kw = {k: dict(v) for k, v in ESN_KW.items()}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        esn = LazyESN({"x": 8}, {"x": 1}, "periodic", 2304, 0.5, 1e-4, **kw)
+    esn.build()
+    esn.train(data[:, :2600], n_spinup=0)
+    assert not np.any(esn.last_info.cpu().numpy())          # Cholesky succeeded: no pivoted fallback on this path
+    W = sp.csr_matrix(esn.W)
+    depth = {0: 1, 1: 0}
+    ref = oc.lazy_train(data[:, :2600], (8,), depth, "periodic", 0, None, W, esn.Win, esn.bias_vector, 0.5, 1e-4)
+    got = esn.Wout_groups
+    assert got.shape[0] == 2
+    assert oc.max_normalised_err(got, ref.reshape(got.shape)) < 1e-4
+    os.environ["XESN_B200_SOLVE_I8_BATCH"] = "0"            # the FP64 DMMA trailing updates give the same readout
+    try:
+        esn.train(data[:, :2600], n_spinup=0)
+    finally:
+        os.environ.pop("XESN_B200_SOLVE_I8_BATCH", None)
+    assert oc.max_normalised_err(esn.Wout_groups, got) < 1e-5

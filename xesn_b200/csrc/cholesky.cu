@@ -251,7 +251,11 @@ int launch_syrk_i8(const double* L, long long ldl, double* C, long long ldc, int
 static bool solve_uses_i8(int n, int batch) {
     const char* e = getenv("XESN_B200_SOLVE_I8");
     const bool on = !(e && e[0] == '0');
-    return on && batch == 1 && n >= 2048;
+    if (batch > 1) {   // several large systems: one SYRK per system and panel (XESN_B200_SOLVE_I8_BATCH=0: FP64 DMMA)
+        const char* b = getenv("XESN_B200_SOLVE_I8_BATCH");
+        if (b && b[0] == '0') return false;
+    }
+    return on && n >= 2048;
 }
 // inverses of the full WB x WB diagonal blocks + one 256 x 256 temporary per block
 static long long wide_inverse_doubles(int n) { return (long long)(n / WB) * (WB * WB + 256 * 256) + 64; }
@@ -410,9 +414,12 @@ static int cholesky_solve_body(SolveCtx& ctx, double* A, long long lda, long lon
             const int syrk_sms = std::max(1, num_sms - free_sms);
             double* w8 = work + strideLinv * batch;
             w8 = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(w8) + 255) & ~(uintptr_t)255);
-            if ((rc = launch_syrk_i8(A + (long long)Jend2 * lda + J, lda, A + (long long)Jend2 * lda + Jend2, lda,
-                                     n - Jend2 + xr, n - Jend2, Jend - J, w8, syrk_sms, stream)))
-                return rc;
+            for (int b = 0; b < batch; ++b) {   // the systems share the digit-plane workspace: one after the other
+                double* Ab = A + (long long)b * strideA;
+                if ((rc = launch_syrk_i8(Ab + (long long)Jend2 * lda + J, lda, Ab + (long long)Jend2 * lda + Jend2, lda,
+                                         n - Jend2 + xr, n - Jend2, Jend - J, w8, syrk_sms, stream)))
+                    return rc;
+            }
         } else if (n - Jend2 > 0) {
             if (xr) {  // right-hand-side rows: B[:, Jend2:] -= Z[:, J:Jend] L[Jend2:, J:Jend]^T
                 GemmArgs t = {};
