@@ -409,7 +409,8 @@ static int cholesky_solve_body(SolveCtx& ctx, double* A, long long lda, long lon
             // the persistent SYRK kernel would otherwise hold every SM until it ends and starve the look-ahead
             // stream: leave some SMs to the panel factorisation (measured at N=16000, ms per solve: 0 free 42.8,
             // 8: 41.9, 16: 41.0, 32: 38.8, 48: 40.3, 64: 43.0)
-            int free_sms = 32;
+            // (several systems, one SYRK after the other: 16 -- cfg 4 share 170.5 / 173.5 / 177.3 / 180.6 ms at 16 / 32 / 48 / 64)
+            int free_sms = batch == 1 ? 32 : 16;
             if (const char* e = getenv("XESN_B200_SYRK_FREE")) free_sms = atoi(e);
             const int syrk_sms = std::max(1, num_sms - free_sms);
             double* w8 = work + strideLinv * batch;
