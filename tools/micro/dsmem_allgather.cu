@@ -167,8 +167,8 @@ void run(int U, int C, int clusters, const char* name) {
             return;
         }
     }
-    long long cyc[64];
-    double chk[64];
+    long long cyc[256];
+    double chk[256];
     cudaMemcpy(cyc, d_cyc, sizeof(long long) * C * clusters, cudaMemcpyDeviceToHost);
     cudaMemcpy(chk, d_chk, sizeof(double) * C * clusters, cudaMemcpyDeviceToHost);
     bool same = true;

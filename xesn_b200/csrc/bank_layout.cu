@@ -7,8 +7,9 @@
 // per CTA, profiles/recur_trace_r02_after.txt).  But the placement is ours to choose: any permutation `slot[j]`
 // works as long as writers and readers agree.  The conflicts of a kernel are known in advance -- lane l of warp w
 // reads column indices[indptr[row] + k] in round k -- so this file picks the bank (slot mod 16) of every state by a
-// min-conflicts local search over those access sets and then numbers the slots bank by bank.  Nothing about the
-// arithmetic changes (same values, same order): the results are bit-identical, only the addresses move.
+// local search over those access sets (swaps of two states inside a warp's run of 32 slots, see plan_bank_layout).
+// Nothing about the arithmetic changes (same values, same order): the results are bit-identical, only the addresses
+// move.  Measured: gather wavefronts per CTA and step 627 -> 456 at N=2000, the recurrence step 4 % shorter.
 #include <algorithm>
 #include <cstdint>
 #include <numeric>
