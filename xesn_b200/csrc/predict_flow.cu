@@ -363,17 +363,19 @@ __global__ void __launch_bounds__(PF_THREADS, 1) predict_flow_kernel(PredictFlow
             }
         }
         XESN_TRACE_MARK(0);  // [0] refresh of the state copy (thread 0's pieces)
-        bar_inputs_ready();
-        XESN_TRACE_MARK(1);  // [1] waiting for the other warps: their pieces, the inputs
 
-        // ================= phase B: update of the owned units =================
+        // ================= phase B1: W r_{n-1} of the owned units =================
+        // needs the states only, not the inputs: done BEFORE the inputs barrier, while the input-polling warps still wait
+        // for the contributions of the previous step to come through the L2 (the owners used to idle there for 39 % of a
+        // step, profiles/predict_flow_cluster_r02b.txt)
+        if (!CL && n >= 2) asm volatile("bar.sync 3, %0;\n" ::"n"(PF_R_THREADS) : "memory");   // every piece of s_r is in place
+        double wr = 0.0;
         if (owner) {
             // all gathers of the row head in flight before the first use (volatile asm keeps them batched)
             double gth[PF_KREG];
 #pragma unroll
             for (int k = 0; k < PF_KREG; ++k)
                 asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(gth[k]) : "r"(s_r_addr + (CL ? cur * copy_bytes : 0u) + (unsigned)ho[k]));
-            double wr = 0.0;
 #pragma unroll
             for (int k = 0; k < PF_KREG; ++k)
                 if (k < row_len) wr = __dadd_rn(wr, __dmul_rn(hv[k], gth[k]));
@@ -382,6 +384,12 @@ __global__ void __launch_bounds__(PF_THREADS, 1) predict_flow_kernel(PredictFlow
                 wr = __dadd_rn(wr, __dmul_rn(sm.s_tval[tail_lo + k - PF_KREG],
                                              sm.s_r[(CL ? (size_t)cur * n_pad : 0) + sm.s_toff[tail_lo + k - PF_KREG]]));
             XESN_TRACE_MARK(3);  // [3] tail of long rows
+        }
+        bar_inputs_ready();
+        XESN_TRACE_MARK(1);  // [1] waiting for the inputs
+
+        // ================= phase B2: input projection, tanh, publish =================
+        if (owner) {
             const double* wrow = sm.s_win + (size_t)tid * sm.ldw;
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
             int k = 0;
