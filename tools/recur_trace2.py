@@ -55,8 +55,9 @@ esn.train(data, n_spinup=0, batch_size=STEPS)
 e1.record()
 torch.cuda.synchronize()
 prof = _lib.profile_read()
+launch_ms = _lib.profile_regions("fused_chunk")
 _lib.profile_enable(False)
 print(f"{KIND} N={N}: train of {CHUNKS * STEPS} steps {e0.elapsed_time(e1):.2f} ms; fused kernels {prof['fused_chunk'][1]:.2f} ms "
       f"= {prof['fused_chunk'][1] * 1e3 / (CHUNKS * STEPS):.3f} us per step")
-print("fused launches, ms: " + " ".join(f"{x:.3f}" for x in _lib.profile_regions("fused_chunk"))) if hasattr(_lib, "profile_regions") else None
+print("fused launches, ms: " + " ".join(f"{x:.3f}" for x in launch_ms))
 show("xesn_debug_trace_fused", STEPS, f"fused {KIND} N={N} (last chunk{', recurrence role alone' if CHUNKS == 1 else ''})")

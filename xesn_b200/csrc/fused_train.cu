@@ -113,27 +113,28 @@ fused_chunk_i8_kernel(RecurArgs rp, int rec_ctas, int team, int member_bytes, gi
         return;
     }
     const int worker = blockIdx.x - rec_ctas, nworkers = gridDim.x - rec_ctas;
-    if (total > 0) {
-        gi8::GramI8Ctx ctx;
-        gi8::gram_i8_setup(ctx, smem_raw);
-        gi8::gram_i8_run<FUSED_I8_THREADS, gi8::NDIG, true>(ctx, gp, &tmA, &tmB, tiles, ntiles, worker, nworkers, tile_counter);
-        gi8::gram_i8_teardown(ctx);
-    }
-    // ybar += Y R of the same (previous) chunk: skinny work items taken by the Gram CTAs as they run out of tiles --
-    // free in recurrence-bound configurations, where the Gram role ends long before the recurrence role
+    // The statically dealt work comes FIRST -- ybar += Y R of the previous chunk (skinny work items) and Win u + b of the
+    // NEXT chunk (few inputs) -- and the Gram tiles, which are drawn from a counter, last: whatever is left when the
+    // recurrence CTAs finish is then work they can share (measured at cfg 3: the launches that carry all three were
+    // bounded by the workers, 3.17 ms against 2.98 for the recurrence).
     if (yrp.M > 0) {
-        __syncthreads();
         const long long items = yr::n_items(yrp);
         for (long long it = worker; it < items; it += nworkers)
             yr::yr_item<FUSED_I8_THREADS>(yrp, it, reinterpret_cast<double*>(smem_raw));
     }
-    // Win u + b of the NEXT chunk (few inputs): likewise taken by the Gram CTAs when their tiles are done
     if constexpr (DRV) {
         if (dvp.m > 0) {
             const long long items = drv::n_items(dvp);
             for (long long it = worker; it < items; it += nworkers)
                 drv::drive_item<FUSED_I8_THREADS>(dvp, it, reinterpret_cast<double*>(smem_raw));
         }
+    }
+    if (total > 0) {
+        __syncthreads();
+        gi8::GramI8Ctx ctx;
+        gi8::gram_i8_setup(ctx, smem_raw);
+        gi8::gram_i8_run<FUSED_I8_THREADS, gi8::NDIG, true>(ctx, gp, &tmA, &tmB, tiles, ntiles, worker, nworkers, tile_counter);
+        gi8::gram_i8_teardown(ctx);
     }
     XESN_CTA_STAMP(1);
 }
@@ -163,14 +164,7 @@ fused_cluster_i8_kernel(RecurArgs rp, int rec_ctas, int team, const int* __restr
         return;
     }
     const int worker = blockIdx.x - rec_ctas, nworkers = gridDim.x - rec_ctas;
-    if (total > 0) {
-        gi8::GramI8Ctx ctx;
-        gi8::gram_i8_setup(ctx, smem_raw);
-        gi8::gram_i8_run<FUSED_I8_THREADS, gi8::NDIG, true>(ctx, gp, &tmA, &tmB, tiles, ntiles, worker, nworkers, tile_counter);
-        gi8::gram_i8_teardown(ctx);
-    }
-    if (yrp.M > 0) {
-        __syncthreads();
+    if (yrp.M > 0) {   // statically dealt work first, the Gram tiles (drawn from a counter) last: see fused_chunk_i8_kernel
         const long long items = yr::n_items(yrp);
         for (long long it = worker; it < items; it += nworkers)
             yr::yr_item<FUSED_I8_THREADS>(yrp, it, reinterpret_cast<double*>(smem_raw));
@@ -181,6 +175,13 @@ fused_cluster_i8_kernel(RecurArgs rp, int rec_ctas, int team, const int* __restr
             for (long long it = worker; it < items; it += nworkers)
                 drv::drive_item<FUSED_I8_THREADS>(dvp, it, reinterpret_cast<double*>(smem_raw));
         }
+    }
+    if (total > 0) {
+        __syncthreads();
+        gi8::GramI8Ctx ctx;
+        gi8::gram_i8_setup(ctx, smem_raw);
+        gi8::gram_i8_run<FUSED_I8_THREADS, gi8::NDIG, true>(ctx, gp, &tmA, &tmB, tiles, ntiles, worker, nworkers, tile_counter);
+        gi8::gram_i8_teardown(ctx);
     }
 }
 
