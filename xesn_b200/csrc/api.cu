@@ -469,7 +469,8 @@ static RecurArgs recur_args(xesn_reservoir* h) {
     r.indptr = h->d_indptr, r.indices = h->d_indices, r.values = h->d_values;
     r.values_gs = h->values_gs, r.alpha_g = h->d_alpha_g, r.param_groups = h->n_param_groups;
     r.N = h->N, r.alpha = h->alpha, r.smem_nnz = h->max_slice_nnz, r.status = h->d_status;
-    r.stagger = getenv("XESN_B200_NO_STAGGER") ? 0 : 1;
+    r.stagger = getenv("XESN_B200_NO_STAGGER") ? 0 : 50;
+    if (const char* e = getenv("XESN_B200_STAGGER_PCT")) r.stagger = atoi(e);   // experiments
     r.debug_no_exchange = getenv("XESN_B200_DEBUG_NO_EXCHANGE") != nullptr;
     r.hint = getenv("XESN_B200_NO_HINT") ? nullptr : h->d_bar + 2;
     if (const char* e = getenv("XESN_B200_POLL_SLEEP1")) r.poll_sleep_retry = atoi(e);

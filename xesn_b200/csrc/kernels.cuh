@@ -33,7 +33,8 @@ struct RecurArgs {
     // cluster engine: conflict-avoiding placement of the state copies in shared memory (bank_layout.cu)
     const int* slot;         // [N] 8-byte slot of state j
     const int* col_off;      // [nnz] byte offset of the slot of indices[k]
-    int stagger;             // cluster engine: the second half of a CTA's warps runs a few hundred cycles behind the first
+    int stagger;             // cluster engine: > 0: percentage of a CTA's warps in the early group; the others run a few
+                             // hundred cycles behind (0: no staggering)
     int n_active_ctas;       // filled by the launcher
 };
 

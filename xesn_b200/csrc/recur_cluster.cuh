@@ -135,7 +135,7 @@ __device__ __forceinline__ void recur_cluster_body(const RecurArgs& p, const uns
     const bool warp_long = __any_sync(0xffffffffu, row_len > CL_KHEAD);
     // staggered halves (warp-uniform): see the step loop
     const int owner_warps = (u1 - u0 + 31) >> 5;
-    const bool late = p.stagger && owner_warps >= 4 && (tid >> 5) >= (owner_warps + 1) / 2;
+    const bool late = p.stagger > 0 && owner_warps >= 4 && (tid >> 5) >= (owner_warps * p.stagger + 99) / 100;
     double d_after = 0.0;
     const unsigned own_off = owner ? (unsigned)p.slot[unit] * 8u : 0u;   // where this unit's state lives in every copy
     if (owner) {
