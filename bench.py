@@ -789,7 +789,7 @@ def run_ours(ctx, args, name, steps, warmup, with_cpu=True, peaks_int8=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)   # ~0.4 s timed at the default workload: several clock samples
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="lazy", choices=sorted(WORKLOADS))
