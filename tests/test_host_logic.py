@@ -590,3 +590,24 @@ def test_bank_layout_is_a_permutation_and_removes_conflicts(n, team):
     assert after - floor <= 0.6 * (natural.value - floor), (floor, after, natural.value)
     # bad arguments are refused
     assert lib.xesn_bank_layout(n, indptr.ctypes.data, indices.ctypes.data, upc, n_slots + 1, slot.ctypes.data, None) < 0
+
+
+def test_gram_and_readout_interleaved_layout():
+    """The Gram matrices and readouts of a training call are views of ONE array (G, N + O, N) when O <= 256 -- the layout the
+    library recognises by `wout == gram + N*N` (include/xesn_b200.h) and factors with the right-hand sides as extra rows --
+    and two separate arrays otherwise."""
+    import torch
+    from xesn_b200.esn import gram_and_readout
+    G, N, O = 3, 20, 5
+    gram, wout, both = gram_and_readout(G, N, O, "cpu")
+    assert both is not None and both.shape == (G, N + O, N)
+    assert gram.shape == (G, N, N) and wout.shape == (G, O, N)
+    assert wout.data_ptr() == gram.data_ptr() + 8 * N * N
+    assert gram.stride() == ((N + O) * N, N, 1) and wout.stride() == ((N + O) * N, N, 1)
+    assert gram[1].data_ptr() == both[1].data_ptr() and wout[2].data_ptr() == both[2, N:].data_ptr()
+    both.zero_()
+    wout[1, 2, 3] = 7.0
+    assert both[1, N + 2, 3] == 7.0 and float(gram.abs().sum()) == 0.0
+    gram2, wout2, both2 = gram_and_readout(2, 10, 300, "cpu")
+    assert both2 is None and gram2.is_contiguous() and wout2.is_contiguous()
+    assert wout2.data_ptr() != gram2.data_ptr() + 8 * 10 * 10
