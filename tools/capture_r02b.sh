@@ -4,6 +4,9 @@
 # two kernels side by side, the forecast is the cluster variant of the dataflow kernel.
 set -u
 mkdir -p gpurun_out
+# ncu runs the two kernels of a chunk launch one after the other: keep the recurrence CTAs from taking the Gram tiles
+# (in the pipeline they only share what is left when their chunk is done)
+export XESN_B200_NO_JOIN=1
 NCU="ncu --set full --clock-control none --import-source on -f"
 B="python bench.py --no-nested --no-cpu-baseline --steps 1 --warmup 3"
 # launch list first (the program has already run to completion without ncu in the calling command)
@@ -15,4 +18,4 @@ timeout 600 $NCU -k regex:fused_chunk_i8_kernel -s 20 -c 1 -o gpurun_out/gram_wo
 # dataflow forecast, cluster variant (16 clusters of 6)
 timeout 600 $NCU -k regex:predict_flow_kernel -s 6 -c 1 -o gpurun_out/flow_cluster_r02b $B > gpurun_out/cap_flowc.log 2>&1
 ls -la gpurun_out/*_r02b*.ncu-rep
-tail -2 gpurun_out/cap_cluster.log gpurun_out/cap_workers.log gpurun_out/cap_flowc.log | cut -c1-200
+for f in cluster workers flowc; do tail -n 2 gpurun_out/cap_$f.log | cut -c1-200; done

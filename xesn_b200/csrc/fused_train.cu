@@ -606,8 +606,12 @@ int launch_fused_cluster_split_i8(RecurArgs rp, int n_groups, int team, const in
     }
     XESN_CUDA_OK(cudaEventRecord(ev_fork, stream));
     XESN_CUDA_OK(cudaStreamWaitEvent(side, ev_fork, 0));
-    if (int rc = launch_fused_cluster_i8(rp, n_groups, team, tail_ptr_dev, tail_cap, gp, tiles, ntiles, GemmArgs{}, drv::DriveArgs{},
-                                         num_sms, stream, tile_counter, true, false))
+    // XESN_B200_NO_JOIN=1: the recurrence CTAs do not help with the Gram tiles.  For profiler captures: ncu serialises the
+    // two kernels, so the recurrence kernel -- run first, alone -- would otherwise take every tile and the worker grid none.
+    const bool join = !getenv("XESN_B200_NO_JOIN");
+    if (int rc = launch_fused_cluster_i8(rp, n_groups, team, tail_ptr_dev, tail_cap, join ? gp : gi8::GramI8Args{},
+                                         join ? tiles : nullptr, join ? ntiles : 0, GemmArgs{}, drv::DriveArgs{}, num_sms, stream,
+                                         tile_counter, true, false))
         return rc;
     int rc = launch_gram_workers_i8(gp, tiles, ntiles, yr_args, drive_args, num_sms - rec_ctas, side, tile_counter, false);
     XESN_CUDA_OK(cudaEventRecord(ev_join, side));
